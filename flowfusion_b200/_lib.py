@@ -1,0 +1,155 @@
+"""ctypes binding of ``libffb200.so`` (C ABI declared in ``include/ffb200.h``).
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is present,
+every entry point raises.  ``build()`` compiles the library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libffb200.so")
+SOURCES = [os.path.join(_HERE, "csrc", "ffb_kernels.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", "ffb_engine.cuh"), os.path.join(ROOT, "include", "ffb200.h")]
+
+MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
+FIELD_NET, FIELD_SCORE = 0, 1
+DIV_NONE, DIV_EXACT, DIV_HUTCH = 0, 1, 2
+M_EULER, M_MIDPOINT, M_RK4, M_EM, M_LEAPFROG = 0, 1, 2, 3, 4
+ST_NONFINITE_STATE, ST_NAN_SAMPLE = 1, 2
+# indices into the per-tile partial sums
+P_X_Y, P_X_F, P_X_DF, P_X_ERR, P_LP_Y, P_LP_F, P_LP_DF, P_LP_ERR, P_C_Y, P_NONFINITE = range(10)
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("in_features", C.c_int32), ("widths", C.c_int32 * MAX_LAYERS),
+                ("weight", C.c_void_p * MAX_LAYERS), ("bias", C.c_void_p * MAX_LAYERS),
+                ("x_col", C.c_int32), ("x_dim", C.c_int32), ("c_col", C.c_int32), ("c_dim", C.c_int32),
+                ("t_col", C.c_int32), ("t_dim", C.c_int32)]
+
+
+class Field(C.Structure):
+    _fields_ = [("n_calls", C.c_int32), ("net", C.c_void_p * 2), ("in_off", C.c_int32 * 2),
+                ("out_off", C.c_int32 * 2), ("out_sign", C.c_float * 2), ("state_dim", C.c_int32),
+                ("cond_dim", C.c_int32), ("kind", C.c_int32), ("use_sigma", C.c_int32),
+                ("has_drift", C.c_int32), ("div_mode", C.c_int32)]
+
+
+class EvalScalars(C.Structure):
+    _fields_ = [("tfeat", C.c_float * MAX_TFEAT), ("a", C.c_float), ("c", C.c_float),
+                ("sigma", C.c_float), ("sign", C.c_float)]
+
+
+EV_FLOATS = MAX_TFEAT + 4
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("y", C.c_void_p), ("fbase", C.c_void_p), ("dlpbase", C.c_void_p),
+                ("h", C.c_float), ("cond", C.c_void_p), ("cond_state", C.c_void_p), ("probes", C.c_void_p),
+                ("f", C.c_void_p),
+                ("dlp", C.c_void_p), ("ev", EvalScalars), ("atol", C.c_float), ("rtol", C.c_float),
+                ("norms", C.c_int32), ("cond_in_state", C.c_int32), ("partials", C.c_void_p),
+                ("status", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+class Dopri5Args(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("y0", C.c_void_p), ("f0", C.c_void_p), ("lp0", C.c_void_p),
+                ("dlp0", C.c_void_p), ("cond", C.c_void_p), ("probes", C.c_void_p), ("y1", C.c_void_p),
+                ("f1", C.c_void_p), ("lp1", C.c_void_p), ("dlp1", C.c_void_p), ("y_out", C.c_void_p),
+                ("lp_out", C.c_void_p), ("ev", EvalScalars * 6), ("cb", (C.c_float * 6) * 6),
+                ("ce", C.c_float * 7), ("cm", C.c_float * 7), ("dt", C.c_float), ("atol", C.c_float),
+                ("rtol", C.c_float), ("x_interp", C.c_float), ("final", C.c_int32),
+                ("partials", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+class FixedArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("method", C.c_int32), ("nsteps", C.c_int32), ("x0", C.c_void_p),
+                ("lp0", C.c_void_p), ("cond", C.c_void_p), ("probes", C.c_void_p), ("noise", C.c_void_p),
+                ("philox_seed", C.c_uint64), ("philox_offset", C.c_uint64), ("row_offset", C.c_int64),
+                ("x_out", C.c_void_p), ("lp_out", C.c_void_p), ("step_table", C.c_void_p),
+                ("ev_table", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+# every symbol include/ffb200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "ffb_abi_version": (C.c_int, []),
+    "ffb_last_error": (C.c_char_p, []),
+    "ffb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 5),
+    "ffb_net_create": (C.c_int, [C.POINTER(NetDesc), C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ffb_net_destroy": (None, [C.c_void_p]),
+    "ffb_net_flops": (C.c_int64, [C.c_void_p]),
+    "ffb_num_tiles": (C.c_int64, [C.POINTER(Field), C.c_int64]),
+    "ffb_scratch_bytes": (C.c_size_t, [C.POINTER(Field)]),
+    "ffb_field_eval": (C.c_int, [C.POINTER(Field), C.POINTER(EvalArgs), C.c_void_p]),
+    "ffb_dopri5_attempt": (C.c_int, [C.POINTER(Field), C.POINTER(Dopri5Args), C.c_void_p]),
+    "ffb_integrate_fixed": (C.c_int, [C.POINTER(Field), C.POINTER(FixedArgs), C.c_void_p]),
+    "ffb_reduce_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ffb_gaussian_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "ffb_philox_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]),
+    "ffb_ffma_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
+    "ffb_launch_count": (C.c_int64, []),
+}
+
+_lib = None
+
+
+class FFBError(RuntimeError):
+    pass
+
+
+def nvcc_command(out=LIB_PATH):
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(_HERE, "csrc"), "-shared",
+            "-Xcompiler", "-fPIC", "-o", out] + SOURCES
+
+
+def needs_build():
+    if not os.path.isfile(LIB_PATH):
+        return True
+    mt = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > mt for p in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile libffb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise FFBError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """dlopen the library and bind every declared symbol.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise FFBError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    if lib.ffb_abi_version() != 1:
+        raise FFBError("libffb200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise FFBError(f"{what}: {load().ffb_last_error().decode()} (status {rc})")
+
+
+def launch_count():
+    return int(load().ffb_launch_count())

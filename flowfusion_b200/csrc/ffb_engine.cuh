@@ -1,0 +1,453 @@
+// ffb_engine.cuh -- the per-CTA "tile engine": a fused MLP forward (+ forward-mode tangents)
+// over a tile of 128 rows, shared by every integrator kernel in ffb_kernels.cu.
+//
+// Design (B200 / sm_100a):
+//   * one persistent CTA per SM: 8 compute warps (256 threads) + 1 producer warp;
+//   * activations live in shared memory k-major: act[k][row] (stride LDA = 132 floats), so a
+//     thread reads 4 consecutive rows with one LDS.128 and the layer output is written back
+//     in place, transposed, without bank conflicts;
+//   * weights are packed once per network (ffb_net_create) into k-major [K][Np] images with
+//     a column permutation that makes each thread's columns contiguous; the producer warp
+//     streams them from L2 with cp.async.bulk (UBLKCP) into a 3-stage ring guarded by
+//     full/empty mbarriers -- the 4x128 networks (221-471 KB) do not fit beside the
+//     activations, and L2 -> SMEM traffic is < 5 B/clk/SM;
+//   * the contraction runs on the FP32 pipe with packed FFMA2 (fma.rn.f32x2, the only way to
+//     reach the 128 FMA/clk/SM FP32 rate on sm_100): 8x8 register tiles, 32 FFMA2 + 4 LDS.128
+//     per k per thread;
+//   * a row is either a trajectory ("primal") or one forward-mode tangent of a trajectory;
+//     tangent rows skip the bias and are gated by silu'(z) of their primal row, which makes the
+//     divergence trace (flow.py:157-161, diffusion.py:483-503) one more block of GEMM rows.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ffb200.h"
+
+namespace ffb {
+
+constexpr int TM = FFB_TILE_ROWS;        // rows per tile
+constexpr int LDA = TM + 4;              // smem row stride (floats) of every k-major buffer
+constexpr int KMAX = FFB_MAX_WIDTH;      // widest layer
+constexpr int NCOMP = 256;               // compute threads
+constexpr int NTHR = NCOMP + 32;         // + producer warp
+constexpr int KC = 32;                   // weight rows per ring stage
+constexpr int NSTAGE = 3;
+constexpr int CHUNK_FLOATS = KC * KMAX;  // 16 KB per stage
+constexpr int NSLOT = 8;                 // per-CTA state slots in global scratch: Y0, K1..K7
+constexpr int SLOT_Y0 = 7;
+
+struct NetDev {
+  int n_layers;
+  int t_dim, x_dim, c_dim;
+  int K[FFB_MAX_LAYERS];       // rows of the packed image (layer 0: x_dim + c_dim rounded up to 4)
+  int N[FFB_MAX_LAYERS];       // real output width
+  int Np[FFB_MAX_LAYERS];      // padded output width: 16, 32, 64 or 128
+  const float* W[FFB_MAX_LAYERS];   // packed [K][Np]
+  const float* b[FFB_MAX_LAYERS];   // packed [Np]
+  const float* Wt;                  // packed time rows [t_dim][Np[0]]
+};
+
+struct FieldDev {
+  int n_calls;
+  NetDev net[2];
+  int in_off[2], out_off[2];
+  float out_sign[2];
+  int state_dim, cond_dim, kind, use_sigma, has_drift, div_mode;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, bulk async copy, named barrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); completes `bytes` on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// barrier over the 256 compute threads only (the producer warp never joins)
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// activation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+
+// ---------------------------------------------------------------------------------------------
+// per-CTA context
+// ---------------------------------------------------------------------------------------------
+// Shared-memory buffers are kept as byte offsets into the dynamic shared block and turned into
+// pointers at the point of use, so the compiler keeps the .shared state space (LDS/STS, not
+// generic LD/ST) even though Ctx itself lives in local memory across non-inlined calls.
+__device__ __forceinline__ unsigned char* smem_base() {
+  extern __shared__ __align__(128) unsigned char ffb_smem_raw[];
+  return ffb_smem_raw;
+}
+struct Ctx {
+  // shared memory (byte offsets)
+  uint32_t o_act;   // [KMAX][LDA]   layer activations, k-major
+  uint32_t o_ring;  // [NSTAGE][CHUNK_FLOATS]
+  uint32_t o_ycur;  // [SD][LDA]     current stage input (primal rows)
+  uint32_t o_cond;  // [CD][LDA]
+  uint32_t o_prb;   // [SD][LDA]     Hutchinson probes (or unused)
+  uint32_t o_gate;  // [KMAX][GS]    silu'(z) of primal rows
+  uint32_t o_beff;  // [KMAX]        layer-0 bias + time-feature contribution (packed order)
+  uint32_t o_klp;   // [NSLOT+2][TM] d(logp)/dt per slot; row NSLOT = lp0, NSLOT+1 = lp_cur
+  uint32_t o_red;   // [8][FFB_NPART] block-reduction scratch (double)
+  uint32_t o_bar;   // full[NSTAGE], empty[NSTAGE]
+  __device__ __forceinline__ float* act() const { return reinterpret_cast<float*>(smem_base() + o_act); }
+  __device__ __forceinline__ float* ring() const { return reinterpret_cast<float*>(smem_base() + o_ring); }
+  __device__ __forceinline__ float* ycur() const { return reinterpret_cast<float*>(smem_base() + o_ycur); }
+  __device__ __forceinline__ float* condb() const { return reinterpret_cast<float*>(smem_base() + o_cond); }
+  __device__ __forceinline__ float* prb() const { return reinterpret_cast<float*>(smem_base() + o_prb); }
+  __device__ __forceinline__ float* gate() const { return reinterpret_cast<float*>(smem_base() + o_gate); }
+  __device__ __forceinline__ float* beff() const { return reinterpret_cast<float*>(smem_base() + o_beff); }
+  __device__ __forceinline__ float* klp() const { return reinterpret_cast<float*>(smem_base() + o_klp); }
+  __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(smem_base() + o_red); }
+  __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(smem_base() + o_bar); }
+  __device__ __forceinline__ uint64_t* empty() const { return full() + NSTAGE; }
+  // global scratch of this CTA: [NSLOT][SD][LDA]
+  float* scr;
+  // tile geometry
+  int S;           // trajectories per tile
+  int T;           // tangents per trajectory
+  int GS;          // gate row stride
+  int SD, CD;
+  // thread coordinates
+  int tid, lane, warp, tx, ty;
+  bool producer;
+  // pipeline state
+  int stage;
+  uint32_t phase;
+};
+
+__device__ __forceinline__ float* slot_ptr(const Ctx& cx, int slot) { return cx.scr + (size_t)slot * cx.SD * LDA; }
+
+__device__ __forceinline__ void pipe_advance(Ctx& cx) {
+  if (++cx.stage == NSTAGE) { cx.stage = 0; cx.phase ^= 1u; }
+}
+
+// size of the dynamic shared memory block for a field (host + device agree through this)
+__host__ __device__ inline size_t smem_layout(int SD, int CD, int T, int hutch, size_t* off /*[12]*/) {
+  int S = TM / (1 + T);
+  int GS = (T > 0) ? (S | 1) : 0;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~size_t(127); return r; };
+  size_t v[12];
+  v[0] = take(sizeof(float) * KMAX * LDA);                 // act
+  v[1] = take(sizeof(float) * NSTAGE * CHUNK_FLOATS);      // ring
+  v[2] = take(sizeof(float) * SD * LDA);                   // ycur
+  v[3] = take(sizeof(float) * (CD > 0 ? CD : 1) * LDA);    // cond
+  v[4] = take(hutch ? sizeof(float) * SD * LDA : 0);       // probes
+  v[5] = take(sizeof(float) * KMAX * (GS > 0 ? GS : 1));   // gate
+  v[6] = take(sizeof(float) * KMAX);                       // beff
+  v[7] = take(sizeof(float) * (NSLOT + 2) * TM);           // klp
+  v[8] = take(sizeof(double) * 8 * FFB_NPART);             // red
+  v[9] = take(sizeof(uint64_t) * 2 * NSTAGE);              // barriers
+  if (off) for (int i = 0; i < 10; ++i) off[i] = v[i];
+  return o;
+}
+
+__device__ inline void ctx_init(Ctx& cx, const FieldDev& f, float* scratch) {
+  int T = (f.div_mode == FFB_DIV_EXACT) ? f.net[0].x_dim : (f.div_mode == FFB_DIV_HUTCH ? 1 : 0);
+  size_t off[12];
+  smem_layout(f.state_dim, f.cond_dim, T, f.div_mode == FFB_DIV_HUTCH, off);
+  cx.o_act = (uint32_t)off[0];
+  cx.o_ring = (uint32_t)off[1];
+  cx.o_ycur = (uint32_t)off[2];
+  cx.o_cond = (uint32_t)off[3];
+  cx.o_prb = (uint32_t)off[4];
+  cx.o_gate = (uint32_t)off[5];
+  cx.o_beff = (uint32_t)off[6];
+  cx.o_klp = (uint32_t)off[7];
+  cx.o_red = (uint32_t)off[8];
+  cx.o_bar = (uint32_t)off[9];
+  cx.T = T;
+  cx.S = TM / (1 + T);
+  cx.GS = (T > 0) ? (cx.S | 1) : 0;
+  cx.SD = f.state_dim;
+  cx.CD = f.cond_dim;
+  cx.tid = threadIdx.x;
+  cx.lane = threadIdx.x & 31;
+  cx.warp = threadIdx.x >> 5;
+  cx.producer = (cx.warp == NCOMP / 32);
+  // warp w covers 4 row-groups x 8 col-groups of the 16 x 16 thread grid
+  cx.ty = ((cx.warp >> 1) << 2) + (cx.lane >> 3);
+  cx.tx = ((cx.warp & 1) << 3) + (cx.lane & 7);
+  cx.scr = scratch + (size_t)blockIdx.x * NSLOT * f.state_dim * LDA;
+  cx.stage = 0;
+  cx.phase = cx.producer ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], NCOMP / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// producer: stream one network's packed weights through the ring
+// ---------------------------------------------------------------------------------------------
+__device__ inline void produce_net(Ctx& cx, const NetDev& net) {
+  for (int l = 0; l < net.n_layers; ++l) {
+    const int K = net.K[l], Np = net.Np[l];
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      const int rows = min(KC, K - k0);
+      if (cx.lane == 0) {
+        mbar_wait(&cx.empty()[cx.stage], cx.phase);
+        const uint32_t bytes = (uint32_t)(rows * Np) * sizeof(float);
+        mbar_expect_tx(&cx.full()[cx.stage], bytes);
+        bulk_g2s(cx.ring() + cx.stage * CHUNK_FLOATS, net.W[l] + (size_t)k0 * Np, bytes, &cx.full()[cx.stage]);
+      }
+      pipe_advance(cx);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// consumer: one layer's contraction for this thread's 8 rows x C columns
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void load_b(float (&b)[C], const float* p) {
+  if constexpr (C == 8) {
+    float4 b0 = *reinterpret_cast<const float4*>(p);
+    float4 b1 = *reinterpret_cast<const float4*>(p + 64);
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+  } else if constexpr (C == 4) {
+    float4 b0 = *reinterpret_cast<const float4*>(p);
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+  } else if constexpr (C == 2) {
+    float2 b0 = *reinterpret_cast<const float2*>(p);
+    b[0] = b0.x; b[1] = b0.y;
+  } else {
+    b[0] = *p;
+  }
+}
+// packed column offset of this thread, and the real column of its j-th packed column
+template <int C>
+__device__ __forceinline__ int col_base(int tx) { return (C == 8) ? tx * 4 : tx * C; }
+template <int C>
+__device__ __forceinline__ int col_real(int tx, int j) { return j * 16 + tx; }   // same formula for every C
+// thread row i (0..7) -> tile row
+__device__ __forceinline__ int row_of(int ty, int i) { return (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4)); }
+
+template <int C>
+__device__ __forceinline__ void gemm_layer(Ctx& cx, const NetDev& net, int l, float2 (&acc)[4][C]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  const int K = net.K[l], Np = net.Np[l];
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    const int rows = min(KC, K - k0);
+    mbar_wait(&cx.full()[cx.stage], cx.phase);
+    const float* ap = cx.act() + (size_t)k0 * LDA + cx.ty * 4;
+    const float* bp = cx.ring() + cx.stage * CHUNK_FLOATS + col_base<C>(cx.tx);
+#pragma unroll 4
+    for (int kk = 0; kk < rows; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * LDA);
+      const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * LDA + 64);
+      float b[C];
+      load_b<C>(b, bp + kk * Np);
+      const float2 a[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                           make_float2(a1.z, a1.w)};
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float2 bb = make_float2(b[j], b[j]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][j] = __ffma2_rn(a[i], bb, acc[i][j]);
+      }
+    }
+    __syncwarp();
+    if (cx.lane == 0) mbar_arrive(&cx.empty()[cx.stage]);
+    pipe_advance(cx);
+  }
+}
+
+// write this thread's outputs for column (real index n) back into act, transposed
+__device__ __forceinline__ void store_col(Ctx& cx, int n, float v0, float v1, float v2, float v3, float v4, float v5,
+                                          float v6, float v7) {
+  float* p = cx.act() + (size_t)n * LDA + cx.ty * 4;
+  *reinterpret_cast<float4*>(p) = make_float4(v0, v1, v2, v3);
+  *reinterpret_cast<float4*>(p + 64) = make_float4(v4, v5, v6, v7);
+}
+
+// One layer: contraction + epilogue.  `bias` is in packed column order.
+//   hidden layers: primal rows  a = silu(z + b),  gate = silu'(z + b)
+//                  tangent rows a = z * gate[primal row of the same trajectory]
+//   last layer:    primal rows  z + b, tangent rows z   (raw, no activation)
+template <int C>
+__device__ __forceinline__ void run_layer(Ctx& cx, const NetDev& net, int l, const float* bias, bool last) {
+  float2 acc[4][C];
+  gemm_layer<C>(cx, net, l, acc);
+  float v[8][C];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < C; ++j) { v[2 * i][j] = acc[i][j].x; v[2 * i + 1][j] = acc[i][j].y; }
+  float bj[C];
+  load_b<C>(bj, bias + col_base<C>(cx.tx));
+  const int S = cx.S;
+  const int live = S * (1 + cx.T);
+  if (cx.T == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        float z = v[i][j] + bj[j];
+        v[i][j] = last ? z : z * sigmoidf_fast(z);
+      }
+    bar_compute();   // every warp has finished reading act
+  } else {
+    int rs[8];       // trajectory index of tangent rows, -1 for primal rows, -2 for dead rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int r = row_of(cx.ty, i);
+      rs[i] = (r < S) ? -1 : (r < live ? (r % S) : -2);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (rs[i] != -1) continue;
+      const int r = row_of(cx.ty, i);
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        float z = v[i][j] + bj[j];
+        if (last) {
+          v[i][j] = z;
+        } else {
+          float sg = sigmoidf_fast(z);
+          v[i][j] = z * sg;
+          cx.gate()[col_real<C>(cx.tx, j) * cx.GS + r] = sg * (1.0f + z * (1.0f - sg));
+        }
+      }
+    }
+    bar_compute();   // act fully read, gates visible
+    if (!last) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (rs[i] == -1) continue;
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+          v[i][j] = (rs[i] >= 0) ? v[i][j] * cx.gate()[col_real<C>(cx.tx, j) * cx.GS + rs[i]] : 0.0f;
+      }
+    }
+  }
+  const int Nreal = net.N[l];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int n = col_real<C>(cx.tx, j);
+    if (!last || n < Nreal)
+      store_col(cx, n, v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+  }
+  bar_compute();     // outputs visible before the next layer reads them
+}
+
+// ---------------------------------------------------------------------------------------------
+// one network forward on the tile (consumer side).  Inputs must already be in cx.act().
+// ---------------------------------------------------------------------------------------------
+__device__ inline void consume_net(Ctx& cx, const NetDev& net) {
+  for (int l = 0; l < net.n_layers; ++l) {
+    const bool last = (l == net.n_layers - 1);
+    const float* bias = (l == 0) ? cx.beff() : net.b[l];
+    switch (net.Np[l]) {
+      case 128: run_layer<8>(cx, net, l, bias, last); break;
+      case 64:  run_layer<4>(cx, net, l, bias, last); break;
+      case 32:  run_layer<2>(cx, net, l, bias, last); break;
+      default:  run_layer<1>(cx, net, l, bias, last); break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluate the vector field at the state held in cx.ycur(); derivative -> scratch slot `dst`,
+// divergence (if any) -> klp[dst].  Called by ALL threads (the producer warp streams weights).
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ void eval_field(Ctx& cx, const FieldDev& f, const ffb_eval_scalars& ev, int dst) {
+  for (int c = 0; c < f.n_calls; ++c) {
+    const NetDev& net = f.net[c];
+    if (cx.producer) { produce_net(cx, net); continue; }
+    const int S = cx.S, T = cx.T, live = S * (1 + T);
+    const int Np0 = net.Np[0], xd = net.x_dim, cd = net.c_dim, K0 = net.K[0];
+    // layer-0 bias with the (row-uniform) time features folded in
+    for (int p = cx.tid; p < Np0; p += NCOMP) {
+      float b = net.b[0][p];
+      for (int j = 0; j < net.t_dim; ++j) b = fmaf(net.Wt[(size_t)j * Np0 + p], ev.tfeat[j], b);
+      cx.beff()[p] = b;
+    }
+    // layer-0 input rows: [x | cond | zero pad]
+    for (int idx = cx.tid; idx < K0 * TM; idx += NCOMP) {
+      const int k = idx / TM, r = idx - k * TM;
+      float val = 0.0f;
+      if (r < S) {
+        if (k < xd) val = cx.ycur()[(f.in_off[c] + k) * LDA + r];
+        else if (k < xd + cd) val = cx.condb()[(k - xd) * LDA + r];
+      } else if (r < live && k < xd) {
+        const int j = r / S - 1, s = r - (j + 1) * S;
+        val = (f.div_mode == FFB_DIV_EXACT) ? (k == j ? 1.0f : 0.0f) : cx.prb()[k * LDA + s];
+      }
+      cx.act()[k * LDA + r] = val;
+    }
+    bar_compute();
+    consume_net(cx, net);
+    // field transform on the primal rows; act[n][r] holds the raw network output
+    const int Dout = net.N[net.n_layers - 1];
+    float* kd = slot_ptr(cx, dst);
+    for (int idx = cx.tid; idx < Dout * S; idx += NCOMP) {
+      const int d = idx / S, r = idx - d * S;
+      const float o = cx.act()[d * LDA + r];
+      float xd_;
+      if (f.kind == FFB_FIELD_SCORE) {
+        const float sc = f.use_sigma ? __fdiv_rn(o, ev.sigma) : o;
+        const float lin = f.has_drift ? __fmul_rn(ev.a, cx.ycur()[(f.out_off[c] + d) * LDA + r]) : 0.0f;
+        xd_ = __fsub_rn(lin, __fmul_rn(ev.c, sc));
+      } else {
+        xd_ = o;
+      }
+      kd[(f.out_off[c] + d) * LDA + r] = xd_ * (ev.sign * f.out_sign[c]);
+    }
+    if (T > 0) {
+      for (int s = cx.tid; s < S; s += NCOMP) {
+        float tr = 0.0f;
+        if (f.div_mode == FFB_DIV_EXACT) {
+          for (int j = 0; j < T; ++j) tr += cx.act()[j * LDA + (j + 1) * S + s];
+        } else {
+          for (int d = 0; d < xd; ++d) tr = fmaf(cx.prb()[d * LDA + s], cx.act()[d * LDA + S + s], tr);
+        }
+        float dv;
+        if (f.kind == FFB_FIELD_SCORE) {
+          const float trs = f.use_sigma ? __fdiv_rn(tr, ev.sigma) : tr;
+          const float lin = f.has_drift ? ev.a * (float)xd : 0.0f;
+          dv = lin - ev.c * trs;
+        } else {
+          dv = tr;
+        }
+        cx.klp()[dst * TM + s] = dv * ev.sign;
+      }
+    }
+    bar_compute();
+  }
+}
+
+}  // namespace ffb

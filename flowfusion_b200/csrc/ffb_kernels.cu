@@ -1,0 +1,840 @@
+// ffb_kernels.cu -- integrator kernels and the C ABI of libffb200.so (see include/ffb200.h).
+//
+// Kernels (all persistent: grid = min(#tiles, #SMs), one 288-thread CTA per SM):
+//   k_field_eval   one evaluation of the vector field (+ torchdiffeq initial-step norms)
+//   k_dopri5       one attempted Dormand-Prince step: 6 fused evaluations, FSAL, error norm
+//                  partials in FP64, dense-output interpolant at t_end
+//   k_fixed        whole fixed-grid trajectory on-chip: euler / midpoint / rk4(3/8) /
+//                  Euler-Maruyama / leapfrog
+//   k_reduce, k_gauss_logprob, k_philox, k_ffma_peak, k_pack_*   small helpers
+//
+// Reference semantics followed (paths relative to the reference checkout):
+//   torchdiffeq dopri5 / fixed-grid drivers  -> restated in oracle/torchdiffeq/_solver.py
+//   diffusion.py:258-279 (PF-ODE drift), :543-562 (Euler-Maruyama), :483-503 / :327-334 (trace)
+//   flow.py:109-166, :553-652 ; symplectic.py:99-123, :186-201
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "ffb200.h"
+#include "ffb_engine.cuh"
+
+using namespace ffb;
+
+// =============================================================================================
+// small device helpers
+// =============================================================================================
+enum { P_X_Y = 0, P_X_F = 1, P_X_DF = 2, P_X_ERR = 3, P_LP_Y = 4, P_LP_F = 5, P_LP_DF = 6, P_LP_ERR = 7,
+       P_C_Y = 8, P_NONFINITE = 9 };
+
+// k-major tile buffer <- row-major global rows [row0, row0+nv); rows nv..S-1 are zero filled
+__device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ src, int64_t row0, int nv, int S,
+                                          int D, int tid) {
+  for (int idx = tid; idx < S * D; idx += NCOMP) {
+    const int r = idx / D, d = idx - r * D;
+    dst[d * LDA + r] = (r < nv) ? src[(row0 + r) * D + d] : 0.0f;
+  }
+}
+__device__ __forceinline__ void store_rows(float* __restrict__ dst, const float* src, int64_t row0, int nv, int D,
+                                           int tid) {
+  for (int idx = tid; idx < nv * D; idx += NCOMP) {
+    const int r = idx / D, d = idx - r * D;
+    dst[(row0 + r) * D + d] = src[d * LDA + r];
+  }
+}
+
+// deterministic block reduction of NV doubles per thread -> out[q] (thread 0 writes)
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(Ctx& cx, double (&v)[NV], double* out, const int (&slot)[NV]) {
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+  }
+  if (cx.lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) cx.red()[cx.warp * FFB_NPART + q] = v[q];
+  }
+  bar_compute();
+  if (cx.tid == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double s = 0.0;
+      for (int w = 0; w < NCOMP / 32; ++w) s += cx.red()[w * FFB_NPART + q];
+      out[slot[q]] = s;
+    }
+  }
+  bar_compute();
+}
+
+__device__ __forceinline__ bool is_finite_f(float x) { return fabsf(x) <= 3.402823466e38f; }
+
+// torchdiffeq's dense-output polynomial (interp.py): coefficients then Horner-like evaluation,
+// every product and sum rounded separately as the eager PyTorch ops do
+__device__ __forceinline__ float dense_output(float y0, float y1, float ymid, float f0, float f1, float dt, float x) {
+  const float A = __fadd_rn(__fsub_rn(__fmul_rn(2.0f * dt, __fsub_rn(f1, f0)), __fmul_rn(8.0f, __fadd_rn(y1, y0))),
+                            __fmul_rn(16.0f, ymid));
+  const float B = __fsub_rn(
+      __fadd_rn(__fadd_rn(__fmul_rn(dt, __fsub_rn(__fmul_rn(5.0f, f0), __fmul_rn(3.0f, f1))), __fmul_rn(18.0f, y0)),
+                __fmul_rn(14.0f, y1)),
+      __fmul_rn(32.0f, ymid));
+  const float C = __fadd_rn(
+      __fsub_rn(__fsub_rn(__fmul_rn(dt, __fsub_rn(f1, __fmul_rn(4.0f, f0))), __fmul_rn(11.0f, y0)),
+                __fmul_rn(5.0f, y1)),
+      __fmul_rn(16.0f, ymid));
+  const float D = __fmul_rn(dt, f0);
+  float total = __fadd_rn(y0, __fmul_rn(x, D));
+  float xp = __fmul_rn(x, x);
+  total = __fadd_rn(total, __fmul_rn(xp, C));
+  xp = __fmul_rn(xp, x);
+  total = __fadd_rn(total, __fmul_rn(xp, B));
+  xp = __fmul_rn(xp, x);
+  total = __fadd_rn(total, __fmul_rn(xp, A));
+  return total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (throughput-mode noise of the Euler-Maruyama kernel)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+// 4 standard normals for (global row, step, group of 4 columns)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset, int64_t grow, int step, int grp) {
+  const uint64_t c1 = offset + (uint64_t)(uint32_t)step;
+  uint4 ctr = make_uint4((uint32_t)grow, (uint32_t)((uint64_t)grow >> 32) ^ ((uint32_t)grp << 8), (uint32_t)c1,
+                         (uint32_t)(c1 >> 32));
+  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = ((float)r.x + 1.0f) * k, u1 = (float)r.y * k;   // (0,1], [0,1)
+  const float u2 = ((float)r.z + 1.0f) * k, u3 = (float)r.w * k;
+  const float r0 = sqrtf(-2.0f * __logf(fminf(u0, 1.0f))), r1 = sqrtf(-2.0f * __logf(fminf(u2, 1.0f)));
+  float s0, c0, s1, c1f;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1f);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1f, r1 * s1);
+}
+
+// =============================================================================================
+// k_field_eval
+// =============================================================================================
+__global__ void __launch_bounds__(NTHR, 1) k_field_eval(const FieldDev f, const ffb_eval_args a, const int64_t ntiles) {
+  Ctx cx;
+  ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
+  const int S = cx.S, SD = cx.SD, CD = cx.CD;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * S;
+    const int nv = (int)min((int64_t)S, a.batch - row0);
+    float* Y0 = slot_ptr(cx, SLOT_Y0);
+    float* FB = slot_ptr(cx, 1);
+    if (!cx.producer) {
+      load_rows(Y0, a.y, row0, nv, S, SD, cx.tid);
+      if (a.fbase) load_rows(FB, a.fbase, row0, nv, S, SD, cx.tid);
+      if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
+      if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
+      bar_compute();
+      for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
+        const int d = idx / S, r = idx - d * S;
+        const int e = d * LDA + r;
+        cx.ycur()[e] = a.fbase ? __fadd_rn(Y0[e], __fmul_rn(a.h, FB[e])) : Y0[e];
+      }
+      bar_compute();
+    }
+    eval_field(cx, f, a.ev, 0);
+    if (!cx.producer) {
+      const float* F = slot_ptr(cx, 0);
+      if (a.f) store_rows(a.f, F, row0, nv, SD, cx.tid);
+      if (a.dlp && cx.T > 0)
+        for (int s = cx.tid; s < nv; s += NCOMP) a.dlp[row0 + s] = cx.klp()[s];
+      if (a.norms) {
+        double v[6] = {0, 0, 0, 0, 0, 0};   // x_y, x_f, x_df, lp_f, lp_df, c_y
+        for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
+          const int d = idx / S, r = idx - d * S;
+          if (r >= nv) continue;
+          const int e = d * LDA + r;
+          const float y0 = Y0[e];
+          const float sc = __fadd_rn(a.atol, __fmul_rn(fabsf(y0), a.rtol));
+          if (a.norms == 1) {
+            const float q0 = __fdiv_rn(y0, sc), q1 = __fdiv_rn(F[e], sc);
+            v[0] += (double)q0 * q0;
+            v[1] += (double)q1 * q1;
+          } else {
+            const float q2 = __fdiv_rn(__fsub_rn(F[e], FB[e]), sc);
+            v[2] += (double)q2 * q2;
+          }
+        }
+        if (cx.T > 0) {
+          for (int s = cx.tid; s < nv; s += NCOMP) {
+            if (a.norms == 1) {
+              const float q = __fdiv_rn(cx.klp()[s], a.atol);
+              v[3] += (double)q * q;
+            } else {
+              const float q = __fdiv_rn(__fsub_rn(cx.klp()[s], a.dlpbase[row0 + s]), a.atol);
+              v[4] += (double)q * q;
+            }
+          }
+        }
+        if (a.cond_in_state && a.norms == 1) {
+          const float* cs = a.cond_state ? a.cond_state : a.cond;
+          for (int idx = cx.tid; idx < CD * nv; idx += NCOMP) {
+            const float c = cs[row0 * CD + idx];
+            const float q = __fdiv_rn(c, __fadd_rn(a.atol, __fmul_rn(fabsf(c), a.rtol)));
+            v[5] += (double)q * q;
+          }
+        }
+        const int slot[6] = {P_X_Y, P_X_F, P_X_DF, P_LP_F, P_LP_DF, P_C_Y};
+        block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
+      }
+      bar_compute();
+    }
+  }
+}
+
+// =============================================================================================
+// k_dopri5: one attempted step
+// =============================================================================================
+__global__ void __launch_bounds__(NTHR, 1) k_dopri5(const FieldDev f, const ffb_dopri5_args a, const int64_t ntiles) {
+  Ctx cx;
+  ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
+  const int S = cx.S, SD = cx.SD, CD = cx.CD;
+  const bool prob = cx.T > 0;
+  float* LP0 = cx.klp() + NSLOT * TM;
+  float* LPC = cx.klp() + (NSLOT + 1) * TM;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * S;
+    const int nv = (int)min((int64_t)S, a.batch - row0);
+    float* Y0 = slot_ptr(cx, SLOT_Y0);
+    double nonfinite = 0.0;
+    if (!cx.producer) {
+      load_rows(Y0, a.y0, row0, nv, S, SD, cx.tid);
+      load_rows(slot_ptr(cx, 0), a.f0, row0, nv, S, SD, cx.tid);
+      if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
+      if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
+      if (prob)
+        for (int s = cx.tid; s < S; s += NCOMP) {
+          LP0[s] = (s < nv) ? a.lp0[row0 + s] : 0.0f;
+          cx.klp()[s] = (s < nv) ? a.dlp0[row0 + s] : 0.0f;
+          if (!is_finite_f(LP0[s])) nonfinite += 1.0;
+        }
+      bar_compute();
+    }
+    for (int i = 1; i <= 6; ++i) {
+      if (!cx.producer) {
+        for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
+          const int d = idx / S, r = idx - d * S;
+          const int e = d * LDA + r;
+          float acc = __fmul_rn(slot_ptr(cx, 0)[e], a.cb[i - 1][0]);
+          for (int j = 1; j < i; ++j) acc = fmaf(slot_ptr(cx, j)[e], a.cb[i - 1][j], acc);
+          const float y0 = Y0[e];
+          if (i == 1 && !is_finite_f(y0)) nonfinite += 1.0;
+          cx.ycur()[e] = __fadd_rn(y0, acc);
+        }
+        bar_compute();
+      }
+      eval_field(cx, f, a.ev[i - 1], i);
+    }
+    if (!cx.producer) {
+      // cx.ycur() now holds y1 (FSAL: the 7th stage input), slot 6 holds f1
+      double v[3] = {0.0, 0.0, nonfinite};
+      float* stage_out = cx.act();   // free between evaluations: staging for the interpolant
+      for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
+        const int d = idx / S, r = idx - d * S;
+        if (r >= nv) continue;
+        const int e = d * LDA + r;
+        const float y0 = Y0[e], y1 = cx.ycur()[e];
+        float err = __fmul_rn(slot_ptr(cx, 0)[e], a.ce[0]);
+        for (int j = 1; j < 7; ++j) err = fmaf(slot_ptr(cx, j)[e], a.ce[j], err);
+        const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0), fabsf(y1))));
+        const float q = __fdiv_rn(err, tol);
+        v[0] += (double)q * q;
+        if (a.final) {
+          float mid = __fmul_rn(slot_ptr(cx, 0)[e], a.cm[0]);
+          for (int j = 1; j < 7; ++j) mid = fmaf(slot_ptr(cx, j)[e], a.cm[j], mid);
+          stage_out[e] = dense_output(y0, y1, __fadd_rn(y0, mid), slot_ptr(cx, 0)[e], slot_ptr(cx, 6)[e], a.dt,
+                                      a.x_interp);
+        }
+      }
+      if (prob) {
+        for (int s = cx.tid; s < nv; s += NCOMP) {
+          const float l0 = LP0[s];
+          float acc = __fmul_rn(cx.klp()[s], a.cb[5][0]);
+          for (int j = 1; j < 6; ++j) acc = fmaf(cx.klp()[j * TM + s], a.cb[5][j], acc);
+          const float l1 = __fadd_rn(l0, acc);
+          float err = __fmul_rn(cx.klp()[s], a.ce[0]);
+          for (int j = 1; j < 7; ++j) err = fmaf(cx.klp()[j * TM + s], a.ce[j], err);
+          const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(l0), fabsf(l1))));
+          const float q = __fdiv_rn(err, tol);
+          v[1] += (double)q * q;
+          a.lp1[row0 + s] = l1;
+          a.dlp1[row0 + s] = cx.klp()[6 * TM + s];
+          if (a.final) {
+            float mid = __fmul_rn(cx.klp()[s], a.cm[0]);
+            for (int j = 1; j < 7; ++j) mid = fmaf(cx.klp()[j * TM + s], a.cm[j], mid);
+            a.lp_out[row0 + s] = dense_output(l0, l1, __fadd_rn(l0, mid), cx.klp()[s], cx.klp()[6 * TM + s], a.dt,
+                                              a.x_interp);
+          }
+        }
+      }
+      (void)LPC;
+      bar_compute();
+      store_rows(a.y1, cx.ycur(), row0, nv, SD, cx.tid);
+      store_rows(a.f1, slot_ptr(cx, 6), row0, nv, SD, cx.tid);
+      if (a.final) store_rows(a.y_out, stage_out, row0, nv, SD, cx.tid);
+      const int slot[3] = {P_X_ERR, P_LP_ERR, P_NONFINITE};
+      block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
+    }
+  }
+}
+
+// =============================================================================================
+// k_fixed: fixed-grid integrators, the whole trajectory of a tile on-chip
+// =============================================================================================
+__device__ __forceinline__ int evals_per_step(int method) {
+  return method == FFB_M_RK4 ? 4 : (method == FFB_M_MIDPOINT ? 2 : (method == FFB_M_LEAPFROG ? 3 : 1));
+}
+
+// evaluate only call `c` of a 2-call field (leapfrog): same as eval_field restricted to one call
+__device__ inline void eval_one_call(Ctx& cx, const FieldDev& f, int c, const ffb_eval_scalars& ev, int dst) {
+  FieldDev g = f;   // (kernel-param copy; small)
+  g.n_calls = 1;
+  g.net[0] = f.net[c];
+  g.in_off[0] = f.in_off[c];
+  g.out_off[0] = f.out_off[c];
+  g.out_sign[0] = f.out_sign[c];
+  eval_field(cx, g, ev, dst);
+}
+
+__global__ void __launch_bounds__(NTHR, 1) k_fixed(const FieldDev f, const ffb_fixed_args a, const int64_t ntiles) {
+  Ctx cx;
+  ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
+  const int S = cx.S, SD = cx.SD, CD = cx.CD;
+  const bool prob = cx.T > 0;
+  const int nev = evals_per_step(a.method);
+  const float third = (float)(1.0 / 3.0);
+  float* LP0 = cx.klp() + NSLOT * TM;        // lp at the start of the step
+  float* LPC = cx.klp() + (NSLOT + 1) * TM;  // running lp
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * S;
+    const int nv = (int)min((int64_t)S, a.batch - row0);
+    float* Y0 = slot_ptr(cx, SLOT_Y0);
+    float* K1 = slot_ptr(cx, 0);
+    float* K2 = slot_ptr(cx, 1);
+    float* K3 = slot_ptr(cx, 2);
+    float* K4 = slot_ptr(cx, 3);
+    bool saw_nan = false;
+    if (!cx.producer) {
+      load_rows(cx.ycur(), a.x0, row0, nv, S, SD, cx.tid);
+      if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
+      if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
+      if (prob)
+        for (int s = cx.tid; s < S; s += NCOMP) LPC[s] = (s < nv && a.lp0) ? a.lp0[row0 + s] : 0.0f;
+      bar_compute();
+    }
+    for (int step = 0; step < a.nsteps; ++step) {
+      const float* st = a.step_table + (size_t)step * FFB_STEP_STRIDE;
+      const ffb_eval_scalars* ev = a.ev_table + (size_t)step * nev;
+      const float dt = st[0];
+#define FOR_STATE(...)                                        \
+  if (!cx.producer) {                                         \
+    for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {      \
+      const int d = idx / S, r = idx - d * S;                 \
+      const int e = d * LDA + r;                              \
+      (void)d; (void)r;                                       \
+      __VA_ARGS__                                             \
+    }                                                         \
+  }
+#define FOR_LP(...)                                           \
+  if (!cx.producer && prob) {                                 \
+    for (int s = cx.tid; s < S; s += NCOMP) { __VA_ARGS__ }   \
+  }
+      if (a.method == FFB_M_EULER) {
+        eval_field(cx, f, ev[0], 0);
+        FOR_STATE(cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(dt, K1[e]));)
+        FOR_LP(LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, cx.klp()[s]));)
+        if (!cx.producer) bar_compute();
+      } else if (a.method == FFB_M_MIDPOINT) {
+        const float half = st[3];
+        eval_field(cx, f, ev[0], 0);
+        FOR_STATE(const float y = cx.ycur()[e]; Y0[e] = y; cx.ycur()[e] = __fadd_rn(y, __fmul_rn(K1[e], half));)
+        if (!cx.producer) bar_compute();
+        eval_field(cx, f, ev[1], 1);
+        FOR_STATE(cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(dt, K2[e]));)
+        FOR_LP(LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, cx.klp()[TM + s]));)
+        if (!cx.producer) bar_compute();
+      } else if (a.method == FFB_M_RK4) {
+        eval_field(cx, f, ev[0], 0);
+        FOR_STATE(const float y = cx.ycur()[e]; Y0[e] = y;
+                  cx.ycur()[e] = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, K1[e]), third));)
+        if (!cx.producer) bar_compute();
+        eval_field(cx, f, ev[1], 1);
+        FOR_STATE(cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(dt, __fsub_rn(K2[e], __fmul_rn(K1[e], third))));)
+        if (!cx.producer) bar_compute();
+        eval_field(cx, f, ev[2], 2);
+        FOR_STATE(cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(K1[e], K2[e]), K3[e])));)
+        if (!cx.producer) bar_compute();
+        eval_field(cx, f, ev[3], 3);
+        FOR_STATE(const float sum = __fadd_rn(__fadd_rn(K1[e], __fmul_rn(3.0f, __fadd_rn(K2[e], K3[e]))), K4[e]);
+                  cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(__fmul_rn(sum, dt), 0.125f));)
+        FOR_LP(const float k1 = cx.klp()[s], k2 = cx.klp()[TM + s], k3 = cx.klp()[2 * TM + s], k4 = cx.klp()[3 * TM + s];
+               const float sum = __fadd_rn(__fadd_rn(k1, __fmul_rn(3.0f, __fadd_rn(k2, k3))), k4);
+               LPC[s] = __fadd_rn(LPC[s], __fmul_rn(__fmul_rn(sum, dt), 0.125f));)
+        if (!cx.producer) bar_compute();
+      } else if (a.method == FFB_M_EM) {
+        // diffusion.py:552-559: f = drift - g^2 score (ev.c = g^2); x_mean = x + f dt; x = x_mean + g dw
+        const float g = st[1], sq = st[2];
+        eval_field(cx, f, ev[0], 0);
+        if (!cx.producer) {
+          if (a.noise) {
+            for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
+              const int r = idx / SD, d = idx - r * SD;
+              if (r >= nv) continue;
+              const int e = d * LDA + r;
+              const float xm = __fadd_rn(cx.ycur()[e], __fmul_rn(K1[e], dt));
+              const float dw = __fmul_rn(a.noise[((size_t)step * a.batch + row0 + r) * SD + d], sq);
+              const float xn = __fadd_rn(xm, __fmul_rn(g, dw));
+              Y0[e] = xm;
+              cx.ycur()[e] = xn;
+              saw_nan |= (xn != xn);
+            }
+          } else {
+            const int ng = (SD + 3) >> 2;
+            for (int idx = cx.tid; idx < ng * S; idx += NCOMP) {
+              const int grp = idx / S, r = idx - grp * S;
+              if (r >= nv) continue;
+              const float4 z = philox_normal4(a.philox_seed, a.philox_offset, a.row_offset + row0 + r, step, grp);
+              const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int d = grp * 4 + q;
+                if (d >= SD) break;
+                const int e = d * LDA + r;
+                const float xm = __fadd_rn(cx.ycur()[e], __fmul_rn(K1[e], dt));
+                const float xn = __fadd_rn(xm, __fmul_rn(g, __fmul_rn(zz[q], sq)));
+                Y0[e] = xm;
+                cx.ycur()[e] = xn;
+                saw_nan |= (xn != xn);
+              }
+            }
+          }
+          bar_compute();
+        }
+      } else {  // FFB_M_LEAPFROG (extension): kick (dt/2) - drift (dt) - kick (dt/2); call 0 = dq/dt(p), call 1 = dp/dt(q)
+        const float half = st[3];
+        if (step == 0) eval_one_call(cx, f, 1, ev[0], 1);      // dp/dt at (q, t0); later steps reuse the last kick
+        FOR_STATE(if (d >= f.out_off[1] && d < f.out_off[1] + f.net[1].N[f.net[1].n_layers - 1])
+                      cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(half, K2[e]));)
+        if (!cx.producer) bar_compute();
+        eval_one_call(cx, f, 0, ev[1], 0);                     // dq/dt at (p_half, t0 + dt/2)
+        FOR_STATE(if (d >= f.out_off[0] && d < f.out_off[0] + f.net[0].N[f.net[0].n_layers - 1])
+                      cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(dt, K1[e]));)
+        if (!cx.producer) bar_compute();
+        eval_one_call(cx, f, 1, ev[2], 1);                     // dp/dt at (q1, t1)
+        FOR_STATE(if (d >= f.out_off[1] && d < f.out_off[1] + f.net[1].N[f.net[1].n_layers - 1])
+                      cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(half, K2[e]));)
+        if (!cx.producer) bar_compute();
+      }
+#undef FOR_STATE
+#undef FOR_LP
+    }
+    if (!cx.producer) {
+      store_rows(a.x_out, (a.method == FFB_M_EM) ? Y0 : cx.ycur(), row0, nv, SD, cx.tid);
+      if (prob && a.lp_out)
+        for (int s = cx.tid; s < nv; s += NCOMP) a.lp_out[row0 + s] = LPC[s];
+      if (saw_nan) atomicOr(a.status, FFB_ST_NAN_SAMPLE);
+      bar_compute();
+    }
+    (void)LP0;
+  }
+}
+
+// =============================================================================================
+// helpers
+// =============================================================================================
+__global__ void k_reduce(const double* __restrict__ partials, int64_t ntiles, double* __restrict__ sums) {
+  // one warp per quantity; fixed strided order + shuffle tree => deterministic
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (q >= FFB_NPART) return;
+  double s = 0.0;
+  for (int64_t t = lane; t < ntiles; t += 32) s += partials[t * FFB_NPART + q];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) sums[q] = s;
+}
+
+__global__ void k_gauss_logprob(const float* __restrict__ x, const float* __restrict__ add, float* __restrict__ out,
+                                int64_t batch, int dim, float sigma, float log_norm) {
+  // one warp per row: sum_d(-(x^2)/(2 sigma^2) - log sigma - 0.5 log 2pi)  (torch Normal.log_prob order)
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= batch) return;
+  const float var2 = 2.0f * sigma * sigma;
+  float s = 0.0f;
+  for (int d = lane; d < dim; d += 32) {
+    const float v = x[row * dim + d];
+    s += -(v * v) / var2 - log_norm;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s + (add ? add[row] : 0.0f);
+}
+
+__global__ void k_philox(float* __restrict__ out, int64_t batch, int dim, uint64_t seed, uint64_t offset, int step,
+                         int64_t row_offset) {
+  const int ng = (dim + 3) >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * ng) return;
+  const int64_t r = idx / ng;
+  const int grp = (int)(idx - r * ng);
+  const float4 z = philox_normal4(seed, offset, row_offset + r, step, grp);
+  const float zz[4] = {z.x, z.y, z.z, z.w};
+  for (int q = 0; q < 4; ++q)
+    if (grp * 4 + q < dim) out[r * dim + grp * 4 + q] = zz[q];
+}
+
+__global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters) {
+  float2 acc[16];
+  const float2 a = make_float2(1.0f + 1e-7f * threadIdx.x, 1.0f - 1e-7f * threadIdx.x);
+  const float2 b = make_float2(1e-9f, -1e-9f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = make_float2((float)i, (float)-i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = __ffma2_rn(acc[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+  if (s == 123.456f) out[0] = s;
+}
+
+// weight packing -------------------------------------------------------------------------------
+// real column n of packed column p for a layer with padded width Np
+__host__ __device__ inline int packed_to_real(int p, int Np) {
+  const int C = Np / 16;
+  if (C == 8) {
+    const int g = p / 64, rem = p % 64, tx = rem / 4, jj = rem % 4;
+    return (g * 4 + jj) * 16 + tx;
+  }
+  const int tx = p / C, j = p % C;
+  return j * 16 + tx;
+}
+// dst[k][p] = W[n(p)][src_col(k)], zero outside; rows_map: k -> source column (or -1)
+__global__ void k_pack_weight(const float* __restrict__ W, int in_features, int out_features, float* __restrict__ dst,
+                              int K, int Np, int x_col, int x_dim, int c_col, int c_dim, int layer0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * Np) return;
+  const int k = idx / Np, p = idx - k * Np;
+  const int n = packed_to_real(p, Np);
+  int col = -1;
+  if (layer0) {
+    if (k < x_dim) col = x_col + k;
+    else if (k < x_dim + c_dim) col = c_col + (k - x_dim);
+  } else if (k < in_features) {
+    col = k;
+  }
+  dst[idx] = (n < out_features && col >= 0) ? W[(size_t)n * in_features + col] : 0.0f;
+}
+__global__ void k_pack_time(const float* __restrict__ W, int in_features, int out_features, float* __restrict__ dst,
+                            int t_dim, int Np, int t_col) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= t_dim * Np) return;
+  const int j = idx / Np, p = idx - j * Np;
+  const int n = packed_to_real(p, Np);
+  dst[idx] = (n < out_features) ? W[(size_t)n * in_features + t_col + j] : 0.0f;
+}
+__global__ void k_pack_bias(const float* __restrict__ b, int out_features, float* __restrict__ dst, int Np) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Np) return;
+  const int n = packed_to_real(p, Np);
+  dst[p] = (n < out_features) ? b[n] : 0.0f;
+}
+
+// =============================================================================================
+// host side: C ABI
+// =============================================================================================
+struct ffb_net {
+  NetDev dev;
+  std::vector<void*> allocs;
+  int64_t flops;
+};
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(FFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
+
+extern "C" int ffb_abi_version(void) { return FFB_ABI_VERSION; }
+extern "C" const char* ffb_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t ffb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int ffb_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc_major, int32_t* cc_minor,
+                               int32_t* clock_khz) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  int v = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+  if (sm_count) *sm_count = v;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem_optin) *smem_optin = v;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major) *cc_major = v;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev));
+  if (cc_minor) *cc_minor = v;
+  CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev));
+  if (clock_khz) *clock_khz = v;
+  return FFB_OK;
+}
+
+static int pad_width(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)); }
+
+extern "C" int ffb_net_create(const ffb_net_desc* d, void* stream_, ffb_net** out) {
+  if (!d || !out) return fail(FFB_ERR_ARG, "ffb_net_create: null argument");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (d->n_layers < 1 || d->n_layers > FFB_MAX_LAYERS) return fail(FFB_ERR_ARG, "ffb_net_create: 1..8 Linear layers supported");
+  if (d->t_dim < 0 || d->t_dim > FFB_MAX_TFEAT) return fail(FFB_ERR_ARG, "ffb_net_create: at most 32 time-feature columns");
+  if (d->x_dim < 1 || d->x_dim + d->c_dim + d->t_dim != d->in_features)
+    return fail(FFB_ERR_ARG, "ffb_net_create: x_dim + c_dim + t_dim must equal in_features");
+  if (d->x_dim + d->c_dim > FFB_MAX_WIDTH) return fail(FFB_ERR_ARG, "ffb_net_create: state + conditional columns exceed 128");
+  for (int l = 0; l < d->n_layers; ++l)
+    if (d->widths[l] < 1 || d->widths[l] > FFB_MAX_WIDTH)
+      return fail(FFB_ERR_ARG, "ffb_net_create: layer widths must be in 1..128");
+  ffb_net* net = new ffb_net();
+  NetDev& nd = net->dev;
+  memset(&nd, 0, sizeof(nd));
+  nd.n_layers = d->n_layers;
+  nd.t_dim = d->t_dim; nd.x_dim = d->x_dim; nd.c_dim = d->c_dim;
+  net->flops = 0;
+  int in_f = d->in_features;
+  auto cleanup = [&]() { for (void* p : net->allocs) cudaFree(p); delete net; };
+  for (int l = 0; l < d->n_layers; ++l) {
+    const int N = d->widths[l], Np = pad_width(N);
+    const int K = (l == 0) ? ((d->x_dim + d->c_dim + 3) & ~3) : nd.Np[l - 1];
+    nd.K[l] = K; nd.N[l] = N; nd.Np[l] = Np;
+    net->flops += 2LL * in_f * N;
+    float *w = nullptr, *b = nullptr;
+    if (cudaMalloc(&w, sizeof(float) * K * Np) != cudaSuccess || cudaMalloc(&b, sizeof(float) * Np) != cudaSuccess) {
+      cleanup();
+      return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed");
+    }
+    net->allocs.push_back(w); net->allocs.push_back(b);
+    k_pack_weight<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, w, K, Np, d->x_col, d->x_dim,
+                                                           d->c_col, d->c_dim, l == 0);
+    k_pack_bias<<<1, 128, 0, stream>>>(d->bias[l], N, b, Np);
+    g_launches += 2;
+    nd.W[l] = w; nd.b[l] = b;
+    if (l == 0) {
+      float* wt = nullptr;
+      const int td = d->t_dim > 0 ? d->t_dim : 1;
+      if (cudaMalloc(&wt, sizeof(float) * td * Np) != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
+      net->allocs.push_back(wt);
+      if (d->t_dim > 0) {
+        k_pack_time<<<(d->t_dim * Np + 255) / 256, 256, 0, stream>>>(d->weight[0], in_f, N, wt, d->t_dim, Np, d->t_col);
+        g_launches += 1;
+      }
+      nd.Wt = wt;
+    }
+    in_f = N;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, std::string("ffb_net_create: ") + cudaGetErrorString(e)); }
+  *out = net;
+  return FFB_OK;
+}
+
+extern "C" void ffb_net_destroy(ffb_net* net) {
+  if (!net) return;
+  for (void* p : net->allocs) cudaFree(p);
+  delete net;
+}
+
+extern "C" int64_t ffb_net_flops(const ffb_net* net) { return net ? net->flops : 0; }
+
+// ---- field validation / conversion -----------------------------------------------------------
+static int tangents_of(const ffb_field* f) {
+  return f->div_mode == FFB_DIV_EXACT ? f->net[0]->dev.x_dim : (f->div_mode == FFB_DIV_HUTCH ? 1 : 0);
+}
+
+static int make_field(const ffb_field* f, FieldDev* out) {
+  if (!f) return fail(FFB_ERR_ARG, "null field");
+  if (f->n_calls < 1 || f->n_calls > 2) return fail(FFB_ERR_ARG, "field: n_calls must be 1 or 2");
+  if (f->state_dim < 1 || f->state_dim > FFB_MAX_STATE) return fail(FFB_ERR_ARG, "field: state_dim must be in 1..128");
+  if (f->cond_dim < 0 || f->cond_dim > FFB_MAX_WIDTH) return fail(FFB_ERR_ARG, "field: bad cond_dim");
+  memset(out, 0, sizeof(*out));
+  out->n_calls = f->n_calls;
+  for (int c = 0; c < f->n_calls; ++c) {
+    if (!f->net[c]) return fail(FFB_ERR_ARG, "field: null net");
+    const NetDev& nd = f->net[c]->dev;
+    const int dout = nd.N[nd.n_layers - 1];
+    if (nd.c_dim != f->cond_dim) return fail(FFB_ERR_ARG, "field: net conditional width differs from field cond_dim");
+    if (f->in_off[c] < 0 || f->in_off[c] + nd.x_dim > f->state_dim) return fail(FFB_ERR_ARG, "field: input block outside the state");
+    if (f->out_off[c] < 0 || f->out_off[c] + dout > f->state_dim) return fail(FFB_ERR_ARG, "field: output block outside the state");
+    out->net[c] = nd;
+    out->in_off[c] = f->in_off[c];
+    out->out_off[c] = f->out_off[c];
+    out->out_sign[c] = f->out_sign[c];
+  }
+  if (f->div_mode != FFB_DIV_NONE) {
+    const NetDev& nd = f->net[0]->dev;
+    if (f->n_calls != 1 || nd.x_dim != f->state_dim || nd.N[nd.n_layers - 1] != f->state_dim)
+      return fail(FFB_ERR_ARG, "field: divergence needs a single network mapping the state to itself");
+    if (f->div_mode == FFB_DIV_EXACT && 1 + nd.x_dim > TM)
+      return fail(FFB_ERR_ARG, "field: exact trace supports at most 127 state columns");
+  }
+  out->state_dim = f->state_dim; out->cond_dim = f->cond_dim; out->kind = f->kind;
+  out->use_sigma = f->use_sigma; out->has_drift = f->has_drift; out->div_mode = f->div_mode;
+  return FFB_OK;
+}
+
+extern "C" int64_t ffb_num_tiles(const ffb_field* f, int64_t batch) {
+  if (!f || !f->net[0]) return -1;
+  const int S = TM / (1 + tangents_of(f));
+  return (batch + S - 1) / S;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+  return n > 0 ? n : 148;
+}
+
+extern "C" size_t ffb_scratch_bytes(const ffb_field* f) {
+  if (!f) return 0;
+  return (size_t)num_sms() * NSLOT * f->state_dim * LDA * sizeof(float);
+}
+
+template <typename Kern, typename Args>
+static int launch_tiles(Kern kern, const char* name, const ffb_field* f, const FieldDev& fd, const Args& a,
+                        int64_t batch, cudaStream_t stream) {
+  const int T = tangents_of(f);
+  const size_t smem = smem_layout(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, nullptr);
+  int dev = 0, optin = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if ((int)smem > optin)
+    return fail(FFB_ERR_ARG, std::string(name) + ": tile needs " + std::to_string(smem) + " B of shared memory, device allows " + std::to_string(optin));
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = ffb_num_tiles(f, batch);
+  if (ntiles <= 0) return FFB_OK;
+  const int grid = (int)std::min<int64_t>(ntiles, num_sms());
+  kern<<<grid, NTHR, smem, stream>>>(fd, a, ntiles);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+
+extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* stream) {
+  FieldDev fd;
+  int rc = make_field(f, &fd);
+  if (rc) return rc;
+  if (!a || !a->y || !a->scratch) return fail(FFB_ERR_ARG, "ffb_field_eval: y and scratch are required");
+  if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_field_eval: cond is required");
+  if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_field_eval: probes are required");
+  if (a->norms && !a->partials) return fail(FFB_ERR_ARG, "ffb_field_eval: partials buffer required for norms");
+  if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
+    return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
+  return launch_tiles(k_field_eval, "ffb_field_eval", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, void* stream) {
+  FieldDev fd;
+  int rc = make_field(f, &fd);
+  if (rc) return rc;
+  if (!a || !a->y0 || !a->f0 || !a->y1 || !a->f1 || !a->partials || !a->scratch)
+    return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: y0, f0, y1, f1, partials, scratch are required");
+  if (fd.div_mode != FFB_DIV_NONE && (!a->lp0 || !a->dlp0 || !a->lp1 || !a->dlp1))
+    return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: log-det buffers are required with a divergence");
+  if (a->final && (!a->y_out || (fd.div_mode != FFB_DIV_NONE && !a->lp_out)))
+    return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: final step needs y_out (and lp_out)");
+  if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
+  if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
+  return launch_tiles(k_dopri5, "ffb_dopri5_attempt", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, void* stream) {
+  FieldDev fd;
+  int rc = make_field(f, &fd);
+  if (rc) return rc;
+  if (!a || !a->x0 || !a->x_out || !a->step_table || !a->ev_table || !a->scratch || !a->status)
+    return fail(FFB_ERR_ARG, "ffb_integrate_fixed: x0, x_out, step_table, ev_table, scratch, status are required");
+  if (a->method < FFB_M_EULER || a->method > FFB_M_LEAPFROG) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: unknown method");
+  if (a->method == FFB_M_LEAPFROG && fd.n_calls != 2) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: leapfrog needs a 2-network (q,p) field");
+  if ((a->method == FFB_M_EM || a->method == FFB_M_LEAPFROG) && fd.div_mode != FFB_DIV_NONE)
+    return fail(FFB_ERR_ARG, "ffb_integrate_fixed: no divergence with this method");
+  if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: cond is required");
+  if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: probes are required");
+  return launch_tiles(k_fixed, "ffb_integrate_fixed", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream) {
+  if (!partials || !sums) return fail(FFB_ERR_ARG, "ffb_reduce_partials: null argument");
+  k_reduce<<<1, 32 * FFB_NPART, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles, sums);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+
+extern "C" int ffb_gaussian_logprob(const float* x, const float* add, float* out, int64_t batch, int32_t dim,
+                                    float sigma, void* stream) {
+  if (!x || !out || dim < 1) return fail(FFB_ERR_ARG, "ffb_gaussian_logprob: bad argument");
+  if (batch == 0) return FFB_OK;
+  const float log_norm = logf(sigma) + 0.918938533204672742f;   // log sigma + log sqrt(2 pi)
+  const int wpb = 8;
+  k_gauss_logprob<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, add, out, batch, dim, sigma, log_norm);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+
+extern "C" int ffb_philox_normal(float* out, int64_t batch, int32_t dim, uint64_t seed, uint64_t offset, int32_t step,
+                                 int64_t row_offset, void* stream) {
+  if (!out || dim < 1) return fail(FFB_ERR_ARG, "ffb_philox_normal: bad argument");
+  const int64_t n = batch * ((dim + 3) / 4);
+  if (n == 0) return FFB_OK;
+  k_philox<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, batch, dim, seed,
+                                                                                             offset, step, row_offset);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+
+extern "C" int ffb_ffma_peak(int32_t iters, float* tflops, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  float* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 4));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int grid = num_sms() * 8;
+  k_ffma_peak<<<grid, 256, 0, stream>>>(d, iters);   // warm-up
+  CUDA_TRY(cudaEventRecord(e0, stream));
+  k_ffma_peak<<<grid, 256, 0, stream>>>(d, iters);
+  CUDA_TRY(cudaEventRecord(e1, stream));
+  g_launches += 2;
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  const double flop = (double)grid * 256.0 * (double)iters * 16.0 * 4.0;   // 16 FFMA2 = 32 FMA = 64 FLOP
+  if (tflops) *tflops = (float)(flop / (ms * 1e-3) / 1e12);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return FFB_OK;
+}

@@ -1,0 +1,316 @@
+"""Device-side plumbing between the model objects and ``libffb200.so``.
+
+``PackedNet``    packs the ``nn.Linear`` weights of one MLP into the kernels' image (once).
+``FieldSpec``    describes a vector field (1-2 networks + the reference's drift formula).
+``CudaBackend``  owns the device buffers of one adaptive solve and launches the kernels.
+``run_fixed``    launches the whole-trajectory fixed-grid kernel.
+
+PyTorch is used for device memory, streams and (in ``solver.py``) the NCCL all-reduce only.
+Nothing here computes on the CPU and nothing falls back: without the CUDA library or a CUDA
+tensor these classes raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise L.FFBError(f"{what} must be a CUDA tensor: flowfusion_b200 has no CPU path "
+                         "(move the model and its inputs to a B200 with .to('cuda'))")
+
+
+def require_cuda_device(dev):
+    if torch.device(dev).type != "cuda":
+        raise L.FFBError("the model must be on a CUDA device (flowfusion_b200 has no CPU path)")
+
+
+class PackedNet:
+    """One MLP, packed for the tile engine.  ``linears``: the nn.Linear modules in order."""
+
+    def __init__(self, linears: Sequence[torch.nn.Linear], x_col, x_dim, c_col, c_dim, t_col, t_dim, device):
+        lib = L.load()
+        if len(linears) > L.MAX_LAYERS:
+            raise NotImplementedError(f"at most {L.MAX_LAYERS} Linear layers are supported")
+        d = L.NetDesc()
+        d.n_layers = len(linears)
+        d.in_features = linears[0].in_features
+        self._keep = []
+        for i, lin in enumerate(linears):
+            if lin.out_features > 128 or lin.in_features > 128 + L.MAX_TFEAT:
+                raise NotImplementedError("layer widths above 128 are not supported by the tile engine yet")
+            w, b = _dev_f32(lin.weight, device), _dev_f32(lin.bias, device)
+            self._keep += [w, b]
+            d.widths[i] = lin.out_features
+            d.weight[i] = w.data_ptr()
+            d.bias[i] = b.data_ptr()
+        d.x_col, d.x_dim, d.c_col, d.c_dim, d.t_col, d.t_dim = x_col, x_dim, c_col, c_dim, t_col, t_dim
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(lib.ffb_net_create(C.byref(d), _stream(), C.byref(h)), "ffb_net_create")
+            torch.cuda.current_stream().synchronize()      # packing kernels read the torch tensors
+        self._keep = []
+        self.handle = h
+        self.flops = int(lib.ffb_net_flops(h))
+        self.dims = [linears[0].in_features] + [l.out_features for l in linears]
+        self.x_dim, self.c_dim, self.t_dim = x_dim, c_dim, t_dim
+        self._lib = lib
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self._lib.ffb_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def weights_fingerprint(linears: Sequence[torch.nn.Linear]):
+    """Cheap change detector so trained / reloaded weights are re-packed."""
+    return tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version, str(l.weight.device))
+                 for l in linears)
+
+
+class FieldSpec:
+    def __init__(self, nets: List[PackedNet], state_dim, cond_dim, kind=L.FIELD_NET, use_sigma=False,
+                 has_drift=False, div_mode=L.DIV_NONE, in_off=(0, 0), out_off=(0, 0), out_sign=(1.0, 1.0)):
+        self.nets, self.state_dim, self.cond_dim = nets, state_dim, cond_dim
+        self.kind, self.use_sigma, self.has_drift, self.div_mode = kind, use_sigma, has_drift, div_mode
+        self.in_off, self.out_off, self.out_sign = in_off, out_off, out_sign
+        f = L.Field()
+        f.n_calls = len(nets)
+        for i, n in enumerate(nets):
+            f.net[i] = n.handle.value
+            f.in_off[i], f.out_off[i], f.out_sign[i] = in_off[i], out_off[i], out_sign[i]
+        f.state_dim, f.cond_dim, f.kind = state_dim, cond_dim, kind
+        f.use_sigma, f.has_drift, f.div_mode = int(use_sigma), int(has_drift), div_mode
+        self.c = f
+
+    def with_div(self, div_mode):
+        return FieldSpec(self.nets, self.state_dim, self.cond_dim, self.kind, self.use_sigma, self.has_drift,
+                         div_mode, self.in_off, self.out_off, self.out_sign)
+
+    @property
+    def ntan(self):
+        return {L.DIV_NONE: 0, L.DIV_EXACT: self.nets[0].x_dim, L.DIV_HUTCH: 1}[self.div_mode]
+
+    def num_tiles(self, batch):
+        return int(L.load().ffb_num_tiles(C.byref(self.c), batch))
+
+    def scratch(self, device):
+        n = int(L.load().ffb_scratch_bytes(C.byref(self.c)))
+        return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+    def flops_per_eval(self):
+        """Algorithmic FLOPs (2*MAC over Linear layers) of one evaluation for one trajectory,
+        with the forward-mode minimum for tangents."""
+        total = sum(n.flops for n in self.nets)
+        if self.div_mode != L.DIV_NONE:
+            d = self.nets[0].dims
+            hidden = sum(2 * d[i] * d[i + 1] for i in range(1, len(d) - 2))
+            if self.div_mode == L.DIV_EXACT:      # layer 0 = column gather, last layer = one output column
+                total += self.nets[0].x_dim * (hidden + 2 * d[-2])
+            else:
+                total += 2 * self.nets[0].x_dim * d[1] + hidden + 2 * d[-2] * d[-1]
+        return total
+
+
+def ev_rows_to_struct(dst_array, rows: np.ndarray):
+    """Copy (n, EV_FLOATS) float32 rows into a ctypes array of EvalScalars."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    C.memmove(C.addressof(dst_array), rows.ctypes.data, rows.nbytes)
+
+
+class CudaBackend:
+    """Device state of ONE adaptive solve (this rank's shard of the batch)."""
+
+    def __init__(self, field: FieldSpec, y0: torch.Tensor, cond=None, probes=None, with_lp=False,
+                 cond_in_state=False, cond_state=None):
+        require_cuda(y0, "state")
+        self.lib = L.load()
+        self.field = field
+        dev = y0.device
+        self.dev = dev
+        B, D = y0.shape
+        assert D == field.state_dim
+        self.B, self.D = B, D
+        self.with_lp = with_lp
+        self.cond_in_state = cond_in_state
+        self.y = [_dev_f32(y0, dev).clone(), torch.empty(B, D, device=dev)]
+        self.f = [torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)]
+        self.y_out = torch.empty(B, D, device=dev)
+        if with_lp:
+            self.lp = [torch.zeros(B, device=dev), torch.empty(B, device=dev)]
+            self.dlp = [torch.empty(B, device=dev), torch.empty(B, device=dev)]
+            self.lp_out = torch.empty(B, device=dev)
+        else:
+            self.lp = self.dlp = [None, None]
+            self.lp_out = None
+        self.cond = None if cond is None else _dev_f32(cond, dev)
+        self.probes = None if probes is None else _dev_f32(probes, dev)
+        self.cond_state = None if cond_state is None else _dev_f32(cond_state, dev)
+        self.ntiles = max(field.num_tiles(B), 1)
+        self.partials = torch.zeros(self.ntiles, L.NPART, dtype=torch.float64, device=dev)
+        self.sums = torch.zeros(L.NPART, dtype=torch.float64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.scratch = field.scratch(dev)
+        self.cur = 0
+        self.dargs = L.Dopri5Args()
+        self.eargs = L.EvalArgs()
+
+    # -- counts for the RMS norms (global over ranks) -------------------------------------------
+    def global_counts(self, group):
+        n = torch.tensor([self.B], dtype=torch.int64, device=self.dev)
+        if group is not None:
+            torch.distributed.all_reduce(n, group=group)
+        Bt = int(n.item())
+        out = {"x": Bt * self.D}
+        if self.with_lp:
+            out["lp"] = Bt
+        if self.cond_in_state and self.cond is not None:
+            out["cond"] = Bt * self.cond.shape[1]
+        return out
+
+    def _reduce(self):
+        L.check(self.lib.ffb_reduce_partials(_ptr(self.partials), self.ntiles, _ptr(self.sums), _stream()),
+                "ffb_reduce_partials")
+        return self.sums
+
+    def _eval(self, ev_row, atol, rtol, norms, h=None):
+        a = self.eargs
+        c = self.cur
+        a.batch = self.B
+        a.y = _ptr(self.y[c])
+        a.fbase = _ptr(self.f[c]) if norms == 2 else None
+        a.dlpbase = _ptr(self.dlp[c]) if (norms == 2 and self.with_lp) else None
+        a.h = float(h) if h is not None else 0.0
+        a.cond, a.probes, a.cond_state = _ptr(self.cond), _ptr(self.probes), _ptr(self.cond_state)
+        a.f = _ptr(self.f[c]) if norms == 1 else None
+        a.dlp = _ptr(self.dlp[c]) if (norms == 1 and self.with_lp) else None
+        ev_rows_to_struct(a.ev, ev_row[None, :])
+        a.atol, a.rtol, a.norms = float(atol), float(rtol), norms
+        a.cond_in_state = int(self.cond_in_state)
+        a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
+        if self.B:
+            L.check(self.lib.ffb_field_eval(C.byref(self.field.c), C.byref(a), _stream()), "ffb_field_eval")
+        return self._reduce()
+
+    def eval0(self, ev_row, atol, rtol):
+        return self._eval(ev_row, atol, rtol, 1)
+
+    def single_eval(self, ev_row):
+        """One field evaluation at the current state -> (f, dlp or None)."""
+        self._eval(ev_row, 1.0, 0.0, 1)
+        return self.f[self.cur], self.dlp[self.cur]
+
+    def eval1(self, h0, ev_row, atol, rtol):
+        return self._eval(ev_row, atol, rtol, 2, h=h0)
+
+    def attempt(self, ev, cb, ce, cm, dt32, atol, rtol, final, x_interp):
+        a = self.dargs
+        c, n = self.cur, 1 - self.cur
+        a.batch = self.B
+        a.y0, a.f0, a.lp0, a.dlp0 = _ptr(self.y[c]), _ptr(self.f[c]), _ptr(self.lp[c]), _ptr(self.dlp[c])
+        a.cond, a.probes = _ptr(self.cond), _ptr(self.probes)
+        a.y1, a.f1, a.lp1, a.dlp1 = _ptr(self.y[n]), _ptr(self.f[n]), _ptr(self.lp[n]), _ptr(self.dlp[n])
+        a.y_out, a.lp_out = _ptr(self.y_out), _ptr(self.lp_out)
+        ev_rows_to_struct(a.ev, ev)
+        C.memmove(C.addressof(a.cb), np.ascontiguousarray(cb, np.float32).ctypes.data, 144)
+        C.memmove(C.addressof(a.ce), np.ascontiguousarray(ce, np.float32).ctypes.data, 28)
+        C.memmove(C.addressof(a.cm), np.ascontiguousarray(cm, np.float32).ctypes.data, 28)
+        a.dt, a.atol, a.rtol, a.x_interp, a.final = float(dt32), float(atol), float(rtol), float(x_interp), int(final)
+        a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
+        if self.B:
+            L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(a), _stream()), "ffb_dopri5_attempt")
+        return self._reduce()
+
+    def accept(self):
+        self.cur = 1 - self.cur
+
+    def output(self):
+        return self.y_out, self.lp_out
+
+
+def run_fixed(field: FieldSpec, method: int, x0: torch.Tensor, step_table: np.ndarray, ev_table: np.ndarray,
+              cond=None, probes=None, lp0=None, noise=None, philox=None, row_offset=0, want_lp=False):
+    """Whole fixed-grid trajectory in one kernel.  ``step_table`` (nsteps, 8) and ``ev_table``
+    (nsteps, nev, EV_FLOATS) are host float32 arrays computed in the reference's op order."""
+    require_cuda(x0, "state")
+    lib = L.load()
+    dev = x0.device
+    x0 = _dev_f32(x0, dev)
+    B, D = x0.shape
+    nsteps = int(step_table.shape[0])
+    st = torch.from_numpy(np.ascontiguousarray(step_table, np.float32)).to(dev)
+    ev = torch.from_numpy(np.ascontiguousarray(ev_table, np.float32).reshape(-1)).to(dev)
+    x_out = torch.empty_like(x0)
+    lp_out = torch.empty(B, device=dev) if want_lp else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    scratch = field.scratch(dev)
+    a = L.FixedArgs()
+    a.batch, a.method, a.nsteps = B, method, nsteps
+    lp0 = None if lp0 is None else _dev_f32(lp0, dev)      # keep a reference until the launch
+    a.x0, a.lp0 = _ptr(x0), _ptr(lp0)
+    cond = None if cond is None else _dev_f32(cond, dev)
+    probes = None if probes is None else _dev_f32(probes, dev)
+    noise = None if noise is None else _dev_f32(noise, dev)
+    a.cond, a.probes, a.noise = _ptr(cond), _ptr(probes), _ptr(noise)
+    seed, offset = philox if philox is not None else (0, 0)
+    a.philox_seed, a.philox_offset, a.row_offset = int(seed), int(offset), int(row_offset)
+    a.x_out, a.lp_out = _ptr(x_out), _ptr(lp_out)
+    a.step_table, a.ev_table = _ptr(st), _ptr(ev)
+    a.status, a.scratch = _ptr(status), _ptr(scratch)
+    if B and nsteps:
+        L.check(lib.ffb_integrate_fixed(C.byref(field.c), C.byref(a), _stream()), "ffb_integrate_fixed")
+    elif B:
+        x_out.copy_(x0)
+    return x_out, lp_out, status
+
+
+def gaussian_logprob(x: torch.Tensor, add: Optional[torch.Tensor], sigma: float = 1.0) -> torch.Tensor:
+    """sum_d log N(x_d; 0, sigma) + add   (flow.py:434, diffusion.py:814, symplectic.py:240-243)."""
+    require_cuda(x, "x")
+    x = _dev_f32(x, x.device)
+    B, D = x.shape
+    out = torch.empty(B, device=x.device)
+    add_c = None if add is None else _dev_f32(add, x.device)
+    L.check(L.load().ffb_gaussian_logprob(_ptr(x), _ptr(add_c), _ptr(out), B, D, float(sigma), _stream()),
+            "ffb_gaussian_logprob")
+    return out
+
+
+def philox_normal(batch, dim, seed, offset, step, row_offset=0, device="cuda"):
+    out = torch.empty(batch, dim, device=device)
+    L.check(L.load().ffb_philox_normal(_ptr(out), batch, dim, int(seed), int(offset), int(step), int(row_offset),
+                                       _stream()), "ffb_philox_normal")
+    return out
+
+
+def ffma_peak_tflops(iters=4096):
+    v = C.c_float(0)
+    L.check(L.load().ffb_ffma_peak(iters, C.byref(v), _stream()), "ffb_ffma_peak")
+    return float(v.value)
+
+
+def device_info():
+    vals = [C.c_int32(0) for _ in range(5)]
+    L.check(L.load().ffb_device_info(*[C.byref(v) for v in vals]), "ffb_device_info")
+    return dict(zip(("sm_count", "smem_optin", "cc_major", "cc_minor", "clock_khz"), (v.value for v in vals)))

@@ -1,0 +1,270 @@
+"""Host-side solver drivers: the control plane of ``torchdiffeq.odeint`` re-built for a
+batch-sharded, kernel-backed state.
+
+The arithmetic on the state (stage evaluations, error partial sums, dense output) happens in the
+CUDA kernels behind a *backend* object (``engine.CudaBackend``); this module only does what
+torchdiffeq does on the host -- time bookkeeping in float64, the Hairer initial step, the
+accept/reject test and the step-size controller -- plus the one collective the path needs:
+a SUM all-reduce of a handful of float64 partial sums per attempted step, so every rank takes
+bit-identical decisions.
+
+Semantics follow torchdiffeq 0.2.x (call sites: reference `diffusion.py:631-639, 744-752`,
+`flow.py:299-303, 371-382, 792-796, 869-880`, `symplectic.py:237`):
+  * state dtype float32, time in float64; stage times are formed in float32 (t0 + alpha*dt);
+  * stages with alpha == 1 are evaluated one float32 ulp before t1;
+  * descending time spans integrate -t with -f;
+  * error norm: RMS for tensor states, max over tuple components of per-component RMS;
+  * no clipping at t_end: the result is the 4th-order dense output of the last accepted step;
+  * ``step_t`` grid points shorten an attempt so that it lands on them.
+"""
+from __future__ import annotations
+
+import bisect
+import dataclasses
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+f32, f64 = np.float32, np.float64
+
+# Dormand-Prince(-Shampine) tableau, float64 then rounded to the state dtype like torchdiffeq does
+_ALPHA = np.array([1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0])
+_BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+_C_ERR = np.array([35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+                   -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0])
+_C_MID = np.array([6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2,
+                   -2691868925 / 45128329728 / 2, 187940372067 / 1594534317056 / 2,
+                   -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2])
+ALPHA32 = _ALPHA.astype(f32)
+BETA32 = np.zeros((6, 6), f32)
+for _i, _row in enumerate(_BETA):
+    BETA32[_i, : len(_row)] = np.array(_row, f64).astype(f32)
+C_ERR32 = _C_ERR.astype(f32)
+C_MID32 = _C_MID.astype(f32)
+
+
+@dataclasses.dataclass
+class SolveStats:
+    method: str = ""
+    nfe: int = 0
+    accepted: int = 0
+    rejected: int = 0
+    first_step: Optional[float] = None
+    dt_history: List[float] = dataclasses.field(default_factory=list)
+    accept_history: List[bool] = dataclasses.field(default_factory=list)
+    ratio_history: List[float] = dataclasses.field(default_factory=list)
+    launches: int = 0
+
+
+class SolverError(AssertionError):
+    """Raised where torchdiffeq raises AssertionError (dt underflow, non-finite state, ...)."""
+
+
+def _allreduce(t: torch.Tensor, group):
+    if group is not None:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=group)
+    return t
+
+
+def _rms32(sumsq: float, n: int) -> np.float32:
+    if n == 0:
+        return f32(np.nan)          # torch: mean of an empty tensor
+    with np.errstate(all="ignore"):
+        return f32(np.sqrt(f64(sumsq) / f64(n)))
+
+
+def _mixed(values: Sequence[np.float32]) -> np.float32:
+    # torchdiffeq's mixed norm is Python's max() over the tuple components, in tuple order
+    return max(values)
+
+
+# ----------------------------------------------------------------------------------------------
+# adaptive Dormand-Prince 5(4)
+# ----------------------------------------------------------------------------------------------
+def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: float, rtol: float,
+           atol: float, options: Optional[dict] = None, group=None) -> SolveStats:
+    """Integrate the backend's state from ``t0`` to ``t1`` (float32-representable floats).
+
+    ``program(times32)`` maps float32 *user* times, shape (n,), to the (n, EV_FLOATS) rows of
+    host-computed evaluation scalars (time features, SDE coefficients).  The result is left in
+    the backend (``backend.output()``)."""
+    opts = dict(options or {})
+    for k in ("norm", "dtype"):
+        opts.pop(k, None)
+    if opts.get("jump_t") is not None:
+        raise NotImplementedError("options['jump_t'] is not supported")
+    min_step = f64(opts.pop("min_step", 0))
+    max_step = f64(opts.pop("max_step", np.inf))
+    first_step = opts.pop("first_step", None)
+    step_t = opts.pop("step_t", None)
+    opts.pop("jump_t", None)
+    safety, ifactor, dfactor = f64(opts.pop("safety", 0.9)), f64(opts.pop("ifactor", 10.0)), f64(opts.pop("dfactor", 0.2))
+    max_num_steps = int(opts.pop("max_num_steps", 2 ** 31 - 1))
+    if opts:
+        raise TypeError(f"unsupported dopri5 options: {sorted(opts)}")
+
+    st = SolveStats(method="dopri5")
+    reverse = t0 > t1
+    sgn = -1.0 if reverse else 1.0
+    ts, te = (f64(-t0), f64(-t1)) if reverse else (f64(t0), f64(t1))
+    if not te > ts:
+        raise ValueError("t must be strictly increasing or decreasing")
+    rtol32, atol32 = f32(rtol), f32(atol)
+
+    def rows(solver_times32: np.ndarray) -> np.ndarray:
+        user = (-solver_times32 if reverse else solver_times32).astype(f32)
+        ev = program(user)
+        ev[:, L.MAX_TFEAT + 3] = sgn
+        return ev
+
+    counts = backend.global_counts(group)          # dict: x, lp, cond element counts (global)
+
+    def norm(sx, slp, sc):
+        comps = [_rms32(sx, counts["x"])]
+        if counts.get("cond"):
+            comps.append(_rms32(sc, counts["cond"]))
+        if counts.get("lp"):
+            comps.append(_rms32(slp, counts["lp"]))
+        return _mixed(comps)
+
+    # ---- f0 and the initial step (Hairer; torchdiffeq `_select_initial_step`, order 4) --------
+    t0_32 = f32(ts)
+    s = _allreduce(backend.eval0(rows(np.array([t0_32], f32))[0], atol32, rtol32), group).cpu().numpy()
+    st.nfe += 1
+    st.launches += 2
+    if first_step is None:
+        with np.errstate(all="ignore"):
+            d0 = abs(norm(s[L.P_X_Y], 0.0, s[L.P_C_Y]))
+            d1 = abs(norm(s[L.P_X_F], s[L.P_LP_F], 0.0))
+            if d0 < 1e-5 or d1 < 1e-5:
+                h0 = f32(1e-6)
+            else:
+                h0 = f32(0.01) * d0 / d1
+            h0 = abs(h0)
+            s = _allreduce(backend.eval1(h0, rows(np.array([t0_32 + h0], f32))[0], atol32, rtol32), group).cpu().numpy()
+            st.nfe += 1
+            st.launches += 2
+            d2 = abs(norm(s[L.P_X_DF], s[L.P_LP_DF], 0.0) / h0)
+            if d1 <= 1e-15 and d2 <= 1e-15:
+                h1 = max(f32(1e-6), h0 * f32(1e-3))
+            else:
+                h1 = (f32(0.01) / max(d1, d2)) ** f32(1.0 / 5.0)
+            h1 = abs(h1)
+            dt = f64(min(f32(100) * h0, h1))
+    else:
+        dt = f64(first_step)
+    st.first_step = float(dt)
+
+    grid: List[float] = []
+    if step_t is not None:
+        g = np.atleast_1d(np.asarray(torch.as_tensor(step_t, dtype=torch.float64).cpu().numpy(), f64))
+        if reverse:
+            g = -g
+        grid = sorted(float(v) for v in g if v >= ts)
+    grid_idx = min(bisect.bisect(grid, float(ts)), len(grid) - 1) if grid else 0
+
+    t = ts
+    n_steps = 0
+    done = False
+    while te > t:
+        if not n_steps < max_num_steps:
+            raise SolverError("max_num_steps exceeded ({}>={})".format(n_steps, max_num_steps))
+        with np.errstate(all="ignore"):
+            if not (t + dt > t):
+                raise SolverError("underflow in dt {}".format(float(dt)))
+            t1s = t + dt
+            dts = dt
+            on_grid = False
+            if grid:
+                nxt = f64(grid[grid_idx])
+                on_grid = bool(t < nxt < t + dt)
+                if on_grid:
+                    t1s = nxt
+                    dts = t1s - t
+            t0_32, dt_32, t1_32 = f32(t), f32(dts), f32(t1s)
+            times = np.empty(6, f32)
+            for i in range(6):
+                if ALPHA32[i] == 1.0:
+                    times[i] = np.nextafter(t1_32, t1_32 - f32(1))
+                else:
+                    times[i] = t0_32 + ALPHA32[i] * dt_32
+            ev = rows(times)
+            cb = BETA32 * dt_32
+            ce = dt_32 * C_ERR32
+            cm = dt_32 * C_MID32
+            final = not (te > t1s)
+            x_interp = f32((te - t) / (t1s - t)) if final else f32(0)
+        s = _allreduce(backend.attempt(ev, cb, ce, cm, dt_32, atol32, rtol32, final, x_interp), group).cpu().numpy()
+        st.nfe += 6
+        st.launches += 2
+        n_steps += 1
+        if s[L.P_NONFINITE] > 0:
+            raise SolverError("non-finite values in state `y`")
+        with np.errstate(all="ignore"):
+            ratio = abs(norm(s[L.P_X_ERR], s[L.P_LP_ERR], 0.0))
+            accept = bool(ratio <= 1)
+            if dts > max_step:
+                accept = False
+            if dts <= min_step:
+                accept = True
+            st.dt_history.append(float(dts)); st.accept_history.append(accept); st.ratio_history.append(float(ratio))
+            if accept:
+                st.accepted += 1
+                backend.accept()
+                if on_grid and grid_idx != len(grid) - 1:
+                    grid_idx += 1
+                t = t1s
+                done = final
+            else:
+                st.rejected += 1
+            # controller (order 5)
+            if ratio == 0:
+                nxt_dt = dts * ifactor
+            else:
+                dfac = f64(1.0) if ratio < 1 else dfactor
+                r = f64(ratio)
+                nxt_dt = dts * np.minimum(ifactor, np.maximum(safety / r ** f64(0.2), dfac))
+            dt = f64(np.clip(nxt_dt, min_step, max_step)) if not np.isnan(nxt_dt) else f64(np.nan)
+    assert done, "internal: integration loop ended without a final step"
+    return st
+
+
+# ----------------------------------------------------------------------------------------------
+# fixed grids (torchdiffeq FixedGridODESolver): time stays in float32
+# ----------------------------------------------------------------------------------------------
+def fixed_grid(t0: float, t1: float, step_size: Optional[float]) -> torch.Tensor:
+    """Solver-time grid (ascending) as torchdiffeq builds it from ``options['step_size']``."""
+    t = torch.tensor([t0, t1], dtype=torch.float32)
+    if t[0] > t[1]:
+        t = -t
+    if step_size is None:
+        return t
+    n = torch.ceil((t[-1] - t[0]) / step_size + 1).item()
+    g = torch.arange(0, n, dtype=t.dtype) * step_size + t[0]
+    g[-1] = t[-1]
+    return g
+
+
+def fixed_eval_times(method: str, grid: torch.Tensor):
+    """(dt, eval_times[nsteps, nev]) in float32, op order of torchdiffeq's step functions."""
+    a, b = grid[:-1], grid[1:]
+    dt = b - a
+    if method == "euler":
+        times = a[:, None]
+    elif method == "midpoint":
+        times = torch.stack([a, a + 0.5 * dt], dim=1)
+    elif method == "rk4":
+        times = torch.stack([a, a + dt * (1 / 3), a + dt * (2 / 3), b], dim=1)
+    else:
+        raise ValueError(method)
+    return dt, times

@@ -1,0 +1,202 @@
+/* ffb200.h -- C ABI of libffb200.so: B200 (sm_100a) kernels for the flowfusion hot path.
+ *
+ * The reference (Cosmo-Pop/flowfusion) has no FFI: its narrowest seam is the call
+ *   torchdiffeq.odeint(func, y0, t, rtol=, atol=, method=, options=)
+ * made from diffusion.py:621,631,734,744, flow.py:288,299,358,371,781,792,855,869 and
+ * symplectic.py:237, plus the two hand-rolled loops diffusion.py:543-562 (Euler-Maruyama)
+ * and symplectic.py:192-197 (forward Euler).  The entry points below are what a binding for
+ * that seam needs: they take plain device pointers, sizes and a cudaStream_t; no torch types.
+ *
+ * Conventions
+ *   - all tensors are FP32, row-major, contiguous, resident on the current CUDA device;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = OK, negative = ffb_status; ffb_last_error() gives the message;
+ *   - the caller owns every buffer, including `scratch` (ffb_scratch_bytes) and `partials`;
+ *   - per-evaluation scalars (time features, SDE coefficients) are computed by the HOST in
+ *     the reference's exact FP32 op order and passed in ffb_eval_scalars, so the kernels
+ *     never re-derive beta(t), sigma(t), sin/cos(2 pi t W) with different rounding.
+ */
+#ifndef FFB200_H
+#define FFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB_ABI_VERSION 1
+#define FFB_MAX_LAYERS 8    /* Linear layers per network                         */
+#define FFB_MAX_WIDTH 128   /* widest layer (input or output) the tile engine holds */
+#define FFB_MAX_TFEAT 32    /* time-feature columns (embedding_dimensions or 1)  */
+#define FFB_MAX_STATE 128   /* ODE state columns                                 */
+#define FFB_TILE_ROWS 128   /* rows (trajectories x (1 + tangents)) per CTA tile */
+#define FFB_NPART 16        /* doubles per tile in the `partials` buffer         */
+
+typedef enum {
+  FFB_OK = 0,
+  FFB_ERR_ARG = -1,        /* bad argument / unsupported shape       */
+  FFB_ERR_CUDA = -2,       /* CUDA runtime error (see ffb_last_error) */
+  FFB_ERR_NOGPU = -3       /* no sm_100 device                        */
+} ffb_status;
+
+/* device-side status word bits (written with atomicOr by the kernels) */
+#define FFB_ST_NONFINITE_STATE 1   /* torchdiffeq: "non-finite values in state `y`"  */
+#define FFB_ST_NAN_SAMPLE 2        /* diffusion.py:560-562 "Diffusion is not stable" */
+
+/* field kinds */
+#define FFB_FIELD_NET 0    /* x_dot = sign * net(x)                 flow.py:118, symplectic.py:120-123 */
+#define FFB_FIELD_SCORE 1  /* x_dot = sign * (a*x - c*score)        diffusion.py:276-279 / :553         */
+
+/* divergence modes */
+#define FFB_DIV_NONE 0
+#define FFB_DIV_EXACT 1      /* D forward-mode tangents  (flow.py:157-161, diffusion.py:483-503) */
+#define FFB_DIV_HUTCH 2      /* one tangent along a fixed Rademacher probe (diffusion.py:327-334) */
+
+/* fixed-grid methods */
+#define FFB_M_EULER 0        /* torchdiffeq 'euler'; also symplectic.py:192-197 */
+#define FFB_M_MIDPOINT 1     /* torchdiffeq 'midpoint'                          */
+#define FFB_M_RK4 2          /* torchdiffeq 'rk4' (3/8 rule)                    */
+#define FFB_M_EM 3           /* Euler-Maruyama, diffusion.py:543-562            */
+#define FFB_M_LEAPFROG 4     /* kick-drift-kick (extension; no reference oracle) */
+
+typedef struct ffb_net ffb_net; /* opaque: packed weights of one MLP */
+
+/* One MLP exactly as torch.nn.Linear stores it (diffusion.py:67-72, flow.py:63-74,
+ * symplectic.py:71-78) plus the column map of its layer-0 input:
+ *   diffusion.MLP      [ sin|cos (t_dim) | x (x_dim) | cond (c_dim) ]     diffusion.py:101-113
+ *   flow.*ODEFlow      [ x | t (t_dim = 1) | cond ]                       flow.py:112-115, 583-586
+ *   symplectic         [ p or q | cond | sin|cos ]                        symplectic.py:109-114   */
+typedef struct {
+  int32_t n_layers;
+  int32_t in_features;
+  int32_t widths[FFB_MAX_LAYERS];       /* out_features of each Linear                    */
+  const float* weight[FFB_MAX_LAYERS];  /* device, [out][in] row-major                    */
+  const float* bias[FFB_MAX_LAYERS];    /* device, [out]                                  */
+  int32_t x_col, x_dim;
+  int32_t c_col, c_dim;
+  int32_t t_col, t_dim;
+} ffb_net_desc;
+
+/* A vector field built from one or two networks acting on column blocks of the state. */
+typedef struct {
+  int32_t n_calls;              /* 1, or 2 for symplectic (mlp_q then mlp_p)           */
+  const ffb_net* net[2];
+  int32_t in_off[2];            /* first state column fed to net[i]                    */
+  int32_t out_off[2];           /* first state column whose derivative net[i] produces */
+  float out_sign[2];            /* +1 / -1 (symplectic.py:121)                         */
+  int32_t state_dim;            /* columns of the state tensor                         */
+  int32_t cond_dim;
+  int32_t kind;                 /* FFB_FIELD_*                                         */
+  int32_t use_sigma;            /* score = net / sigma(t)  (diffusion.py:236)          */
+  int32_t has_drift;            /* 0 for VE (diffusion.py:905)                         */
+  int32_t div_mode;             /* FFB_DIV_*                                           */
+} ffb_field;
+
+/* Host-computed scalars of ONE function evaluation. */
+typedef struct {
+  float tfeat[FFB_MAX_TFEAT];   /* sin|cos(((t*W)*2)*pi) or raw t                              */
+  float a;                      /* drift coefficient, e.g. fl(-0.5*beta(t))                    */
+  float c;                      /* score coefficient: fl(0.5*g^2) (PF-ODE) or fl(g^2) (SDE)    */
+  float sigma;                  /* sigma(t) when use_sigma                                      */
+  float sign;                   /* -1 when torchdiffeq integrates reversed time, else +1       */
+} ffb_eval_scalars;
+
+/* ---- single evaluation (+ the norms of torchdiffeq's initial-step heuristic) ---------- */
+typedef struct {
+  int64_t batch;
+  const float* y;               /* (B, state_dim)                                              */
+  const float* fbase;           /* optional: evaluate at y + h*fbase                           */
+  const float* dlpbase;         /* optional: d(logp)/dt that goes with fbase                   */
+  float h;
+  const float* cond;            /* (B, cond_dim) network input (already normalised) or NULL    */
+  const float* cond_state;      /* (B, cond_dim) raw conditional as carried in the ODE state   */
+  const float* probes;          /* (B, state_dim) Rademacher, FFB_DIV_HUTCH only               */
+  float* f;                     /* out (B, state_dim) or NULL                                  */
+  float* dlp;                   /* out (B,) divergence, or NULL                                */
+  ffb_eval_scalars ev;
+  float atol, rtol;
+  int32_t norms;                /* 0 none; 1: sum (y/sc)^2, (f/sc)^2; 2: sum ((f-fbase)/sc)^2  */
+  int32_t cond_in_state;        /* ConditionalODEFlow carries cond in the ODE state (flow.py:857-861) */
+  double* partials;             /* (n_tiles, FFB_NPART)                                        */
+  int32_t* status;
+  void* scratch;
+} ffb_eval_args;
+
+/* ---- one attempted dopri5 step (6 fused evaluations + error norm + dense output) ------- */
+typedef struct {
+  int64_t batch;
+  const float* y0;   const float* f0;       /* state and FSAL derivative at t0                 */
+  const float* lp0;  const float* dlp0;     /* log-det column and its derivative (or NULL)     */
+  const float* cond; const float* probes;
+  float* y1;  float* f1;  float* lp1;  float* dlp1;
+  float* y_out;  float* lp_out;             /* interpolant at t_end, written when final != 0   */
+  ffb_eval_scalars ev[6];                   /* stages 2..7                                     */
+  float cb[6][6];                           /* fl32(beta_ij * dt)                              */
+  float ce[7];                              /* fl32(dt * c_err_j)                              */
+  float cm[7];                              /* fl32(dt * c_mid_j)                              */
+  float dt, atol, rtol, x_interp;
+  int32_t final;
+  double* partials;
+  int32_t* status;
+  void* scratch;
+} ffb_dopri5_args;
+
+/* ---- fixed-grid integrators, whole trajectory on-chip ---------------------------------- */
+#define FFB_STEP_STRIDE 8   /* floats per step in step_table: dt, g, sqrt(-dt), then method constants */
+typedef struct {
+  int64_t batch;
+  int32_t method;
+  int32_t nsteps;
+  const float* x0;               /* (B, state_dim)                                             */
+  const float* lp0;              /* (B,) or NULL                                               */
+  const float* cond;
+  const float* probes;
+  const float* noise;            /* EM comparison mode: (nsteps, B, state_dim) unit normals     */
+  uint64_t philox_seed;          /* EM throughput mode (noise == NULL)                          */
+  uint64_t philox_offset;
+  int64_t row_offset;            /* global index of row 0 (multi-GPU shards share one stream)   */
+  float* x_out;                  /* (B, state_dim); EM: x_mean of the last step (diffusion.py:563) */
+  float* lp_out;
+  const float* step_table;       /* device (nsteps, FFB_STEP_STRIDE)                            */
+  const ffb_eval_scalars* ev_table; /* device (nsteps, evals_per_step)                          */
+  int32_t* status;
+  void* scratch;
+} ffb_fixed_args;
+
+int ffb_abi_version(void);
+const char* ffb_last_error(void);
+/* sm count, opt-in shared memory per block, compute capability, SM clock (kHz) */
+int ffb_device_info(int32_t* sm_count, int32_t* smem_optin, int32_t* cc_major, int32_t* cc_minor,
+                    int32_t* clock_khz);
+
+int ffb_net_create(const ffb_net_desc* desc, void* stream, ffb_net** out);
+void ffb_net_destroy(ffb_net* net);
+/* algorithmic FLOPs (2*MAC over the Linear layers) of one forward pass of one row */
+int64_t ffb_net_flops(const ffb_net* net);
+
+int64_t ffb_num_tiles(const ffb_field* field, int64_t batch);
+size_t ffb_scratch_bytes(const ffb_field* field);
+
+int ffb_field_eval(const ffb_field* field, const ffb_eval_args* args, void* stream);
+int ffb_dopri5_attempt(const ffb_field* field, const ffb_dopri5_args* args, void* stream);
+int ffb_integrate_fixed(const ffb_field* field, const ffb_fixed_args* args, void* stream);
+
+/* sums[FFB_NPART] = sum over tiles of partials, in tile order (deterministic) */
+int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream);
+/* out[b] = sum_d ( -0.5*x^2 - 0.5*log(2*pi*var) ) + (add ? add[b] : 0)   (flow.py:434, diffusion.py:814) */
+int ffb_gaussian_logprob(const float* x, const float* add, float* out, int64_t batch, int32_t dim,
+                         float sigma, void* stream);
+/* the normals the EM kernel would draw for (seed, offset, step): for statistical tests */
+int ffb_philox_normal(float* out, int64_t batch, int32_t dim, uint64_t seed, uint64_t offset,
+                      int32_t step, int64_t row_offset, void* stream);
+/* FP32 FFMA2 peak probe: returns achieved TFLOP/s through *tflops (roofline denominator) */
+int ffb_ffma_peak(int32_t iters, float* tflops, void* stream);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t ffb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB200_H */

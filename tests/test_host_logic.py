@@ -1,0 +1,152 @@
+"""Host logic on CPU: the package's classes, scalar programs and dopri5 controller driven
+through the torch-CPU kernel model (tests/kernel_model.py) must reproduce the golden vectors
+that the UNMODIFIED reference produced (tests/golden, oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_row_err
+from kernel_model import patched_engine
+
+import flowfusion_b200.diffusion as D
+import flowfusion_b200.flow as F
+import flowfusion_b200.symplectic as Sy
+
+TOL = 2e-5   # the model and the oracle differ only by FP32 summation order
+
+
+def check_stats(stats, meta_stats):
+    assert (stats.accepted, stats.rejected) == (meta_stats["accepted"], meta_stats["rejected"])
+    assert stats.nfe == meta_stats["nfe"]
+
+
+def test_cfg1_flow_sample():
+    meta, sd, ins, outs = load_golden("cfg1_flow_sample")
+    m = F.ODEFlow(**meta["ctor"]).eval()
+    m.load_state_dict(sd)
+    with patched_engine():
+        x = m.sample(ins["xT"])
+    assert rel_row_err(outs["x"], x) < 1e-4
+    # rtol 1e-7 is below FP32 resolution: the step count is rounding noise, do not pin it
+
+
+def test_cfg3_flow_logprob():
+    meta, sd, ins, outs = load_golden("cfg3_flow_logprob")
+    m = F.ODEFlow(**meta["ctor"], target_shift=sd["target_shift"], target_scale=sd["target_scale"]).eval()
+    m.load_state_dict(sd)
+    with patched_engine():
+        lp = m.log_prob(ins["x"])
+    assert lp.shape == outs["log_prob"].shape
+    assert float((lp - outs["log_prob"]).abs().max()) < 1e-3
+    check_stats(m.last_stats, meta["stats"])
+
+
+def test_conditional_flow():
+    meta, sd, ins, outs = load_golden("cflow_sample_logprob")
+    m = F.ConditionalODEFlow(**meta["ctor"]).eval()
+    m.load_state_dict(sd)
+    with patched_engine():
+        x = m.sample(ins["xT"], ins["cond"])
+        assert rel_row_err(outs["x"], x) < 1e-4
+        lp = m.log_prob(outs["x"], ins["cond"], atol=1e-6, rtol=1e-6)
+    assert float((lp - outs["log_prob"]).abs().max()) < 1e-3
+    check_stats(m.last_stats, meta["stats_logprob"])
+
+
+def _score_model(meta, sd):
+    net = D.MLP(**meta["ctor"])
+    sde = {"vp": D.VPSDE, "ve": D.VESDE, "subvp": D.SUBVPSDE}[meta["sde"]]()
+    sm = D.ScoreModel(net, sde, no_sigma=meta["no_sigma"]).eval()
+    sm.load_state_dict(sd)
+    return sm
+
+
+def test_cfg2_pfode_all_methods():
+    meta, sd, ins, outs = load_golden("cfg2_vp_pfode")
+    sm = _score_model(meta, sd)
+    with patched_engine():
+        x, aux = sm.sample_ode_from_base(ins["base"], ins["cond"], atol=1e-5, rtol=1e-5,
+                                         options={"step_t": torch.tensor([1e-3])})
+        assert aux == []
+        assert rel_row_err(outs["x_dopri5"], x) < 1e-4
+        check_stats(sm.last_stats, meta["stats"])
+        x4, _ = sm.sample_ode_from_base(ins["base"], ins["cond"], method="rk4", options={"step_size": 1 / 64})
+        assert rel_row_err(outs["x_rk4"], x4) < TOL
+        xe, _ = sm.sample_ode_from_base(ins["base"], ins["cond"], method="euler", options={"step_size": 1 / 128})
+        assert rel_row_err(outs["x_euler"], xe) < TOL
+
+
+@pytest.mark.parametrize("kind", ["ve", "subvp", "vp"])
+def test_sigma_pfode(kind):
+    meta, sd, ins, outs = load_golden(f"{kind}_sigma_pfode")
+    sm = _score_model(meta, sd)
+    opts = None if meta["call"]["step_t"] is None else {"step_t": torch.tensor([meta["call"]["step_t"]])}
+    with patched_engine():
+        x, _ = sm.sample_ode_from_base(ins["base"], atol=1e-5, rtol=1e-5, options=opts)
+    assert rel_row_err(outs["x_dopri5"], x) < 1e-4
+    check_stats(sm.last_stats, meta["stats"])
+
+
+def test_score_logprob_exact_and_hutch():
+    meta, sd, ins, outs = load_golden("score_logprob_vp")
+    sm = _score_model(meta, sd)
+    with patched_engine():
+        lp = sm.log_prob(ins["x0"], ins["cond"])
+        assert lp.shape == outs["lp_exact"].shape == (ins["x0"].shape[0], 1)
+        assert float((lp - outs["lp_exact"]).abs().max()) < 1e-3
+        check_stats(sm.last_stats, meta["stats"])
+        sm.hutch = True
+        lph = sm.log_prob(ins["x0"], ins["cond"], probes=ins["probes"])
+        assert float((lph - outs["lp_hutch"]).abs().max()) < 1e-3
+        check_stats(sm.last_stats, meta["stats_hutch"])
+
+
+def test_score_logprob_ve():
+    meta, sd, ins, outs = load_golden("score_logprob_ve")
+    sm = _score_model(meta, sd)
+    with patched_engine():
+        lp = sm.log_prob(ins["x0"])
+    assert float((lp - outs["lp_exact"]).abs().max()) < 1e-3
+    check_stats(sm.last_stats, meta["stats"])
+
+
+def _replay_em_noise(seed, B, D, steps, scale=1.0):
+    torch.manual_seed(seed)
+    x0 = torch.distributions.Normal(torch.zeros(D), scale).sample([B])
+    dw = torch.stack([torch.randn_like(x0) for _ in range(steps)])
+    return x0, dw
+
+
+def test_cfg4_euler_maruyama():
+    meta, sd, ins, outs = load_golden("cfg4_vp_em")
+    sm = _score_model(meta, sd)
+    for run in meta["runs"]:
+        x0, dw = _replay_em_noise(run["seed"], run["B"], 32, run["steps"])
+        with patched_engine():
+            x = sm.sample_sde((run["B"], 32), steps=run["steps"], x0=x0, noise=dw)
+        assert rel_row_err(outs[f"x_{run['steps']}"], x) < TOL
+
+
+def test_em_ve_conditional():
+    meta, sd, ins, outs = load_golden("ve_em_cond")
+    sm = _score_model(meta, sd)
+    with patched_engine():
+        x = sm.sample_sde((96, 3), conditional=ins["cond"], steps=50, x0=ins["x0"], noise=ins["dw"])
+    assert rel_row_err(outs["x"], x) < TOL
+
+
+@pytest.mark.parametrize("name", ["cfg5_symplectic", "symplectic_cond"])
+def test_symplectic(name):
+    meta, sd, ins, outs = load_golden(name)
+    net = Sy.SymplecticMLP(**meta["ctor"])
+    m = Sy.SymplecticFlowModel(net, sd["shift"], sd["scale"], sd["conditional_shift"], sd["conditional_scale"]).eval()
+    m.load_state_dict(sd)
+    cond = ins.get("cond")
+    D_ = meta["ctor"]["n_data_dims"]
+    with patched_engine():
+        x = m.sample((ins["z0"].shape[0], D_), conditional=cond, num_steps=meta["num_steps"], z0=ins["z0"])
+        assert rel_row_err(outs["x_sample"], x) < TOL
+        lp = m.log_prob(ins["x"], conditional=cond, p0=ins["p0"])
+    assert lp.shape == outs["log_prob"].shape
+    assert float((lp - outs["log_prob"]).abs().max()) < 1e-3
+    check_stats(m.last_stats, meta["stats_logprob"])
