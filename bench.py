@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the flowfusion hot path on B200 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+A "step" is one complete pass of the hot path over one batch of synthetic inputs.  Default
+workload = BASELINE.json configs[1] ("cfg2"): 16-D conditional VP-SDE
+diffusion (4x128 MLP), probability-flow ODE sampling of 1M samples with dopri5
+(atol = rtol = 1e-5, options={'step_t': [eps]}) through ``ScoreModel.sample_ode_from_base``.
+Other workloads (cfg3 exact-trace log_prob, cfg4 Euler-Maruyama, cfg5 symplectic, cfg1) are
+selectable for the profiles; they are parity-test cases, not the bench line.
+
+N > 1 (launched by torchrun, one rank per GPU): weak scaling -- every rank integrates its own
+batch of the same size; dopri5 all-reduces its error-norm partial sums (NCCL) so all ranks take
+the same steps.  Time = max over ranks of the CUDA-event time of exactly K steps.
+
+``--impl reference`` times the CPU oracle port (oracle/port.py: the reference's algorithm on the
+restated torchdiffeq) on the box's host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WSEED = 1234
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads: build(module namespace) -> model; inputs(B) -> dict of CPU tensors
+# ----------------------------------------------------------------------------------------------
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+WORKLOADS = {
+    "cfg1": dict(desc="ODEFlow(2,[64]*3).sample, dopri5 torchdiffeq defaults (rtol 1e-7, atol 1e-9)", B=10_000,
+                 cpu_B=10_000, metric="samples/s", unit="samples/s"),
+    "cfg2": dict(desc="MLP(16,4,8,[128]*4)+VPSDE no_sigma: PF-ODE sampling, dopri5 atol=rtol=1e-5, step_t=[eps]",
+                 B=1_000_000, cpu_B=20_000, metric="samples/s", unit="samples/s"),
+    "cfg3": dict(desc="ODEFlow(16,[128]*4).log_prob, exact divergence trace, dopri5 atol=rtol=1e-5", B=4_000_000,
+                 cpu_B=4_000, metric="log_prob evals/s", unit="evals/s"),
+    "cfg4": dict(desc="MLP(32,0,8,[128]*4)+VPSDE no_sigma: reverse-SDE Euler-Maruyama, 1000 steps, in-kernel Philox",
+                 B=1_250_000, cpu_B=10_000, metric="samples/s", unit="samples/s"),
+    "cfg5": dict(desc="SymplecticMLP(32,0,8,[128]*4): forward-Euler sampling, 100 steps, 64-D phase space",
+                 B=4_000_000, cpu_B=20_000, metric="samples/s", unit="samples/s"),
+}
+
+
+def make_model(name, ns):
+    """ns: object with .D/.F/.Sy modules exposing the reference class names."""
+    torch.manual_seed(WSEED)
+    if name == "cfg1":
+        return ns.F.ODEFlow(2, [64, 64, 64]).eval()
+    if name == "cfg2":
+        return ns.D.ScoreModel(ns.D.MLP(16, 4, 8, [128] * 4), ns.D.VPSDE(), no_sigma=True).eval()
+    if name == "cfg3":
+        return ns.F.ODEFlow(16, [128] * 4).eval()
+    if name == "cfg4":
+        return ns.D.ScoreModel(ns.D.MLP(32, 0, 8, [128] * 4), ns.D.VPSDE(), no_sigma=True).eval()
+    if name == "cfg5":
+        net = ns.Sy.SymplecticMLP(32, 0, 8, [128] * 4)
+        return ns.Sy.SymplecticFlowModel(net, torch.zeros(32), torch.ones(32), torch.zeros(0), torch.ones(0)).eval()
+    raise KeyError(name)
+
+
+def make_inputs(name, B, rank=0):
+    s = 1000 * rank
+    if name == "cfg1":
+        return {"xT": torch.randn(B, 2, generator=_gen(1 + s))}
+    if name == "cfg2":
+        return {"base": torch.randn(B, 16, generator=_gen(2 + s)), "cond": torch.randn(B, 4, generator=_gen(3 + s))}
+    if name == "cfg3":
+        return {"x": torch.randn(B, 16, generator=_gen(4 + s))}
+    if name == "cfg4":
+        return {"x0": torch.randn(B, 32, generator=_gen(6 + s))}
+    if name == "cfg5":
+        return {"z0": torch.randn(B, 64, generator=_gen(8 + s))}
+    raise KeyError(name)
+
+
+def run_gpu(name, model, inp):
+    """One step through the package's public API; returns the result tensor (on device)."""
+    if name == "cfg1":
+        return model.sample(inp["xT"])
+    if name == "cfg2":
+        return model.sample_ode_from_base(inp["base"], inp["cond"], atol=1e-5, rtol=1e-5,
+                                          options={"step_t": torch.tensor([1e-3])})[0]
+    if name == "cfg3":
+        return model.log_prob(inp["x"])
+    if name == "cfg4":
+        return model.sample_sde(tuple(inp["x0"].shape), steps=1000, x0=inp["x0"], seed=5)
+    if name == "cfg5":
+        return model.sample((inp["z0"].shape[0], 32), num_steps=100, z0=inp["z0"])
+    raise KeyError(name)
+
+
+def run_cpu_port(name, model, inp):
+    """The same call on the CPU oracle port (weights taken from the model's state_dict)."""
+    from oracle import port
+    sd = model.state_dict()
+    if name == "cfg1":
+        return port.flow_sample(port.flow_from_state_dict(sd), inp["xT"])
+    if name == "cfg2":
+        M = port.score_model_from_state_dict(sd, port.make_sde("vp"), True)
+        return port.sample_ode_from_base(M, inp["base"], inp["cond"], 1e-5, 1e-5, options={"step_t": torch.tensor([1e-3])})[0]
+    if name == "cfg3":
+        return port.flow_log_prob(port.flow_from_state_dict(sd), inp["x"])
+    if name == "cfg4":
+        M = port.score_model_from_state_dict(sd, port.make_sde("vp"), True)
+        dw = torch.randn(1000, *inp["x0"].shape, generator=_gen(7))
+        return port.sample_sde(M, inp["x0"], dw)
+    if name == "cfg5":
+        return port.symplectic_sample(port.symplectic_from_state_dict(sd), inp["z0"], None, 100)
+    raise KeyError(name)
+
+
+def nfe_of(name, model):
+    if name == "cfg4":
+        return 1000
+    if name == "cfg5":
+        return 100
+    return model.last_stats.nfe if hasattr(model, "last_stats") and model.last_stats else None
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def cpu_baseline(name, cpu_B):
+    import types
+    import flowfusion_b200.diffusion as D, flowfusion_b200.flow as F, flowfusion_b200.symplectic as Sy  # noqa: E401
+    torch.set_num_threads(os.cpu_count())
+    model = make_model(name, types.SimpleNamespace(D=D, F=F, Sy=Sy))
+    inp = make_inputs(name, cpu_B)
+    t0 = time.perf_counter()
+    run_cpu_port(name, model, inp)
+    dt = time.perf_counter() - t0
+    return {"value": cpu_B / dt, "unit": WORKLOADS[name]["unit"], "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{cpu_B} rows of the same workload, one call of the oracle port (oracle/port.py), {dt:.1f} s"}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import types
+    import flowfusion_b200.diffusion as D, flowfusion_b200.flow as F, flowfusion_b200.symplectic as Sy  # noqa: E401
+    name = args.workload
+    w = WORKLOADS[name]
+    torch.set_num_threads(os.cpu_count())
+    model = make_model(name, types.SimpleNamespace(D=D, F=F, Sy=Sy))
+    B = max(1000, min(w["cpu_B"], int(w["cpu_B"] * args.ref_scale)))
+    inp = make_inputs(name, B)
+    for _ in range(args.warmup):
+        run_cpu_port(name, model, inp)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_cpu_port(name, model, inp)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = B / dt
+    line = {"impl": "reference", "metric": w["metric"], "value": val, "unit": w["unit"], "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: {w['desc']}", "rows_per_step": B,
+                       "note": "CPU oracle port of the reference algorithm on the restated torchdiffeq; bounded sample"},
+            "cpu_baseline": {"value": val, "unit": w["unit"], "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{B} rows per step"},
+            "e2e": {"value": val, "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="rows per GPU (default: the workload's size)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import types
+    import torch.distributed as td
+    import flowfusion_b200.diffusion as D, flowfusion_b200.flow as F, flowfusion_b200.symplectic as Sy  # noqa: E401
+    from flowfusion_b200 import _lib, engine, dist as fdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+        group = td.group.WORLD
+    _lib.load()
+    name = args.workload
+    w = WORKLOADS[name]
+    B = args.batch or w["B"]
+    model = make_model(name, types.SimpleNamespace(D=D, F=F, Sy=Sy)).to(dev)
+    host = {k: v.pin_memory() for k, v in make_inputs(name, B, rank).items()}
+    inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    ctx = fdist.use_group(group)
+    with ctx:
+        for _ in range(args.warmup):
+            out = run_gpu(name, model, inp)
+        barrier()
+        # ---- timed region: exactly K steps, device-resident inputs -------------------------------
+        engine.profiler.reset(True)
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                out = run_gpu(name, model, inp)
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - n0
+        prof = engine.profiler.summary()
+        engine.profiler.reset(False)
+        nfe = nfe_of(name, model)
+        stats = getattr(model, "last_stats", None)
+        # ---- end-to-end: host buffers in, host result out, copies inside the timed region --------
+        e2e_s = 0.0
+        if not args.no_e2e:
+            res_host = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                dinp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                o = run_gpu(name, model, dinp)
+                res_host.copy_(o, non_blocking=True)
+                torch.cuda.synchronize()
+            barrier()
+            e2e_s = (time.perf_counter() - t0)
+    tmax = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(tmax, op=td.ReduceOp.MAX)
+    ms, e2e_ms = float(tmax[0]), float(tmax[1])
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+    total_rows = B * world * args.steps
+    value = total_rows / (ms * 1e-3)
+    peaks, peak_src = measured_peaks()
+    # ---- roofline of the dominant kernel: algorithmic FLOPs per launch / mean launch time ---------
+    kname = max(prof, key=lambda k: prof[k][1]) if prof else None
+    roof = None
+    if kname:
+        n_l, k_ms, k_rows = prof[kname]
+        field_flops = {"cfg1": 17024, "cfg2": 109568, "cfg3": 1683712, "cfg4": 116736, "cfg5": 233472}[name]
+        evals_per_launch = {"dopri5_attempt": 6, "field_eval": 1, "integrate_fixed": nfe or 1}[kname]
+        flop_per_launch = field_flops * evals_per_launch * (k_rows / n_l)
+        achieved = flop_per_launch / (k_ms / n_l * 1e-3) / 1e12
+        ffma_peak = engine.ffma_peak_tflops()
+        tensor_fp32_equiv = peaks["bf16_tflops"] / 6.0
+        roof = {"bound": "tensor", "achieved": achieved, "peak": tensor_fp32_equiv, "unit": "TFLOP/s",
+                "frac": achieved / tensor_fp32_equiv, "traffic": None,
+                "kernel": kname, "launches": n_l, "avg_launch_ms": k_ms / n_l, "share_of_step": k_ms / ms,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}) / 6 = 3xTF32 FP32-equivalent tensor peak",
+                "fp32_ffma2_peak_measured": ffma_peak, "frac_of_ffma2_peak": achieved / ffma_peak,
+                "flop_per_launch": flop_per_launch}
+    line = {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: {w['desc']}", "rows_per_gpu": B, "nfe": nfe,
+                       "dopri5_steps": None if stats is None else [stats.accepted, stats.rejected],
+                       "l2": "working set (state + derivative ping-pong buffers) exceeds the 126 MB L2; no flush needed",
+                       "weights": "random init, torch.manual_seed(1234), reference construction order"},
+            "clocks": clk.summary(), "gpu_launches": launches, "roofline": roof}
+    if not args.no_e2e:
+        hb = sum(v.numel() * 4 for v in host.values())
+        line["e2e"] = {"value": total_rows / (e2e_ms * 1e-3), "unit": w["unit"], "h2d_bytes_per_step": hb,
+                       "d2h_bytes_per_step": int(out.numel() * 4), "ms_per_step": e2e_ms / args.steps}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(name, w["cpu_B"])
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,45 @@ import torch
 from . import _lib as L
 
 
+class _Profiler:
+    """Optional CUDA-event timing of the integrator launches (bench.py's roofline leg).
+    Events are recorded on torch's current stream, which is the stream the kernels run on."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []          # (name, start_event, end_event, rows)
+
+    def reset(self, enabled=True):
+        self.enabled, self.records = enabled, []
+
+    def summary(self):
+        """name -> (launches, total_ms, total_rows); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, e0, e1, rows in self.records:
+            n, ms, r = out.get(name, (0, 0.0, 0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1), r + rows)
+        return out
+
+
+profiler = _Profiler()
+
+
+class _timed:
+    def __init__(self, name, rows):
+        self.name, self.rows = name, rows
+
+    def __enter__(self):
+        if profiler.enabled:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if profiler.enabled:
+            self.e1.record()
+            profiler.records.append((self.name, self.e0, self.e1, self.rows))
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -210,7 +249,8 @@ class CudaBackend:
         a.cond_in_state = int(self.cond_in_state)
         a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
         if self.B:
-            L.check(self.lib.ffb_field_eval(C.byref(self.field.c), C.byref(a), _stream()), "ffb_field_eval")
+            with _timed("field_eval", self.B):
+                L.check(self.lib.ffb_field_eval(C.byref(self.field.c), C.byref(a), _stream()), "ffb_field_eval")
         return self._reduce()
 
     def eval0(self, ev_row, atol, rtol):
@@ -239,7 +279,8 @@ class CudaBackend:
         a.dt, a.atol, a.rtol, a.x_interp, a.final = float(dt32), float(atol), float(rtol), float(x_interp), int(final)
         a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
         if self.B:
-            L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(a), _stream()), "ffb_dopri5_attempt")
+            with _timed("dopri5_attempt", self.B):
+                L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(a), _stream()), "ffb_dopri5_attempt")
         return self._reduce()
 
     def accept(self):
@@ -279,7 +320,8 @@ def run_fixed(field: FieldSpec, method: int, x0: torch.Tensor, step_table: np.nd
     a.step_table, a.ev_table = _ptr(st), _ptr(ev)
     a.status, a.scratch = _ptr(status), _ptr(scratch)
     if B and nsteps:
-        L.check(lib.ffb_integrate_fixed(C.byref(field.c), C.byref(a), _stream()), "ffb_integrate_fixed")
+        with _timed("integrate_fixed", B):
+            L.check(lib.ffb_integrate_fixed(C.byref(field.c), C.byref(a), _stream()), "ffb_integrate_fixed")
     elif B:
         x_out.copy_(x0)
     return x_out, lp_out, status
