@@ -48,13 +48,13 @@ WORKLOADS = {
     "cfg1": dict(desc="ODEFlow(2,[64]*3).sample, dopri5 torchdiffeq defaults (rtol 1e-7, atol 1e-9)", B=10_000,
                  cpu_B=10_000, metric="samples/s", unit="samples/s"),
     "cfg2": dict(desc="MLP(16,4,8,[128]*4)+VPSDE no_sigma: PF-ODE sampling, dopri5 atol=rtol=1e-5, step_t=[eps]",
-                 B=1_000_000, cpu_B=20_000, metric="samples/s", unit="samples/s"),
+                 B=1_000_000, cpu_B=400_000, metric="samples/s", unit="samples/s"),
     "cfg3": dict(desc="ODEFlow(16,[128]*4).log_prob, exact divergence trace, dopri5 atol=rtol=1e-5", B=4_000_000,
-                 cpu_B=4_000, metric="log_prob evals/s", unit="evals/s"),
+                 cpu_B=20_000, metric="log_prob evals/s", unit="evals/s"),
     "cfg4": dict(desc="MLP(32,0,8,[128]*4)+VPSDE no_sigma: reverse-SDE Euler-Maruyama, 1000 steps, in-kernel Philox",
-                 B=1_250_000, cpu_B=10_000, metric="samples/s", unit="samples/s"),
+                 B=1_250_000, cpu_B=20_000, metric="samples/s", unit="samples/s"),
     "cfg5": dict(desc="SymplecticMLP(32,0,8,[128]*4): forward-Euler sampling, 100 steps, 64-D phase space",
-                 B=4_000_000, cpu_B=20_000, metric="samples/s", unit="samples/s"),
+                 B=4_000_000, cpu_B=200_000, metric="samples/s", unit="samples/s"),
 }
 
 
@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="rows per GPU (default: the workload's size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-scale", type=float, default=1.0)
+    ap.add_argument("--ref-scale", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
