@@ -52,6 +52,7 @@ struct FieldDev {
   int in_off[2], out_off[2];
   float out_sign[2];
   int state_dim, cond_dim, kind, use_sigma, has_drift, div_mode;
+  int slots_smem;   // 1: the Y0 / K1..K7 state slots live in shared memory, 0: in the global scratch
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -94,7 +95,14 @@ __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" 
 // ---------------------------------------------------------------------------------------------
 // activation
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+// sigmoid(z) = 1 / (1 + 2^(-z log2 e)) on the SFU: MUFU.EX2 + MUFU.RCP (each <= 2 ulp), 3 FP32 ops.
+// z -> -inf gives rcp(+inf) = 0, z -> +inf gives rcp(1) = 1: no range fix-ups needed.
+__device__ __forceinline__ float sigmoidf_fast(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------
 // per-CTA context
@@ -118,6 +126,8 @@ struct Ctx {
   uint32_t o_klp;   // [NSLOT+2][TM] d(logp)/dt per slot; row NSLOT = lp0, NSLOT+1 = lp_cur
   uint32_t o_red;   // [8][FFB_NPART] block-reduction scratch (double)
   uint32_t o_bar;   // full[NSTAGE], empty[NSTAGE]
+  uint32_t o_slots; // [NSLOT][SD][LDA] state slots (when they fit)
+  int slots_smem;
   __device__ __forceinline__ float* act() const { return reinterpret_cast<float*>(smem_base() + o_act); }
   __device__ __forceinline__ float* ring() const { return reinterpret_cast<float*>(smem_base() + o_ring); }
   __device__ __forceinline__ float* ycur() const { return reinterpret_cast<float*>(smem_base() + o_ycur); }
@@ -144,14 +154,17 @@ struct Ctx {
   uint32_t phase;
 };
 
-__device__ __forceinline__ float* slot_ptr(const Ctx& cx, int slot) { return cx.scr + (size_t)slot * cx.SD * LDA; }
+__device__ __forceinline__ float* slot_ptr(const Ctx& cx, int slot) {
+  float* base = cx.slots_smem ? reinterpret_cast<float*>(smem_base() + cx.o_slots) : cx.scr;
+  return base + (size_t)slot * cx.SD * LDA;
+}
 
 __device__ __forceinline__ void pipe_advance(Ctx& cx) {
   if (++cx.stage == NSTAGE) { cx.stage = 0; cx.phase ^= 1u; }
 }
 
 // size of the dynamic shared memory block for a field (host + device agree through this)
-__host__ __device__ inline size_t smem_layout(int SD, int CD, int T, int hutch, size_t* off /*[12]*/) {
+__host__ __device__ inline size_t smem_layout(int SD, int CD, int T, int hutch, int slots_smem, size_t* off /*[12]*/) {
   int S = TM / (1 + T);
   int GS = (T > 0) ? (S | 1) : 0;
   size_t o = 0;
@@ -167,14 +180,15 @@ __host__ __device__ inline size_t smem_layout(int SD, int CD, int T, int hutch, 
   v[7] = take(sizeof(float) * (NSLOT + 2) * TM);           // klp
   v[8] = take(sizeof(double) * 8 * FFB_NPART);             // red
   v[9] = take(sizeof(uint64_t) * 2 * NSTAGE);              // barriers
-  if (off) for (int i = 0; i < 10; ++i) off[i] = v[i];
+  v[10] = take(slots_smem ? sizeof(float) * NSLOT * SD * LDA : 0);   // state slots
+  if (off) for (int i = 0; i < 11; ++i) off[i] = v[i];
   return o;
 }
 
-__device__ inline void ctx_init(Ctx& cx, const FieldDev& f, float* scratch) {
+__device__ __forceinline__ void ctx_init(Ctx& cx, const FieldDev& f, float* scratch) {
   int T = (f.div_mode == FFB_DIV_EXACT) ? f.net[0].x_dim : (f.div_mode == FFB_DIV_HUTCH ? 1 : 0);
   size_t off[12];
-  smem_layout(f.state_dim, f.cond_dim, T, f.div_mode == FFB_DIV_HUTCH, off);
+  smem_layout(f.state_dim, f.cond_dim, T, f.div_mode == FFB_DIV_HUTCH, f.slots_smem, off);
   cx.o_act = (uint32_t)off[0];
   cx.o_ring = (uint32_t)off[1];
   cx.o_ycur = (uint32_t)off[2];
@@ -185,6 +199,8 @@ __device__ inline void ctx_init(Ctx& cx, const FieldDev& f, float* scratch) {
   cx.o_klp = (uint32_t)off[7];
   cx.o_red = (uint32_t)off[8];
   cx.o_bar = (uint32_t)off[9];
+  cx.o_slots = (uint32_t)off[10];
+  cx.slots_smem = f.slots_smem;
   cx.T = T;
   cx.S = TM / (1 + T);
   cx.GS = (T > 0) ? (cx.S | 1) : 0;
@@ -210,7 +226,7 @@ __device__ inline void ctx_init(Ctx& cx, const FieldDev& f, float* scratch) {
 // ---------------------------------------------------------------------------------------------
 // producer: stream one network's packed weights through the ring
 // ---------------------------------------------------------------------------------------------
-__device__ inline void produce_net(Ctx& cx, const NetDev& net) {
+__device__ __forceinline__ void produce_net(Ctx& cx, const NetDev& net) {
   for (int l = 0; l < net.n_layers; ++l) {
     const int K = net.K[l], Np = net.Np[l];
     for (int k0 = 0; k0 < K; k0 += KC) {
@@ -367,7 +383,7 @@ __device__ __forceinline__ void run_layer(Ctx& cx, const NetDev& net, int l, con
 // ---------------------------------------------------------------------------------------------
 // one network forward on the tile (consumer side).  Inputs must already be in cx.act().
 // ---------------------------------------------------------------------------------------------
-__device__ inline void consume_net(Ctx& cx, const NetDev& net) {
+__device__ __forceinline__ void consume_net(Ctx& cx, const NetDev& net) {
   for (int l = 0; l < net.n_layers; ++l) {
     const bool last = (l == net.n_layers - 1);
     const float* bias = (l == 0) ? cx.beff() : net.b[l];
@@ -384,8 +400,10 @@ __device__ inline void consume_net(Ctx& cx, const NetDev& net) {
 // evaluate the vector field at the state held in cx.ycur(); derivative -> scratch slot `dst`,
 // divergence (if any) -> klp[dst].  Called by ALL threads (the producer warp streams weights).
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void eval_field(Ctx& cx, const FieldDev& f, const ffb_eval_scalars& ev, int dst) {
+__device__ __forceinline__ void eval_field(Ctx& cx, const FieldDev& f, const ffb_eval_scalars& ev, int dst,
+                                           unsigned call_mask = 3u) {
   for (int c = 0; c < f.n_calls; ++c) {
+    if (!((call_mask >> c) & 1u)) continue;
     const NetDev& net = f.net[c];
     if (cx.producer) { produce_net(cx, net); continue; }
     const int S = cx.S, T = cx.T, live = S * (1 + T);

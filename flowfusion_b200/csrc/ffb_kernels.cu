@@ -130,7 +130,8 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset,
 // =============================================================================================
 // k_field_eval
 // =============================================================================================
-__global__ void __launch_bounds__(NTHR, 1) k_field_eval(const FieldDev f, const ffb_eval_args a, const int64_t ntiles) {
+__global__ void __launch_bounds__(NTHR, 1) k_field_eval(const __grid_constant__ FieldDev f,
+                                                        const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
   Ctx cx;
   ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
   const int S = cx.S, SD = cx.SD, CD = cx.CD;
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_field_eval(const FieldDev f, const 
 // =============================================================================================
 // k_dopri5: one attempted step
 // =============================================================================================
-__global__ void __launch_bounds__(NTHR, 1) k_dopri5(const FieldDev f, const ffb_dopri5_args a, const int64_t ntiles) {
+__global__ void __launch_bounds__(NTHR, 1) k_dopri5(const __grid_constant__ FieldDev f,
+                                                    const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
   Ctx cx;
   ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
   const int S = cx.S, SD = cx.SD, CD = cx.CD;
@@ -305,34 +307,26 @@ __device__ __forceinline__ int evals_per_step(int method) {
   return method == FFB_M_RK4 ? 4 : (method == FFB_M_MIDPOINT ? 2 : (method == FFB_M_LEAPFROG ? 3 : 1));
 }
 
-// evaluate only call `c` of a 2-call field (leapfrog): same as eval_field restricted to one call
-__device__ inline void eval_one_call(Ctx& cx, const FieldDev& f, int c, const ffb_eval_scalars& ev, int dst) {
-  FieldDev g = f;   // (kernel-param copy; small)
-  g.n_calls = 1;
-  g.net[0] = f.net[c];
-  g.in_off[0] = f.in_off[c];
-  g.out_off[0] = f.out_off[c];
-  g.out_sign[0] = f.out_sign[c];
-  eval_field(cx, g, ev, dst);
-}
-
-__global__ void __launch_bounds__(NTHR, 1) k_fixed(const FieldDev f, const ffb_fixed_args a, const int64_t ntiles) {
+__global__ void __launch_bounds__(NTHR, 1) k_fixed(const __grid_constant__ FieldDev f,
+                                                   const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
   Ctx cx;
   ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
   const int S = cx.S, SD = cx.SD, CD = cx.CD;
   const bool prob = cx.T > 0;
   const int nev = evals_per_step(a.method);
   const float third = (float)(1.0 / 3.0);
-  float* LP0 = cx.klp() + NSLOT * TM;        // lp at the start of the step
   float* LPC = cx.klp() + (NSLOT + 1) * TM;  // running lp
+  // column ranges produced by the two networks of a symplectic field (leapfrog only)
+  const int q_lo = f.out_off[0], q_hi = f.out_off[0] + f.net[0].N[f.net[0].n_layers - 1];
+  const int p_lo = f.out_off[1], p_hi = f.out_off[1] + f.net[1].N[f.net[1].n_layers > 0 ? f.net[1].n_layers - 1 : 0];
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * S;
     const int nv = (int)min((int64_t)S, a.batch - row0);
     float* Y0 = slot_ptr(cx, SLOT_Y0);
-    float* K1 = slot_ptr(cx, 0);
-    float* K2 = slot_ptr(cx, 1);
-    float* K3 = slot_ptr(cx, 2);
-    float* K4 = slot_ptr(cx, 3);
+    const float* K1 = slot_ptr(cx, 0);
+    const float* K2 = slot_ptr(cx, 1);
+    const float* K3 = slot_ptr(cx, 2);
+    const float* K4 = slot_ptr(cx, 3);
     bool saw_nan = false;
     if (!cx.producer) {
       load_rows(cx.ycur(), a.x0, row0, nv, S, SD, cx.tid);
@@ -345,67 +339,72 @@ __global__ void __launch_bounds__(NTHR, 1) k_fixed(const FieldDev f, const ffb_f
     for (int step = 0; step < a.nsteps; ++step) {
       const float* st = a.step_table + (size_t)step * FFB_STEP_STRIDE;
       const ffb_eval_scalars* ev = a.ev_table + (size_t)step * nev;
-      const float dt = st[0];
-#define FOR_STATE(...)                                        \
-  if (!cx.producer) {                                         \
-    for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {      \
-      const int d = idx / S, r = idx - d * S;                 \
-      const int e = d * LDA + r;                              \
-      (void)d; (void)r;                                       \
-      __VA_ARGS__                                             \
-    }                                                         \
-  }
-#define FOR_LP(...)                                           \
-  if (!cx.producer && prob) {                                 \
-    for (int s = cx.tid; s < S; s += NCOMP) { __VA_ARGS__ }   \
-  }
-      if (a.method == FFB_M_EULER) {
-        eval_field(cx, f, ev[0], 0);
-        FOR_STATE(cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(dt, K1[e]));)
-        FOR_LP(LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, cx.klp()[s]));)
-        if (!cx.producer) bar_compute();
-      } else if (a.method == FFB_M_MIDPOINT) {
-        const float half = st[3];
-        eval_field(cx, f, ev[0], 0);
-        FOR_STATE(const float y = cx.ycur()[e]; Y0[e] = y; cx.ycur()[e] = __fadd_rn(y, __fmul_rn(K1[e], half));)
-        if (!cx.producer) bar_compute();
-        eval_field(cx, f, ev[1], 1);
-        FOR_STATE(cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(dt, K2[e]));)
-        FOR_LP(LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, cx.klp()[TM + s]));)
-        if (!cx.producer) bar_compute();
-      } else if (a.method == FFB_M_RK4) {
-        eval_field(cx, f, ev[0], 0);
-        FOR_STATE(const float y = cx.ycur()[e]; Y0[e] = y;
-                  cx.ycur()[e] = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, K1[e]), third));)
-        if (!cx.producer) bar_compute();
-        eval_field(cx, f, ev[1], 1);
-        FOR_STATE(cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(dt, __fsub_rn(K2[e], __fmul_rn(K1[e], third))));)
-        if (!cx.producer) bar_compute();
-        eval_field(cx, f, ev[2], 2);
-        FOR_STATE(cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(dt, __fadd_rn(__fsub_rn(K1[e], K2[e]), K3[e])));)
-        if (!cx.producer) bar_compute();
-        eval_field(cx, f, ev[3], 3);
-        FOR_STATE(const float sum = __fadd_rn(__fadd_rn(K1[e], __fmul_rn(3.0f, __fadd_rn(K2[e], K3[e]))), K4[e]);
-                  cx.ycur()[e] = __fadd_rn(Y0[e], __fmul_rn(__fmul_rn(sum, dt), 0.125f));)
-        FOR_LP(const float k1 = cx.klp()[s], k2 = cx.klp()[TM + s], k3 = cx.klp()[2 * TM + s], k4 = cx.klp()[3 * TM + s];
-               const float sum = __fadd_rn(__fadd_rn(k1, __fmul_rn(3.0f, __fadd_rn(k2, k3))), k4);
-               LPC[s] = __fadd_rn(LPC[s], __fmul_rn(__fmul_rn(sum, dt), 0.125f));)
-        if (!cx.producer) bar_compute();
-      } else if (a.method == FFB_M_EM) {
-        // diffusion.py:552-559: f = drift - g^2 score (ev.c = g^2); x_mean = x + f dt; x = x_mean + g dw
-        const float g = st[1], sq = st[2];
-        eval_field(cx, f, ev[0], 0);
-        if (!cx.producer) {
+      const float dt = st[0], half = st[3];
+      for (int e = 0; e < nev; ++e) {
+        // ---- which networks this evaluation runs, and where the derivative goes -----------------
+        unsigned mask = 3u;
+        int dst = e;
+        if (a.method == FFB_M_LEAPFROG) {         // e0: dp/dt(q, t0) [first step only], e1: dq/dt, e2: dp/dt
+          if (e == 0 && step > 0) mask = 0u;      // reuse the previous step's closing kick
+          else mask = (e == 1) ? 1u : 2u;
+          dst = (e == 1) ? 0 : 1;
+        }
+        if (mask) eval_field(cx, f, ev[e], dst, mask);
+        if (cx.producer) continue;
+        // ---- stage algebra after evaluation e (op order of torchdiffeq's step functions) ---------
+        for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
+          const int d = idx / S, r = idx - d * S;
+          const int i = d * LDA + r;
+          float* y = cx.ycur();
+          switch (a.method) {
+            case FFB_M_EULER:
+              y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i]));
+              break;
+            case FFB_M_MIDPOINT:
+              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(K1[i], half)); }
+              else y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, K2[i]));
+              break;
+            case FFB_M_RK4:
+              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(__fmul_rn(dt, K1[i]), third)); }
+              else if (e == 1) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fsub_rn(K2[i], __fmul_rn(K1[i], third))));
+              else if (e == 2) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(K1[i], K2[i]), K3[i])));
+              else {
+                const float sum = __fadd_rn(__fadd_rn(K1[i], __fmul_rn(3.0f, __fadd_rn(K2[i], K3[i]))), K4[i]);
+                y[i] = __fadd_rn(Y0[i], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+              }
+              break;
+            case FFB_M_LEAPFROG:
+              if (e == 1) { if (d >= q_lo && d < q_hi) y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i])); }
+              else if (d >= p_lo && d < p_hi) y[i] = __fadd_rn(y[i], __fmul_rn(half, K2[i]));
+              break;
+            default: break;   // EM handled below (its noise is indexed row-major)
+          }
+        }
+        if (prob) {
+          for (int s = cx.tid; s < S; s += NCOMP) {
+            const float* kl = cx.klp();
+            if (a.method == FFB_M_EULER) LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, kl[s]));
+            else if (a.method == FFB_M_MIDPOINT && e == 1) LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, kl[TM + s]));
+            else if (a.method == FFB_M_RK4 && e == 3) {
+              const float sum = __fadd_rn(__fadd_rn(kl[s], __fmul_rn(3.0f, __fadd_rn(kl[TM + s], kl[2 * TM + s]))), kl[3 * TM + s]);
+              LPC[s] = __fadd_rn(LPC[s], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+            }
+          }
+        }
+        if (a.method == FFB_M_EM) {
+          // diffusion.py:552-559: f = drift - g^2 score (ev.c = g^2); x_mean = x + f dt; x = x_mean + g dw
+          const float g = st[1], sq = st[2];
+          float* y = cx.ycur();
           if (a.noise) {
             for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
               const int r = idx / SD, d = idx - r * SD;
               if (r >= nv) continue;
-              const int e = d * LDA + r;
-              const float xm = __fadd_rn(cx.ycur()[e], __fmul_rn(K1[e], dt));
+              const int i = d * LDA + r;
+              const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
               const float dw = __fmul_rn(a.noise[((size_t)step * a.batch + row0 + r) * SD + d], sq);
               const float xn = __fadd_rn(xm, __fmul_rn(g, dw));
-              Y0[e] = xm;
-              cx.ycur()[e] = xn;
+              Y0[i] = xm;
+              y[i] = xn;
               saw_nan |= (xn != xn);
             }
           } else {
@@ -419,34 +418,18 @@ __global__ void __launch_bounds__(NTHR, 1) k_fixed(const FieldDev f, const ffb_f
               for (int q = 0; q < 4; ++q) {
                 const int d = grp * 4 + q;
                 if (d >= SD) break;
-                const int e = d * LDA + r;
-                const float xm = __fadd_rn(cx.ycur()[e], __fmul_rn(K1[e], dt));
+                const int i = d * LDA + r;
+                const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
                 const float xn = __fadd_rn(xm, __fmul_rn(g, __fmul_rn(zz[q], sq)));
-                Y0[e] = xm;
-                cx.ycur()[e] = xn;
+                Y0[i] = xm;
+                y[i] = xn;
                 saw_nan |= (xn != xn);
               }
             }
           }
-          bar_compute();
         }
-      } else {  // FFB_M_LEAPFROG (extension): kick (dt/2) - drift (dt) - kick (dt/2); call 0 = dq/dt(p), call 1 = dp/dt(q)
-        const float half = st[3];
-        if (step == 0) eval_one_call(cx, f, 1, ev[0], 1);      // dp/dt at (q, t0); later steps reuse the last kick
-        FOR_STATE(if (d >= f.out_off[1] && d < f.out_off[1] + f.net[1].N[f.net[1].n_layers - 1])
-                      cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(half, K2[e]));)
-        if (!cx.producer) bar_compute();
-        eval_one_call(cx, f, 0, ev[1], 0);                     // dq/dt at (p_half, t0 + dt/2)
-        FOR_STATE(if (d >= f.out_off[0] && d < f.out_off[0] + f.net[0].N[f.net[0].n_layers - 1])
-                      cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(dt, K1[e]));)
-        if (!cx.producer) bar_compute();
-        eval_one_call(cx, f, 1, ev[2], 1);                     // dp/dt at (q1, t1)
-        FOR_STATE(if (d >= f.out_off[1] && d < f.out_off[1] + f.net[1].N[f.net[1].n_layers - 1])
-                      cx.ycur()[e] = __fadd_rn(cx.ycur()[e], __fmul_rn(half, K2[e]));)
-        if (!cx.producer) bar_compute();
+        bar_compute();
       }
-#undef FOR_STATE
-#undef FOR_LP
     }
     if (!cx.producer) {
       store_rows(a.x_out, (a.method == FFB_M_EM) ? Y0 : cx.ycur(), row0, nv, SD, cx.tid);
@@ -455,7 +438,6 @@ __global__ void __launch_bounds__(NTHR, 1) k_fixed(const FieldDev f, const ffb_f
       if (saw_nan) atomicOr(a.status, FFB_ST_NAN_SAMPLE);
       bar_compute();
     }
-    (void)LP0;
   }
 }
 
@@ -701,6 +683,12 @@ static int make_field(const ffb_field* f, FieldDev* out) {
   }
   out->state_dim = f->state_dim; out->cond_dim = f->cond_dim; out->kind = f->kind;
   out->use_sigma = f->use_sigma; out->has_drift = f->has_drift; out->div_mode = f->div_mode;
+  // keep the Y0 / K1..K7 slots in shared memory whenever the tile still fits in one SM
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t with_slots = smem_layout(out->state_dim, out->cond_dim, tangents_of(f), out->div_mode == FFB_DIV_HUTCH, 1, nullptr);
+  out->slots_smem = (optin > 0 && with_slots <= (size_t)optin) ? 1 : 0;
   return FFB_OK;
 }
 
@@ -725,7 +713,7 @@ template <typename Kern, typename Args>
 static int launch_tiles(Kern kern, const char* name, const ffb_field* f, const FieldDev& fd, const Args& a,
                         int64_t batch, cudaStream_t stream) {
   const int T = tangents_of(f);
-  const size_t smem = smem_layout(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, nullptr);
+  const size_t smem = smem_layout(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, fd.slots_smem, nullptr);
   int dev = 0, optin = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
