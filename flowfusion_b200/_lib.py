@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libffb200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "ffb_kernels.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "ffb_engine.cuh"), os.path.join(ROOT, "include", "ffb200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", "ffb_engine.cuh"), os.path.join(_HERE, "csrc", "ffb_engine_tc.cuh"),
+           os.path.join(ROOT, "include", "ffb200.h")]
 
 MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
 FIELD_NET, FIELD_SCORE = 0, 1
@@ -92,6 +93,8 @@ SYMBOLS = {
     "ffb_gaussian_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "ffb_philox_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]),
     "ffb_ffma_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
+    "ffb_set_engine": (C.c_int, [C.c_int]),
+    "ffb_get_engine": (C.c_int, []),
     "ffb_launch_count": (C.c_int64, []),
 }
 

@@ -129,6 +129,7 @@ struct Ctx {
   uint32_t o_slots; // [NSLOT][SD][LDA] state slots (when they fit)
   int slots_smem;
   __device__ __forceinline__ float* act() const { return reinterpret_cast<float*>(smem_base() + o_act); }
+  __device__ __forceinline__ float* stage_buf() const { return act(); }   // free between evaluations
   __device__ __forceinline__ float* ring() const { return reinterpret_cast<float*>(smem_base() + o_ring); }
   __device__ __forceinline__ float* ycur() const { return reinterpret_cast<float*>(smem_base() + o_ycur); }
   __device__ __forceinline__ float* condb() const { return reinterpret_cast<float*>(smem_base() + o_cond); }
@@ -467,5 +468,16 @@ __device__ __forceinline__ void eval_field(Ctx& cx, const FieldDev& f, const ffb
     bar_compute();
   }
 }
+
+struct EngineFFMA {
+  using Ctx = ffb::Ctx;
+  static constexpr int NTHR = ffb::NTHR;
+  static __device__ __forceinline__ void init(Ctx& cx, const FieldDev& f, float* scratch) { ctx_init(cx, f, scratch); }
+  static __device__ __forceinline__ void fini(Ctx&) {}
+  static __device__ __forceinline__ void eval(Ctx& cx, const FieldDev& f, const ffb_eval_scalars& ev, int dst,
+                                              unsigned call_mask = 3u) {
+    eval_field(cx, f, ev, dst, call_mask);
+  }
+};
 
 }  // namespace ffb

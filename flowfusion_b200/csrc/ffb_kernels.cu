@@ -22,6 +22,7 @@
 
 #include "ffb200.h"
 #include "ffb_engine.cuh"
+#include "ffb_engine_tc.cuh"
 
 using namespace ffb;
 
@@ -48,8 +49,8 @@ __device__ __forceinline__ void store_rows(float* __restrict__ dst, const float*
 }
 
 // deterministic block reduction of NV doubles per thread -> out[q] (thread 0 writes)
-template <int NV>
-__device__ __forceinline__ void block_reduce_store(Ctx& cx, double (&v)[NV], double* out, const int (&slot)[NV]) {
+template <int NV, class CTX>
+__device__ __forceinline__ void block_reduce_store(CTX& cx, double (&v)[NV], double* out, const int (&slot)[NV]) {
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
 #pragma unroll
@@ -130,10 +131,11 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset,
 // =============================================================================================
 // k_field_eval
 // =============================================================================================
-__global__ void __launch_bounds__(NTHR, 1) k_field_eval(const __grid_constant__ FieldDev f,
-                                                        const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
-  Ctx cx;
-  ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
+template <class ENG>
+__global__ void __launch_bounds__(ENG::NTHR, 1) k_field_eval(const __grid_constant__ FieldDev f,
+        const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
+  typename ENG::Ctx cx;
+  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch));
   const int S = cx.S, SD = cx.SD, CD = cx.CD;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * S;
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_field_eval(const __grid_constant__ 
       }
       bar_compute();
     }
-    eval_field(cx, f, a.ev, 0);
+    ENG::eval(cx, f, a.ev, 0);
     if (!cx.producer) {
       const float* F = slot_ptr(cx, 0);
       if (a.f) store_rows(a.f, F, row0, nv, SD, cx.tid);
@@ -201,15 +203,17 @@ __global__ void __launch_bounds__(NTHR, 1) k_field_eval(const __grid_constant__ 
       bar_compute();
     }
   }
+  ENG::fini(cx);
 }
 
 // =============================================================================================
 // k_dopri5: one attempted step
 // =============================================================================================
-__global__ void __launch_bounds__(NTHR, 1) k_dopri5(const __grid_constant__ FieldDev f,
-                                                    const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
-  Ctx cx;
-  ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
+template <class ENG>
+__global__ void __launch_bounds__(ENG::NTHR, 1) k_dopri5(const __grid_constant__ FieldDev f,
+        const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
+  typename ENG::Ctx cx;
+  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch));
   const int S = cx.S, SD = cx.SD, CD = cx.CD;
   const bool prob = cx.T > 0;
   float* LP0 = cx.klp() + NSLOT * TM;
@@ -245,12 +249,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_dopri5(const __grid_constant__ Fiel
         }
         bar_compute();
       }
-      eval_field(cx, f, a.ev[i - 1], i);
+      ENG::eval(cx, f, a.ev[i - 1], i);
     }
     if (!cx.producer) {
       // cx.ycur() now holds y1 (FSAL: the 7th stage input), slot 6 holds f1
       double v[3] = {0.0, 0.0, nonfinite};
-      float* stage_out = cx.act();   // free between evaluations: staging for the interpolant
+      float* stage_out = cx.stage_buf();   // free between evaluations: staging for the interpolant
       for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
         const int d = idx / S, r = idx - d * S;
         if (r >= nv) continue;
@@ -298,6 +302,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_dopri5(const __grid_constant__ Fiel
       block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
     }
   }
+  ENG::fini(cx);
 }
 
 // =============================================================================================
@@ -307,10 +312,11 @@ __device__ __forceinline__ int evals_per_step(int method) {
   return method == FFB_M_RK4 ? 4 : (method == FFB_M_MIDPOINT ? 2 : (method == FFB_M_LEAPFROG ? 3 : 1));
 }
 
-__global__ void __launch_bounds__(NTHR, 1) k_fixed(const __grid_constant__ FieldDev f,
-                                                   const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
-  Ctx cx;
-  ctx_init(cx, f, reinterpret_cast<float*>(a.scratch));
+template <class ENG>
+__global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ FieldDev f,
+        const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
+  typename ENG::Ctx cx;
+  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch));
   const int S = cx.S, SD = cx.SD, CD = cx.CD;
   const bool prob = cx.T > 0;
   const int nev = evals_per_step(a.method);
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_fixed(const __grid_constant__ Field
           else mask = (e == 1) ? 1u : 2u;
           dst = (e == 1) ? 0 : 1;
         }
-        if (mask) eval_field(cx, f, ev[e], dst, mask);
+        if (mask) ENG::eval(cx, f, ev[e], dst, mask);
         if (cx.producer) continue;
         // ---- stage algebra after evaluation e (op order of torchdiffeq's step functions) ---------
         for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
@@ -439,6 +445,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_fixed(const __grid_constant__ Field
       bar_compute();
     }
   }
+  ENG::fini(cx);
 }
 
 // =============================================================================================
@@ -541,14 +548,64 @@ __global__ void k_pack_bias(const float* __restrict__ b, int out_features, float
   dst[p] = (n < out_features) ? b[n] : 0.0f;
 }
 
+// ---- tensor-core image: per chunk of 32 k-rows [W_hi | W_lo], each in the canonical no-swizzle
+// K-major UMMA layout: element (n, k) at kc*(Np*16 B) + (n/8)*128 B + (n%8)*16 B + (k%4)*4 B, kc = k/4
+__global__ void k_pack_weight_tc(const float* __restrict__ W, int in_features, int out_features,
+                                 float* __restrict__ dst, int K, int Np, int x_col, int x_dim, int c_col, int c_dim,
+                                 int layer0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * Np) return;
+  const int k = idx / Np, n = idx - k * Np;
+  int col = -1;
+  if (layer0) {
+    if (k < x_dim) col = x_col + k;
+    else if (k < x_dim + c_dim) col = c_col + (k - x_dim);
+  } else if (k < in_features) {
+    col = k;
+  }
+  const float w = (n < out_features && col >= 0) ? W[(size_t)n * in_features + col] : 0.0f;
+  uint32_t hi, lo;
+  tf32_split(w, hi, lo);
+  const int c = k / KC, kk = k - c * KC, rows = min(KC, K - c * KC);
+  const size_t base = (size_t)c * 2 * KC * Np;
+  const size_t off = (size_t)(kk >> 2) * (Np * 4) + (size_t)(n >> 3) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
+  dst[base + off] = __uint_as_float(hi);
+  dst[base + (size_t)rows * Np + off] = __uint_as_float(lo);
+}
+__global__ void k_pack_time_tc(const float* __restrict__ W, int in_features, int out_features, float* __restrict__ dst,
+                               int t_dim, int Np, int t_col) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= t_dim * Np) return;
+  const int j = idx / Np, n = idx - j * Np;
+  dst[idx] = (n < out_features) ? W[(size_t)n * in_features + t_col + j] : 0.0f;
+}
+__global__ void k_pack_bias_tc(const float* __restrict__ b, int out_features, float* __restrict__ dst, int Np) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Np) return;
+  dst[n] = (n < out_features) ? b[n] : 0.0f;
+}
+
 // =============================================================================================
 // host side: C ABI
 // =============================================================================================
 struct ffb_net {
-  NetDev dev;
+  NetDev dev;   // FP32 FFMA2 engine image
+  NetDev tc;    // tensor-core (3xTF32) engine image
   std::vector<void*> allocs;
   int64_t flops;
 };
+
+// engine selection: 1 = tensor cores (default), 0 = FP32 FFMA2 (FFB_ENGINE=ffma or ffb_set_engine(0))
+static int g_engine = -1;
+static int engine() {
+  if (g_engine < 0) {
+    const char* e = getenv("FFB_ENGINE");
+    g_engine = (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) ? 0 : 1;
+  }
+  return g_engine;
+}
+extern "C" int ffb_set_engine(int e) { g_engine = e ? 1 : 0; return g_engine; }
+extern "C" int ffb_get_engine(void) { return engine(); }
 
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
@@ -636,6 +693,40 @@ extern "C" int ffb_net_create(const ffb_net_desc* d, void* stream_, ffb_net** ou
     }
     in_f = N;
   }
+  // ---- tensor-core image ---------------------------------------------------------------------
+  NetDev& nt = net->tc;
+  memset(&nt, 0, sizeof(nt));
+  nt.n_layers = d->n_layers;
+  nt.t_dim = d->t_dim; nt.x_dim = d->x_dim; nt.c_dim = d->c_dim;
+  in_f = d->in_features;
+  for (int l = 0; l < d->n_layers; ++l) {
+    const int N = d->widths[l], Np = (N + 31) & ~31;
+    const int K = (l == 0) ? ((d->x_dim + d->c_dim + 7) & ~7) : nt.Np[l - 1];
+    nt.K[l] = K; nt.N[l] = N; nt.Np[l] = Np;
+    float *w = nullptr, *b = nullptr;
+    if (cudaMalloc(&w, sizeof(float) * 2 * K * Np) != cudaSuccess || cudaMalloc(&b, sizeof(float) * Np) != cudaSuccess) {
+      cleanup();
+      return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed");
+    }
+    net->allocs.push_back(w); net->allocs.push_back(b);
+    k_pack_weight_tc<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, w, K, Np, d->x_col, d->x_dim,
+                                                              d->c_col, d->c_dim, l == 0);
+    k_pack_bias_tc<<<1, 128, 0, stream>>>(d->bias[l], N, b, Np);
+    g_launches += 2;
+    nt.W[l] = w; nt.b[l] = b;
+    if (l == 0) {
+      float* wt = nullptr;
+      const int td = d->t_dim > 0 ? d->t_dim : 1;
+      if (cudaMalloc(&wt, sizeof(float) * td * Np) != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
+      net->allocs.push_back(wt);
+      if (d->t_dim > 0) {
+        k_pack_time_tc<<<(d->t_dim * Np + 255) / 256, 256, 0, stream>>>(d->weight[0], in_f, N, wt, d->t_dim, Np, d->t_col);
+        g_launches += 1;
+      }
+      nt.Wt = wt;
+    }
+    in_f = N;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, std::string("ffb_net_create: ") + cudaGetErrorString(e)); }
   *out = net;
@@ -655,6 +746,11 @@ static int tangents_of(const ffb_field* f) {
   return f->div_mode == FFB_DIV_EXACT ? f->net[0]->dev.x_dim : (f->div_mode == FFB_DIV_HUTCH ? 1 : 0);
 }
 
+static size_t field_smem(const FieldDev& fd, int T, int slots) {
+  return engine() ? smem_layout_tc(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, slots, nullptr)
+                  : smem_layout(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, slots, nullptr);
+}
+
 static int make_field(const ffb_field* f, FieldDev* out) {
   if (!f) return fail(FFB_ERR_ARG, "null field");
   if (f->n_calls < 1 || f->n_calls > 2) return fail(FFB_ERR_ARG, "field: n_calls must be 1 or 2");
@@ -669,7 +765,7 @@ static int make_field(const ffb_field* f, FieldDev* out) {
     if (nd.c_dim != f->cond_dim) return fail(FFB_ERR_ARG, "field: net conditional width differs from field cond_dim");
     if (f->in_off[c] < 0 || f->in_off[c] + nd.x_dim > f->state_dim) return fail(FFB_ERR_ARG, "field: input block outside the state");
     if (f->out_off[c] < 0 || f->out_off[c] + dout > f->state_dim) return fail(FFB_ERR_ARG, "field: output block outside the state");
-    out->net[c] = nd;
+    out->net[c] = engine() ? f->net[c]->tc : nd;
     out->in_off[c] = f->in_off[c];
     out->out_off[c] = f->out_off[c];
     out->out_sign[c] = f->out_sign[c];
@@ -687,7 +783,7 @@ static int make_field(const ffb_field* f, FieldDev* out) {
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t with_slots = smem_layout(out->state_dim, out->cond_dim, tangents_of(f), out->div_mode == FFB_DIV_HUTCH, 1, nullptr);
+  const size_t with_slots = field_smem(*out, tangents_of(f), 1);
   out->slots_smem = (optin > 0 && with_slots <= (size_t)optin) ? 1 : 0;
   return FFB_OK;
 }
@@ -710,10 +806,10 @@ extern "C" size_t ffb_scratch_bytes(const ffb_field* f) {
 }
 
 template <typename Kern, typename Args>
-static int launch_tiles(Kern kern, const char* name, const ffb_field* f, const FieldDev& fd, const Args& a,
+static int launch_tiles(Kern kern, int nthr, const char* name, const ffb_field* f, const FieldDev& fd, const Args& a,
                         int64_t batch, cudaStream_t stream) {
   const int T = tangents_of(f);
-  const size_t smem = smem_layout(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, fd.slots_smem, nullptr);
+  const size_t smem = field_smem(fd, T, fd.slots_smem);
   int dev = 0, optin = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -723,7 +819,7 @@ static int launch_tiles(Kern kern, const char* name, const ffb_field* f, const F
   const int64_t ntiles = ffb_num_tiles(f, batch);
   if (ntiles <= 0) return FFB_OK;
   const int grid = (int)std::min<int64_t>(ntiles, num_sms());
-  kern<<<grid, NTHR, smem, stream>>>(fd, a, ntiles);
+  kern<<<grid, nthr, smem, stream>>>(fd, a, ntiles);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return FFB_OK;
@@ -739,7 +835,9 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
   if (a->norms && !a->partials) return fail(FFB_ERR_ARG, "ffb_field_eval: partials buffer required for norms");
   if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
-  return launch_tiles(k_field_eval, "ffb_field_eval", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  if (engine())
+    return launch_tiles(k_field_eval<EngineTC>, EngineTC::NTHR, "ffb_field_eval", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  return launch_tiles(k_field_eval<EngineFFMA>, EngineFFMA::NTHR, "ffb_field_eval", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, void* stream) {
@@ -754,7 +852,9 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
     return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: final step needs y_out (and lp_out)");
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
-  return launch_tiles(k_dopri5, "ffb_dopri5_attempt", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  if (engine())
+    return launch_tiles(k_dopri5<EngineTC>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  return launch_tiles(k_dopri5<EngineFFMA>, EngineFFMA::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, void* stream) {
@@ -769,7 +869,9 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
     return fail(FFB_ERR_ARG, "ffb_integrate_fixed: no divergence with this method");
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: probes are required");
-  return launch_tiles(k_fixed, "ffb_integrate_fixed", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  if (engine())
+    return launch_tiles(k_fixed<EngineTC>, EngineTC::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  return launch_tiles(k_fixed<EngineFFMA>, EngineFFMA::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream) {

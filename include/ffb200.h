@@ -193,6 +193,10 @@ int ffb_philox_normal(float* out, int64_t batch, int32_t dim, uint64_t seed, uin
                       int32_t step, int64_t row_offset, void* stream);
 /* FP32 FFMA2 peak probe: returns achieved TFLOP/s through *tflops (roofline denominator) */
 int ffb_ffma_peak(int32_t iters, float* tflops, void* stream);
+/* contraction engine: 1 = tcgen05 tensor cores, 3xTF32 (default); 0 = FP32 FFMA2 (debug / A-B checks).
+ * The environment variable FFB_ENGINE=ffma selects 0 at load time. */
+int ffb_set_engine(int engine);
+int ffb_get_engine(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t ffb_launch_count(void);
 
