@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libffb200.so")
+LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "ffb_kernels.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "ffb_engine.cuh"), os.path.join(_HERE, "csrc", "ffb_engine_tc.cuh"),
            os.path.join(ROOT, "include", "ffb200.h")]

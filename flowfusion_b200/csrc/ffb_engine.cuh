@@ -160,6 +160,12 @@ __device__ __forceinline__ float* slot_ptr(const Ctx& cx, int slot) {
   return base + (size_t)slot * cx.SD * LDA;
 }
 
+template <bool SS>
+__device__ __forceinline__ float* slot_ptr_t(const Ctx& cx, int slot) {
+  if (SS) return reinterpret_cast<float*>(smem_base() + cx.o_slots) + (size_t)slot * cx.SD * LDA;
+  return cx.scr + (size_t)slot * cx.SD * LDA;
+}
+
 __device__ __forceinline__ void pipe_advance(Ctx& cx) {
   if (++cx.stage == NSTAGE) { cx.stage = 0; cx.phase ^= 1u; }
 }
@@ -474,6 +480,7 @@ struct EngineFFMA {
   static constexpr int NTHR = ffb::NTHR;
   static __device__ __forceinline__ void init(Ctx& cx, const FieldDev& f, float* scratch) { ctx_init(cx, f, scratch); }
   static __device__ __forceinline__ void fini(Ctx&) {}
+  template <bool SS>
   static __device__ __forceinline__ void eval(Ctx& cx, const FieldDev& f, const ffb_eval_scalars& ev, int dst,
                                               unsigned call_mask = 3u) {
     eval_field(cx, f, ev, dst, call_mask);

@@ -25,6 +25,7 @@ namespace ffb {
 
 constexpr int TC_NTHR = NCOMP + 64;              // + loader warp + MMA warp
 constexpr int TC_STAGE_FLOATS = 2 * KC * KMAX;   // W_hi | W_lo chunk of 32 k-rows: 32 KB
+constexpr int TC_NSTAGE = 4;                     // one whole 128x128 layer (hi+lo) in flight
 constexpr int ZS = LDA;                          // row stride of the z / gate buffers
 constexpr uint32_t TM_COL_DMAIN = 0, TM_COL_DCROSS = 128, TM_COL_AHI = 256, TM_COL_ALO = 384;
 
@@ -55,6 +56,13 @@ __device__ __forceinline__ void tc_st8(uint32_t addr, const uint32_t (&v)[8]) {
                ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// one elected lane of a fully converged warp (the MMA / commit instructions are issued by one thread,
+// but every operand is computed warp-uniformly so it can live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem_d] (+)= A[tmem_a] * B[smem desc]   (kind::tf32, cta_group::1, A from tensor memory)
 __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -74,11 +82,22 @@ __device__ __forceinline__ void tf32_split(float a, uint32_t& hi, uint32_t& lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(a - __uint_as_float(hi)));
 }
 
+// optional timeline trace (debug): CTA 0 records clock64() at layer hand-offs
+__device__ long long* g_trace = nullptr;
+__device__ int g_trace_pos = 0;
+__device__ __forceinline__ void trace(int tag, int layer) {
+  if (g_trace && blockIdx.x == 0) {
+    const int i = atomicAdd(&g_trace_pos, 1);
+    if (i < 4096) { g_trace[2 * i] = clock64(); g_trace[2 * i + 1] = tag * 100 + layer; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
 struct CtxT {
-  uint32_t o_ring, o_ycur, o_cond, o_prb, o_zb, o_gate, o_out, o_beff, o_sbias, o_klp, o_red, o_bar, o_slots;
+  uint32_t o_ring, o_ycur, o_cond, o_prb, o_zb, o_gate, o_out, o_beff, o_sbias, o_klp, o_red, o_bar, o_slots, o_wt;
+  int tdim;
   int slots_smem;
   __device__ __forceinline__ float* ring() const { return reinterpret_cast<float*>(smem_base() + o_ring); }
   __device__ __forceinline__ float* ycur() const { return reinterpret_cast<float*>(smem_base() + o_ycur); }
@@ -90,13 +109,14 @@ struct CtxT {
   __device__ __forceinline__ float* stage_buf() const { return outb(); }
   __device__ __forceinline__ float* beff() const { return reinterpret_cast<float*>(smem_base() + o_beff); }
   __device__ __forceinline__ float* sbias() const { return reinterpret_cast<float*>(smem_base() + o_sbias); }
+  __device__ __forceinline__ float* swt() const { return reinterpret_cast<float*>(smem_base() + o_wt); }
   __device__ __forceinline__ float* klp() const { return reinterpret_cast<float*>(smem_base() + o_klp); }
   __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(smem_base() + o_red); }
   __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(smem_base() + o_bar); }
-  __device__ __forceinline__ uint64_t* empty() const { return full() + NSTAGE; }
-  __device__ __forceinline__ uint64_t* a_ready() const { return full() + 2 * NSTAGE; }
-  __device__ __forceinline__ uint64_t* d_ready() const { return full() + 2 * NSTAGE + 1; }
-  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(full() + 2 * NSTAGE + 2); }
+  __device__ __forceinline__ uint64_t* empty() const { return full() + TC_NSTAGE; }
+  __device__ __forceinline__ uint64_t* a_ready() const { return full() + 2 * TC_NSTAGE; }
+  __device__ __forceinline__ uint64_t* d_ready() const { return full() + 2 * TC_NSTAGE + 1; }
+  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(full() + 2 * TC_NSTAGE + 2); }
   float* scr;
   int S, T, SD, CD;
   int tid, lane, warp;
@@ -113,16 +133,35 @@ __device__ __forceinline__ float* slot_ptr(const CtxT& cx, int slot) {
   float* base = cx.slots_smem ? reinterpret_cast<float*>(smem_base() + cx.o_slots) : cx.scr;
   return base + (size_t)slot * cx.SD * LDA;
 }
+// compile-time variant: SS = slots in shared memory (LDS/STS) or in the global scratch (LDG/STG);
+// the run-time ternary above degrades every access to a generic LD/ST
+template <bool SS>
+__device__ __forceinline__ float* slot_ptr_t(const CtxT& cx, int slot) {
+  if (SS) return reinterpret_cast<float*>(smem_base() + cx.o_slots) + (size_t)slot * cx.SD * LDA;
+  return cx.scr + (size_t)slot * cx.SD * LDA;
+}
+// one lane polls the mbarrier, the warp then reconverges: 32x less polling traffic on the shared-memory
+// pipe that also feeds the tensor core's B operand
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+#ifdef FFB_POLL_ONE
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  (void)lane;
+  mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void pipe_advance(CtxT& cx) {
-  if (++cx.stage == NSTAGE) { cx.stage = 0; cx.phase ^= 1u; }
+  if (++cx.stage == TC_NSTAGE) { cx.stage = 0; cx.phase ^= 1u; }
 }
 
-__host__ __device__ inline size_t smem_layout_tc(int SD, int CD, int T, int hutch, int slots_smem, size_t* off /*[16]*/) {
+__host__ __device__ inline size_t smem_layout_tc(int SD, int CD, int T, int hutch, int slots_smem, int ncalls, int tdim,
+                                                 size_t* off /*[16]*/) {
   const int S = TM / (1 + T);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~size_t(127); return r; };
   size_t v[16];
-  v[0] = take(sizeof(float) * NSTAGE * TC_STAGE_FLOATS);          // ring
+  v[0] = take(sizeof(float) * TC_NSTAGE * TC_STAGE_FLOATS);       // ring
   v[1] = take(sizeof(float) * SD * LDA);                          // ycur
   v[2] = take(sizeof(float) * (CD > 0 ? CD : 1) * LDA);           // cond
   v[3] = take(hutch ? sizeof(float) * SD * LDA : 0);              // probes
@@ -130,13 +169,19 @@ __host__ __device__ inline size_t smem_layout_tc(int SD, int CD, int T, int hutc
   v[5] = take(T > 0 ? sizeof(float) * S * ZS : 0);                // gate = silu'(z)
   v[6] = take(sizeof(float) * SD * LDA);                          // raw output of the last layer [n][row]
   v[7] = take(sizeof(float) * KMAX);                              // beff
-  v[8] = take(sizeof(float) * 2 * FFB_MAX_LAYERS * KMAX);         // biases of both networks
-  v[9] = take(sizeof(float) * (NSLOT + 2) * TM);                  // klp
+  v[8] = take(sizeof(float) * ncalls * FFB_MAX_LAYERS * KMAX);    // biases, every layer of every network
+  v[9] = take(T > 0 ? sizeof(float) * (NSLOT + 2) * TM : 0);      // klp
   v[10] = take(sizeof(double) * 8 * FFB_NPART);                   // red
-  v[11] = take(sizeof(uint64_t) * (2 * NSTAGE + 4));              // barriers + tmem slot
+  v[11] = take(sizeof(uint64_t) * (2 * TC_NSTAGE + 4));           // barriers + tmem slot
   v[12] = take(slots_smem ? sizeof(float) * NSLOT * SD * LDA : 0);
-  if (off) for (int i = 0; i < 13; ++i) off[i] = v[i];
+  v[13] = take(sizeof(float) * ncalls * (tdim > 0 ? tdim : 1) * KMAX);   // layer-0 time-feature rows
+  if (off) for (int i = 0; i < 14; ++i) off[i] = v[i];
   return o;
+}
+__host__ __device__ inline int field_tdim(const FieldDev& f) {
+  int t = f.net[0].t_dim;
+  if (f.n_calls > 1 && f.net[1].t_dim > t) t = f.net[1].t_dim;
+  return t;
 }
 
 struct EngineTC {
@@ -146,12 +191,14 @@ struct EngineTC {
   static __device__ __forceinline__ void init(CtxT& cx, const FieldDev& f, float* scratch) {
     const int T = (f.div_mode == FFB_DIV_EXACT) ? f.net[0].x_dim : (f.div_mode == FFB_DIV_HUTCH ? 1 : 0);
     size_t off[16];
-    smem_layout_tc(f.state_dim, f.cond_dim, T, f.div_mode == FFB_DIV_HUTCH, f.slots_smem, off);
+    cx.tdim = field_tdim(f);
+    smem_layout_tc(f.state_dim, f.cond_dim, T, f.div_mode == FFB_DIV_HUTCH, f.slots_smem, f.n_calls, cx.tdim, off);
     cx.o_ring = (uint32_t)off[0]; cx.o_ycur = (uint32_t)off[1]; cx.o_cond = (uint32_t)off[2];
     cx.o_prb = (uint32_t)off[3]; cx.o_zb = (uint32_t)off[4]; cx.o_gate = (uint32_t)off[5];
     cx.o_out = (uint32_t)off[6]; cx.o_beff = (uint32_t)off[7]; cx.o_sbias = (uint32_t)off[8];
     cx.o_klp = (uint32_t)off[9]; cx.o_red = (uint32_t)off[10]; cx.o_bar = (uint32_t)off[11];
     cx.o_slots = (uint32_t)off[12];
+    cx.o_wt = (uint32_t)off[13];
     cx.slots_smem = f.slots_smem;
     cx.T = T; cx.S = TM / (1 + T); cx.SD = f.state_dim; cx.CD = f.cond_dim;
     cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
@@ -163,7 +210,7 @@ struct EngineTC {
     cx.phase = (cx.warp == NCOMP / 32) ? 1u : 0u;     // loader starts with all stages free
     cx.ph_a = 0; cx.ph_d = 0;
     if (threadIdx.x == 0) {
-      for (int s = 0; s < NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], 1); }
+      for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], 1); }
       mbar_init(cx.a_ready(), NCOMP / 32);
       mbar_init(cx.d_ready(), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,10 +220,15 @@ struct EngineTC {
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // biases of every layer to shared memory once (real column order, zero padded)
-    for (int c = 0; c < f.n_calls; ++c)
+    for (int c = 0; c < f.n_calls; ++c) {
       for (int l = 0; l < f.net[c].n_layers; ++l)
         for (int n = threadIdx.x; n < KMAX; n += TC_NTHR)
           cx.sbias()[(c * FFB_MAX_LAYERS + l) * KMAX + n] = (n < f.net[c].Np[l]) ? f.net[c].b[l][n] : 0.0f;
+      for (int i = threadIdx.x; i < f.net[c].t_dim * KMAX; i += TC_NTHR) {
+        const int j = i / KMAX, n = i - j * KMAX;
+        cx.swt()[(c * cx.tdim + j) * KMAX + n] = (n < f.net[c].Np[0]) ? f.net[c].Wt[(size_t)j * f.net[c].Np[0] + n] : 0.0f;
+      }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -195,55 +247,66 @@ struct EngineTC {
 
   // ---- loader warp: stream one network's W_hi|W_lo chunks through the ring -------------------
   static __device__ __forceinline__ void load_net(CtxT& cx, const NetDev& net) {
+    if (cx.lane != 0) return;
     for (int l = 0; l < net.n_layers; ++l) {
       const int K = net.K[l], Np = net.Np[l];
       for (int k0 = 0; k0 < K; k0 += KC) {
         const int rows = min(KC, K - k0);
-        if (cx.lane == 0) {
-          mbar_wait(&cx.empty()[cx.stage], cx.phase);
-          const uint32_t bytes = (uint32_t)(2 * rows * Np) * sizeof(float);
-          mbar_expect_tx(&cx.full()[cx.stage], bytes);
-          bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, net.W[l] + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
-        }
+        mbar_wait(&cx.empty()[cx.stage], cx.phase);
+        const uint32_t bytes = (uint32_t)(2 * rows * Np) * sizeof(float);
+        mbar_expect_tx(&cx.full()[cx.stage], bytes);
+        bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, net.W[l] + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
         pipe_advance(cx);
       }
     }
   }
 
   // ---- MMA warp: issue the 3xTF32 contraction of every layer ----------------------------------
+  // Measured (csrc/tc_rate.cu): a tcgen05.mma kind::tf32 M128 N128 K8 retires every ~67 cycles
+  // whatever the accumulator pattern, so issue overhead must stay well below that.  The warp runs
+  // convergently so descriptors / addresses live in uniform registers (issuing from a divergent
+  // single-lane region makes the compiler wrap every MMA in an ELECT + 5x R2UR waterfall loop),
+  // and there is ONE elected region per ring stage (12 MMAs + commit), not one per MMA.
   static __device__ __forceinline__ void mma_net(CtxT& cx, const NetDev& net) {
     for (int l = 0; l < net.n_layers; ++l) {
       const int K = net.K[l], Np = net.Np[l];
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t lbo = (uint32_t)Np * 16u;        // bytes between the two 16-byte K chunks of one MMA
-      if (cx.lane == 0) {
-        mbar_wait(cx.a_ready(), cx.ph_a);             // the epilogue has written this layer's A operand
-        tc_fence_after();
-      }
+      const uint64_t kstep = (uint64_t)(lbo >> 3);    // descriptor increment of one MMA k-step (2*lbo bytes >> 4)
+      const uint32_t d_main = cx.tmem + TM_COL_DMAIN, d_cross = cx.tmem + TM_COL_DCROSS;
+      mbar_wait_warp(cx.a_ready(), cx.ph_a, cx.lane);   // the epilogue has written this layer's A operand
+      tc_fence_after();
       cx.ph_a ^= 1u;
-      uint32_t acc_main = 0, acc_cross = 0;
+      if (cx.lane == 0) trace(1, l);
+      uint32_t acc = 0;
       for (int k0 = 0; k0 < K; k0 += KC) {
-        const int rows = min(KC, K - k0);
-        if (cx.lane == 0) {
-          mbar_wait(&cx.full()[cx.stage], cx.phase);
-          tc_fence_after();
-          const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
-          const uint32_t lo_base = hi_base + (uint32_t)(rows * Np) * 4u;
-          for (int j = 0; j < rows / 8; ++j) {
-            const uint64_t d_hi = tc_desc(hi_base + (uint32_t)j * 2u * lbo, lbo, 128u);
-            const uint64_t d_lo = tc_desc(lo_base + (uint32_t)j * 2u * lbo, lbo, 128u);
-            const uint32_t a_hi = cx.tmem + TM_COL_AHI + (uint32_t)(k0 + 8 * j);
-            const uint32_t a_lo = cx.tmem + TM_COL_ALO + (uint32_t)(k0 + 8 * j);
-            tc_mma_ts(cx.tmem + TM_COL_DMAIN, a_hi, d_hi, idesc, acc_main);
-            tc_mma_ts(cx.tmem + TM_COL_DCROSS, a_hi, d_lo, idesc, acc_cross);
-            tc_mma_ts(cx.tmem + TM_COL_DCROSS, a_lo, d_hi, idesc, 1u);
-            acc_main = 1u; acc_cross = 1u;
+        const int nj = min(KC, K - k0) >> 3;           // MMA k-steps in this stage (1..4)
+        mbar_wait_warp(&cx.full()[cx.stage], cx.phase, cx.lane);
+        tc_fence_after();
+        const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
+        const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
+        const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
+        const uint32_t a_hi0 = cx.tmem + TM_COL_AHI + (uint32_t)k0, a_lo0 = cx.tmem + TM_COL_ALO + (uint32_t)k0;
+        uint64_t* ebar = &cx.empty()[cx.stage];
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KC / 8; ++j) {
+            if (j < nj) {
+              const uint64_t d_hi = dh0 + (uint64_t)j * kstep, d_lo = dl0 + (uint64_t)j * kstep;
+              tc_mma_ts(d_main, a_hi0 + 8u * j, d_hi, idesc, (j == 0) ? acc : 1u);
+              tc_mma_ts(d_cross, a_hi0 + 8u * j, d_lo, idesc, (j == 0) ? acc : 1u);
+              tc_mma_ts(d_cross, a_lo0 + 8u * j, d_hi, idesc, 1u);
+            }
           }
-          tc_commit(&cx.empty()[cx.stage]);            // frees the ring stage when these MMAs retire
+          tc_commit(ebar);                              // frees the ring stage when these MMAs retire
         }
+        __syncwarp();
+        acc = 1u;
         pipe_advance(cx);
       }
-      if (cx.lane == 0) tc_commit(cx.d_ready());       // accumulators of this layer are complete
+      if (elect_one()) tc_commit(cx.d_ready());        // accumulators of this layer are complete
+      __syncwarp();
+      if (cx.lane == 0) trace(2, l);
     }
   }
 
@@ -255,12 +318,13 @@ struct EngineTC {
     if (cx.lane == 0) mbar_arrive(cx.a_ready());
   }
   static __device__ __forceinline__ void wait_d_ready(CtxT& cx) {
-    mbar_wait(cx.d_ready(), cx.ph_d);
+    mbar_wait_warp(cx.d_ready(), cx.ph_d, cx.lane);
     cx.ph_d ^= 1u;
     tc_fence_after();
   }
 
   // ---- evaluate the vector field at cx.ycur(); derivative -> slot dst, divergence -> klp[dst] ----
+  template <bool SS>
   static __device__ __forceinline__ void eval(CtxT& cx, const FieldDev& f, const ffb_eval_scalars& ev, int dst,
                                               unsigned call_mask = 3u) {
     for (int c = 0; c < f.n_calls; ++c) {
@@ -271,10 +335,12 @@ struct EngineTC {
       const int S = cx.S, T = cx.T, live = S * (1 + T);
       const int r = cx.row, h = cx.half;
       const int Np0 = net.Np[0], xd = net.x_dim, cd = net.c_dim, K0 = net.K[0];
+      if (cx.tid == 0) trace(7, 0);
       // layer-0 bias with the (row-uniform) time features folded in
       for (int n = cx.tid; n < Np0; n += NCOMP) {
         float b = cx.sbias()[(c * FFB_MAX_LAYERS) * KMAX + n];
-        for (int j = 0; j < net.t_dim; ++j) b = fmaf(net.Wt[(size_t)j * Np0 + n], ev.tfeat[j], b);
+        const float* wt = cx.swt() + (c * cx.tdim) * KMAX + n;
+        for (int j = 0; j < net.t_dim; ++j) b = fmaf(wt[j * KMAX], ev.tfeat[j], b);
         cx.beff()[n] = b;
       }
       // layer-0 A operand: this thread's row, column groups of 8 interleaved between the two halves
@@ -300,7 +366,9 @@ struct EngineTC {
         }
       }
       bar_compute();                      // beff visible to every epilogue thread
+      if (cx.tid == 0) trace(8, 0);
       signal_a_ready(cx);
+      if (cx.tid == 0) trace(0, 0);
 
       const int nl = net.n_layers;
       for (int l = 0; l < nl; ++l) {
@@ -309,6 +377,7 @@ struct EngineTC {
         const float* bias = (l == 0) ? cx.beff() : cx.sbias() + (c * FFB_MAX_LAYERS + l) * KMAX;
         const int cbeg = h * (Np >> 1), cend = cbeg + (Np >> 1);     // Np is a multiple of 32
         wait_d_ready(cx);
+        if (cx.tid == 0) trace(3, l);
         if (last) {
           // raw network output (primal: + bias) -> outb[n][row]
           for (int c0 = cbeg; c0 < cend; c0 += 16) {
@@ -326,20 +395,39 @@ struct EngineTC {
           }
           tc_fence_before();
         } else if (T == 0) {
-          for (int c0 = cbeg; c0 < cend; c0 += 16) {
-            uint32_t m[16], x[16], hi[16], lo[16];
-            tc_ld16(cx.lane_addr + TM_COL_DMAIN + c0, m);
-            tc_ld16(cx.lane_addr + TM_COL_DCROSS + c0, x);
-            tc_wait_ld();
+          // software-pipelined: the TMEM loads of column group g+1 are in flight while group g is
+          // pushed through bias + SiLU + TF32 split and stored back as the next layer's A operand
+          const int ng = (cend - cbeg) >> 4;            // 1..4 groups of 16 columns
+          uint32_t m[2][16], x[2][16];
+          tc_ld16(cx.lane_addr + TM_COL_DMAIN + cbeg, m[0]);
+          tc_ld16(cx.lane_addr + TM_COL_DCROSS + cbeg, x[0]);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const float z = (__uint_as_float(m[q]) + __uint_as_float(x[q])) + bias[c0 + q];
-              tf32_split(z * sigmoidf_fast(z), hi[q], lo[q]);
+          for (int g = 0; g < 4; ++g) {
+            if (g < ng) {
+              const int c0 = cbeg + 16 * g;
+              tc_wait_ld();
+              if (g + 1 < ng) {
+                tc_ld16(cx.lane_addr + TM_COL_DMAIN + c0 + 16, m[(g + 1) & 1]);
+                tc_ld16(cx.lane_addr + TM_COL_DCROSS + c0 + 16, x[(g + 1) & 1]);
+              }
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int q = 0; q < 16; q += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + q);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float z = (__uint_as_float(m[g & 1][q + u]) + __uint_as_float(x[g & 1][q + u])) + bb[u];
+                  tf32_split(z * sigmoidf_fast(z), hi[q + u], lo[q + u]);
+                }
+              }
+              tc_st16(cx.lane_addr + TM_COL_AHI + c0, hi);
+              tc_st16(cx.lane_addr + TM_COL_ALO + c0, lo);
             }
-            tc_st16(cx.lane_addr + TM_COL_AHI + c0, hi);
-            tc_st16(cx.lane_addr + TM_COL_ALO + c0, lo);
           }
+          if (cx.tid == 0) trace(4, l);
           signal_a_ready(cx);
+          if (cx.tid == 0) trace(0, l + 1);
         } else {
           // primal rows publish z; all threads share the SiLU / gate work; tangent rows are gated
           float* zb = cx.zb();
@@ -397,22 +485,29 @@ struct EngineTC {
         }
       }
       bar_compute();                      // outb complete
+      if (cx.tid == 0) trace(5, 0);
       // ---- field transform on the primal rows (same arithmetic as the FFMA engine) ----------------
       const int Dout = net.N[nl - 1];
-      float* kd = slot_ptr(cx, dst);
+      float* kd = slot_ptr_t<SS>(cx, dst) + f.out_off[c] * LDA;
       const float* ob = cx.outb();
-      for (int idx = cx.tid; idx < Dout * S; idx += NCOMP) {
-        const int d = idx / S, rr = idx - d * S;
-        const float o = ob[d * LDA + rr];
-        float xd_;
-        if (f.kind == FFB_FIELD_SCORE) {
-          const float sc = f.use_sigma ? __fdiv_rn(o, ev.sigma) : o;
-          const float lin = f.has_drift ? __fmul_rn(ev.a, cx.ycur()[(f.out_off[c] + d) * LDA + rr]) : 0.0f;
-          xd_ = __fsub_rn(lin, __fmul_rn(ev.c, sc));
-        } else {
-          xd_ = o;
+      const float* yc = cx.ycur() + f.out_off[c] * LDA;
+      const float sgn = ev.sign * f.out_sign[c];
+      {
+        const int rr = cx.tid & (TM - 1);
+        if (rr < S) {
+          for (int d = cx.tid >> 7; d < Dout; d += NCOMP / TM) {
+            const float o = ob[d * LDA + rr];
+            float xd_;
+            if (f.kind == FFB_FIELD_SCORE) {
+              const float sc = f.use_sigma ? __fdiv_rn(o, ev.sigma) : o;
+              const float lin = f.has_drift ? __fmul_rn(ev.a, yc[d * LDA + rr]) : 0.0f;
+              xd_ = __fsub_rn(lin, __fmul_rn(ev.c, sc));
+            } else {
+              xd_ = o;
+            }
+            kd[d * LDA + rr] = xd_ * sgn;
+          }
         }
-        kd[(f.out_off[c] + d) * LDA + rr] = xd_ * (ev.sign * f.out_sign[c]);
       }
       if (T > 0) {
         for (int s = cx.tid; s < S; s += NCOMP) {
@@ -434,6 +529,7 @@ struct EngineTC {
         }
       }
       bar_compute();
+      if (cx.tid == 0) trace(6, 0);
     }
   }
 };

@@ -32,19 +32,27 @@ using namespace ffb;
 enum { P_X_Y = 0, P_X_F = 1, P_X_DF = 2, P_X_ERR = 3, P_LP_Y = 4, P_LP_F = 5, P_LP_DF = 6, P_LP_ERR = 7,
        P_C_Y = 8, P_NONFINITE = 9 };
 
+// idx / D for D in 1..128 and idx < 2^25 without the ~25-instruction integer division sequence
+__device__ __forceinline__ int fast_div(int idx, int D) {
+  return D == 1 ? idx : (int)__umulhi((unsigned)idx, (unsigned)((0x100000000ull + (unsigned)D - 1u) / (unsigned)D));
+}
 // k-major tile buffer <- row-major global rows [row0, row0+nv); rows nv..S-1 are zero filled
 __device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ src, int64_t row0, int nv, int S,
                                           int D, int tid) {
+  const float* __restrict__ base = src + row0 * D;
+#pragma unroll 4
   for (int idx = tid; idx < S * D; idx += NCOMP) {
-    const int r = idx / D, d = idx - r * D;
-    dst[d * LDA + r] = (r < nv) ? src[(row0 + r) * D + d] : 0.0f;
+    const int r = fast_div(idx, D), d = idx - r * D;
+    dst[d * LDA + r] = (r < nv) ? base[idx] : 0.0f;
   }
 }
 __device__ __forceinline__ void store_rows(float* __restrict__ dst, const float* src, int64_t row0, int nv, int D,
                                            int tid) {
+  float* __restrict__ base = dst + row0 * D;
+#pragma unroll 4
   for (int idx = tid; idx < nv * D; idx += NCOMP) {
-    const int r = idx / D, d = idx - r * D;
-    dst[(row0 + r) * D + d] = src[d * LDA + r];
+    const int r = fast_div(idx, D), d = idx - r * D;
+    base[idx] = src[d * LDA + r];
   }
 }
 
@@ -131,7 +139,7 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset,
 // =============================================================================================
 // k_field_eval
 // =============================================================================================
-template <class ENG>
+template <class ENG, bool SS>
 __global__ void __launch_bounds__(ENG::NTHR, 1) k_field_eval(const __grid_constant__ FieldDev f,
         const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
   typename ENG::Ctx cx;
@@ -140,31 +148,29 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_field_eval(const __grid_consta
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * S;
     const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* Y0 = slot_ptr(cx, SLOT_Y0);
-    float* FB = slot_ptr(cx, 1);
+    float* Y0 = slot_ptr_t<SS>(cx, SLOT_Y0);
+    float* FB = slot_ptr_t<SS>(cx, 1);
     if (!cx.producer) {
       load_rows(Y0, a.y, row0, nv, S, SD, cx.tid);
       if (a.fbase) load_rows(FB, a.fbase, row0, nv, S, SD, cx.tid);
       if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
       if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
       bar_compute();
-      for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
-        const int d = idx / S, r = idx - d * S;
+      for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
         const int e = d * LDA + r;
         cx.ycur()[e] = a.fbase ? __fadd_rn(Y0[e], __fmul_rn(a.h, FB[e])) : Y0[e];
       }
       bar_compute();
     }
-    ENG::eval(cx, f, a.ev, 0);
+    ENG::template eval<SS>(cx, f, a.ev, 0);
     if (!cx.producer) {
-      const float* F = slot_ptr(cx, 0);
+      const float* F = slot_ptr_t<SS>(cx, 0);
       if (a.f) store_rows(a.f, F, row0, nv, SD, cx.tid);
       if (a.dlp && cx.T > 0)
         for (int s = cx.tid; s < nv; s += NCOMP) a.dlp[row0 + s] = cx.klp()[s];
       if (a.norms) {
         double v[6] = {0, 0, 0, 0, 0, 0};   // x_y, x_f, x_df, lp_f, lp_df, c_y
-        for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
-          const int d = idx / S, r = idx - d * S;
+        for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
           if (r >= nv) continue;
           const int e = d * LDA + r;
           const float y0 = Y0[e];
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_field_eval(const __grid_consta
 // =============================================================================================
 // k_dopri5: one attempted step
 // =============================================================================================
-template <class ENG>
+template <class ENG, bool SS>
 __global__ void __launch_bounds__(ENG::NTHR, 1) k_dopri5(const __grid_constant__ FieldDev f,
         const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
   typename ENG::Ctx cx;
@@ -221,11 +227,11 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_dopri5(const __grid_constant__
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * S;
     const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* Y0 = slot_ptr(cx, SLOT_Y0);
+    float* Y0 = slot_ptr_t<SS>(cx, SLOT_Y0);
     double nonfinite = 0.0;
     if (!cx.producer) {
       load_rows(Y0, a.y0, row0, nv, S, SD, cx.tid);
-      load_rows(slot_ptr(cx, 0), a.f0, row0, nv, S, SD, cx.tid);
+      load_rows(slot_ptr_t<SS>(cx, 0), a.f0, row0, nv, S, SD, cx.tid);
       if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
       if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
       if (prob)
@@ -238,38 +244,44 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_dopri5(const __grid_constant__
     }
     for (int i = 1; i <= 6; ++i) {
       if (!cx.producer) {
-        for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
-          const int d = idx / S, r = idx - d * S;
+        for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
           const int e = d * LDA + r;
-          float acc = __fmul_rn(slot_ptr(cx, 0)[e], a.cb[i - 1][0]);
-          for (int j = 1; j < i; ++j) acc = fmaf(slot_ptr(cx, j)[e], a.cb[i - 1][j], acc);
+          float kv[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) kv[j] = (j < i) ? slot_ptr_t<SS>(cx, j)[e] : 0.0f;
           const float y0 = Y0[e];
+          float acc = __fmul_rn(kv[0], a.cb[i - 1][0]);
+#pragma unroll
+          for (int j = 1; j < 6; ++j) if (j < i) acc = fmaf(kv[j], a.cb[i - 1][j], acc);
           if (i == 1 && !is_finite_f(y0)) nonfinite += 1.0;
           cx.ycur()[e] = __fadd_rn(y0, acc);
         }
         bar_compute();
       }
-      ENG::eval(cx, f, a.ev[i - 1], i);
+      ENG::template eval<SS>(cx, f, a.ev[i - 1], i);
     }
     if (!cx.producer) {
       // cx.ycur() now holds y1 (FSAL: the 7th stage input), slot 6 holds f1
       double v[3] = {0.0, 0.0, nonfinite};
       float* stage_out = cx.stage_buf();   // free between evaluations: staging for the interpolant
-      for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
-        const int d = idx / S, r = idx - d * S;
+      for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
         if (r >= nv) continue;
         const int e = d * LDA + r;
         const float y0 = Y0[e], y1 = cx.ycur()[e];
-        float err = __fmul_rn(slot_ptr(cx, 0)[e], a.ce[0]);
-        for (int j = 1; j < 7; ++j) err = fmaf(slot_ptr(cx, j)[e], a.ce[j], err);
+        float kv[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kv[j] = slot_ptr_t<SS>(cx, j)[e];
+        float err = __fmul_rn(kv[0], a.ce[0]);
+#pragma unroll
+        for (int j = 1; j < 7; ++j) err = fmaf(kv[j], a.ce[j], err);
         const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0), fabsf(y1))));
         const float q = __fdiv_rn(err, tol);
         v[0] += (double)q * q;
         if (a.final) {
-          float mid = __fmul_rn(slot_ptr(cx, 0)[e], a.cm[0]);
-          for (int j = 1; j < 7; ++j) mid = fmaf(slot_ptr(cx, j)[e], a.cm[j], mid);
-          stage_out[e] = dense_output(y0, y1, __fadd_rn(y0, mid), slot_ptr(cx, 0)[e], slot_ptr(cx, 6)[e], a.dt,
-                                      a.x_interp);
+          float mid = __fmul_rn(kv[0], a.cm[0]);
+#pragma unroll
+          for (int j = 1; j < 7; ++j) mid = fmaf(kv[j], a.cm[j], mid);
+          stage_out[e] = dense_output(y0, y1, __fadd_rn(y0, mid), kv[0], kv[6], a.dt, a.x_interp);
         }
       }
       if (prob) {
@@ -296,7 +308,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_dopri5(const __grid_constant__
       (void)LPC;
       bar_compute();
       store_rows(a.y1, cx.ycur(), row0, nv, SD, cx.tid);
-      store_rows(a.f1, slot_ptr(cx, 6), row0, nv, SD, cx.tid);
+      store_rows(a.f1, slot_ptr_t<SS>(cx, 6), row0, nv, SD, cx.tid);
       if (a.final) store_rows(a.y_out, stage_out, row0, nv, SD, cx.tid);
       const int slot[3] = {P_X_ERR, P_LP_ERR, P_NONFINITE};
       block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
@@ -312,7 +324,7 @@ __device__ __forceinline__ int evals_per_step(int method) {
   return method == FFB_M_RK4 ? 4 : (method == FFB_M_MIDPOINT ? 2 : (method == FFB_M_LEAPFROG ? 3 : 1));
 }
 
-template <class ENG>
+template <class ENG, bool SS>
 __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ FieldDev f,
         const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
   typename ENG::Ctx cx;
@@ -328,11 +340,11 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * S;
     const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* Y0 = slot_ptr(cx, SLOT_Y0);
-    const float* K1 = slot_ptr(cx, 0);
-    const float* K2 = slot_ptr(cx, 1);
-    const float* K3 = slot_ptr(cx, 2);
-    const float* K4 = slot_ptr(cx, 3);
+    float* Y0 = slot_ptr_t<SS>(cx, SLOT_Y0);
+    const float* K1 = slot_ptr_t<SS>(cx, 0);
+    const float* K2 = slot_ptr_t<SS>(cx, 1);
+    const float* K3 = slot_ptr_t<SS>(cx, 2);
+    const float* K4 = slot_ptr_t<SS>(cx, 3);
     bool saw_nan = false;
     if (!cx.producer) {
       load_rows(cx.ycur(), a.x0, row0, nv, S, SD, cx.tid);
@@ -355,11 +367,10 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
           else mask = (e == 1) ? 1u : 2u;
           dst = (e == 1) ? 0 : 1;
         }
-        if (mask) ENG::eval(cx, f, ev[e], dst, mask);
+        if (mask) ENG::template eval<SS>(cx, f, ev[e], dst, mask);
         if (cx.producer) continue;
         // ---- stage algebra after evaluation e (op order of torchdiffeq's step functions) ---------
-        for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
-          const int d = idx / S, r = idx - d * S;
+        for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
           const int i = d * LDA + r;
           float* y = cx.ycur();
           switch (a.method) {
@@ -403,7 +414,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
           float* y = cx.ycur();
           if (a.noise) {
             for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
-              const int r = idx / SD, d = idx - r * SD;
+              const int r = fast_div(idx, SD), d = idx - r * SD;
               if (r >= nv) continue;
               const int i = d * LDA + r;
               const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
@@ -416,7 +427,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
           } else {
             const int ng = (SD + 3) >> 2;
             for (int idx = cx.tid; idx < ng * S; idx += NCOMP) {
-              const int grp = idx / S, r = idx - grp * S;
+              const int grp = fast_div(idx, S), r = idx - grp * S;
               if (r >= nv) continue;
               const float4 z = philox_normal4(a.philox_seed, a.philox_offset, a.row_offset + row0 + r, step, grp);
               const float zz[4] = {z.x, z.y, z.z, z.w};
@@ -604,6 +615,13 @@ static int engine() {
   }
   return g_engine;
 }
+// debug: timeline trace buffer (2 * 4096 int64) or NULL to disable
+extern "C" int ffb_debug_trace(long long* buf) {
+  int zero = 0;
+  cudaMemcpyToSymbol(ffb::g_trace, &buf, sizeof(buf));
+  cudaMemcpyToSymbol(ffb::g_trace_pos, &zero, sizeof(zero));
+  return 0;
+}
 extern "C" int ffb_set_engine(int e) { g_engine = e ? 1 : 0; return g_engine; }
 extern "C" int ffb_get_engine(void) { return engine(); }
 
@@ -747,7 +765,7 @@ static int tangents_of(const ffb_field* f) {
 }
 
 static size_t field_smem(const FieldDev& fd, int T, int slots) {
-  return engine() ? smem_layout_tc(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, slots, nullptr)
+  return engine() ? smem_layout_tc(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, slots, fd.n_calls, field_tdim(fd), nullptr)
                   : smem_layout(fd.state_dim, fd.cond_dim, T, fd.div_mode == FFB_DIV_HUTCH, slots, nullptr);
 }
 
@@ -835,9 +853,13 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
   if (a->norms && !a->partials) return fail(FFB_ERR_ARG, "ffb_field_eval: partials buffer required for norms");
   if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
-  if (engine())
-    return launch_tiles(k_field_eval<EngineTC>, EngineTC::NTHR, "ffb_field_eval", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
-  return launch_tiles(k_field_eval<EngineFFMA>, EngineFFMA::NTHR, "ffb_field_eval", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (engine()) {
+    if (fd.slots_smem) return launch_tiles(k_field_eval<EngineTC, true>, EngineTC::NTHR, "ffb_field_eval", f, fd, *a, a->batch, st_);
+    return launch_tiles(k_field_eval<EngineTC, false>, EngineTC::NTHR, "ffb_field_eval", f, fd, *a, a->batch, st_);
+  }
+  if (fd.slots_smem) return launch_tiles(k_field_eval<EngineFFMA, true>, EngineFFMA::NTHR, "ffb_field_eval", f, fd, *a, a->batch, st_);
+  return launch_tiles(k_field_eval<EngineFFMA, false>, EngineFFMA::NTHR, "ffb_field_eval", f, fd, *a, a->batch, st_);
 }
 
 extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, void* stream) {
@@ -852,9 +874,13 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
     return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: final step needs y_out (and lp_out)");
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
-  if (engine())
-    return launch_tiles(k_dopri5<EngineTC>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
-  return launch_tiles(k_dopri5<EngineFFMA>, EngineFFMA::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (engine()) {
+    if (fd.slots_smem) return launch_tiles(k_dopri5<EngineTC, true>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
+    return launch_tiles(k_dopri5<EngineTC, false>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
+  }
+  if (fd.slots_smem) return launch_tiles(k_dopri5<EngineFFMA, true>, EngineFFMA::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
+  return launch_tiles(k_dopri5<EngineFFMA, false>, EngineFFMA::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
 }
 
 extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, void* stream) {
@@ -869,9 +895,13 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
     return fail(FFB_ERR_ARG, "ffb_integrate_fixed: no divergence with this method");
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: probes are required");
-  if (engine())
-    return launch_tiles(k_fixed<EngineTC>, EngineTC::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
-  return launch_tiles(k_fixed<EngineFFMA>, EngineFFMA::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (engine()) {
+    if (fd.slots_smem) return launch_tiles(k_fixed<EngineTC, true>, EngineTC::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);
+    return launch_tiles(k_fixed<EngineTC, false>, EngineTC::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);
+  }
+  if (fd.slots_smem) return launch_tiles(k_fixed<EngineFFMA, true>, EngineFFMA::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);
+  return launch_tiles(k_fixed<EngineFFMA, false>, EngineFFMA::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);
 }
 
 extern "C" int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream) {

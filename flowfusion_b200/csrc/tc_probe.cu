@@ -97,6 +97,26 @@ probe(const float* __restrict__ A, const float* __restrict__ Bhi_img, const floa
     const uint32_t kstep_bytes = 2 * lbo;   // one MMA consumes K = 8 tf32 = two 16-byte K chunks
     uint32_t acc = 0, acc2 = 0;
     const uint32_t colD2 = 384;
+    if (mode & 4) {
+      // single accumulator, pass-ordered: (mode & 8) ? main first : cross first
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool do_main = ((mode & 8) != 0) == (pass == 0);
+        for (int ks = 0; ks < K / 8; ++ks) {
+          const uint64_t dhi = make_desc(smem_u32(sBhi) + ks * kstep_bytes, lbo, sbo);
+          const uint64_t dlo = make_desc(smem_u32(sBlo) + ks * kstep_bytes, lbo, sbo);
+          const uint32_t a_hi = tb + colAhi + ks * 8, a_lo = tb + colAlo + ks * 8;
+          for (int p = (do_main ? 0 : 1); p < (do_main ? 1 : 3); ++p) {
+            const uint32_t a = (p == 2) ? a_lo : a_hi;
+            const uint64_t d = (p == 1) ? dlo : dhi;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                ::"r"(tb + colD), "r"(a), "l"(d), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+            acc = 1;
+          }
+        }
+      }
+    } else
     for (int ks = 0; ks < K / 8; ++ks) {
       const uint64_t dhi = make_desc(smem_u32(sBhi) + ks * kstep_bytes, lbo, sbo);
       const uint64_t dlo = make_desc(smem_u32(sBlo) + ks * kstep_bytes, lbo, sbo);

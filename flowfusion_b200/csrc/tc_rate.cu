@@ -1,0 +1,84 @@
+// tc_rate.cu -- micro-benchmark: cycles per tcgen05.mma (kind::tf32, M=128, K=8) for accumulate chains.
+//   NACC = number of independent accumulators used round-robin; SS = A operand from shared memory (else TMEM)
+// Run: ./tc_rate   (prints a table)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__host__ __device__ constexpr uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+template <bool SS>
+__device__ __forceinline__ void mma(uint32_t d, uint32_t a, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  if (SS)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5,%5,%5,%5}, p;\n\t}"
+                 ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5,%5,%5,%5}, p;\n\t}"
+                 ::"r"(d), "r"(a), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+template <int N, int NACC, bool SS>
+__global__ void __launch_bounds__(64, 1) rate(int reps, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.001f * (i % 7);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_base_s;
+  if (threadIdx.x == 32) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sb = smem_u32(smem);
+    const uint64_t db = make_desc(sb, N * 16, 128);
+    const uint64_t da = make_desc(sb + 16384, 128 * 16, 128);
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        mma<SS>(tb + (uint32_t)(i % NACC) * 128u, tb + 384u + (uint32_t)i * 8u, da, db + (uint64_t)(i * 16), idesc, (r | (i >= NACC)) ? 1u : 0u);
+    }
+    long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+    long long t2 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
+}
+template <int N, int NACC, bool SS>
+void run(long long* d) {
+  const int reps = 8;
+  cudaFuncSetAttribute(rate<N, NACC, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  long long h[2];
+  for (int rep = 0; rep < 2; ++rep) {
+    rate<N, NACC, SS><<<1, 64, 64 * 1024>>>(reps, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    if (rep) printf("N=%3d nacc=%d %s: issue %6lld complete %6lld cyc for %d MMAs -> %.1f cyc/MMA (%s)\n", N, NACC, SS ? "SS" : "TS", h[0], h[1],
+                    reps * 12, (double)h[1] / (reps * 12), cudaGetErrorString(e));
+  }
+}
+int main() {
+  long long* d; cudaMalloc(&d, 16);
+  run<128, 1, false>(d); run<128, 2, false>(d); run<128, 3, false>(d);
+  run<128, 1, true>(d);  run<128, 3, true>(d);
+  run<64, 1, false>(d);  run<64, 2, false>(d);  run<64, 3, false>(d);
+  run<32, 1, false>(d);  run<32, 2, false>(d);  run<32, 3, false>(d); run<32, 1, true>(d);
+  run<256, 1, false>(d); run<256, 1, true>(d);
+  return 0;
+}
