@@ -77,9 +77,21 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
 // round-to-nearest TF32 split: a ~= hi + lo, |a - hi - lo| <= 2^-24 |a|
-__device__ __forceinline__ void tf32_split(float a, uint32_t& hi, uint32_t& lo) {
+__device__ __forceinline__ void tf32_split_rn(float a, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(a));
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(a - __uint_as_float(hi)));
+}
+// hot-path variant: cvt.rna.tf32.f32 is emulated on sm_100a (FSETP + predicated IADD + LOP3 + a
+// constant move per conversion).  hi = round-half-away on the integer image (2 ALU ops, identical to
+// cvt.rna for finite inputs); lo = a - hi is exact in FP32 and is left unrounded: the tensor core
+// ignores the low 13 mantissa bits of a TF32 operand, a truncation error of 2^-21 |a|.
+__device__ __forceinline__ void tf32_split(float a, uint32_t& hi, uint32_t& lo) {
+#ifdef FFB_SPLIT_CVT
+  tf32_split_rn(a, hi, lo);
+#else
+  hi = (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(a - __uint_as_float(hi));
+#endif
 }
 
 // optional timeline trace (debug): CTA 0 records clock64() at layer hand-offs

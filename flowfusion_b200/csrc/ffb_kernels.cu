@@ -576,7 +576,7 @@ __global__ void k_pack_weight_tc(const float* __restrict__ W, int in_features, i
   }
   const float w = (n < out_features && col >= 0) ? W[(size_t)n * in_features + col] : 0.0f;
   uint32_t hi, lo;
-  tf32_split(w, hi, lo);
+  tf32_split_rn(w, hi, lo);
   const int c = k / KC, kk = k - c * KC, rows = min(KC, K - c * KC);
   const size_t base = (size_t)c * 2 * KC * Np;
   const size_t off = (size_t)(kk >> 2) * (Np * 4) + (size_t)(n >> 3) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
