@@ -1,0 +1,369 @@
+// ffb_engine_rr.cuh -- "row-resident" tensor-core tile engine for fields WITHOUT tangent rows
+// (sampling paths: PF-ODE, reverse SDE, flow sampling, symplectic).  Same arithmetic as
+// ffb_engine_tc.cuh (tcgen05 kind::tf32, 3 products per k-step, FP32 accumulate in tensor memory),
+// different schedule:
+//
+//   * 16 epilogue warps: warp w owns TMEM lane quarter q = w & 3 (rows 32q .. 32q+31) and column
+//     group cg = w >> 2: columns [32c + 8cg, 32c + 8cg + 8) of every 32-column chunk c.  A thread is
+//     one row x 8 columns of a chunk, so every chunk of a layer's output is finished by all 16 warps
+//     together and chunks complete one after the other (4 warps per scheduler hide the SFU / TMEM
+//     latencies of each other);
+//   * chunk hand-off: as soon as chunk c of the next A operand (A_hi | A_lo, written with tcgen05.st)
+//     is in tensor memory the MMA warp issues that chunk's 12 MMAs of the NEXT layer into the other
+//     accumulator buffer (D0 | D1 | A_hi | A_lo = 4 x 128 TMEM columns), so the tensor core trails
+//     the epilogue by one chunk instead of waiting for the whole layer;
+//   * everything between two network evaluations is row-local: the thread that reads column n of
+//     the last layer's accumulator applies the field transform, writes the stage derivative into
+//     its own element of the state slot, runs the integrator's stage algebra for the state columns
+//     it owns ((d >> 3) & 3 == cg) and splits the next layer-0 operand straight back into tensor
+//     memory.  The only synchronisation is a 128-thread named barrier between the 4 warps that
+//     share a lane quarter -- no CTA-wide barrier inside a trajectory;
+//   * the layer-0 bias with the time features folded in (one vector per evaluation) is prepared
+//     ahead of the evaluation that uses it.
+//
+// Accumulation order: per 32-row K chunk the two cross products (A_hi W_lo, A_lo W_hi) are issued
+// before the main product (A_hi W_hi).  csrc/tc_probe.cu measures the orders: cross-first over the
+// whole K 3.8e-7 rms, per-k-step interleave 1.1e-6, FP32 FMA chain 2.3e-7 (relative to rms |out|).
+#pragma once
+#include "ffb_engine_tc.cuh"
+
+namespace ffb {
+
+constexpr int RR_NCOMP = 512;
+constexpr int RR_NTHR = RR_NCOMP + 64;
+constexpr int RR_WLOAD = RR_NCOMP / 32;
+constexpr int RR_WMMA = RR_NCOMP / 32 + 1;
+constexpr int RR_NCHUNK = KMAX / KC;
+constexpr uint32_t RR_COL_AHI = 256, RR_COL_ALO = 384;     // D0 = 0, D1 = 128
+
+__device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(addr));
+}
+
+struct CtxR {
+  uint32_t o_ring, o_ycur, o_cond, o_sbias, o_beff, o_wt, o_red, o_bar, o_slots;
+  __device__ __forceinline__ float* ring() const { return reinterpret_cast<float*>(smem_base() + o_ring); }
+  __device__ __forceinline__ float* ycur() const { return reinterpret_cast<float*>(smem_base() + o_ycur); }
+  __device__ __forceinline__ float* condb() const { return reinterpret_cast<float*>(smem_base() + o_cond); }
+  __device__ __forceinline__ float* sbias() const { return reinterpret_cast<float*>(smem_base() + o_sbias); }
+  __device__ __forceinline__ float* beff() const { return reinterpret_cast<float*>(smem_base() + o_beff); }
+  __device__ __forceinline__ float* swt() const { return reinterpret_cast<float*>(smem_base() + o_wt); }
+  __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(smem_base() + o_red); }
+  __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(smem_base() + o_bar); }
+  __device__ __forceinline__ uint64_t* empty() const { return full() + TC_NSTAGE; }
+  __device__ __forceinline__ uint64_t* a_chunk() const { return full() + 2 * TC_NSTAGE; }
+  __device__ __forceinline__ uint64_t* d_ready() const { return full() + 2 * TC_NSTAGE + RR_NCHUNK; }
+  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(full() + 2 * TC_NSTAGE + RR_NCHUNK + 1); }
+  float* scr;
+  int SD, CD, tdim, ncalls;
+  int tid, lane, warp;
+  int q, cg, row;       // lane quarter, column group, tile row (= TMEM lane) of a compute thread
+  bool producer;
+  uint32_t tmem, lane_addr;
+  int stage; uint32_t phase;       // weight ring (loader / MMA warp)
+  uint32_t ph_a, ph_d, dbuf;       // a_chunk parity bits (MMA warp), d_ready parity (compute), accumulator buffer
+};
+
+template <bool SS>
+__device__ __forceinline__ float* rr_slot(const CtxR& cx, int slot) {
+  if (SS) return reinterpret_cast<float*>(smem_base() + cx.o_slots) + (size_t)slot * cx.SD * LDA;
+  return cx.scr + (size_t)slot * cx.SD * LDA;
+}
+
+// the 512 compute threads / the 4 warps of one lane quarter
+__device__ __forceinline__ void rr_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void rr_qbar(const CtxR& cx) { asm volatile("bar.sync %0, 128;" ::"r"(2 + cx.q) : "memory"); }
+
+__host__ __device__ inline size_t smem_layout_rr(int SD, int CD, int nslot_smem, int ncalls, int tdim, int nbeff,
+                                                 size_t* off /*[12]*/) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~size_t(127); return r; };
+  size_t v[12];
+  v[0] = take(sizeof(float) * TC_NSTAGE * TC_STAGE_FLOATS);                 // weight ring
+  v[1] = take(sizeof(float) * SD * LDA);                                    // ycur
+  v[2] = take(sizeof(float) * (CD > 0 ? CD : 1) * LDA);                     // cond
+  v[3] = take(sizeof(float) * ncalls * FFB_MAX_LAYERS * KMAX);              // biases
+  v[4] = take(sizeof(float) * nbeff * ncalls * KMAX);                       // layer-0 bias + time features, per evaluation
+  v[5] = take(sizeof(float) * ncalls * (tdim > 0 ? tdim : 1) * KMAX);       // layer-0 time-feature rows
+  v[6] = take(sizeof(double) * (RR_NCOMP / 32) * FFB_NPART);                // block-reduction scratch
+  v[7] = take(sizeof(uint64_t) * (2 * TC_NSTAGE + RR_NCHUNK + 4));          // mbarriers + TMEM base slot
+  v[8] = take(sizeof(float) * (size_t)nslot_smem * SD * LDA);               // state slots (0 when they live in global scratch)
+  if (off) for (int i = 0; i < 9; ++i) off[i] = v[i];
+  return o;
+}
+
+struct EngineRR {
+  static constexpr int NTHR = RR_NTHR;
+
+  static __device__ __forceinline__ void init(CtxR& cx, const FieldDev& f, float* scratch, int nslot, int nbeff) {
+    size_t off[12];
+    cx.tdim = field_tdim(f);
+    smem_layout_rr(f.state_dim, f.cond_dim, f.slots_smem ? nslot : 0, f.n_calls, cx.tdim, nbeff, off);
+    cx.o_ring = (uint32_t)off[0]; cx.o_ycur = (uint32_t)off[1]; cx.o_cond = (uint32_t)off[2];
+    cx.o_sbias = (uint32_t)off[3]; cx.o_beff = (uint32_t)off[4]; cx.o_wt = (uint32_t)off[5];
+    cx.o_red = (uint32_t)off[6]; cx.o_bar = (uint32_t)off[7]; cx.o_slots = (uint32_t)off[8];
+    cx.SD = f.state_dim; cx.CD = f.cond_dim; cx.ncalls = f.n_calls;
+    cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
+    cx.producer = cx.warp >= RR_WLOAD;
+    cx.q = cx.warp & 3; cx.cg = (cx.warp >> 2) & 3;
+    cx.row = (cx.q << 5) + cx.lane;
+    cx.scr = scratch + (size_t)blockIdx.x * NSLOT * f.state_dim * LDA;
+    cx.stage = 0;
+    cx.phase = (cx.warp == RR_WLOAD) ? 1u : 0u;     // the loader starts with every stage free
+    cx.ph_a = 0; cx.ph_d = 0; cx.dbuf = 0;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], 1); }
+      for (int s = 0; s < RR_NCHUNK; ++s) mbar_init(&cx.a_chunk()[s], RR_NCOMP / 32);   // every compute warp arrives
+      mbar_init(cx.d_ready(), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (cx.warp == RR_WMMA) {    // the MMA warp owns the tensor memory: all 512 columns
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(cx.tmem_slot())), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int c = 0; c < f.n_calls; ++c) {
+      for (int l = 0; l < f.net[c].n_layers; ++l)
+        for (int n = threadIdx.x; n < KMAX; n += RR_NTHR)
+          cx.sbias()[(c * FFB_MAX_LAYERS + l) * KMAX + n] = (n < f.net[c].Np[l]) ? f.net[c].b[l][n] : 0.0f;
+      for (int i = threadIdx.x; i < f.net[c].t_dim * KMAX; i += RR_NTHR) {
+        const int j = i / KMAX, n = i - j * KMAX;
+        cx.swt()[(c * cx.tdim + j) * KMAX + n] = (n < f.net[c].Np[0]) ? f.net[c].Wt[(size_t)j * f.net[c].Np[0] + n] : 0.0f;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cx.tmem = *cx.tmem_slot();
+    cx.lane_addr = cx.tmem + ((uint32_t)(cx.q << 5) << 16);
+  }
+
+  static __device__ __forceinline__ void fini(CtxR& cx) {
+    tc_fence_before();
+    __syncthreads();
+    if (cx.warp == RR_WMMA) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"(512));
+    }
+  }
+
+  static __device__ __forceinline__ void advance(CtxR& cx) {
+    if (++cx.stage == TC_NSTAGE) { cx.stage = 0; cx.phase ^= 1u; }
+  }
+
+  // layer-0 bias of every call of one evaluation with the (row-uniform) time features folded in
+  static __device__ __forceinline__ void prep_beff(CtxR& cx, const FieldDev& f, const float* tfeat, float* buf) {
+    for (int i = cx.tid; i < f.n_calls * KMAX; i += RR_NCOMP) {
+      const int c = i / KMAX, n = i - c * KMAX;
+      float b = cx.sbias()[(c * FFB_MAX_LAYERS) * KMAX + n];
+      const float* wt = cx.swt() + (c * cx.tdim) * KMAX + n;
+      for (int j = 0; j < f.net[c].t_dim; ++j) b = fmaf(wt[j * KMAX], tfeat[j], b);
+      buf[i] = b;
+    }
+  }
+
+  // ---- loader warp -----------------------------------------------------------------------------
+  static __device__ __forceinline__ void load_net(CtxR& cx, const NetDev& net) {
+    if (cx.lane != 0) return;
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int K = net.K[l], Np = net.Np[l];
+      for (int k0 = 0; k0 < K; k0 += KC) {
+        const int rows = min(KC, K - k0);
+        mbar_wait(&cx.empty()[cx.stage], cx.phase);
+        const uint32_t bytes = (uint32_t)(2 * rows * Np) * sizeof(float);
+        mbar_expect_tx(&cx.full()[cx.stage], bytes);
+        bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, net.W[l] + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
+        advance(cx);
+      }
+    }
+  }
+
+  // ---- MMA warp: chunk c of layer l as soon as the epilogue of layer l-1 has released it --------
+  static __device__ __forceinline__ void mma_net(CtxR& cx, const NetDev& net) {
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int K = net.K[l], Np = net.Np[l];
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t lbo = (uint32_t)Np * 16u;
+      const uint64_t kstep = (uint64_t)(lbo >> 3);
+      const uint32_t d_acc = cx.tmem + cx.dbuf * 128u;
+      cx.dbuf ^= 1u;
+      uint32_t acc = 0;
+      int ci = 0;
+      for (int k0 = 0; k0 < K; k0 += KC, ++ci) {
+        const int nj = min(KC, K - k0) >> 3;
+        mbar_wait(&cx.a_chunk()[ci], (cx.ph_a >> ci) & 1u);     // A columns [k0, k0+32) are in tensor memory
+        cx.ph_a ^= (1u << ci);
+        mbar_wait(&cx.full()[cx.stage], cx.phase);              // W chunk has landed
+        tc_fence_after();
+        const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
+        const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
+        const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
+        const uint32_t a_hi0 = cx.tmem + RR_COL_AHI + (uint32_t)k0, a_lo0 = cx.tmem + RR_COL_ALO + (uint32_t)k0;
+        uint64_t* ebar = &cx.empty()[cx.stage];
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KC / 8; ++j) {
+            if (j < nj) {
+              tc_mma_ts(d_acc, a_hi0 + 8u * j, dl0 + (uint64_t)j * kstep, idesc, (j == 0) ? acc : 1u);
+              tc_mma_ts(d_acc, a_lo0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < KC / 8; ++j)
+            if (j < nj) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+          tc_commit(ebar);                                      // frees the ring stage when these MMAs retire
+        }
+        __syncwarp();
+        acc = 1u;
+        advance(cx);
+      }
+      if (elect_one()) tc_commit(cx.d_ready());                 // the accumulator of this layer is complete
+      __syncwarp();
+    }
+  }
+
+  // ---- compute warps ---------------------------------------------------------------------------
+  static __device__ __forceinline__ void signal_chunk(CtxR& cx, int ci) {
+    tc_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (cx.lane == 0) mbar_arrive(&cx.a_chunk()[ci]);
+  }
+  static __device__ __forceinline__ void wait_d_ready(CtxR& cx) {
+    mbar_wait(cx.d_ready(), cx.ph_d);
+    cx.ph_d ^= 1u;
+    tc_fence_after();
+  }
+
+  // layer-0 operand of call c from cx.ycur() / cx.condb(): this thread's row, its 8 columns per chunk
+  static __device__ __forceinline__ void build_A(CtxR& cx, const FieldDev& f, int c) {
+    const NetDev& net = f.net[c];
+    const int K0 = net.K[0], xd = net.x_dim, cd = net.c_dim;
+    const float* yc = cx.ycur() + f.in_off[c] * LDA + cx.row;
+    const float* cb = cx.condb() + cx.row;
+    int ci = 0;
+    for (int k0 = 0; k0 < K0; k0 += KC, ++ci) {
+      const int k8 = k0 + 8 * cx.cg;
+      if (k8 < K0) {                                             // warp-uniform
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k8 + j;
+          float val = 0.0f;
+          if (k < xd) val = yc[k * LDA];
+          else if (k < xd + cd) val = cb[(k - xd) * LDA];
+          tf32_split(val, hi[j], lo[j]);
+        }
+        tc_st8(cx.lane_addr + RR_COL_AHI + k8, hi);
+        tc_st8(cx.lane_addr + RR_COL_ALO + k8, lo);
+      }
+      signal_chunk(cx, ci);
+    }
+  }
+
+  // hidden layers: accumulator chunk -> + bias -> SiLU -> TF32 split -> next A operand chunk -> hand off
+  static __device__ __forceinline__ void hidden(CtxR& cx, const NetDev& net, int c, const float* beff) {
+    for (int l = 0; l + 1 < net.n_layers; ++l) {
+      const int nc = net.Np[l] / KC;
+      const float* bias = (l == 0) ? beff : cx.sbias() + (c * FFB_MAX_LAYERS + l) * KMAX;
+      const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
+      cx.dbuf ^= 1u;
+      wait_d_ready(cx);
+      uint32_t m[2][8];
+      tc_ld8(dcol, m[0]);
+#pragma unroll
+      for (int ci = 0; ci < RR_NCHUNK; ++ci) {
+        if (ci < nc) {
+          const int c0 = KC * ci + 8 * cx.cg;
+          tc_wait_ld();
+          if (ci + 1 < nc) tc_ld8(dcol + KC * (ci + 1), m[(ci + 1) & 1]);
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float z = __uint_as_float(m[ci & 1][u]) + bb[u];
+            tf32_split(z * sigmoidf_fast(z), hi[u], lo[u]);
+          }
+          tc_st8(cx.lane_addr + RR_COL_AHI + c0, hi);
+          tc_st8(cx.lane_addr + RR_COL_ALO + c0, lo);
+          signal_chunk(cx, ci);
+        }
+      }
+    }
+  }
+
+  // last layer: fn(n, raw output + bias) for every real column n this thread owns
+  template <class F>
+  static __device__ __forceinline__ void last(CtxR& cx, const NetDev& net, int c, const float* beff, F&& fn) {
+    const int nl = net.n_layers, Nreal = net.N[nl - 1];
+    const float* bias = (nl == 1) ? beff : cx.sbias() + (c * FFB_MAX_LAYERS + nl - 1) * KMAX;
+    const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
+    cx.dbuf ^= 1u;
+    wait_d_ready(cx);
+    for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += KC) {              // warp-uniform trip count
+      uint32_t m[8];
+      tc_ld8(dcol + (uint32_t)(c0 - 8 * cx.cg), m);
+      tc_wait_ld();
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u < Nreal) fn(c0 + u, __uint_as_float(m[u]) + bias[c0 + u]);
+    }
+    tc_fence_before();
+  }
+
+  // ---- one evaluation of the field at cx.ycur(): derivative -> slot dst -------------------------
+  // Every warp of the CTA calls this; on return the compute warps of a lane quarter have passed a
+  // quarter barrier, i.e. slot dst is complete for the rows of that quarter.  `overlap()` runs on the
+  // compute warps right after the first layer-0 operand has been handed to the MMA warp (idle time).
+  struct NoOverlap { __device__ __forceinline__ void operator()() const {} };
+  template <bool SS, class OV = NoOverlap>
+  static __device__ __forceinline__ void eval(CtxR& cx, const FieldDev& f, float ev_a, float ev_c, float ev_sigma,
+                                              float ev_sign, const float* beff, int dst, unsigned call_mask = 3u,
+                                              OV&& overlap = OV()) {
+    bool first = true;
+    for (int c = 0; c < f.n_calls; ++c) {
+      if (!((call_mask >> c) & 1u)) continue;
+      const NetDev& net = f.net[c];
+      if (cx.warp == RR_WLOAD) { load_net(cx, net); continue; }
+      if (cx.warp == RR_WMMA) { mma_net(cx, net); continue; }
+      rr_qbar(cx);                           // cx.ycur() of this lane quarter is final
+      build_A(cx, f, c);
+      if (first) { overlap(); first = false; }
+      hidden(cx, net, c, beff + c * KMAX);
+      float* kd = rr_slot<SS>(cx, dst) + cx.row;
+      const float* yc = cx.ycur() + cx.row;
+      const float sgn = ev_sign * f.out_sign[c];
+      const int ooff = f.out_off[c];
+      last(cx, net, c, beff + c * KMAX, [&](int n, float o) {
+        const int d = ooff + n;
+        float xd_;
+        if (f.kind == FFB_FIELD_SCORE) {
+          const float sc = f.use_sigma ? __fdiv_rn(o, ev_sigma) : o;
+          const float lin = f.has_drift ? __fmul_rn(ev_a, yc[d * LDA]) : 0.0f;
+          xd_ = __fsub_rn(lin, __fmul_rn(ev_c, sc));
+        } else {
+          xd_ = o;
+        }
+        kd[d * LDA] = xd_ * sgn;
+      });
+    }
+    if (!cx.producer) rr_qbar(cx);
+  }
+};
+
+// fn(d, element index) for every state column this thread owns in its row
+template <class F>
+__device__ __forceinline__ void rr_for_owned(const CtxR& cx, F&& fn) {
+  for (int d0 = 8 * cx.cg; d0 < cx.SD; d0 += 32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int d = d0 + j;
+      if (d < cx.SD) fn(d, d * LDA + cx.row);
+    }
+  }
+}
+
+}  // namespace ffb

@@ -459,6 +459,8 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
   ENG::fini(cx);
 }
 
+#include "ffb_kernels_rr.cuh"
+
 // =============================================================================================
 // helpers
 // =============================================================================================
@@ -611,7 +613,7 @@ static int g_engine = -1;
 static int engine() {
   if (g_engine < 0) {
     const char* e = getenv("FFB_ENGINE");
-    g_engine = (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) ? 0 : 1;
+    g_engine = (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) ? 0 : ((e && (!strcmp(e, "tc_tile") || !strcmp(e, "2"))) ? 2 : 1);
   }
   return g_engine;
 }
@@ -622,7 +624,7 @@ extern "C" int ffb_debug_trace(long long* buf) {
   cudaMemcpyToSymbol(ffb::g_trace_pos, &zero, sizeof(zero));
   return 0;
 }
-extern "C" int ffb_set_engine(int e) { g_engine = e ? 1 : 0; return g_engine; }
+extern "C" int ffb_set_engine(int e) { g_engine = (e == 2) ? 2 : (e ? 1 : 0); return g_engine; }
 extern "C" int ffb_get_engine(void) { return engine(); }
 
 static thread_local std::string g_err;
@@ -843,6 +845,37 @@ static int launch_tiles(Kern kern, int nthr, const char* name, const ffb_field* 
   return FFB_OK;
 }
 
+// ---- row-resident tensor-core kernels (fields without tangent rows) -----------------------------
+// FFB_ENGINE=tc_tile (or ffb_set_engine(2)) keeps the older whole-layer hand-off tile engine for A/B runs
+static bool use_rr(const FieldDev& fd) { return engine() == 1 && fd.div_mode == FFB_DIV_NONE; }
+
+static int smem_optin() {
+  static int v = 0;
+  if (!v) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); }
+  return v;
+}
+// decide where the state slots live (shared memory when the tile still fits) and return the block size
+static size_t rr_pick_smem(FieldDev* fd, int nslot, int nbeff) {
+  const int td = field_tdim(*fd);
+  const size_t with_slots = smem_layout_rr(fd->state_dim, fd->cond_dim, nslot, fd->n_calls, td, nbeff, nullptr);
+  fd->slots_smem = (with_slots <= (size_t)smem_optin()) ? 1 : 0;
+  return fd->slots_smem ? with_slots : smem_layout_rr(fd->state_dim, fd->cond_dim, 0, fd->n_calls, td, nbeff, nullptr);
+}
+template <typename Kern, typename Args>
+static int launch_rr(Kern kern, size_t smem, const char* name, const FieldDev& fd, const Args& a, int64_t batch,
+                     cudaStream_t stream) {
+  if ((int)smem > smem_optin())
+    return fail(FFB_ERR_ARG, std::string(name) + ": tile needs " + std::to_string(smem) + " B of shared memory, device allows " + std::to_string(smem_optin()));
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (batch + TM - 1) / TM;
+  if (ntiles <= 0) return FFB_OK;
+  const int grid = (int)std::min<int64_t>(ntiles, num_sms());
+  kern<<<grid, RR_NTHR, smem, stream>>>(fd, a, ntiles);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+
 extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* stream) {
   FieldDev fd;
   int rc = make_field(f, &fd);
@@ -875,6 +908,11 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (use_rr(fd)) {
+    const size_t smem = rr_pick_smem(&fd, NSLOT, 6);
+    if (fd.slots_smem) return launch_rr(k_dopri5_rr<true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+    return launch_rr(k_dopri5_rr<false>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+  }
   if (engine()) {
     if (fd.slots_smem) return launch_tiles(k_dopri5<EngineTC, true>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
     return launch_tiles(k_dopri5<EngineTC, false>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
@@ -896,6 +934,11 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (use_rr(fd)) {
+    const size_t smem = rr_pick_smem(&fd, rr_fixed_slots(a->method), 8);
+    if (fd.slots_smem) return launch_rr(k_fixed_rr<true>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
+    return launch_rr(k_fixed_rr<false>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
+  }
   if (engine()) {
     if (fd.slots_smem) return launch_tiles(k_fixed<EngineTC, true>, EngineTC::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);
     return launch_tiles(k_fixed<EngineTC, false>, EngineTC::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);

@@ -1,0 +1,296 @@
+// ffb_kernels_rr.cuh -- integrator kernels on the row-resident tensor-core engine (ffb_engine_rr.cuh):
+// fields without tangent rows (div_mode == FFB_DIV_NONE).  Included by ffb_kernels.cu.
+//
+//   k_dopri5_rr   one attempted Dormand-Prince step (6 fused evaluations, FSAL, FP64 error partials,
+//                 dense output at t_end) -- same contract as k_dopri5
+//   k_fixed_rr    whole fixed-grid trajectory on-chip -- same contract as k_fixed
+//
+// Persistent: grid = min(#tiles, #SMs), one 576-thread CTA per SM (16 epilogue warps, a weight loader
+// warp, an MMA warp).  Between the tile load and the tile store no CTA-wide barrier is executed.
+#pragma once
+#include "ffb_engine_rr.cuh"
+
+namespace ffb {
+
+template <int NT>
+__device__ __forceinline__ void load_rows_t(float* dst, const float* __restrict__ src, int64_t row0, int nv, int S,
+                                            int D, int tid) {
+  const float* __restrict__ base = src + row0 * D;
+#pragma unroll 4
+  for (int idx = tid; idx < S * D; idx += NT) {
+    const int r = fast_div(idx, D), d = idx - r * D;
+    dst[d * LDA + r] = (r < nv) ? base[idx] : 0.0f;
+  }
+}
+template <int NT>
+__device__ __forceinline__ void store_rows_t(float* __restrict__ dst, const float* src, int64_t row0, int nv, int D,
+                                             int tid) {
+  float* __restrict__ base = dst + row0 * D;
+#pragma unroll 4
+  for (int idx = tid; idx < nv * D; idx += NT) {
+    const int r = fast_div(idx, D), d = idx - r * D;
+    base[idx] = src[d * LDA + r];
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void rr_block_reduce_store(CtxR& cx, double (&v)[NV], double* out, const int (&slot)[NV]) {
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+  }
+  if (cx.lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) cx.red()[cx.warp * FFB_NPART + q] = v[q];
+  }
+  rr_bar();
+  if (cx.tid == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double s = 0.0;
+      for (int w = 0; w < RR_NCOMP / 32; ++w) s += cx.red()[w * FFB_NPART + q];
+      out[slot[q]] = s;
+    }
+  }
+  rr_bar();
+}
+
+// state slots a fixed-grid method needs: K_e in slot e, Y0 (when the method keeps it) in the last slot
+__host__ __device__ inline int rr_fixed_slots(int method) {
+  return method == FFB_M_RK4 ? 5 : (method == FFB_M_MIDPOINT ? 3 : (method == FFB_M_EULER ? 1 : 2));
+}
+
+}  // namespace ffb
+
+// =============================================================================================
+// k_dopri5_rr
+// =============================================================================================
+template <bool SS>
+__global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_constant__ ffb::FieldDev f,
+        const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
+  using namespace ffb;
+  CtxR cx;
+  EngineRR::init(cx, f, reinterpret_cast<float*>(a.scratch), NSLOT, 6);
+  const int SD = cx.SD, CD = cx.CD;
+  const int bstride = f.n_calls * KMAX;
+  if (!cx.producer) {
+    for (int s = 0; s < 6; ++s) EngineRR::prep_beff(cx, f, a.ev[s].tfeat, cx.beff() + s * bstride);
+    rr_bar();
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TM;
+    const int nv = (int)min((int64_t)TM, a.batch - row0);
+    float* Y0 = rr_slot<SS>(cx, SLOT_Y0);
+    double nonfinite = 0.0;
+    if (!cx.producer) {
+      load_rows_t<RR_NCOMP>(Y0, a.y0, row0, nv, TM, SD, cx.tid);
+      load_rows_t<RR_NCOMP>(rr_slot<SS>(cx, 0), a.f0, row0, nv, TM, SD, cx.tid);
+      if (CD) load_rows_t<RR_NCOMP>(cx.condb(), a.cond, row0, nv, TM, CD, cx.tid);
+      rr_bar();
+      const float* K1 = rr_slot<SS>(cx, 0);
+      const float c00 = a.cb[0][0];
+      rr_for_owned(cx, [&](int, int e) {
+        const float y0 = Y0[e];
+        if (!is_finite_f(y0)) nonfinite += 1.0;
+        cx.ycur()[e] = __fadd_rn(y0, __fmul_rn(K1[e], c00));
+      });
+    }
+    for (int i = 1; i <= 6; ++i) {
+      const ffb_eval_scalars& ev = a.ev[i - 1];
+      EngineRR::eval<SS>(cx, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * bstride, i);
+      if (!cx.producer && i < 6) {
+        // input of stage i+1: y0 + sum_j cb[i][j] k_j  (the 7th stage input is y1: FSAL)
+        rr_for_owned(cx, [&](int, int e) {
+          float acc = __fmul_rn(rr_slot<SS>(cx, 0)[e], a.cb[i][0]);
+#pragma unroll
+          for (int j = 1; j < 6; ++j)
+            if (j <= i) acc = fmaf(rr_slot<SS>(cx, j)[e], a.cb[i][j], acc);
+          cx.ycur()[e] = __fadd_rn(Y0[e], acc);
+        });
+      }
+    }
+    if (!cx.producer) {
+      // cx.ycur() holds y1, slot 6 holds f1
+      double v[2] = {0.0, nonfinite};
+      float* OUT = rr_slot<SS>(cx, 1);     // K2 of an element is dead once its error / mid sums are formed
+      if (cx.row < nv) {
+        rr_for_owned(cx, [&](int, int e) {
+          const float y0 = Y0[e], y1 = cx.ycur()[e];
+          float kv[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) kv[j] = rr_slot<SS>(cx, j)[e];
+          float err = __fmul_rn(kv[0], a.ce[0]);
+#pragma unroll
+          for (int j = 1; j < 7; ++j) err = fmaf(kv[j], a.ce[j], err);
+          const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0), fabsf(y1))));
+          const float q = __fdiv_rn(err, tol);
+          v[0] += (double)q * q;
+          if (a.final) {
+            float mid = __fmul_rn(kv[0], a.cm[0]);
+#pragma unroll
+            for (int j = 1; j < 7; ++j) mid = fmaf(kv[j], a.cm[j], mid);
+            OUT[e] = dense_output(y0, y1, __fadd_rn(y0, mid), kv[0], kv[6], a.dt, a.x_interp);
+          }
+        });
+      }
+      rr_bar();
+      store_rows_t<RR_NCOMP>(a.y1, cx.ycur(), row0, nv, SD, cx.tid);
+      store_rows_t<RR_NCOMP>(a.f1, rr_slot<SS>(cx, 6), row0, nv, SD, cx.tid);
+      if (a.final) store_rows_t<RR_NCOMP>(a.y_out, OUT, row0, nv, SD, cx.tid);
+      const int slot[2] = {P_X_ERR, P_NONFINITE};
+      rr_block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
+      if (cx.tid == 0) a.partials[tile * FFB_NPART + P_LP_ERR] = 0.0;
+    }
+  }
+  EngineRR::fini(cx);
+}
+
+// =============================================================================================
+// k_fixed_rr
+// =============================================================================================
+template <bool SS>
+__global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_constant__ ffb::FieldDev f,
+        const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
+  using namespace ffb;
+  CtxR cx;
+  const int nslot = rr_fixed_slots(a.method);
+  EngineRR::init(cx, f, reinterpret_cast<float*>(a.scratch), nslot, 8);
+  const int SD = cx.SD, CD = cx.CD;
+  const int nev = evals_per_step(a.method);
+  const float third = (float)(1.0 / 3.0);
+  const int bstride = f.n_calls * KMAX;
+  const int first_e = (a.method == FFB_M_LEAPFROG) ? 1 : 0;   // first evaluation of every step but the first
+  // per-quarter double buffer of the layer-0 bias: beff[(parity * 4 + q)][call][n]
+  auto beff_buf = [&](uint32_t parity) { return cx.beff() + (size_t)((parity & 1u) * 4 + cx.q) * bstride; };
+  auto prep_q = [&](const ffb_eval_scalars* evp, float* buf) {
+    for (int i = cx.cg * 32 + cx.lane; i < bstride; i += 128) {
+      const int c = i / KMAX, n = i - c * KMAX;
+      float b = cx.sbias()[(c * FFB_MAX_LAYERS) * KMAX + n];
+      const float* wt = cx.swt() + (c * cx.tdim) * KMAX + n;
+      for (int j = 0; j < f.net[c].t_dim; ++j) b = fmaf(wt[j * KMAX], evp->tfeat[j], b);
+      buf[i] = b;
+    }
+  };
+  const int q_lo = f.out_off[0], q_hi = f.out_off[0] + f.net[0].N[f.net[0].n_layers - 1];
+  const int p_lo = f.out_off[1], p_hi = f.out_off[1] + f.net[1].N[f.net[1].n_layers > 0 ? f.net[1].n_layers - 1 : 0];
+  uint32_t nbuf = 0;                                          // evaluations done by this CTA (buffer parity)
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TM;
+    const int nv = (int)min((int64_t)TM, a.batch - row0);
+    float* Y0 = rr_slot<SS>(cx, nslot - 1);
+    const float* K1 = rr_slot<SS>(cx, 0);
+    const float* K2 = rr_slot<SS>(cx, nslot > 1 ? 1 : 0);
+    const float* K3 = rr_slot<SS>(cx, nslot > 2 ? 2 : 0);
+    const float* K4 = rr_slot<SS>(cx, nslot > 3 ? 3 : 0);
+    bool saw_nan = false;
+    if (!cx.producer) {
+      load_rows_t<RR_NCOMP>(cx.ycur(), a.x0, row0, nv, TM, SD, cx.tid);
+      if (CD) load_rows_t<RR_NCOMP>(cx.condb(), a.cond, row0, nv, TM, CD, cx.tid);
+      prep_q(a.ev_table, beff_buf(nbuf));                     // first evaluation of the trajectory
+      rr_bar();
+    }
+    for (int step = 0; step < a.nsteps; ++step) {
+      const float* st = a.step_table + (size_t)step * FFB_STEP_STRIDE;
+      const ffb_eval_scalars* ev = a.ev_table + (size_t)step * nev;
+      for (int e = 0; e < nev; ++e) {
+        unsigned mask = 3u;
+        int dst = e;
+        if (a.method == FFB_M_LEAPFROG) {         // e0: dp/dt(q, t0) [first step only], e1: dq/dt, e2: dp/dt
+          if (e == 0 && step > 0) mask = 0u;
+          else mask = (e == 1) ? 1u : 2u;
+          dst = (e == 1) ? 0 : 1;
+        }
+        if (mask) {
+          // the evaluation after this one (its layer-0 bias is prepared while this one's MMAs run)
+          const ffb_eval_scalars* nxt = nullptr;
+          if (e + 1 < nev) nxt = ev + e + 1;
+          else if (step + 1 < a.nsteps) nxt = ev + nev + first_e;
+          float ea = 0.f, ec = 0.f, es = 1.f, esg = 1.f;
+          if (!cx.producer) { ea = ev[e].a; ec = ev[e].c; es = ev[e].sigma; esg = ev[e].sign; }
+          EngineRR::eval<SS>(cx, f, ea, ec, es, esg, beff_buf(nbuf), dst, mask,
+                             [&]() { if (nxt) prep_q(nxt, beff_buf(nbuf + 1)); });
+          ++nbuf;
+        }
+        if (cx.producer) continue;
+        const float dt = st[0], half = st[3];
+        float* y = cx.ycur();
+        switch (a.method) {
+          case FFB_M_EULER:
+            rr_for_owned(cx, [&](int, int i) { y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i])); });
+            break;
+          case FFB_M_MIDPOINT:
+            rr_for_owned(cx, [&](int, int i) {
+              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(K1[i], half)); }
+              else y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, K2[i]));
+            });
+            break;
+          case FFB_M_RK4:
+            rr_for_owned(cx, [&](int, int i) {
+              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(__fmul_rn(dt, K1[i]), third)); }
+              else if (e == 1) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fsub_rn(K2[i], __fmul_rn(K1[i], third))));
+              else if (e == 2) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(K1[i], K2[i]), K3[i])));
+              else {
+                const float sum = __fadd_rn(__fadd_rn(K1[i], __fmul_rn(3.0f, __fadd_rn(K2[i], K3[i]))), K4[i]);
+                y[i] = __fadd_rn(Y0[i], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+              }
+            });
+            break;
+          case FFB_M_LEAPFROG:
+            rr_for_owned(cx, [&](int d, int i) {
+              if (e == 1) { if (d >= q_lo && d < q_hi) y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i])); }
+              else if (d >= p_lo && d < p_hi) y[i] = __fadd_rn(y[i], __fmul_rn(half, K2[i]));
+            });
+            break;
+          case FFB_M_EM: {
+            // diffusion.py:552-559: f = drift - g^2 score (ev.c = g^2); x_mean = x + f dt; x = x_mean + g dw
+            const float g = st[1], sq = st[2];
+            if (cx.row < nv) {
+              if (a.noise) {
+                const float* nz = a.noise + ((size_t)step * a.batch + row0 + cx.row) * SD;
+                rr_for_owned(cx, [&](int d, int i) {
+                  const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
+                  const float dw = __fmul_rn(nz[d], sq);
+                  const float xn = __fadd_rn(xm, __fmul_rn(g, dw));
+                  Y0[i] = xm;
+                  y[i] = xn;
+                  saw_nan |= (xn != xn);
+                });
+              } else {
+                for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+#pragma unroll
+                  for (int hg = 0; hg < 2; ++hg) {
+                    const int dg = d0 + 4 * hg;
+                    if (dg >= SD) break;
+                    const float4 z = philox_normal4(a.philox_seed, a.philox_offset, a.row_offset + row0 + cx.row, step, dg >> 2);
+                    const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const int d = dg + u;
+                      if (d >= SD) break;
+                      const int i = d * LDA + cx.row;
+                      const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
+                      const float xn = __fadd_rn(xm, __fmul_rn(g, __fmul_rn(zz[u], sq)));
+                      Y0[i] = xm;
+                      y[i] = xn;
+                      saw_nan |= (xn != xn);
+                    }
+                  }
+                }
+              }
+            }
+            break;
+          }
+          default: break;
+        }
+      }
+    }
+    if (!cx.producer) {
+      rr_bar();
+      store_rows_t<RR_NCOMP>(a.x_out, (a.method == FFB_M_EM) ? Y0 : cx.ycur(), row0, nv, SD, cx.tid);
+      if (saw_nan) atomicOr(a.status, FFB_ST_NAN_SAMPLE);
+      rr_bar();
+    }
+  }
+  EngineRR::fini(cx);
+}
