@@ -35,6 +35,13 @@ constexpr int RR_WLOAD = RR_NCOMP / 32;
 constexpr int RR_WMMA = RR_NCOMP / 32 + 1;
 constexpr int RR_NCHUNK = KMAX / KC;
 constexpr uint32_t RR_COL_AHI = 256, RR_COL_ALO = 384;     // D0 = 0, D1 = 128
+// Synchronisation of one ring stage (= one 32-row K chunk of one layer): ONE mbarrier `full[s]` collects
+// both conditions the MMA warp needs -- the weight chunk has landed (loader: arrive.expect_tx + the copy's
+// complete_tx) and the matching 32 columns of the A operand are in tensor memory (one arrive per compute
+// warp) -- because every mbarrier poll costs the MMA warp ~130 cycles while the epilogue warps keep the
+// shared-memory pipe busy (measured with the -DFFB_TRACE timeline), and the tensor pipe's queue only
+// hides ~250 cycles.  Compute warps and MMA warp walk the ring in the same order (layer by layer, chunk
+// by chunk), so both sides know the stage of every chunk without exchanging it.
 
 __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -42,7 +49,17 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
                : "r"(addr));
 }
 
+// Debug timeline (compiled in with -DFFB_TRACE only): CTA 0 records clock64() at hand-off points, one
+// private region per role (0: compute warp 0, 1: MMA warp, 2: compute warp 15), no atomics.
+#ifdef FFB_TRACE
+#define RR_TRACE(cx, tag) rr_trace(cx, tag)
+#else
+#define RR_TRACE(cx, tag) do {} while (0)
+#endif
+constexpr int RR_TRACE_CAP = 2048;
+
 struct CtxR {
+  int tr_role, tr_n;
   uint32_t o_ring, o_ycur, o_cond, o_sbias, o_beff, o_wt, o_red, o_bar, o_slots;
   __device__ __forceinline__ float* ring() const { return reinterpret_cast<float*>(smem_base() + o_ring); }
   __device__ __forceinline__ float* ycur() const { return reinterpret_cast<float*>(smem_base() + o_ycur); }
@@ -53,18 +70,25 @@ struct CtxR {
   __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(smem_base() + o_red); }
   __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(smem_base() + o_bar); }
   __device__ __forceinline__ uint64_t* empty() const { return full() + TC_NSTAGE; }
-  __device__ __forceinline__ uint64_t* a_chunk() const { return full() + 2 * TC_NSTAGE; }
-  __device__ __forceinline__ uint64_t* d_ready() const { return full() + 2 * TC_NSTAGE + RR_NCHUNK; }
-  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(full() + 2 * TC_NSTAGE + RR_NCHUNK + 1); }
+  __device__ __forceinline__ uint64_t* d_ready() const { return full() + 2 * TC_NSTAGE; }
+  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(full() + 2 * TC_NSTAGE + 1); }
   float* scr;
   int SD, CD, tdim, ncalls;
   int tid, lane, warp;
   int q, cg, row;       // lane quarter, column group, tile row (= TMEM lane) of a compute thread
   bool producer;
   uint32_t tmem, lane_addr;
-  int stage; uint32_t phase;       // weight ring (loader / MMA warp)
-  uint32_t ph_a, ph_d, dbuf;       // a_chunk parity bits (MMA warp), d_ready parity (compute), accumulator buffer
+  int stage; uint32_t phase;       // ring position: loader / MMA warp (with phase); compute warps (stage of the next chunk they hand over)
+  uint32_t ph_d, dbuf;             // d_ready parity (compute warps), accumulator buffer of the current layer
 };
+
+__device__ __forceinline__ void rr_trace(CtxR& cx, int tag) {
+  if (cx.tr_role >= 0 && g_trace && cx.tr_n < RR_TRACE_CAP) {
+    long long* p = g_trace + 2 * (cx.tr_role * RR_TRACE_CAP + cx.tr_n);
+    p[0] = clock64(); p[1] = tag;
+    ++cx.tr_n;
+  }
+}
 
 template <bool SS>
 __device__ __forceinline__ float* rr_slot(const CtxR& cx, int slot) {
@@ -112,10 +136,11 @@ struct EngineRR {
     cx.scr = scratch + (size_t)blockIdx.x * NSLOT * f.state_dim * LDA;
     cx.stage = 0;
     cx.phase = (cx.warp == RR_WLOAD) ? 1u : 0u;     // the loader starts with every stage free
-    cx.ph_a = 0; cx.ph_d = 0; cx.dbuf = 0;
+    cx.ph_d = 0; cx.dbuf = 0;
+    cx.tr_n = 0;
+    cx.tr_role = (blockIdx.x != 0 || cx.lane != 0) ? -1 : (cx.warp == 0 ? 0 : (cx.warp == RR_WMMA ? 1 : (cx.warp == RR_NCOMP / 32 - 1 ? 2 : -1)));
     if (threadIdx.x == 0) {
-      for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], 1); }
-      for (int s = 0; s < RR_NCHUNK; ++s) mbar_init(&cx.a_chunk()[s], RR_NCOMP / 32);   // every compute warp arrives
+      for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1 + RR_NCOMP / 32); mbar_init(&cx.empty()[s], 1); }   // loader + every compute warp
       mbar_init(cx.d_ready(), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,6 +197,10 @@ struct EngineRR {
         const int rows = min(KC, K - k0);
         mbar_wait(&cx.empty()[cx.stage], cx.phase);
         const uint32_t bytes = (uint32_t)(2 * rows * Np) * sizeof(float);
+#ifdef FFB_ABL_NOLOAD   // ablation (wrong results): stop streaming weights after the first pass over the ring
+        if (cx.tr_n >= TC_NSTAGE) { mbar_arrive(&cx.full()[cx.stage]); advance(cx); continue; }
+        ++cx.tr_n;
+#endif
         mbar_expect_tx(&cx.full()[cx.stage], bytes);
         bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, net.W[l] + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
         advance(cx);
@@ -179,7 +208,22 @@ struct EngineRR {
     }
   }
 
-  // ---- MMA warp: chunk c of layer l as soon as the epilogue of layer l-1 has released it --------
+  // ---- MMA warp: chunk c of layer l as soon as its weights and its A columns are there ------------
+  // NJ > 0: compile-time number of k-steps per chunk (4 for a full 32-row chunk) -> no per-MMA branches
+  template <int NJ>
+  static __device__ __forceinline__ void issue_chunk(uint32_t d_acc, uint32_t a_hi0, uint32_t a_lo0, uint64_t dh0, uint64_t dl0,
+                                                     uint64_t kstep, uint32_t idesc, uint32_t acc0, int nj) {
+#pragma unroll
+    for (int j = 0; j < KC / 8; ++j) {
+      if ((NJ > 0) ? (j < NJ) : (j < nj)) {
+        tc_mma_ts(d_acc, a_hi0 + 8u * j, dl0 + (uint64_t)j * kstep, idesc, (j == 0) ? acc0 : 1u);
+        tc_mma_ts(d_acc, a_lo0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < KC / 8; ++j)
+      if ((NJ > 0) ? (j < NJ) : (j < nj)) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+  }
   static __device__ __forceinline__ void mma_net(CtxR& cx, const NetDev& net) {
     for (int l = 0; l < net.n_layers; ++l) {
       const int K = net.K[l], Np = net.Np[l];
@@ -192,43 +236,38 @@ struct EngineRR {
       int ci = 0;
       for (int k0 = 0; k0 < K; k0 += KC, ++ci) {
         const int nj = min(KC, K - k0) >> 3;
-        mbar_wait(&cx.a_chunk()[ci], (cx.ph_a >> ci) & 1u);     // A columns [k0, k0+32) are in tensor memory
-        cx.ph_a ^= (1u << ci);
-        mbar_wait(&cx.full()[cx.stage], cx.phase);              // W chunk has landed
+        mbar_wait(&cx.full()[cx.stage], cx.phase);              // W chunk landed AND A columns [k0, k0+32) written
         tc_fence_after();
+        RR_TRACE(cx, 100 + 10 * l + ci);
         const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
         const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
         const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
         const uint32_t a_hi0 = cx.tmem + RR_COL_AHI + (uint32_t)k0, a_lo0 = cx.tmem + RR_COL_ALO + (uint32_t)k0;
         uint64_t* ebar = &cx.empty()[cx.stage];
+        const bool lastc = (k0 + KC >= K);
         if (elect_one()) {
-#pragma unroll
-          for (int j = 0; j < KC / 8; ++j) {
-            if (j < nj) {
-              tc_mma_ts(d_acc, a_hi0 + 8u * j, dl0 + (uint64_t)j * kstep, idesc, (j == 0) ? acc : 1u);
-              tc_mma_ts(d_acc, a_lo0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < KC / 8; ++j)
-            if (j < nj) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+          if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
+          else issue_chunk<0>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
           tc_commit(ebar);                                      // frees the ring stage when these MMAs retire
+          if (lastc) tc_commit(cx.d_ready());                   // the accumulator of this layer is complete
         }
         __syncwarp();
+        RR_TRACE(cx, 300 + ci);
         acc = 1u;
         advance(cx);
       }
-      if (elect_one()) tc_commit(cx.d_ready());                 // the accumulator of this layer is complete
-      __syncwarp();
+      RR_TRACE(cx, 190 + l);
     }
   }
 
   // ---- compute warps ---------------------------------------------------------------------------
-  static __device__ __forceinline__ void signal_chunk(CtxR& cx, int ci) {
+  // "my part of the next A chunk is in tensor memory": arrive on the ring stage that chunk will use
+  static __device__ __forceinline__ void signal_chunk(CtxR& cx) {
     tc_wait_st();
     tc_fence_before();
     __syncwarp();
-    if (cx.lane == 0) mbar_arrive(&cx.a_chunk()[ci]);
+    if (cx.lane == 0) mbar_arrive(&cx.full()[cx.stage]);
+    if (++cx.stage == TC_NSTAGE) cx.stage = 0;
   }
   static __device__ __forceinline__ void wait_d_ready(CtxR& cx) {
     mbar_wait(cx.d_ready(), cx.ph_d);
@@ -236,7 +275,9 @@ struct EngineRR {
     tc_fence_after();
   }
 
-  // layer-0 operand of call c from cx.ycur() / cx.condb(): this thread's row, its 8 columns per chunk
+  // layer-0 operand of call c from cx.ycur() / cx.condb(): this thread's row, its 8 columns per chunk.
+  // Loads are unconditional (clamped index) so that all 8 are in flight together; a group of 8 columns that
+  // holds no state column (conditional / zero padding only) skips the state loads.
   static __device__ __forceinline__ void build_A(CtxR& cx, const FieldDev& f, int c) {
     const NetDev& net = f.net[c];
     const int K0 = net.K[0], xd = net.x_dim, cd = net.c_dim;
@@ -247,18 +288,34 @@ struct EngineRR {
       const int k8 = k0 + 8 * cx.cg;
       if (k8 < K0) {                                             // warp-uniform
         uint32_t hi[8], lo[8];
+        if (k8 + 8 <= xd) {                                      // state columns only (warp-uniform)
+          float vx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = k8 + j;
-          float val = 0.0f;
-          if (k < xd) val = yc[k * LDA];
-          else if (k < xd + cd) val = cb[(k - xd) * LDA];
-          tf32_split(val, hi[j], lo[j]);
+          for (int j = 0; j < 8; ++j) vx[j] = yc[(k8 + j) * LDA];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tf32_split(vx[j], hi[j], lo[j]);
+        } else if (k8 >= xd + cd) {                              // zero padding only
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { hi[j] = 0u; lo[j] = 0u; }
+        } else {
+          float vx[8], vc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = k8 + j;
+            vx[j] = (k8 < xd) ? yc[min(k, xd - 1) * LDA] : 0.0f;
+            vc[j] = (cd > 0) ? cb[min(max(k - xd, 0), cd - 1) * LDA] : 0.0f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = k8 + j;
+            const float val = (k < xd) ? vx[j] : ((k < xd + cd) ? vc[j] : 0.0f);
+            tf32_split(val, hi[j], lo[j]);
+          }
         }
         tc_st8(cx.lane_addr + RR_COL_AHI + k8, hi);
         tc_st8(cx.lane_addr + RR_COL_ALO + k8, lo);
       }
-      signal_chunk(cx, ci);
+      signal_chunk(cx);
     }
   }
 
@@ -270,6 +327,7 @@ struct EngineRR {
       const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
       cx.dbuf ^= 1u;
       wait_d_ready(cx);
+      RR_TRACE(cx, 200 + 10 * l);
       uint32_t m[2][8];
       tc_ld8(dcol, m[0]);
 #pragma unroll
@@ -289,13 +347,15 @@ struct EngineRR {
           }
           tc_st8(cx.lane_addr + RR_COL_AHI + c0, hi);
           tc_st8(cx.lane_addr + RR_COL_ALO + c0, lo);
-          signal_chunk(cx, ci);
+          signal_chunk(cx);
+          RR_TRACE(cx, 201 + 10 * l + ci);
         }
       }
     }
   }
 
-  // last layer: fn(n, raw output + bias) for every real column n this thread owns
+  // last layer: fn(c0, o[8]) with o[u] = raw output + bias of column c0 + u, for every 8-column group this
+  // thread owns that holds a real column (columns >= N[last] of the group are padding)
   template <class F>
   static __device__ __forceinline__ void last(CtxR& cx, const NetDev& net, int c, const float* beff, F&& fn) {
     const int nl = net.n_layers, Nreal = net.N[nl - 1];
@@ -303,13 +363,18 @@ struct EngineRR {
     const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
     cx.dbuf ^= 1u;
     wait_d_ready(cx);
+    RR_TRACE(cx, 290);
     for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += KC) {              // warp-uniform trip count
       uint32_t m[8];
       tc_ld8(dcol + (uint32_t)(c0 - 8 * cx.cg), m);
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       tc_wait_ld();
+      float o[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (c0 + u < Nreal) fn(c0 + u, __uint_as_float(m[u]) + bias[c0 + u]);
+      for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(m[u]) + bb[u];
+      fn(c0, o);
     }
     tc_fence_before();
   }
@@ -330,40 +395,63 @@ struct EngineRR {
       if (cx.warp == RR_WLOAD) { load_net(cx, net); continue; }
       if (cx.warp == RR_WMMA) { mma_net(cx, net); continue; }
       rr_qbar(cx);                           // cx.ycur() of this lane quarter is final
+      RR_TRACE(cx, 10);
       build_A(cx, f, c);
+      RR_TRACE(cx, 11);
       if (first) { overlap(); first = false; }
       hidden(cx, net, c, beff + c * KMAX);
       float* kd = rr_slot<SS>(cx, dst) + cx.row;
       const float* yc = cx.ycur() + cx.row;
       const float sgn = ev_sign * f.out_sign[c];
-      const int ooff = f.out_off[c];
-      last(cx, net, c, beff + c * KMAX, [&](int n, float o) {
-        const int d = ooff + n;
-        float xd_;
-        if (f.kind == FFB_FIELD_SCORE) {
-          const float sc = f.use_sigma ? __fdiv_rn(o, ev_sigma) : o;
-          const float lin = f.has_drift ? __fmul_rn(ev_a, yc[d * LDA]) : 0.0f;
-          xd_ = __fsub_rn(lin, __fmul_rn(ev_c, sc));
-        } else {
-          xd_ = o;
+      const int ooff = f.out_off[c], Nreal = net.N[net.n_layers - 1];
+      const bool score = (f.kind == FFB_FIELD_SCORE), use_sigma = f.use_sigma != 0, has_drift = f.has_drift != 0;
+      last(cx, net, c, beff + c * KMAX, [&](int c0, const float (&o)[8]) {
+        float yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) yv[u] = (score && has_drift) ? yc[(ooff + min(c0 + u, Nreal - 1)) * LDA] : 0.0f;
+        float xd_[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (score) {
+            const float sc = use_sigma ? __fdiv_rn(o[u], ev_sigma) : o[u];
+            const float lin = has_drift ? __fmul_rn(ev_a, yv[u]) : 0.0f;
+            xd_[u] = __fsub_rn(lin, __fmul_rn(ev_c, sc)) * sgn;
+          } else {
+            xd_[u] = o[u] * sgn;
+          }
         }
-        kd[d * LDA] = xd_ * sgn;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u < Nreal) kd[(ooff + c0 + u) * LDA] = xd_[u];
       });
     }
+    RR_TRACE(cx, 12);
     if (!cx.producer) rr_qbar(cx);
+    RR_TRACE(cx, 13);
   }
 };
 
-// fn(d, element index) for every state column this thread owns in its row
+// ---- row-local stage algebra helpers --------------------------------------------------------------
+// A thread owns, in its row, the state columns d with (d >> 3) & 3 == cg: blocks of 8 columns starting at
+// d0 = 8 cg + 32 b.  rr_load8 reads a block of a [d][row] buffer with unconditional loads (columns past
+// SD are clamped to SD - 1: valid memory, value unused) so the 8 loads are in flight together;
+// rr_store8 writes the real columns only.
 template <class F>
-__device__ __forceinline__ void rr_for_owned(const CtxR& cx, F&& fn) {
-  for (int d0 = 8 * cx.cg; d0 < cx.SD; d0 += 32) {
+__device__ __forceinline__ void rr_for_blocks(const CtxR& cx, F&& fn) {
+  for (int d0 = 8 * cx.cg; d0 < cx.SD; d0 += 32) fn(d0);
+}
+__device__ __forceinline__ void rr_load8(const CtxR& cx, const float* buf, int d0, float (&v)[8]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int d = d0 + j;
-      if (d < cx.SD) fn(d, d * LDA + cx.row);
-    }
-  }
+  for (int u = 0; u < 8; ++u) v[u] = buf[min(d0 + u, cx.SD - 1) * LDA + cx.row];
+}
+__device__ __forceinline__ void rr_load8_if(const CtxR& cx, bool on, const float* buf, int d0, float (&v)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = on ? buf[min(d0 + u, cx.SD - 1) * LDA + cx.row] : 0.0f;
+}
+__device__ __forceinline__ void rr_store8(const CtxR& cx, float* buf, int d0, const float (&v)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (d0 + u < cx.SD) buf[(d0 + u) * LDA + cx.row] = v[u];
 }
 
 }  // namespace ffb

@@ -90,10 +90,16 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
       rr_bar();
       const float* K1 = rr_slot<SS>(cx, 0);
       const float c00 = a.cb[0][0];
-      rr_for_owned(cx, [&](int, int e) {
-        const float y0 = Y0[e];
-        if (!is_finite_f(y0)) nonfinite += 1.0;
-        cx.ycur()[e] = __fadd_rn(y0, __fmul_rn(K1[e], c00));
+      rr_for_blocks(cx, [&](int d0) {
+        float y0v[8], kv[8], y[8];
+        rr_load8(cx, Y0, d0, y0v);
+        rr_load8(cx, K1, d0, kv);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (d0 + u < SD && !is_finite_f(y0v[u])) nonfinite += 1.0;
+          y[u] = __fadd_rn(y0v[u], __fmul_rn(kv[u], c00));
+        }
+        rr_store8(cx, cx.ycur(), d0, y);
       });
     }
     for (int i = 1; i <= 6; ++i) {
@@ -101,12 +107,24 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
       EngineRR::eval<SS>(cx, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * bstride, i);
       if (!cx.producer && i < 6) {
         // input of stage i+1: y0 + sum_j cb[i][j] k_j  (the 7th stage input is y1: FSAL)
-        rr_for_owned(cx, [&](int, int e) {
-          float acc = __fmul_rn(rr_slot<SS>(cx, 0)[e], a.cb[i][0]);
+        float cbi[6];
 #pragma unroll
-          for (int j = 1; j < 6; ++j)
-            if (j <= i) acc = fmaf(rr_slot<SS>(cx, j)[e], a.cb[i][j], acc);
-          cx.ycur()[e] = __fadd_rn(Y0[e], acc);
+        for (int j = 0; j < 6; ++j) cbi[j] = a.cb[i][j];
+        rr_for_blocks(cx, [&](int d0) {
+          float y0v[8], kv[8], acc[8];
+          rr_load8(cx, Y0, d0, y0v);
+          rr_load8(cx, rr_slot<SS>(cx, 0), d0, kv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = __fmul_rn(kv[u], cbi[0]);
+#pragma unroll
+          for (int j = 1; j < 6; ++j) {
+            rr_load8_if(cx, j <= i, rr_slot<SS>(cx, j), d0, kv);      // k_j = 0 for the stages not yet taken
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = fmaf(kv[u], cbi[j], acc[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = __fadd_rn(y0v[u], acc[u]);
+          rr_store8(cx, cx.ycur(), d0, acc);
         });
       }
     }
@@ -115,23 +133,32 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
       double v[2] = {0.0, nonfinite};
       float* OUT = rr_slot<SS>(cx, 1);     // K2 of an element is dead once its error / mid sums are formed
       if (cx.row < nv) {
-        rr_for_owned(cx, [&](int, int e) {
-          const float y0 = Y0[e], y1 = cx.ycur()[e];
-          float kv[7];
+        float ce[7], cm[7];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) kv[j] = rr_slot<SS>(cx, j)[e];
-          float err = __fmul_rn(kv[0], a.ce[0]);
+        for (int j = 0; j < 7; ++j) { ce[j] = a.ce[j]; cm[j] = a.cm[j]; }
+        rr_for_blocks(cx, [&](int d0) {
+          float y0v[8], y1v[8], k0[8], kv[8], err[8], mid[8];
+          rr_load8(cx, Y0, d0, y0v);
+          rr_load8(cx, cx.ycur(), d0, y1v);
+          rr_load8(cx, rr_slot<SS>(cx, 0), d0, k0);
 #pragma unroll
-          for (int j = 1; j < 7; ++j) err = fmaf(kv[j], a.ce[j], err);
-          const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0), fabsf(y1))));
-          const float q = __fdiv_rn(err, tol);
-          v[0] += (double)q * q;
-          if (a.final) {
-            float mid = __fmul_rn(kv[0], a.cm[0]);
+          for (int u = 0; u < 8; ++u) { err[u] = __fmul_rn(k0[u], ce[0]); mid[u] = __fmul_rn(k0[u], cm[0]); }
 #pragma unroll
-            for (int j = 1; j < 7; ++j) mid = fmaf(kv[j], a.cm[j], mid);
-            OUT[e] = dense_output(y0, y1, __fadd_rn(y0, mid), kv[0], kv[6], a.dt, a.x_interp);
+          for (int j = 1; j < 7; ++j) {
+            rr_load8(cx, rr_slot<SS>(cx, j), d0, kv);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { err[u] = fmaf(kv[u], ce[j], err[u]); mid[u] = fmaf(kv[u], cm[j], mid[u]); }
           }
+          // kv now holds k7 = f1
+          float out[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0v[u]), fabsf(y1v[u]))));
+            const float q = __fdiv_rn(err[u], tol);
+            if (d0 + u < SD) v[0] += (double)q * q;
+            out[u] = a.final ? dense_output(y0v[u], y1v[u], __fadd_rn(y0v[u], mid[u]), k0[u], kv[u], a.dt, a.x_interp) : 0.0f;
+          }
+          if (a.final) rr_store8(cx, OUT, d0, out);
         });
       }
       rr_bar();
@@ -193,6 +220,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
     for (int step = 0; step < a.nsteps; ++step) {
       const float* st = a.step_table + (size_t)step * FFB_STEP_STRIDE;
       const ffb_eval_scalars* ev = a.ev_table + (size_t)step * nev;
+      const float dt = st[0], g = st[1], sq = st[2], half = st[3];    // loaded before the evaluations that hide the latency
       for (int e = 0; e < nev; ++e) {
         unsigned mask = 3u;
         int dst = e;
@@ -213,71 +241,103 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
           ++nbuf;
         }
         if (cx.producer) continue;
-        const float dt = st[0], half = st[3];
         float* y = cx.ycur();
         switch (a.method) {
           case FFB_M_EULER:
-            rr_for_owned(cx, [&](int, int i) { y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i])); });
+            rr_for_blocks(cx, [&](int d0) {
+              float yv[8], k1[8];
+              rr_load8(cx, y, d0, yv); rr_load8(cx, K1, d0, k1);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(yv[u], __fmul_rn(dt, k1[u]));
+              rr_store8(cx, y, d0, yv);
+            });
             break;
           case FFB_M_MIDPOINT:
-            rr_for_owned(cx, [&](int, int i) {
-              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(K1[i], half)); }
-              else y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, K2[i]));
+            rr_for_blocks(cx, [&](int d0) {
+              float yv[8], kv[8];
+              if (e == 0) {
+                rr_load8(cx, y, d0, yv); rr_load8(cx, K1, d0, kv);
+                rr_store8(cx, Y0, d0, yv);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(yv[u], __fmul_rn(kv[u], half));
+              } else {
+                rr_load8(cx, Y0, d0, yv); rr_load8(cx, K2, d0, kv);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(yv[u], __fmul_rn(dt, kv[u]));
+              }
+              rr_store8(cx, y, d0, yv);
             });
             break;
           case FFB_M_RK4:
-            rr_for_owned(cx, [&](int, int i) {
-              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(__fmul_rn(dt, K1[i]), third)); }
-              else if (e == 1) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fsub_rn(K2[i], __fmul_rn(K1[i], third))));
-              else if (e == 2) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(K1[i], K2[i]), K3[i])));
-              else {
-                const float sum = __fadd_rn(__fadd_rn(K1[i], __fmul_rn(3.0f, __fadd_rn(K2[i], K3[i]))), K4[i]);
-                y[i] = __fadd_rn(Y0[i], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+            rr_for_blocks(cx, [&](int d0) {
+              float y0v[8], k1[8], k2[8], k3[8], k4[8], yv[8];
+              rr_load8(cx, K1, d0, k1);
+              if (e == 0) {
+                rr_load8(cx, y, d0, y0v);
+                rr_store8(cx, Y0, d0, y0v);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(y0v[u], __fmul_rn(__fmul_rn(dt, k1[u]), third));
+              } else if (e == 1) {
+                rr_load8(cx, Y0, d0, y0v); rr_load8(cx, K2, d0, k2);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(y0v[u], __fmul_rn(dt, __fsub_rn(k2[u], __fmul_rn(k1[u], third))));
+              } else if (e == 2) {
+                rr_load8(cx, Y0, d0, y0v); rr_load8(cx, K2, d0, k2); rr_load8(cx, K3, d0, k3);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(y0v[u], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[u], k2[u]), k3[u])));
+              } else {
+                rr_load8(cx, Y0, d0, y0v); rr_load8(cx, K2, d0, k2); rr_load8(cx, K3, d0, k3); rr_load8(cx, K4, d0, k4);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const float sum = __fadd_rn(__fadd_rn(k1[u], __fmul_rn(3.0f, __fadd_rn(k2[u], k3[u]))), k4[u]);
+                  yv[u] = __fadd_rn(y0v[u], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+                }
               }
+              rr_store8(cx, y, d0, yv);
             });
             break;
           case FFB_M_LEAPFROG:
-            rr_for_owned(cx, [&](int d, int i) {
-              if (e == 1) { if (d >= q_lo && d < q_hi) y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i])); }
-              else if (d >= p_lo && d < p_hi) y[i] = __fadd_rn(y[i], __fmul_rn(half, K2[i]));
+            rr_for_blocks(cx, [&](int d0) {
+              float yv[8], kv[8];
+              rr_load8(cx, y, d0, yv); rr_load8(cx, (e == 1) ? K1 : K2, d0, kv);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int d = d0 + u;
+                if (e == 1) { if (d >= q_lo && d < q_hi) yv[u] = __fadd_rn(yv[u], __fmul_rn(dt, kv[u])); }
+                else if (d >= p_lo && d < p_hi) yv[u] = __fadd_rn(yv[u], __fmul_rn(half, kv[u]));
+              }
+              rr_store8(cx, y, d0, yv);
             });
             break;
           case FFB_M_EM: {
             // diffusion.py:552-559: f = drift - g^2 score (ev.c = g^2); x_mean = x + f dt; x = x_mean + g dw
-            const float g = st[1], sq = st[2];
             if (cx.row < nv) {
-              if (a.noise) {
-                const float* nz = a.noise + ((size_t)step * a.batch + row0 + cx.row) * SD;
-                rr_for_owned(cx, [&](int d, int i) {
-                  const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
-                  const float dw = __fmul_rn(nz[d], sq);
-                  const float xn = __fadd_rn(xm, __fmul_rn(g, dw));
-                  Y0[i] = xm;
-                  y[i] = xn;
-                  saw_nan |= (xn != xn);
-                });
-              } else {
-                for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+              const float* nz = a.noise ? a.noise + ((size_t)step * a.batch + row0 + cx.row) * SD : nullptr;
+              rr_for_blocks(cx, [&](int d0) {
+                float yv[8], k1[8], zz[8], xm[8];
+                rr_load8(cx, y, d0, yv); rr_load8(cx, K1, d0, k1);
+                if (nz) {
 #pragma unroll
-                  for (int hg = 0; hg < 2; ++hg) {
-                    const int dg = d0 + 4 * hg;
-                    if (dg >= SD) break;
-                    const float4 z = philox_normal4(a.philox_seed, a.philox_offset, a.row_offset + row0 + cx.row, step, dg >> 2);
-                    const float zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                      const int d = dg + u;
-                      if (d >= SD) break;
-                      const int i = d * LDA + cx.row;
-                      const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
-                      const float xn = __fadd_rn(xm, __fmul_rn(g, __fmul_rn(zz[u], sq)));
-                      Y0[i] = xm;
-                      y[i] = xn;
-                      saw_nan |= (xn != xn);
-                    }
+                  for (int u = 0; u < 8; ++u) zz[u] = nz[min(d0 + u, SD - 1)];
+                } else {
+                  const float4 za = philox_normal4(a.philox_seed, a.philox_offset, a.row_offset + row0 + cx.row, step, d0 >> 2);
+                  zz[0] = za.x; zz[1] = za.y; zz[2] = za.z; zz[3] = za.w;
+                  if (d0 + 4 < SD) {
+                    const float4 zb = philox_normal4(a.philox_seed, a.philox_offset, a.row_offset + row0 + cx.row, step, (d0 >> 2) + 1);
+                    zz[4] = zb.x; zz[5] = zb.y; zz[6] = zb.z; zz[7] = zb.w;
+                  } else {
+                    zz[4] = zz[5] = zz[6] = zz[7] = 0.0f;
                   }
                 }
-              }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  xm[u] = __fadd_rn(yv[u], __fmul_rn(k1[u], dt));
+                  yv[u] = __fadd_rn(xm[u], __fmul_rn(g, __fmul_rn(zz[u], sq)));
+                  if (d0 + u < SD) saw_nan |= (yv[u] != yv[u]);
+                }
+                rr_store8(cx, Y0, d0, xm);
+                rr_store8(cx, y, d0, yv);
+              });
             }
             break;
           }
