@@ -49,6 +49,14 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
                : "r"(addr));
 }
 
+// Ring-stage release: a tcgen05.commit costs the tensor pipe 60-190 cycles (csrc/tc_rate.cu), so only the
+// stages of the first RR_EARLY chunks of a layer are released by a commit as soon as their MMAs retire (the
+// next layer's first weight chunks are then prefetched while this layer still runs); the stages of the
+// remaining chunks are released by compute thread 0 when it sees the layer's d_ready.
+#ifndef RR_EARLY
+#define RR_EARLY 0
+#endif
+
 // Debug timeline (compiled in with -DFFB_TRACE only): CTA 0 records clock64() at hand-off points, one
 // private region per role (0: compute warp 0, 1: MMA warp, 2: compute warp 15), no atomics.
 #ifdef FFB_TRACE
@@ -80,6 +88,7 @@ struct CtxR {
   uint32_t tmem, lane_addr;
   int stage; uint32_t phase;       // ring position: loader / MMA warp (with phase); compute warps (stage of the next chunk they hand over)
   uint32_t ph_d, dbuf;             // d_ready parity (compute warps), accumulator buffer of the current layer
+  int rstage;                      // compute warps: ring stage of the first chunk of the layer whose d_ready is awaited next
 };
 
 __device__ __forceinline__ void rr_trace(CtxR& cx, int tag) {
@@ -136,7 +145,7 @@ struct EngineRR {
     cx.scr = scratch + (size_t)blockIdx.x * NSLOT * f.state_dim * LDA;
     cx.stage = 0;
     cx.phase = (cx.warp == RR_WLOAD) ? 1u : 0u;     // the loader starts with every stage free
-    cx.ph_d = 0; cx.dbuf = 0;
+    cx.ph_d = 0; cx.dbuf = 0; cx.rstage = 0;
     cx.tr_n = 0;
     cx.tr_role = (blockIdx.x != 0 || cx.lane != 0) ? -1 : (cx.warp == 0 ? 0 : (cx.warp == RR_WMMA ? 1 : (cx.warp == RR_NCOMP / 32 - 1 ? 2 : -1)));
     if (threadIdx.x == 0) {
@@ -248,7 +257,7 @@ struct EngineRR {
         if (elect_one()) {
           if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
           else issue_chunk<0>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
-          tc_commit(ebar);                                      // frees the ring stage when these MMAs retire
+          if (ci < RR_EARLY) tc_commit(ebar);                   // frees the ring stage when these MMAs retire
           if (lastc) tc_commit(cx.d_ready());                   // the accumulator of this layer is complete
         }
         __syncwarp();
@@ -269,10 +278,16 @@ struct EngineRR {
     if (cx.lane == 0) mbar_arrive(&cx.full()[cx.stage]);
     if (++cx.stage == TC_NSTAGE) cx.stage = 0;
   }
-  static __device__ __forceinline__ void wait_d_ready(CtxR& cx) {
+  // K = rows of the layer whose accumulator is awaited; its late ring stages are released here
+  static __device__ __forceinline__ void wait_d_ready(CtxR& cx, int K) {
     mbar_wait(cx.d_ready(), cx.ph_d);
     cx.ph_d ^= 1u;
     tc_fence_after();
+    int ci = 0;
+    for (int k0 = 0; k0 < K; k0 += KC, ++ci) {
+      if (ci >= RR_EARLY && cx.tid == 0) mbar_arrive(&cx.empty()[cx.rstage]);
+      if (++cx.rstage == TC_NSTAGE) cx.rstage = 0;
+    }
   }
 
   // layer-0 operand of call c from cx.ycur() / cx.condb(): this thread's row, its 8 columns per chunk.
@@ -326,7 +341,7 @@ struct EngineRR {
       const float* bias = (l == 0) ? beff : cx.sbias() + (c * FFB_MAX_LAYERS + l) * KMAX;
       const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
       cx.dbuf ^= 1u;
-      wait_d_ready(cx);
+      wait_d_ready(cx, net.K[l]);
       RR_TRACE(cx, 200 + 10 * l);
       uint32_t m[2][8];
       tc_ld8(dcol, m[0]);
@@ -362,7 +377,7 @@ struct EngineRR {
     const float* bias = (nl == 1) ? beff : cx.sbias() + (c * FFB_MAX_LAYERS + nl - 1) * KMAX;
     const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
     cx.dbuf ^= 1u;
-    wait_d_ready(cx);
+    wait_d_ready(cx, net.K[nl - 1]);
     RR_TRACE(cx, 290);
     for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += KC) {              // warp-uniform trip count
       uint32_t m[8];
