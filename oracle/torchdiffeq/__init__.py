@@ -9,7 +9,7 @@ downloaded, so this module restates its *published algorithm* (adaptive Dormand-
 dense-output interpolant, and the fixed-grid Euler / midpoint / 3-8-rule RK4 drivers) from
 the upstream documentation and behaviour.  PARITY UNPINNED: upstream's own tests cannot be
 run against it here; it is pinned instead by (i) scipy's independent RK45 (same tableau),
-(ii) closed-form ODE solutions and (iii) the property tests in ``tests/test_oracle_shim.py``.
+(ii) closed-form ODE solutions and (iii) the property tests in ``tests/test_oracle.py``.
 
 Only ``tests/``, ``__graft_entry__.smoke()``, ``oracle/make_golden.py`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this package.  The
