@@ -338,8 +338,15 @@ def main():
         achieved = flop_per_launch / (k_ms / n_l * 1e-3) / 1e12
         ffma_peak = engine.ffma_peak_tflops()
         tensor_fp32_equiv = peaks["bf16_tflops"] / 6.0
+        # DRAM bytes of the dominant kernel from the committed ncu --set full capture, scaled to this launch's rows
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath):
+            t = json.load(open(tpath)).get(name)
+            if t and t["kernel"].startswith({"dopri5_attempt": "k_dopri5", "integrate_fixed": "k_fixed", "field_eval": "k_field_eval"}[kname]):
+                traffic = t["dram_bytes_per_launch"] / t["rows"] * (k_rows / n_l)
         roof = {"bound": "tensor", "achieved": achieved, "peak": tensor_fp32_equiv, "unit": "TFLOP/s",
-                "frac": achieved / tensor_fp32_equiv, "traffic": None,
+                "frac": achieved / tensor_fp32_equiv, "traffic": traffic,
                 "kernel": kname, "launches": n_l, "avg_launch_ms": k_ms / n_l, "share_of_step": k_ms / ms,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}) / 6 = 3xTF32 FP32-equivalent tensor peak",
                 "fp32_ffma2_peak_measured": ffma_peak, "frac_of_ffma2_peak": achieved / ffma_peak,

@@ -887,6 +887,11 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
   if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (use_rr(fd)) {
+    const size_t smem = rr_pick_smem(&fd, 3, 1);
+    if (fd.slots_smem) return launch_rr(k_field_eval_rr<true>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
+    return launch_rr(k_field_eval_rr<false>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
+  }
   if (engine()) {
     if (fd.slots_smem) return launch_tiles(k_field_eval<EngineTC, true>, EngineTC::NTHR, "ffb_field_eval", f, fd, *a, a->batch, st_);
     return launch_tiles(k_field_eval<EngineTC, false>, EngineTC::NTHR, "ffb_field_eval", f, fd, *a, a->batch, st_);

@@ -64,6 +64,85 @@ __host__ __device__ inline int rr_fixed_slots(int method) {
 }  // namespace ffb
 
 // =============================================================================================
+// k_field_eval_rr: one evaluation (+ the norms of torchdiffeq's initial-step heuristic)
+// =============================================================================================
+template <bool SS>
+__global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rr(const __grid_constant__ ffb::FieldDev f,
+        const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
+  using namespace ffb;
+  CtxR cx;
+  EngineRR::init(cx, f, reinterpret_cast<float*>(a.scratch), 3, 1);
+  const int SD = cx.SD, CD = cx.CD;
+  if (!cx.producer) {
+    EngineRR::prep_beff(cx, f, a.ev.tfeat, cx.beff());
+    rr_bar();
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TM;
+    const int nv = (int)min((int64_t)TM, a.batch - row0);
+    float* F = rr_slot<SS>(cx, 0);
+    float* Y0 = rr_slot<SS>(cx, 1);
+    float* FB = rr_slot<SS>(cx, 2);
+    if (!cx.producer) {
+      load_rows_t<RR_NCOMP>(Y0, a.y, row0, nv, TM, SD, cx.tid);
+      if (a.fbase) load_rows_t<RR_NCOMP>(FB, a.fbase, row0, nv, TM, SD, cx.tid);
+      if (CD) load_rows_t<RR_NCOMP>(cx.condb(), a.cond, row0, nv, TM, CD, cx.tid);
+      rr_bar();
+      rr_for_blocks(cx, [&](int d0) {
+        float y0v[8], fb[8];
+        rr_load8(cx, Y0, d0, y0v);
+        rr_load8_if(cx, a.fbase != nullptr, FB, d0, fb);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) y0v[u] = a.fbase ? __fadd_rn(y0v[u], __fmul_rn(a.h, fb[u])) : y0v[u];
+        rr_store8(cx, cx.ycur(), d0, y0v);
+      });
+    }
+    EngineRR::eval<SS>(cx, f, a.ev.a, a.ev.c, a.ev.sigma, a.ev.sign, cx.beff(), 0);
+    if (!cx.producer) {
+      double v[6] = {0, 0, 0, 0, 0, 0};   // x_y, x_f, x_df, lp_f, lp_df, c_y
+      if (a.norms && cx.row < nv) {
+        rr_for_blocks(cx, [&](int d0) {
+          float y0v[8], fv[8], fb[8];
+          rr_load8(cx, Y0, d0, y0v);
+          rr_load8(cx, F, d0, fv);
+          rr_load8_if(cx, a.norms == 2, FB, d0, fb);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (d0 + u >= SD) continue;
+            const float sc = __fadd_rn(a.atol, __fmul_rn(fabsf(y0v[u]), a.rtol));
+            if (a.norms == 1) {
+              const float q0 = __fdiv_rn(y0v[u], sc), q1 = __fdiv_rn(fv[u], sc);
+              v[0] += (double)q0 * q0;
+              v[1] += (double)q1 * q1;
+            } else {
+              const float q2 = __fdiv_rn(__fsub_rn(fv[u], fb[u]), sc);
+              v[2] += (double)q2 * q2;
+            }
+          }
+        });
+      }
+      rr_bar();                                            // slot 0 complete for every row
+      if (a.f) store_rows_t<RR_NCOMP>(a.f, F, row0, nv, SD, cx.tid);
+      if (a.norms) {
+        if (a.cond_in_state && a.norms == 1) {
+          const float* cs = a.cond_state ? a.cond_state : a.cond;
+          for (int idx = cx.tid; idx < CD * nv; idx += RR_NCOMP) {
+            const float c = cs[row0 * CD + idx];
+            const float q = __fdiv_rn(c, __fadd_rn(a.atol, __fmul_rn(fabsf(c), a.rtol)));
+            v[5] += (double)q * q;
+          }
+        }
+        const int slot[6] = {P_X_Y, P_X_F, P_X_DF, P_LP_F, P_LP_DF, P_C_Y};
+        rr_block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
+      } else {
+        rr_bar();
+      }
+    }
+  }
+  EngineRR::fini(cx);
+}
+
+// =============================================================================================
 // k_dopri5_rr
 // =============================================================================================
 template <bool SS>
