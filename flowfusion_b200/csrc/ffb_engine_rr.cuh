@@ -132,8 +132,12 @@ struct EngineRR {
 
   static __device__ __forceinline__ void init(CtxR& cx, const FieldDev& f, float* scratch, int nslot, int nbeff) {
     size_t off[12];
+    smem_layout_rr(f.state_dim, f.cond_dim, f.slots_smem ? nslot : 0, f.n_calls, field_tdim(f), nbeff, off);
+    init_at(cx, f, scratch, off);
+  }
+  // off[0..8]: ring, ycur, cond, biases, beff, time rows, reduction scratch, barriers, slots
+  static __device__ __forceinline__ void init_at(CtxR& cx, const FieldDev& f, float* scratch, const size_t* off) {
     cx.tdim = field_tdim(f);
-    smem_layout_rr(f.state_dim, f.cond_dim, f.slots_smem ? nslot : 0, f.n_calls, cx.tdim, nbeff, off);
     cx.o_ring = (uint32_t)off[0]; cx.o_ycur = (uint32_t)off[1]; cx.o_cond = (uint32_t)off[2];
     cx.o_sbias = (uint32_t)off[3]; cx.o_beff = (uint32_t)off[4]; cx.o_wt = (uint32_t)off[5];
     cx.o_red = (uint32_t)off[6]; cx.o_bar = (uint32_t)off[7]; cx.o_slots = (uint32_t)off[8];

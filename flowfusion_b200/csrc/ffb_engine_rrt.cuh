@@ -1,0 +1,513 @@
+// ffb_engine_rrt.cuh -- the chunk-pipelined tensor-core engine (ffb_engine_rr.cuh) with forward-mode
+// TANGENT rows: the divergence trace of the log-likelihood paths (flow.py:122-166, 598-652;
+// diffusion.py:483-503 exact, :327-334 Hutchinson) as extra rows of the same 128-row tile.
+//
+// Row layout.  A trajectory ("sample") owns 1 primal row P and T tangent rows (T = D for the exact
+// trace: tangent j carries d(activation)/dx_j; T = 1 for Hutchinson: the tangent along the probe).
+// The hidden-layer epilogue of a tangent row needs silu'(z) of its primal row.  Rows are TMEM lanes and a
+// warp can only read the 32 lanes of its quarter, so samples are packed back to back and whenever a
+// sample's tangents continue into the next lane quarter a DUPLICATE primal row P' is inserted at the
+// start of that quarter.  Every quarter is then self-contained: the primal's z reaches its tangents with
+// one warp shuffle per column -- no shared-memory gate buffer and no barrier inside a layer.
+//   D = 16: 7 samples use 122 of the 128 rows (2 duplicates); T = 1: 64 (P, T) pairs.
+//
+// All lanes evaluate sigmoid(z_primal) themselves (uniform code, the SFU cost of a warp instruction does
+// not depend on the active lanes):  primal rows  a = z sg;  tangent rows  a = D * sg (1 + z (1 - sg)).
+//
+// State (y, k_1..k_7, log-det) is per SAMPLE: shared-memory buffers [d][ld], ld = samples per tile
+// rounded up to 4.  The primal OWNER row of a sample does the stage algebra for the state columns its
+// column group owns; two CTA barriers per evaluation order it against the operand build of the duplicates.
+#pragma once
+#include "ffb_kernels_rr.cuh"
+
+namespace ffb {
+
+enum { RT_IDLE = 0, RT_OWNER = 1, RT_DUP = 2, RT_TAN = 3 };
+struct RowMap { int kind, smp, tj, plane; };
+
+// Place samples of (1 + T) rows into 4 quarters of 32 lanes; returns the samples per tile and, for `row`,
+// what that row is.  Deterministic and shared by host (tile count) and device (per-thread role).
+__host__ __device__ inline int rrt_rowmap(int T, int row, RowMap* out) {
+  int r = 0, S = 0;
+  if (out) { out->kind = RT_IDLE; out->smp = 0; out->tj = -1; out->plane = row & 31; }
+  for (;;) {
+    int rr = r + 1;
+    for (int j = 0; j < T; ++j) { if ((rr & 31) == 0) ++rr; ++rr; }
+    if (rr > TM) break;
+    int plane = r & 31;
+    if (out && r == row) { out->kind = RT_OWNER; out->smp = S; out->tj = -1; out->plane = plane; }
+    ++r;
+    for (int j = 0; j < T; ++j) {
+      if ((r & 31) == 0) {
+        plane = 0;
+        if (out && r == row) { out->kind = RT_DUP; out->smp = S; out->tj = -1; out->plane = 0; }
+        ++r;
+      }
+      if (out && r == row) { out->kind = RT_TAN; out->smp = S; out->tj = j; out->plane = plane; }
+      ++r;
+    }
+    ++S;
+  }
+  return S;
+}
+__host__ __device__ inline int rrt_ld(int S) { return ((S + 3) & ~3) < 4 ? 4 : ((S + 3) & ~3); }
+
+struct TanCtx {
+  int kind, smp, tj, plane;     // this thread's row
+  int S, T, ld;                 // samples per tile, tangents per sample, sample stride of the state buffers
+  bool exact;
+  uint32_t o_klp, o_diag, o_prb;
+  __device__ __forceinline__ float* klp() const { return reinterpret_cast<float*>(smem_base() + o_klp); }
+  __device__ __forceinline__ float* diag() const { return reinterpret_cast<float*>(smem_base() + o_diag); }
+  __device__ __forceinline__ float* prb() const { return reinterpret_cast<float*>(smem_base() + o_prb); }
+  __device__ __forceinline__ bool primal() const { return kind == RT_OWNER || kind == RT_DUP; }
+};
+
+constexpr int RRT_KLP_ROWS = NSLOT + 3;     // d(logp)/dt per slot, lp0, spare
+constexpr int RRT_DIAG_FLOATS = 1024;       // exact: S*T <= 128 diagonal entries; Hutchinson: 16 partials per sample
+
+__host__ __device__ inline size_t smem_layout_rrt(int SD, int CD, int ld, int hutch, int nslot, int tdim, int nbeff,
+                                                  size_t* off /*[12]*/) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~size_t(127); return r; };
+  size_t v[12];
+  v[0] = take(sizeof(float) * TC_NSTAGE * TC_STAGE_FLOATS);
+  v[1] = take(sizeof(float) * SD * ld);                            // ycur [d][sample]
+  v[2] = take(sizeof(float) * (CD > 0 ? CD : 1) * ld);             // cond
+  v[3] = take(sizeof(float) * FFB_MAX_LAYERS * KMAX);              // biases
+  v[4] = take(sizeof(float) * nbeff * KMAX);                       // layer-0 bias + time features per evaluation
+  v[5] = take(sizeof(float) * (tdim > 0 ? tdim : 1) * KMAX);       // time-feature rows
+  v[6] = take(sizeof(double) * (RR_NCOMP / 32) * FFB_NPART);
+  v[7] = take(sizeof(uint64_t) * (2 * TC_NSTAGE + 4));
+  v[8] = take(sizeof(float) * (size_t)nslot * SD * ld);            // state slots [slot][d][sample]
+  v[9] = take(sizeof(float) * RRT_KLP_ROWS * ld);
+  v[10] = take(sizeof(float) * RRT_DIAG_FLOATS);
+  v[11] = take(hutch ? sizeof(float) * SD * ld : 0);               // probes [d][sample]
+  if (off) for (int i = 0; i < 12; ++i) off[i] = v[i];
+  return o;
+}
+
+struct EngineRRT {
+  static __device__ __forceinline__ void init(CtxR& cx, TanCtx& tc, const FieldDev& f, int nslot, int nbeff) {
+    tc.exact = (f.div_mode == FFB_DIV_EXACT);
+    tc.T = tc.exact ? f.net[0].x_dim : 1;
+    RowMap m;
+    const int row = ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31);
+    tc.S = rrt_rowmap(tc.T, row, &m);
+    tc.kind = m.kind; tc.smp = m.smp; tc.tj = m.tj; tc.plane = m.plane;
+    tc.ld = rrt_ld(tc.S);
+    size_t off[12];
+    smem_layout_rrt(f.state_dim, f.cond_dim, tc.ld, !tc.exact, nslot, field_tdim(f), nbeff, off);
+    tc.o_klp = (uint32_t)off[9]; tc.o_diag = (uint32_t)off[10]; tc.o_prb = (uint32_t)off[11];
+    EngineRR::init_at(cx, f, nullptr, off);
+  }
+  static __device__ __forceinline__ float* slot(const CtxR& cx, const TanCtx& tc, int s) {
+    return reinterpret_cast<float*>(smem_base() + cx.o_slots) + (size_t)s * cx.SD * tc.ld;
+  }
+
+  // layer-0 operand: primal rows x | cond, tangent rows e_j (exact) or the probe (Hutchinson)
+  static __device__ __forceinline__ void build_A(CtxR& cx, const TanCtx& tc, const FieldDev& f) {
+    const NetDev& net = f.net[0];
+    const int K0 = net.K[0], xd = net.x_dim, cd = net.c_dim, ld = tc.ld, s = tc.smp;
+    const bool prim = tc.primal(), tan = (tc.kind == RT_TAN);
+    const float* yc = cx.ycur() + s;
+    const float* cb = cx.condb() + s;
+    const float* pb = tc.prb() + s;
+    for (int k0 = 0; k0 < K0; k0 += KC) {
+      const int k8 = k0 + 8 * cx.cg;
+      if (k8 < K0) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k8 + j;
+          float val = 0.0f;
+          if (prim) {
+            if (k < xd) val = yc[k * ld];
+            else if (k < xd + cd) val = cb[(k - xd) * ld];
+          } else if (tan && k < xd) {
+            val = tc.exact ? (k == tc.tj ? 1.0f : 0.0f) : pb[k * ld];
+          }
+          tf32_split(val, hi[j], lo[j]);
+        }
+        tc_st8(cx.lane_addr + RR_COL_AHI + k8, hi);
+        tc_st8(cx.lane_addr + RR_COL_ALO + k8, lo);
+      }
+      EngineRR::signal_chunk(cx);
+    }
+  }
+
+  static __device__ __forceinline__ void hidden(CtxR& cx, const TanCtx& tc, const NetDev& net, const float* beff) {
+    const bool prim = tc.primal(), tan = (tc.kind == RT_TAN);
+    for (int l = 0; l + 1 < net.n_layers; ++l) {
+      const int nc = net.Np[l] / KC;
+      const float* bias = (l == 0) ? beff : cx.sbias() + l * KMAX;
+      const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
+      cx.dbuf ^= 1u;
+      EngineRR::wait_d_ready(cx, net.K[l]);
+      uint32_t m[2][8];
+      tc_ld8(dcol, m[0]);
+#pragma unroll
+      for (int ci = 0; ci < RR_NCHUNK; ++ci) {
+        if (ci < nc) {
+          const int c0 = KC * ci + 8 * cx.cg;
+          tc_wait_ld();
+          if (ci + 1 < nc) tc_ld8(dcol + KC * (ci + 1), m[(ci + 1) & 1]);
+          const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float d = __uint_as_float(m[ci & 1][u]);
+            const float z = __shfl_sync(0xffffffffu, d + bb[u], tc.plane);      // z of this row's primal
+            const float sg = sigmoidf_fast(z);
+            const float a = prim ? z * sg : (tan ? d * (sg * (1.0f + z * (1.0f - sg))) : 0.0f);
+            tf32_split(a, hi[u], lo[u]);
+          }
+          tc_st8(cx.lane_addr + RR_COL_AHI + c0, hi);
+          tc_st8(cx.lane_addr + RR_COL_ALO + c0, lo);
+          EngineRR::signal_chunk(cx);
+        }
+      }
+    }
+  }
+
+  // one evaluation at cx.ycur(): derivative -> slot dst, divergence -> klp[dst]
+  static __device__ __forceinline__ void eval(CtxR& cx, const TanCtx& tc, const FieldDev& f, float ev_a, float ev_c,
+                                              float ev_sigma, float ev_sign, const float* beff, int dst) {
+    const NetDev& net = f.net[0];
+    if (cx.warp == RR_WLOAD) { EngineRR::load_net(cx, net); return; }
+    if (cx.warp == RR_WMMA) { EngineRR::mma_net(cx, net); return; }
+    const int ld = tc.ld, s = tc.smp, xd = net.x_dim;
+    rr_bar();                                  // cx.ycur() is final for every sample of the tile
+    build_A(cx, tc, f);
+    hidden(cx, tc, net, beff);
+    // ---- last layer ---------------------------------------------------------------------------------
+    const int nl = net.n_layers, Nreal = net.N[nl - 1];
+    const float* bias = (nl == 1) ? beff : cx.sbias() + (nl - 1) * KMAX;
+    const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
+    cx.dbuf ^= 1u;
+    EngineRR::wait_d_ready(cx, net.K[nl - 1]);
+    float* kd = slot(cx, tc, dst) + s;
+    const float* yc = cx.ycur() + s;
+    const bool score = (f.kind == FFB_FIELD_SCORE), use_sigma = f.use_sigma != 0, has_drift = f.has_drift != 0;
+    for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += KC) {
+      uint32_t m[8];
+      tc_ld8(dcol + (uint32_t)(c0 - 8 * cx.cg), m);
+      tc_wait_ld();
+      if (tc.kind == RT_OWNER) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int n = c0 + u;
+          if (n < Nreal) {
+            const float o = __uint_as_float(m[u]) + bias[n];
+            float xd_;
+            if (score) {
+              const float sc = use_sigma ? __fdiv_rn(o, ev_sigma) : o;
+              const float lin = has_drift ? __fmul_rn(ev_a, yc[n * ld]) : 0.0f;
+              xd_ = __fsub_rn(lin, __fmul_rn(ev_c, sc));
+            } else {
+              xd_ = o;
+            }
+            kd[n * ld] = xd_ * ev_sign;
+          }
+        }
+      } else if (tc.kind == RT_TAN) {
+        if (tc.exact) {
+          float v = 0.0f;
+          bool mine = false;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (c0 + u == tc.tj) { v = __uint_as_float(m[u]); mine = true; }
+          if (mine) tc.diag()[s * tc.T + tc.tj] = v;                      // d f_j / d x_j
+        } else {
+          float part = 0.0f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (c0 + u < xd) part = fmaf(tc.prb()[(c0 + u) * ld + s], __uint_as_float(m[u]), part);
+          tc.diag()[s * 16 + (c0 >> 3)] = part;                          // e^T J e, 8 columns at a time
+        }
+      }
+    }
+    tc_fence_before();
+    rr_bar();                                  // slot dst and the trace pieces are complete
+    if (tc.kind == RT_OWNER && cx.cg == 0) {
+      float tr = 0.0f;
+      if (tc.exact) { for (int j = 0; j < tc.T; ++j) tr += tc.diag()[s * tc.T + j]; }
+      else { for (int g = 0; 8 * g < xd; ++g) tr += tc.diag()[s * 16 + g]; }
+      float dv;
+      if (score) {
+        const float trs = use_sigma ? __fdiv_rn(tr, ev_sigma) : tr;
+        const float lin = has_drift ? ev_a * (float)xd : 0.0f;
+        dv = lin - ev_c * trs;
+      } else {
+        dv = tr;
+      }
+      tc.klp()[dst * ld + s] = dv * ev_sign;
+    }
+  }
+};
+
+// ---- per-sample state helpers (the owner row's thread, 8 state columns at a time) -----------------------
+__device__ __forceinline__ void rt_load8(const CtxR& cx, const TanCtx& tc, const float* buf, int d0, float (&v)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = buf[min(d0 + u, cx.SD - 1) * tc.ld + tc.smp];
+}
+__device__ __forceinline__ void rt_load8_if(const CtxR& cx, const TanCtx& tc, bool on, const float* buf, int d0, float (&v)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = on ? buf[min(d0 + u, cx.SD - 1) * tc.ld + tc.smp] : 0.0f;
+}
+__device__ __forceinline__ void rt_store8(const CtxR& cx, const TanCtx& tc, float* buf, int d0, const float (&v)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (d0 + u < cx.SD) buf[(d0 + u) * tc.ld + tc.smp] = v[u];
+}
+// [d][sample] tile buffer <- row-major global rows [row0, row0 + nv); samples nv..S-1 are zero filled
+__device__ __forceinline__ void rt_load_rows(float* dst, const float* __restrict__ src, int64_t row0, int nv, int S, int ld,
+                                             int D, int tid) {
+  const float* __restrict__ base = src + row0 * D;
+  for (int idx = tid; idx < S * D; idx += RR_NCOMP) {
+    const int r = fast_div(idx, D), d = idx - r * D;
+    dst[d * ld + r] = (r < nv) ? base[idx] : 0.0f;
+  }
+}
+__device__ __forceinline__ void rt_store_rows(float* __restrict__ dst, const float* src, int64_t row0, int nv, int ld, int D,
+                                              int tid) {
+  float* __restrict__ base = dst + row0 * D;
+  for (int idx = tid; idx < nv * D; idx += RR_NCOMP) {
+    const int r = fast_div(idx, D), d = idx - r * D;
+    base[idx] = src[d * ld + r];
+  }
+}
+
+}  // namespace ffb
+
+// =============================================================================================
+// k_field_eval_rrt: one evaluation with the divergence (+ torchdiffeq's initial-step norms)
+// =============================================================================================
+__global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rrt(const __grid_constant__ ffb::FieldDev f,
+        const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
+  using namespace ffb;
+  CtxR cx; TanCtx tc;
+  EngineRRT::init(cx, tc, f, 3, 1);
+  const int SD = cx.SD, CD = cx.CD, S = tc.S, ld = tc.ld;
+  const bool owner = (tc.kind == RT_OWNER);
+  if (!cx.producer) {
+    EngineRR::prep_beff(cx, f, a.ev.tfeat, cx.beff());
+    rr_bar();
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * S;
+    const int nv = (int)min((int64_t)S, a.batch - row0);
+    float* F = EngineRRT::slot(cx, tc, 0);
+    float* Y0 = EngineRRT::slot(cx, tc, 1);
+    float* FB = EngineRRT::slot(cx, tc, 2);
+    if (!cx.producer) {
+      rt_load_rows(Y0, a.y, row0, nv, S, ld, SD, cx.tid);
+      if (a.fbase) rt_load_rows(FB, a.fbase, row0, nv, S, ld, SD, cx.tid);
+      if (CD) rt_load_rows(cx.condb(), a.cond, row0, nv, S, ld, CD, cx.tid);
+      if (!tc.exact) rt_load_rows(tc.prb(), a.probes, row0, nv, S, ld, SD, cx.tid);
+      rr_bar();
+      if (owner) {
+        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+          float y0v[8], fb[8];
+          rt_load8(cx, tc, Y0, d0, y0v);
+          rt_load8_if(cx, tc, a.fbase != nullptr, FB, d0, fb);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) y0v[u] = a.fbase ? __fadd_rn(y0v[u], __fmul_rn(a.h, fb[u])) : y0v[u];
+          rt_store8(cx, tc, cx.ycur(), d0, y0v);
+        }
+      }
+    }
+    EngineRRT::eval(cx, tc, f, a.ev.a, a.ev.c, a.ev.sigma, a.ev.sign, cx.beff(), 0);
+    if (!cx.producer) {
+      rr_bar();                                           // klp[0] of every sample is written
+      double v[6] = {0, 0, 0, 0, 0, 0};   // x_y, x_f, x_df, lp_f, lp_df, c_y
+      if (a.norms && owner && tc.smp < nv) {
+        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+          float y0v[8], fv[8], fb[8];
+          rt_load8(cx, tc, Y0, d0, y0v);
+          rt_load8(cx, tc, F, d0, fv);
+          rt_load8_if(cx, tc, a.norms == 2, FB, d0, fb);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (d0 + u >= SD) continue;
+            const float sc = __fadd_rn(a.atol, __fmul_rn(fabsf(y0v[u]), a.rtol));
+            if (a.norms == 1) {
+              const float q0 = __fdiv_rn(y0v[u], sc), q1 = __fdiv_rn(fv[u], sc);
+              v[0] += (double)q0 * q0;
+              v[1] += (double)q1 * q1;
+            } else {
+              const float q2 = __fdiv_rn(__fsub_rn(fv[u], fb[u]), sc);
+              v[2] += (double)q2 * q2;
+            }
+          }
+        }
+        if (cx.cg == 0) {
+          const float dl = tc.klp()[tc.smp];
+          if (a.norms == 1) {
+            const float q = __fdiv_rn(dl, a.atol);
+            v[3] += (double)q * q;
+          } else {
+            const float q = __fdiv_rn(__fsub_rn(dl, a.dlpbase[row0 + tc.smp]), a.atol);
+            v[4] += (double)q * q;
+          }
+        }
+      }
+      if (a.f) rt_store_rows(a.f, F, row0, nv, ld, SD, cx.tid);
+      if (a.dlp)
+        for (int s = cx.tid; s < nv; s += RR_NCOMP) a.dlp[row0 + s] = tc.klp()[s];
+      if (a.norms) {
+        if (a.cond_in_state && a.norms == 1) {
+          const float* cs = a.cond_state ? a.cond_state : a.cond;
+          for (int idx = cx.tid; idx < CD * nv; idx += RR_NCOMP) {
+            const float c = cs[row0 * CD + idx];
+            const float q = __fdiv_rn(c, __fadd_rn(a.atol, __fmul_rn(fabsf(c), a.rtol)));
+            v[5] += (double)q * q;
+          }
+        }
+        const int slot[6] = {P_X_Y, P_X_F, P_X_DF, P_LP_F, P_LP_DF, P_C_Y};
+        rr_block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
+      } else {
+        rr_bar();
+      }
+    }
+  }
+  EngineRR::fini(cx);
+}
+
+// =============================================================================================
+// k_dopri5_rrt: one attempted Dormand-Prince step of (x, log-det)
+// =============================================================================================
+__global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_constant__ ffb::FieldDev f,
+        const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
+  using namespace ffb;
+  CtxR cx; TanCtx tc;
+  EngineRRT::init(cx, tc, f, NSLOT, 6);
+  const int SD = cx.SD, CD = cx.CD, S = tc.S, ld = tc.ld;
+  const bool owner = (tc.kind == RT_OWNER);
+  float* LP0 = tc.klp() + NSLOT * ld;
+  if (!cx.producer) {
+    for (int s = 0; s < 6; ++s) EngineRR::prep_beff(cx, f, a.ev[s].tfeat, cx.beff() + s * KMAX);
+    rr_bar();
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * S;
+    const int nv = (int)min((int64_t)S, a.batch - row0);
+    float* Y0 = EngineRRT::slot(cx, tc, SLOT_Y0);
+    double nonfinite = 0.0;
+    if (!cx.producer) {
+      rt_load_rows(Y0, a.y0, row0, nv, S, ld, SD, cx.tid);
+      rt_load_rows(EngineRRT::slot(cx, tc, 0), a.f0, row0, nv, S, ld, SD, cx.tid);
+      if (CD) rt_load_rows(cx.condb(), a.cond, row0, nv, S, ld, CD, cx.tid);
+      if (!tc.exact) rt_load_rows(tc.prb(), a.probes, row0, nv, S, ld, SD, cx.tid);
+      for (int s = cx.tid; s < S; s += RR_NCOMP) {
+        LP0[s] = (s < nv) ? a.lp0[row0 + s] : 0.0f;
+        tc.klp()[s] = (s < nv) ? a.dlp0[row0 + s] : 0.0f;
+        if (!is_finite_f(LP0[s])) nonfinite += 1.0;
+      }
+      rr_bar();
+      if (owner) {
+        const float c00 = a.cb[0][0];
+        const float* K1 = EngineRRT::slot(cx, tc, 0);
+        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+          float y0v[8], kv[8], y[8];
+          rt_load8(cx, tc, Y0, d0, y0v);
+          rt_load8(cx, tc, K1, d0, kv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (d0 + u < SD && !is_finite_f(y0v[u])) nonfinite += 1.0;
+            y[u] = __fadd_rn(y0v[u], __fmul_rn(kv[u], c00));
+          }
+          rt_store8(cx, tc, cx.ycur(), d0, y);
+        }
+      }
+    }
+    for (int i = 1; i <= 6; ++i) {
+      const ffb_eval_scalars& ev = a.ev[i - 1];
+      EngineRRT::eval(cx, tc, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * KMAX, i);
+      if (!cx.producer && owner && i < 6) {
+        float cbi[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) cbi[j] = a.cb[i][j];
+        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+          float y0v[8], kv[8], acc[8];
+          rt_load8(cx, tc, Y0, d0, y0v);
+          rt_load8(cx, tc, EngineRRT::slot(cx, tc, 0), d0, kv);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = __fmul_rn(kv[u], cbi[0]);
+#pragma unroll
+          for (int j = 1; j < 6; ++j) {
+            rt_load8_if(cx, tc, j <= i, EngineRRT::slot(cx, tc, j), d0, kv);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = fmaf(kv[u], cbi[j], acc[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = __fadd_rn(y0v[u], acc[u]);
+          rt_store8(cx, tc, cx.ycur(), d0, acc);
+        }
+      }
+    }
+    if (!cx.producer) {
+      rr_bar();                                            // klp[6] of every sample is written
+      double v[3] = {0.0, 0.0, nonfinite};
+      float* OUT = EngineRRT::slot(cx, tc, 1);              // K2 of an element is dead once its sums are formed
+      if (owner && tc.smp < nv) {
+        float ce[7], cm[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { ce[j] = a.ce[j]; cm[j] = a.cm[j]; }
+        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+          float y0v[8], y1v[8], k0[8], kv[8], err[8], mid[8];
+          rt_load8(cx, tc, Y0, d0, y0v);
+          rt_load8(cx, tc, cx.ycur(), d0, y1v);
+          rt_load8(cx, tc, EngineRRT::slot(cx, tc, 0), d0, k0);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { err[u] = __fmul_rn(k0[u], ce[0]); mid[u] = __fmul_rn(k0[u], cm[0]); }
+#pragma unroll
+          for (int j = 1; j < 7; ++j) {
+            rt_load8(cx, tc, EngineRRT::slot(cx, tc, j), d0, kv);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { err[u] = fmaf(kv[u], ce[j], err[u]); mid[u] = fmaf(kv[u], cm[j], mid[u]); }
+          }
+          float out[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0v[u]), fabsf(y1v[u]))));
+            const float q = __fdiv_rn(err[u], tol);
+            if (d0 + u < SD) v[0] += (double)q * q;
+            out[u] = a.final ? dense_output(y0v[u], y1v[u], __fadd_rn(y0v[u], mid[u]), k0[u], kv[u], a.dt, a.x_interp) : 0.0f;
+          }
+          if (a.final) rt_store8(cx, tc, OUT, d0, out);
+        }
+        if (cx.cg == 0) {
+          // the log-det column: same formulas on (lp0, d(logp)/dt of the 7 stages)
+          const int s = tc.smp;
+          const float* kl = tc.klp();
+          const float l0 = LP0[s];
+          float acc = __fmul_rn(kl[s], a.cb[5][0]);
+          for (int j = 1; j < 6; ++j) acc = fmaf(kl[j * ld + s], a.cb[5][j], acc);
+          const float l1 = __fadd_rn(l0, acc);
+          float err = __fmul_rn(kl[s], ce[0]);
+          for (int j = 1; j < 7; ++j) err = fmaf(kl[j * ld + s], ce[j], err);
+          const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(l0), fabsf(l1))));
+          const float q = __fdiv_rn(err, tol);
+          v[1] += (double)q * q;
+          a.lp1[row0 + s] = l1;
+          a.dlp1[row0 + s] = kl[6 * ld + s];
+          if (a.final) {
+            float mid = __fmul_rn(kl[s], cm[0]);
+            for (int j = 1; j < 7; ++j) mid = fmaf(kl[j * ld + s], cm[j], mid);
+            a.lp_out[row0 + s] = dense_output(l0, l1, __fadd_rn(l0, mid), kl[s], kl[6 * ld + s], a.dt, a.x_interp);
+          }
+        }
+      }
+      rr_bar();
+      rt_store_rows(a.y1, cx.ycur(), row0, nv, ld, SD, cx.tid);
+      rt_store_rows(a.f1, EngineRRT::slot(cx, tc, 6), row0, nv, ld, SD, cx.tid);
+      if (a.final) rt_store_rows(a.y_out, OUT, row0, nv, ld, SD, cx.tid);
+      const int slot[3] = {P_X_ERR, P_LP_ERR, P_NONFINITE};
+      rr_block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
+    }
+  }
+  EngineRR::fini(cx);
+}

@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
 }
 
 #include "ffb_kernels_rr.cuh"
+#include "ffb_engine_rrt.cuh"
 
 // =============================================================================================
 // helpers
@@ -808,10 +809,19 @@ static int make_field(const ffb_field* f, FieldDev* out) {
   return FFB_OK;
 }
 
+// samples per tile of the tangent-row engine (0: a sample does not fit one tile -> tile engine only)
+static int rrt_samples(const ffb_field* f) {
+  return f->div_mode == FFB_DIV_NONE ? 0 : rrt_rowmap(tangents_of(f), -1, nullptr);
+}
+// Tiles of `batch` rows: the caller sizes `partials` with this, so it is the maximum over the tile shapes
+// the field's kernels use (dense rows for the tile engine, quarter-packed samples for the tangent engine).
 extern "C" int64_t ffb_num_tiles(const ffb_field* f, int64_t batch) {
   if (!f || !f->net[0]) return -1;
   const int S = TM / (1 + tangents_of(f));
-  return (batch + S - 1) / S;
+  int64_t n = (batch + S - 1) / S;
+  const int St = rrt_samples(f);
+  if (St > 0) n = std::max<int64_t>(n, (batch + St - 1) / St);
+  return n;
 }
 
 static int num_sms() {
@@ -836,7 +846,8 @@ static int launch_tiles(Kern kern, int nthr, const char* name, const ffb_field* 
   if ((int)smem > optin)
     return fail(FFB_ERR_ARG, std::string(name) + ": tile needs " + std::to_string(smem) + " B of shared memory, device allows " + std::to_string(optin));
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t ntiles = ffb_num_tiles(f, batch);
+  const int Sd = TM / (1 + T);
+  const int64_t ntiles = (batch + Sd - 1) / Sd;
   if (ntiles <= 0) return FFB_OK;
   const int grid = (int)std::min<int64_t>(ntiles, num_sms());
   kern<<<grid, nthr, smem, stream>>>(fd, a, ntiles);
@@ -876,6 +887,30 @@ static int launch_rr(Kern kern, size_t smem, const char* name, const FieldDev& f
   return FFB_OK;
 }
 
+// ---- tangent-row engine (log-likelihood paths) ------------------------------------------------------------
+// returns 0 when the field cannot run on it (a sample does not fit a tile, or the tile does not fit shared memory)
+static size_t rrt_smem(const ffb_field* f, const FieldDev& fd, int nslot, int nbeff) {
+  if (engine() != 1 || fd.div_mode == FFB_DIV_NONE) return 0;
+  const int S = rrt_samples(f);
+  if (S <= 0) return 0;
+  const size_t smem = smem_layout_rrt(fd.state_dim, fd.cond_dim, rrt_ld(S), fd.div_mode == FFB_DIV_HUTCH, nslot, field_tdim(fd), nbeff, nullptr);
+  return smem <= (size_t)smem_optin() ? smem : 0;
+}
+template <typename Kern, typename Args>
+static int launch_rrt(Kern kern, size_t smem, const char* name, const ffb_field* f, const FieldDev& fd, const Args& a,
+                      int64_t batch, cudaStream_t stream) {
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int S = rrt_samples(f);
+  const int64_t ntiles = (batch + S - 1) / S;
+  if (ntiles <= 0) return FFB_OK;
+  const int grid = (int)std::min<int64_t>(ntiles, num_sms());
+  kern<<<grid, RR_NTHR, smem, stream>>>(fd, a, ntiles);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  (void)name;
+  return FFB_OK;
+}
+
 extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* stream) {
   FieldDev fd;
   int rc = make_field(f, &fd);
@@ -887,6 +922,7 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
   if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (const size_t smt = rrt_smem(f, fd, 3, 1)) return launch_rrt(k_field_eval_rrt, smt, "ffb_field_eval", f, fd, *a, a->batch, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, 3, 1);
     if (fd.slots_smem) return launch_rr(k_field_eval_rr<true>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
@@ -913,6 +949,7 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (const size_t smt = rrt_smem(f, fd, NSLOT, 6)) return launch_rrt(k_dopri5_rrt, smt, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, NSLOT, 6);
     if (fd.slots_smem) return launch_rr(k_dopri5_rr<true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);

@@ -74,9 +74,12 @@ class MLP(torch.nn.Module):
                                              t_dim=emb, device=dev))
         return self._packed[1]
 
-    def _time_features(self, t32: torch.Tensor) -> torch.Tensor:
-        """(n,) float32 CPU times -> (n, emb) features, op order of `diffusion.py:109-110`."""
-        proj = t32[:, None] * self.W.detach().cpu()[None, :] * 2 * self.pi.detach().cpu()
+    def _time_features(self, t32: torch.Tensor, W_cpu=None, pi_cpu=None) -> torch.Tensor:
+        """(n,) float32 CPU times -> (n, emb) features, op order of `diffusion.py:109-110`.
+        Solver loops pass host copies of W and pi (a device->host copy per call would stall the stream)."""
+        W = self.W.detach().cpu() if W_cpu is None else W_cpu
+        pi = self.pi.detach().cpu() if pi_cpu is None else pi_cpu
+        proj = t32[:, None] * W[None, :] * 2 * pi
         return torch.cat([torch.sin(proj), torch.cos(proj)], dim=1)
 
     def forward(self, t, x, conditional=None):
@@ -246,11 +249,12 @@ class ScoreModel(torch.nn.Module):
         (`diffusion.py:276-278` for the PF-ODE, `:552-553` for the reverse SDE)."""
         sde = copy.deepcopy(self.sde).cpu()
         model, emb = self.model, self.model.embedding_dimensions
+        W_cpu, pi_cpu = model.W.detach().cpu(), model.pi.detach().cpu()     # once per solve, not per step
 
         def program(times32: np.ndarray) -> np.ndarray:
             t = torch.from_numpy(np.ascontiguousarray(times32, np.float32))
             rows = np.zeros((t.shape[0], L.EV_FLOATS), np.float32)
-            rows[:, :emb] = model._time_features(t).numpy()
+            rows[:, :emb] = model._time_features(t, W_cpu, pi_cpu).numpy()
             g = sde._g(t)
             a = sde._drift_coeff(t)
             rows[:, L.MAX_TFEAT + 0] = 0.0 if a is None else a.numpy()
