@@ -56,6 +56,10 @@ struct TanCtx {
   int kind, smp, tj, plane;     // this thread's row
   int S, T, ld;                 // samples per tile, tangents per sample, sample stride of the state buffers
   bool exact;
+  // transposed activation path (<= 4 primal rows per lane quarter): lane i evaluates sigmoid for primal row i / 8 of
+  // the quarter, column i % 8 of the warp's 8 columns
+  bool use_tr;
+  int gsrc, my_u, pbase;        // lane of that primal row; i % 8; 8 * (index of THIS row's primal among the quarter's primal rows)
   uint32_t o_klp, o_diag, o_prb;
   __device__ __forceinline__ float* klp() const { return reinterpret_cast<float*>(smem_base() + o_klp); }
   __device__ __forceinline__ float* diag() const { return reinterpret_cast<float*>(smem_base() + o_diag); }
@@ -100,6 +104,33 @@ struct EngineRRT {
     smem_layout_rrt(f.state_dim, f.cond_dim, tc.ld, !tc.exact, nslot, field_tdim(f), nbeff, off);
     tc.o_klp = (uint32_t)off[9]; tc.o_diag = (uint32_t)off[10]; tc.o_prb = (uint32_t)off[11];
     EngineRR::init_at(cx, f, nullptr, off);
+    // which rows are primal rows -> shared memory (borrowing the trace buffer), then every thread reads its quarter
+    int* rk = reinterpret_cast<int*>(tc.diag());
+    if (threadIdx.x < TM) {
+      RowMap mm;
+      rrt_rowmap(tc.T, threadIdx.x, &mm);
+      rk[threadIdx.x] = (mm.kind == RT_OWNER || mm.kind == RT_DUP) ? 1 : 0;
+    }
+    __syncthreads();
+    const int q0 = ((threadIdx.x >> 5) & 3) * 32, lane = threadIdx.x & 31;
+    int ppos = 0, found = -1, cnt = 0, worst = 0;
+    for (int l = 0; l < 32; ++l) {
+      if (rk[q0 + l]) {
+        if (l < tc.plane) ++ppos;
+        if (cnt == (lane >> 3)) found = l;
+        ++cnt;
+      }
+    }
+    for (int qq = 0; qq < 4; ++qq) {
+      int c = 0;
+      for (int l = 0; l < 32; ++l) c += rk[qq * 32 + l];
+      worst = max(worst, c);
+    }
+    tc.use_tr = (worst <= 4);
+    tc.gsrc = (found >= 0) ? found : lane;
+    tc.my_u = lane & 7;
+    tc.pbase = 8 * min(ppos, 3);
+    __syncthreads();
   }
   static __device__ __forceinline__ float* slot(const CtxR& cx, const TanCtx& tc, int s) {
     return reinterpret_cast<float*>(smem_base() + cx.o_slots) + (size_t)s * cx.SD * tc.ld;
@@ -117,17 +148,20 @@ struct EngineRRT {
       const int k8 = k0 + 8 * cx.cg;
       if (k8 < K0) {
         uint32_t hi[8], lo[8];
+        float vx[8], vc[8], vp[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                        // unconditional loads (clamped), selects below
+          const int k = k8 + j;
+          vx[j] = yc[min(k, xd - 1) * ld];
+          vc[j] = (cd > 0) ? cb[min(max(k - xd, 0), cd - 1) * ld] : 0.0f;
+          vp[j] = tc.exact ? 0.0f : pb[min(k, xd - 1) * ld];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int k = k8 + j;
-          float val = 0.0f;
-          if (prim) {
-            if (k < xd) val = yc[k * ld];
-            else if (k < xd + cd) val = cb[(k - xd) * ld];
-          } else if (tan && k < xd) {
-            val = tc.exact ? (k == tc.tj ? 1.0f : 0.0f) : pb[k * ld];
-          }
-          tf32_split(val, hi[j], lo[j]);
+          const float pv = (k < xd) ? vx[j] : ((k < xd + cd) ? vc[j] : 0.0f);
+          const float tv = (k < xd) ? (tc.exact ? (k == tc.tj ? 1.0f : 0.0f) : vp[j]) : 0.0f;
+          tf32_split(prim ? pv : (tan ? tv : 0.0f), hi[j], lo[j]);
         }
         tc_st8(cx.lane_addr + RR_COL_AHI + k8, hi);
         tc_st8(cx.lane_addr + RR_COL_ALO + k8, lo);
@@ -144,6 +178,7 @@ struct EngineRRT {
       const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
       cx.dbuf ^= 1u;
       EngineRR::wait_d_ready(cx, net.K[l]);
+      RR_TRACE(cx, 200 + 10 * l);
       uint32_t m[2][8];
       tc_ld8(dcol, m[0]);
 #pragma unroll
@@ -156,17 +191,37 @@ struct EngineRRT {
           const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           uint32_t hi[8], lo[8];
+          if (tc.use_tr) {
+            // gather z of (primal row lane/8, column lane%8) into this lane, one sigmoid per lane, scatter back
+            float zz = 0.0f;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float d = __uint_as_float(m[ci & 1][u]);
-            const float z = __shfl_sync(0xffffffffu, d + bb[u], tc.plane);      // z of this row's primal
-            const float sg = sigmoidf_fast(z);
-            const float a = prim ? z * sg : (tan ? d * (sg * (1.0f + z * (1.0f - sg))) : 0.0f);
-            tf32_split(a, hi[u], lo[u]);
+            for (int u = 0; u < 8; ++u) {
+              const float t = __shfl_sync(0xffffffffu, __uint_as_float(m[ci & 1][u]) + bb[u], tc.gsrc);
+              zz = (tc.my_u == u) ? t : zz;
+            }
+            const float sg = sigmoidf_fast(zz);
+            const float aval = zz * sg, gate = sg * (1.0f + zz * (1.0f - sg));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float g = __shfl_sync(0xffffffffu, gate, tc.pbase + u);
+              const float av = __shfl_sync(0xffffffffu, aval, tc.pbase + u);
+              const float a = prim ? av : (tan ? __uint_as_float(m[ci & 1][u]) * g : 0.0f);
+              tf32_split(a, hi[u], lo[u]);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float d = __uint_as_float(m[ci & 1][u]);
+              const float z = __shfl_sync(0xffffffffu, d + bb[u], tc.plane);      // z of this row's primal
+              const float sg = sigmoidf_fast(z);
+              const float a = prim ? z * sg : (tan ? d * (sg * (1.0f + z * (1.0f - sg))) : 0.0f);
+              tf32_split(a, hi[u], lo[u]);
+            }
           }
           tc_st8(cx.lane_addr + RR_COL_AHI + c0, hi);
           tc_st8(cx.lane_addr + RR_COL_ALO + c0, lo);
           EngineRR::signal_chunk(cx);
+          RR_TRACE(cx, 201 + 10 * l + ci);
         }
       }
     }
@@ -180,7 +235,9 @@ struct EngineRRT {
     if (cx.warp == RR_WMMA) { EngineRR::mma_net(cx, net); return; }
     const int ld = tc.ld, s = tc.smp, xd = net.x_dim;
     rr_bar();                                  // cx.ycur() is final for every sample of the tile
+    RR_TRACE(cx, 10);
     build_A(cx, tc, f);
+    RR_TRACE(cx, 11);
     hidden(cx, tc, net, beff);
     // ---- last layer ---------------------------------------------------------------------------------
     const int nl = net.n_layers, Nreal = net.N[nl - 1];
@@ -188,6 +245,7 @@ struct EngineRRT {
     const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
     cx.dbuf ^= 1u;
     EngineRR::wait_d_ready(cx, net.K[nl - 1]);
+    RR_TRACE(cx, 290);
     float* kd = slot(cx, tc, dst) + s;
     const float* yc = cx.ycur() + s;
     const bool score = (f.kind == FFB_FIELD_SCORE), use_sigma = f.use_sigma != 0, has_drift = f.has_drift != 0;
@@ -230,7 +288,9 @@ struct EngineRRT {
       }
     }
     tc_fence_before();
+    RR_TRACE(cx, 12);
     rr_bar();                                  // slot dst and the trace pieces are complete
+    RR_TRACE(cx, 13);
     if (tc.kind == RT_OWNER && cx.cg == 0) {
       float tr = 0.0f;
       if (tc.exact) { for (int j = 0; j < tc.T; ++j) tr += tc.diag()[s * tc.T + j]; }

@@ -11,11 +11,17 @@ sm = D.ScoreModel(D.MLP(16, 4, 8, [128] * 4), D.VPSDE(), no_sigma=True).eval().t
 B = 148 * 128 * 2
 base, cond = torch.randn(B, 16, device=dev), torch.randn(B, 4, device=dev)
 meth = sys.argv[1] if len(sys.argv) > 1 else 'rk4'
+import flowfusion_b200.flow as F
 sm.sample_ode_from_base(base, cond, method='euler', options={'step_size': 0.5})   # warm up
 CAP = 2048
 buf = torch.zeros(3 * CAP * 2, dtype=torch.int64, device=dev)
 lib.ffb_debug_trace(C.c_void_p(buf.data_ptr()))
-if meth == 'dopri5':
+if meth == 'cfg3':
+    torch.manual_seed(1234)
+    fl = F.ODEFlow(16, [128] * 4).eval().to(dev)
+    xs = torch.randn(148 * 7 * 2, 16, device=dev)
+    fl.log_prob(xs)
+elif meth == 'dopri5':
     try:
         sm.sample_ode_from_base(base, cond, atol=1e-5, rtol=1e-5, options={'step_t': torch.tensor([1e-3]), 'first_step': 0.05, 'max_num_steps': 1})
     except Exception as e:
