@@ -30,9 +30,20 @@
 namespace ffb {
 
 constexpr int RR_NCOMP = 512;
+// Warp roles.  With -DRR_SPECIAL_FIRST the MMA warp is warp 0 and the loader warp 1 (two spare warps keep the
+// compute warps' index a multiple of 4 so that warp & 3 is still the TMEM lane quarter): the oldest warp of a
+// scheduler is favoured when several are ready, and the MMA warp must not starve behind 4 busy epilogue warps.
+#ifdef RR_SPECIAL_FIRST
+constexpr int RR_CW0 = 4;                      // first compute warp
+constexpr int RR_NTHR = RR_NCOMP + 128;
+constexpr int RR_WMMA = 0;
+constexpr int RR_WLOAD = 1;
+#else
+constexpr int RR_CW0 = 0;
 constexpr int RR_NTHR = RR_NCOMP + 64;
 constexpr int RR_WLOAD = RR_NCOMP / 32;
 constexpr int RR_WMMA = RR_NCOMP / 32 + 1;
+#endif
 constexpr int RR_NCHUNK = KMAX / KC;
 constexpr uint32_t RR_COL_AHI = 256, RR_COL_ALO = 384;     // D0 = 0, D1 = 128
 // Synchronisation of one ring stage (= one 32-row K chunk of one layer): ONE mbarrier `full[s]` collects
@@ -82,7 +93,7 @@ struct CtxR {
   __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(full() + 2 * TC_NSTAGE + 1); }
   float* scr;
   int SD, CD, tdim, ncalls;
-  int tid, lane, warp;
+  int tid, lane, warp, cwarp;
   int q, cg, row;       // lane quarter, column group, tile row (= TMEM lane) of a compute thread
   bool producer;
   uint32_t tmem, lane_addr;
@@ -142,16 +153,17 @@ struct EngineRR {
     cx.o_sbias = (uint32_t)off[3]; cx.o_beff = (uint32_t)off[4]; cx.o_wt = (uint32_t)off[5];
     cx.o_red = (uint32_t)off[6]; cx.o_bar = (uint32_t)off[7]; cx.o_slots = (uint32_t)off[8];
     cx.SD = f.state_dim; cx.CD = f.cond_dim; cx.ncalls = f.n_calls;
-    cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
-    cx.producer = cx.warp >= RR_WLOAD;
-    cx.q = cx.warp & 3; cx.cg = (cx.warp >> 2) & 3;
+    cx.tid = (int)threadIdx.x - 32 * RR_CW0; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
+    cx.cwarp = cx.warp - RR_CW0;                    // compute-warp index 0..15 (meaningless on the special warps)
+    cx.producer = cx.cwarp < 0 || cx.cwarp >= RR_NCOMP / 32;
+    cx.q = cx.warp & 3; cx.cg = (cx.cwarp >> 2) & 3;
     cx.row = (cx.q << 5) + cx.lane;
     cx.scr = scratch + (size_t)blockIdx.x * NSLOT * f.state_dim * LDA;
     cx.stage = 0;
     cx.phase = (cx.warp == RR_WLOAD) ? 1u : 0u;     // the loader starts with every stage free
     cx.ph_d = 0; cx.dbuf = 0; cx.rstage = 0;
     cx.tr_n = 0;
-    cx.tr_role = (blockIdx.x != 0 || cx.lane != 0) ? -1 : (cx.warp == 0 ? 0 : (cx.warp == RR_WMMA ? 1 : (cx.warp == RR_NCOMP / 32 - 1 ? 2 : -1)));
+    cx.tr_role = (blockIdx.x != 0 || cx.lane != 0) ? -1 : (cx.warp == RR_WMMA ? 1 : (cx.cwarp == 0 ? 0 : (cx.cwarp == RR_NCOMP / 32 - 1 ? 2 : -1)));
     if (threadIdx.x == 0) {
       for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1 + RR_NCOMP / 32); mbar_init(&cx.empty()[s], 1); }   // loader + every compute warp
       mbar_init(cx.d_ready(), 1);
@@ -413,6 +425,7 @@ struct EngineRR {
       const NetDev& net = f.net[c];
       if (cx.warp == RR_WLOAD) { load_net(cx, net); continue; }
       if (cx.warp == RR_WMMA) { mma_net(cx, net); continue; }
+      if (cx.producer) continue;             // spare warps
       rr_qbar(cx);                           // cx.ycur() of this lane quarter is final
       RR_TRACE(cx, 10);
       build_A(cx, f, c);

@@ -233,6 +233,7 @@ struct EngineRRT {
     const NetDev& net = f.net[0];
     if (cx.warp == RR_WLOAD) { EngineRR::load_net(cx, net); return; }
     if (cx.warp == RR_WMMA) { EngineRR::mma_net(cx, net); return; }
+    if (cx.producer) return;                   // spare warps
     const int ld = tc.ld, s = tc.smp, xd = net.x_dim;
     rr_bar();                                  // cx.ycur() is final for every sample of the tile
     RR_TRACE(cx, 10);

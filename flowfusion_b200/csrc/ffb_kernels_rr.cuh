@@ -42,7 +42,7 @@ __device__ __forceinline__ void rr_block_reduce_store(CtxR& cx, double (&v)[NV],
   }
   if (cx.lane == 0) {
 #pragma unroll
-    for (int q = 0; q < NV; ++q) cx.red()[cx.warp * FFB_NPART + q] = v[q];
+    for (int q = 0; q < NV; ++q) cx.red()[cx.cwarp * FFB_NPART + q] = v[q];
   }
   rr_bar();
   if (cx.tid == 0) {
