@@ -13,8 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "ffb_kernels.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", "ffb_engine.cuh"), os.path.join(_HERE, "csrc", "ffb_engine_tc.cuh"),
-           os.path.join(ROOT, "include", "ffb200.h")]
+HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
+                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh")] + \
+          [os.path.join(ROOT, "include", "ffb200.h")]
 
 MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
 FIELD_NET, FIELD_SCORE = 0, 1

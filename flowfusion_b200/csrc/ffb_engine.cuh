@@ -53,6 +53,7 @@ struct FieldDev {
   float out_sign[2];
   int state_dim, cond_dim, kind, use_sigma, has_drift, div_mode;
   int slots_smem;   // 1: the Y0 / K1..K7 state slots live in shared memory, 0: in the global scratch
+  int rrt_cap;      // tangent-row engine: samples per tile (0 = as many as fit the 128 rows)
 };
 
 // ---------------------------------------------------------------------------------------------

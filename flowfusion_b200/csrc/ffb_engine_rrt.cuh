@@ -27,13 +27,14 @@ struct RowMap { int kind, smp, tj, plane; };
 
 // Place samples of (1 + T) rows into 4 quarters of 32 lanes; returns the samples per tile and, for `row`,
 // what that row is.  Deterministic and shared by host (tile count) and device (per-thread role).
-__host__ __device__ inline int rrt_rowmap(int T, int row, RowMap* out) {
+// `cap` > 0 limits the samples per tile (used when the per-sample state would not fit shared memory).
+__host__ __device__ inline int rrt_rowmap(int T, int row, RowMap* out, int cap = 0) {
   int r = 0, S = 0;
   if (out) { out->kind = RT_IDLE; out->smp = 0; out->tj = -1; out->plane = row & 31; }
   for (;;) {
     int rr = r + 1;
     for (int j = 0; j < T; ++j) { if ((rr & 31) == 0) ++rr; ++rr; }
-    if (rr > TM) break;
+    if (rr > TM || (cap > 0 && S >= cap)) break;
     int plane = r & 31;
     if (out && r == row) { out->kind = RT_OWNER; out->smp = S; out->tj = -1; out->plane = plane; }
     ++r;
@@ -97,7 +98,7 @@ struct EngineRRT {
     tc.T = tc.exact ? f.net[0].x_dim : 1;
     RowMap m;
     const int row = ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31);
-    tc.S = rrt_rowmap(tc.T, row, &m);
+    tc.S = rrt_rowmap(tc.T, row, &m, f.rrt_cap);
     tc.kind = m.kind; tc.smp = m.smp; tc.tj = m.tj; tc.plane = m.plane;
     tc.ld = rrt_ld(tc.S);
     size_t off[12];
@@ -108,7 +109,7 @@ struct EngineRRT {
     int* rk = reinterpret_cast<int*>(tc.diag());
     if (threadIdx.x < TM) {
       RowMap mm;
-      rrt_rowmap(tc.T, threadIdx.x, &mm);
+      rrt_rowmap(tc.T, threadIdx.x, &mm, f.rrt_cap);
       rk[threadIdx.x] = (mm.kind == RT_OWNER || mm.kind == RT_DUP) ? 1 : 0;
     }
     __syncthreads();

@@ -809,9 +809,22 @@ static int make_field(const ffb_field* f, FieldDev* out) {
   return FFB_OK;
 }
 
-// samples per tile of the tangent-row engine (0: a sample does not fit one tile -> tile engine only)
-static int rrt_samples(const ffb_field* f) {
-  return f->div_mode == FFB_DIV_NONE ? 0 : rrt_rowmap(tangents_of(f), -1, nullptr);
+static int smem_optin();
+// Tangent-row engine plan: samples per tile (<= what the 128 rows hold, reduced until the per-sample state fits
+// shared memory) and the dynamic shared-memory size; 0 samples = the field cannot run on it.
+static int rrt_plan(const ffb_field* f, int state_dim, int cond_dim, int tdim, int nslot, int nbeff, size_t* smem_out) {
+  if (f->div_mode == FFB_DIV_NONE) return 0;
+  int S = rrt_rowmap(tangents_of(f), -1, nullptr);
+  for (; S >= 1; --S) {
+    const size_t smem = smem_layout_rrt(state_dim, cond_dim, rrt_ld(S), f->div_mode == FFB_DIV_HUTCH, nslot, tdim, nbeff, nullptr);
+    if (smem <= (size_t)smem_optin()) { if (smem_out) *smem_out = smem; return S; }
+  }
+  return 0;
+}
+static int field_tdim_host(const ffb_field* f) {
+  int t = f->net[0]->tc.t_dim;
+  if (f->n_calls > 1 && f->net[1] && f->net[1]->tc.t_dim > t) t = f->net[1]->tc.t_dim;
+  return t;
 }
 // Tiles of `batch` rows: the caller sizes `partials` with this, so it is the maximum over the tile shapes
 // the field's kernels use (dense rows for the tile engine, quarter-packed samples for the tangent engine).
@@ -819,8 +832,14 @@ extern "C" int64_t ffb_num_tiles(const ffb_field* f, int64_t batch) {
   if (!f || !f->net[0]) return -1;
   const int S = TM / (1 + tangents_of(f));
   int64_t n = (batch + S - 1) / S;
-  const int St = rrt_samples(f);
-  if (St > 0) n = std::max<int64_t>(n, (batch + St - 1) / St);
+  if (f->div_mode != FFB_DIV_NONE) {
+    const int td = field_tdim_host(f);
+    const int configs[2][2] = {{NSLOT, 6}, {3, 1}};          // dopri5 attempt, single evaluation
+    for (auto& c : configs) {
+      const int St = rrt_plan(f, f->state_dim, f->cond_dim, td, c[0], c[1], nullptr);
+      if (St > 0) n = std::max<int64_t>(n, (batch + St - 1) / St);
+    }
+  }
   return n;
 }
 
@@ -888,19 +907,20 @@ static int launch_rr(Kern kern, size_t smem, const char* name, const FieldDev& f
 }
 
 // ---- tangent-row engine (log-likelihood paths) ------------------------------------------------------------
-// returns 0 when the field cannot run on it (a sample does not fit a tile, or the tile does not fit shared memory)
-static size_t rrt_smem(const ffb_field* f, const FieldDev& fd, int nslot, int nbeff) {
-  if (engine() != 1 || fd.div_mode == FFB_DIV_NONE) return 0;
-  const int S = rrt_samples(f);
+// returns 0 when the field cannot run on it; otherwise sets fd->rrt_cap and returns the shared-memory size
+static size_t rrt_smem(const ffb_field* f, FieldDev* fd, int nslot, int nbeff) {
+  if (engine() != 1 || fd->div_mode == FFB_DIV_NONE) return 0;
+  size_t smem = 0;
+  const int S = rrt_plan(f, fd->state_dim, fd->cond_dim, field_tdim(*fd), nslot, nbeff, &smem);
   if (S <= 0) return 0;
-  const size_t smem = smem_layout_rrt(fd.state_dim, fd.cond_dim, rrt_ld(S), fd.div_mode == FFB_DIV_HUTCH, nslot, field_tdim(fd), nbeff, nullptr);
-  return smem <= (size_t)smem_optin() ? smem : 0;
+  fd->rrt_cap = S;
+  return smem;
 }
 template <typename Kern, typename Args>
-static int launch_rrt(Kern kern, size_t smem, const char* name, const ffb_field* f, const FieldDev& fd, const Args& a,
-                      int64_t batch, cudaStream_t stream) {
+static int launch_rrt(Kern kern, size_t smem, const char* name, const FieldDev& fd, const Args& a, int64_t batch,
+                      cudaStream_t stream) {
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int S = rrt_samples(f);
+  const int S = fd.rrt_cap;
   const int64_t ntiles = (batch + S - 1) / S;
   if (ntiles <= 0) return FFB_OK;
   const int grid = (int)std::min<int64_t>(ntiles, num_sms());
@@ -922,7 +942,7 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
   if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
-  if (const size_t smt = rrt_smem(f, fd, 3, 1)) return launch_rrt(k_field_eval_rrt, smt, "ffb_field_eval", f, fd, *a, a->batch, st_);
+  if (const size_t smt = rrt_smem(f, &fd, 3, 1)) return launch_rrt(k_field_eval_rrt, smt, "ffb_field_eval", fd, *a, a->batch, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, 3, 1);
     if (fd.slots_smem) return launch_rr(k_field_eval_rr<true>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
@@ -949,7 +969,7 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
-  if (const size_t smt = rrt_smem(f, fd, NSLOT, 6)) return launch_rrt(k_dopri5_rrt, smt, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
+  if (const size_t smt = rrt_smem(f, &fd, NSLOT, 6)) return launch_rrt(k_dopri5_rrt, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, NSLOT, 6);
     if (fd.slots_smem) return launch_rr(k_dopri5_rr<true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);

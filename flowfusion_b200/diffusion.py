@@ -250,6 +250,7 @@ class ScoreModel(torch.nn.Module):
         sde = copy.deepcopy(self.sde).cpu()
         model, emb = self.model, self.model.embedding_dimensions
         W_cpu, pi_cpu = model.W.detach().cpu(), model.pi.detach().cpu()     # once per solve, not per step
+        use_sigma = not self.no_sigma
 
         def program(times32: np.ndarray) -> np.ndarray:
             t = torch.from_numpy(np.ascontiguousarray(times32, np.float32))
@@ -259,7 +260,7 @@ class ScoreModel(torch.nn.Module):
             a = sde._drift_coeff(t)
             rows[:, L.MAX_TFEAT + 0] = 0.0 if a is None else a.numpy()
             rows[:, L.MAX_TFEAT + 1] = (g ** 2 if sde_mode else 0.5 * g ** 2).numpy()
-            rows[:, L.MAX_TFEAT + 2] = sde.sigma(t).numpy()
+            rows[:, L.MAX_TFEAT + 2] = sde.sigma(t).numpy() if use_sigma else 1.0    # unused by the kernels otherwise
             rows[:, L.MAX_TFEAT + 3] = 1.0
             return rows
 

@@ -214,6 +214,7 @@ class CudaBackend:
         self.cur = 0
         self.dargs = L.Dopri5Args()
         self._dargs_static = False
+        self._stream = _stream()           # torch.cuda.current_stream() costs ~20 us per call: once per solve
         self.eargs = L.EvalArgs()
 
     # -- counts for the RMS norms (global over ranks) -------------------------------------------
@@ -230,7 +231,7 @@ class CudaBackend:
         return out
 
     def _reduce(self):
-        L.check(self.lib.ffb_reduce_partials(_ptr(self.partials), self.ntiles, _ptr(self.sums), _stream()),
+        L.check(self.lib.ffb_reduce_partials(_ptr(self.partials), self.ntiles, _ptr(self.sums), self._stream),
                 "ffb_reduce_partials")
         return self.sums
 
@@ -251,7 +252,7 @@ class CudaBackend:
         a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
         if self.B:
             with _timed("field_eval", self.B):
-                L.check(self.lib.ffb_field_eval(C.byref(self.field.c), C.byref(a), _stream()), "ffb_field_eval")
+                L.check(self.lib.ffb_field_eval(C.byref(self.field.c), C.byref(a), self._stream), "ffb_field_eval")
         return self._reduce()
 
     def eval0(self, ev_row, atol, rtol):
@@ -286,7 +287,7 @@ class CudaBackend:
         a.dt, a.atol, a.rtol, a.x_interp, a.final = float(dt32), float(atol), float(rtol), float(x_interp), int(final)
         if self.B:
             with _timed("dopri5_attempt", self.B):
-                L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(a), _stream()), "ffb_dopri5_attempt")
+                L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(a), self._stream), "ffb_dopri5_attempt")
         return self._reduce()
 
     def accept(self):

@@ -1,0 +1,206 @@
+"""GPU tests of the generic code paths of the tensor-core engines (run with `pytest -m gpu`):
+state / conditional widths that span several 32-column chunks, tangent tiles with few samples, networks
+with one Linear layer, ragged tiles -- each against the CPU oracle (oracle/port.py) on fresh seeded inputs
+and against the FP32 FFMA2 engine of the same library; plus size-independent properties at the full
+BASELINE sizes (determinism, partition invariance, linearity of the Euler-Maruyama noise path)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_row_err
+
+pytestmark = pytest.mark.gpu
+
+SAMPLE_TOL = 1e-4
+LP_TOL = 1e-3
+
+
+def _mods():
+    import flowfusion_b200.diffusion as D
+    import flowfusion_b200.flow as F
+    import flowfusion_b200.symplectic as Sy
+    return D, F, Sy
+
+
+class engine:
+    """with engine(0): FP32 FFMA2 kernels; engine(1): tensor cores (default); engine(2): tile engine only."""
+
+    def __init__(self, e):
+        self.e = e
+
+    def __enter__(self):
+        from flowfusion_b200 import _lib
+        self.lib = _lib.load()
+        self.prev = self.lib.ffb_get_engine()
+        self.lib.ffb_set_engine(self.e)
+
+    def __exit__(self, *exc):
+        self.lib.ffb_set_engine(self.prev)
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ---------------------------------------------------------------------------------------------
+# wide states: several operand chunks, several owned column blocks per thread, slots in global scratch
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D_,C_,units", [(40, 3, [96, 128]), (70, 0, [128]), (33, 37, [64, 64, 64]), (3, 0, [])])
+def test_wide_pfode_dopri5_and_fixed(cuda_dev, D_, C_, units):
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(100 + D_)
+    sm = D.ScoreModel(D.MLP(D_, C_, 8, units), D.VESDE(), no_sigma=False).eval()
+    B = 300
+    base = torch.randn(B, D_, generator=gen(1)); cond = torch.randn(B, C_, generator=gen(2)) if C_ else None
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("ve"), False)
+    ref = port.sample_ode_from_base(M, base, cond, 1e-5, 1e-5)[0]
+    rs = port.last_stats()
+    ref4 = port.sample_ode_from_base(M, base, cond, method="rk4", options={"step_size": 1 / 8})[0]
+    refm = port.sample_ode_from_base(M, base, cond, method="midpoint", options={"step_size": 1 / 8})[0]
+    sm.to(cuda_dev)
+    cb = None if cond is None else cond.to(cuda_dev)
+    x, _ = sm.sample_ode_from_base(base.to(cuda_dev), cb, atol=1e-5, rtol=1e-5)
+    assert rel_row_err(ref, x) < SAMPLE_TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected) == (rs.accepted, rs.rejected)
+    x4, _ = sm.sample_ode_from_base(base.to(cuda_dev), cb, method="rk4", options={"step_size": 1 / 8})
+    assert rel_row_err(ref4, x4) < SAMPLE_TOL
+    xm, _ = sm.sample_ode_from_base(base.to(cuda_dev), cb, method="midpoint", options={"step_size": 1 / 8})
+    assert rel_row_err(refm, xm) < SAMPLE_TOL
+    with engine(0):                                      # the FP32 FFMA2 kernels agree with the 3xTF32 ones
+        xf, _ = sm.sample_ode_from_base(base.to(cuda_dev), cb, method="rk4", options={"step_size": 1 / 8})
+    assert rel_row_err(xf, x4) < 2e-5
+
+
+def test_wide_euler_maruyama(cuda_dev):
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(5)
+    sm = D.ScoreModel(D.MLP(48, 5, 8, [128, 96]), D.VPSDE(), no_sigma=True).eval()
+    B, steps = 200, 40
+    x0 = torch.randn(B, 48, generator=gen(3)); dw = torch.randn(steps, B, 48, generator=gen(4))
+    cond = torch.randn(B, 5, generator=gen(5))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    ref = port.sample_sde(M, x0, dw, cond)
+    sm.to(cuda_dev)
+    x = sm.sample_sde((B, 48), conditional=cond.to(cuda_dev), steps=steps, x0=x0.to(cuda_dev), noise=dw.to(cuda_dev))
+    assert rel_row_err(ref, x) < SAMPLE_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# tangent tiles: few samples per tile (large D), many (Hutchinson), conditional flows
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D_,hidden", [(40, [64, 128]), (7, [96]), (31, [128, 128]), (2, [64, 64, 64])])
+def test_flow_logprob_exact_various_widths(cuda_dev, D_, hidden):
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(200 + D_)
+    m = F.ODEFlow(D_, hidden).eval()
+    x = torch.randn(97, D_, generator=gen(6))
+    ref = port.flow_log_prob(port.flow_from_state_dict(m.state_dict()), x)
+    rs = port.last_stats()
+    m.to(cuda_dev)
+    lp = m.log_prob(x.to(cuda_dev))
+    assert float((lp.cpu() - ref).abs().max()) < LP_TOL
+    assert (m.last_stats.accepted, m.last_stats.rejected) == (rs.accepted, rs.rejected)
+    with engine(2):                                      # whole-layer hand-off tile engine: same answer
+        lp2 = m.log_prob(x.to(cuda_dev))
+    assert float((lp2 - lp).abs().max()) < 2e-4
+
+
+def test_conditional_flow_logprob_wide_cond(cuda_dev):
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(9)
+    m = F.ConditionalODEFlow(12, 20, [128, 64]).eval()
+    x = torch.randn(150, 12, generator=gen(7)); c = torch.randn(150, 20, generator=gen(8))
+    ref = port.flow_log_prob(port.flow_from_state_dict(m.state_dict()), x, c)
+    rs = port.last_stats()
+    m.to(cuda_dev)
+    lp = m.log_prob(x.to(cuda_dev), c.to(cuda_dev))
+    assert float((lp.cpu() - ref).abs().max()) < LP_TOL
+    assert (m.last_stats.accepted, m.last_stats.rejected) == (rs.accepted, rs.rejected)
+
+
+def test_score_logprob_hutchinson_wide(cuda_dev):
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(11)
+    sm = D.ScoreModel(D.MLP(36, 2, 8, [128, 128]), D.VPSDE(), no_sigma=True, hutchinson=True).eval()
+    x0 = torch.randn(130, 36, generator=gen(9)); cond = torch.randn(130, 2, generator=gen(10))
+    e = torch.sign(torch.randn(130, 36, generator=gen(11)))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    ref = port.score_log_prob(M, x0, cond, probes=e)
+    rs = port.last_stats()
+    sm.to(cuda_dev)
+    lp = sm.log_prob(x0.to(cuda_dev), cond.to(cuda_dev), probes=e.to(cuda_dev))
+    assert float((lp.cpu() - ref).abs().max()) < LP_TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected) == (rs.accepted, rs.rejected)
+
+
+# ---------------------------------------------------------------------------------------------
+# properties at the full BASELINE sizes (no oracle: it would take hours)
+# ---------------------------------------------------------------------------------------------
+def test_cfg2_full_size_partition_invariance(cuda_dev):
+    """1M rows, fixed grid: any row's result is independent of the batch it is integrated in."""
+    D, F, Sy = _mods()
+    torch.manual_seed(1234)
+    sm = D.ScoreModel(D.MLP(16, 4, 8, [128] * 4), D.VPSDE(), no_sigma=True).eval().to(cuda_dev)
+    B = 1_000_000
+    base = torch.randn(B, 16, generator=gen(2)).to(cuda_dev); cond = torch.randn(B, 4, generator=gen(3)).to(cuda_dev)
+    opt = {"step_size": 1 / 4}
+    full, _ = sm.sample_ode_from_base(base, cond, method="rk4", options=opt)
+    assert torch.isfinite(full).all()
+    for lo, hi in ((0, 1000), (499_937, 500_070), (B - 777, B)):
+        part, _ = sm.sample_ode_from_base(base[lo:hi], cond[lo:hi], method="rk4", options=opt)
+        assert torch.equal(full[lo:hi], part)
+    again, _ = sm.sample_ode_from_base(base, cond, method="rk4", options=opt)
+    assert torch.equal(full, again)
+
+
+def test_cfg2_full_size_dopri5_matches_sharded_steps(cuda_dev):
+    """dopri5 on 1M rows vs the same rows solved as 4 independent quarters: the quarters use their own
+    (slightly different) global step sizes, so samples agree to the solver tolerance, not bit-wise."""
+    D, F, Sy = _mods()
+    torch.manual_seed(1234)
+    sm = D.ScoreModel(D.MLP(16, 4, 8, [128] * 4), D.VPSDE(), no_sigma=True).eval().to(cuda_dev)
+    B = 1_000_000
+    base = torch.randn(B, 16, generator=gen(2)).to(cuda_dev); cond = torch.randn(B, 4, generator=gen(3)).to(cuda_dev)
+    opts = {"step_t": torch.tensor([1e-3])}
+    full, _ = sm.sample_ode_from_base(base, cond, atol=1e-5, rtol=1e-5, options=opts)
+    steps_full = (sm.last_stats.accepted, sm.last_stats.rejected)
+    q = B // 4
+    part, _ = sm.sample_ode_from_base(base[q:2 * q], cond[q:2 * q], atol=1e-5, rtol=1e-5, options=opts)
+    assert abs(sm.last_stats.accepted - steps_full[0]) <= 1
+    assert rel_row_err(full[q:2 * q], part) < 5e-4
+
+
+def test_cfg4_em_noise_linearity_full_width(cuda_dev):
+    """Euler-Maruyama with a zero-weight network is linear in (x0, noise): x_T = A x0 + sum_k B_k dw_k.
+    Checks the in-kernel noise path / step table at cfg4's width without an oracle."""
+    D, F, Sy = _mods()
+    torch.manual_seed(3)
+    net = D.MLP(32, 0, 8, [128] * 4)
+    with torch.no_grad():
+        for p in net.NN.parameters():
+            p.zero_()
+    sm = D.ScoreModel(net, D.VPSDE(), no_sigma=True).eval().to(cuda_dev)
+    B, steps = 4096, 50
+    x0a = torch.randn(B, 32, generator=gen(1)).to(cuda_dev); x0b = torch.randn(B, 32, generator=gen(2)).to(cuda_dev)
+    dwa = torch.randn(steps, B, 32, generator=gen(3)).to(cuda_dev); dwb = torch.randn(steps, B, 32, generator=gen(4)).to(cuda_dev)
+    f = lambda x0, dw: sm.sample_sde((B, 32), steps=steps, x0=x0, noise=dw)      # noqa: E731
+    lhs = f(x0a + x0b, dwa + dwb)
+    rhs = f(x0a, dwa) + f(x0b, dwb)
+    assert rel_row_err(rhs, lhs) < 1e-5
+
+
+def test_cfg3_logprob_partition_invariance_fixed_grid(cuda_dev):
+    """Exact-trace log-prob on a fixed grid (no global coupling): rows are independent of their tile."""
+    D, F, Sy = _mods()
+    torch.manual_seed(1234)
+    m = F.ODEFlow(16, [128] * 4).eval().to(cuda_dev)
+    x = torch.randn(20_000, 16, generator=gen(4)).to(cuda_dev)
+    lp = m.log_prob(x, method="rk4", options={"step_size": 0.25})
+    assert torch.isfinite(lp).all()
+    lp2 = m.log_prob(x[123:4000], method="rk4", options={"step_size": 0.25})
+    assert torch.equal(lp[123:4000], lp2)
