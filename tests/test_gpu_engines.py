@@ -204,3 +204,60 @@ def test_cfg3_logprob_partition_invariance_fixed_grid(cuda_dev):
     assert torch.isfinite(lp).all()
     lp2 = m.log_prob(x[123:4000], method="rk4", options={"step_size": 0.25})
     assert torch.equal(lp[123:4000], lp2)
+
+
+def test_population_wrappers_row_a10(cuda_dev):
+    """PopulationModelDiffusionConditional.forward / .log_prob / .sample_sde (quirks Q6-Q8) vs the oracle port."""
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(77)
+    shift, scale = torch.linspace(-1, 1, 5), torch.linspace(0.5, 2.0, 5)
+    cshift, cscale = torch.tensor([0.3, -0.2]), torch.tensor([1.5, 0.7])
+    pm = D.PopulationModelDiffusionConditional(D.MLP(5, 2, 6, [32, 48]), D.VESDE(), shift, scale, cshift, cscale).eval()
+    base = torch.randn(200, 5, generator=gen(1)) * 10.0
+    cond = torch.randn(200, 2, generator=gen(2))
+    M = port.score_model_from_state_dict(pm.score_model.state_dict(), port.make_sde("ve"), False)
+    ref = port.population_forward(M, base, shift, scale, cond, cshift, cscale)
+    ref_lp = port.population_log_prob(M, ref[:64], shift, scale, cond[:64], cshift, cscale)
+    pm.to(cuda_dev)
+    x = pm.forward(base.to(cuda_dev), cond.to(cuda_dev))
+    assert rel_row_err(ref, x) < SAMPLE_TOL
+    lp = pm.log_prob(ref[:64].to(cuda_dev), cond[:64].to(cuda_dev))
+    assert lp.shape == (64, 1)
+    # random-init VE score with sigma division: |log p| ~ 60..440 nats, one FP32 ulp there is 3e-5 nats, so the
+    # 1e-3 nat tolerance gets a relative part (2e-5 |log p| = under one ulp per unit of |log p| / 1.5)
+    assert bool(((lp.cpu() - ref_lp).abs() < LP_TOL + 2e-5 * ref_lp.abs()).all())
+    # Q6: the wrapper ignores `steps` (always 100)
+    x0 = torch.randn(50, 5, generator=gen(3)).to(cuda_dev) * 10.0
+    dw = torch.randn(100, 50, 5, generator=gen(4)).to(cuda_dev)
+    a = pm.sample_sde((50, 5), conditional=cond[:50].to(cuda_dev), steps=7, x0=x0, noise=dw)
+    b = pm.sample_sde((50, 5), conditional=cond[:50].to(cuda_dev), steps=100, x0=x0, noise=dw)
+    assert torch.equal(a, b)
+
+
+def test_maximum_sizes(cuda_dev):
+    """The limits in include/ffb200.h: 128 state columns, 8 Linear layers of width 128, and their error paths."""
+    D, F, Sy = _mods()
+    from oracle import port
+    from flowfusion_b200 import _lib
+    torch.manual_seed(21)
+    sm = D.ScoreModel(D.MLP(128, 0, 8, [128] * 7), D.VESDE(), no_sigma=True).eval()
+    base = torch.randn(150, 128, generator=gen(1))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("ve"), True)
+    ref = port.sample_ode_from_base(M, base, None, method="rk4", options={"step_size": 0.25})[0]
+    refd = port.sample_ode_from_base(M, base, None, 1e-4, 1e-4)[0]
+    rs = port.last_stats()
+    sm.to(cuda_dev)
+    x, _ = sm.sample_ode_from_base(base.to(cuda_dev), method="rk4", options={"step_size": 0.25})
+    assert rel_row_err(ref, x) < SAMPLE_TOL
+    xd, _ = sm.sample_ode_from_base(base.to(cuda_dev), atol=1e-4, rtol=1e-4)
+    assert rel_row_err(refd, xd) < SAMPLE_TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected) == (rs.accepted, rs.rejected)
+    # one layer too many / one column too wide: refused with NotImplementedError, nothing is launched
+    with pytest.raises(NotImplementedError):
+        D.ScoreModel(D.MLP(4, 0, 8, [32] * 8), D.VESDE()).eval().to(cuda_dev).sample_ode_from_base(torch.zeros(4, 4, device=cuda_dev))
+    with pytest.raises(NotImplementedError):
+        D.ScoreModel(D.MLP(4, 0, 8, [129]), D.VESDE()).eval().to(cuda_dev).sample_ode_from_base(torch.zeros(4, 4, device=cuda_dev))
+    # a CPU tensor is refused: there is no CPU path
+    with pytest.raises(_lib.FFBError):
+        sm.sample_ode_from_base(base)

@@ -216,3 +216,38 @@ def test_solver_agrees_with_scipy_rk45_on_solutions():
     got = tde.odeint(f, torch.tensor([1.0, 0.5], dtype=torch.float64), torch.tensor([0.0, 3.0], dtype=torch.float64),
                      rtol=1e-10, atol=1e-12)[-1]
     assert np.allclose(got.numpy(), ref, rtol=1e-7, atol=1e-9)
+
+
+@needs_ref
+def test_reference_population_wrappers_and_accelerate():
+    """Row a10: the population-level wrappers (affine glue, quirks Q6-Q8) -- live reference vs port, and
+    flowfusion_b200.accelerate() building a twin with identical weights (construction only: no GPU here)."""
+    import flowfusion_b200 as ffb
+    D, F, S = loader.load_reference()
+    torch.manual_seed(77)
+    shift, scale = torch.linspace(-1, 1, 5), torch.linspace(0.5, 2.0, 5)
+    cshift, cscale = torch.tensor([0.3, -0.2]), torch.tensor([1.5, 0.7])
+    pm = D.PopulationModelDiffusionConditional(D.MLP(5, 2, 6, [32, 48]), D.VESDE(), shift, scale, cshift, cscale).eval()
+    base = torch.randn(25, 5, generator=torch.Generator().manual_seed(1)) * 10.0     # VE prior scale
+    cond = torch.randn(25, 2, generator=torch.Generator().manual_seed(2))
+    M = port.score_model_from_state_dict(pm.score_model.state_dict(), port.make_sde("ve"), False)
+    ref = pm.forward(base, cond).detach()
+    got = port.population_forward(M, base, shift, scale, cond, cshift, cscale)
+    assert rel_row_err(ref, got) < TIGHT
+    x = ref[:10]
+    ref_lp = pm.log_prob(x, cond[:10]).detach()
+    got_lp = port.population_log_prob(M, x, shift, scale, cond[:10], cshift, cscale)
+    assert ref_lp.shape == got_lp.shape == (10, 1)
+    assert float((ref_lp - got_lp).abs().max()) < 1e-4
+    twin = ffb.accelerate(pm, device="cpu")
+    assert type(twin).__name__ == "PopulationModelDiffusionConditional"
+    sd_ref, sd_twin = pm.state_dict(), twin.state_dict()
+    assert set(sd_ref) == set(sd_twin)
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k], sd_twin[k]), k
+    for obj in (F.ODEFlow(3, [16, 16]), F.ConditionalODEFlow(3, 2, [16]), S.SymplecticFlowModel(
+            S.SymplecticMLP(4, 1, 4, [16]), torch.zeros(4), torch.ones(4), torch.zeros(1), torch.ones(1))):
+        tw = ffb.accelerate(obj.eval(), device="cpu")
+        assert set(obj.state_dict()) == set(tw.state_dict())
+        for k, v in obj.state_dict().items():
+            assert torch.equal(v, tw.state_dict()[k]), k
