@@ -44,6 +44,7 @@ struct NetDev {
   const float* W[FFB_MAX_LAYERS];   // packed [K][Np]
   const float* b[FFB_MAX_LAYERS];   // packed [Np]
   const float* Wt;                  // packed time rows [t_dim][Np[0]]
+  int act;                          // FFB_ACT_* of the hidden layers
 };
 
 struct FieldDev {
@@ -104,6 +105,42 @@ __device__ __forceinline__ float sigmoidf_fast(float z) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return r;
 }
+
+// hidden-layer activation a(z) and its derivative g(z) (the gate of the tangent rows), selected at compile time
+template <int ACT>
+__device__ __forceinline__ void act_fwd_grad(float z, float& a, float& g) {
+  if (ACT == FFB_ACT_SILU) {
+    const float sg = sigmoidf_fast(z);
+    a = z * sg; g = sg * (1.0f + z * (1.0f - sg));
+  } else if (ACT == FFB_ACT_TANH) {
+    const float t = fmaf(2.0f, sigmoidf_fast(2.0f * z), -1.0f);       // tanh z = 2 sigmoid(2 z) - 1
+    a = t; g = 1.0f - t * t;
+  } else if (ACT == FFB_ACT_RELU) {
+    a = fmaxf(z, 0.0f); g = z > 0.0f ? 1.0f : 0.0f;
+  } else if (ACT == FFB_ACT_SOFTPLUS) {
+    a = z > 20.0f ? z : log1pf(expf(z));                               // torch: beta = 1, threshold = 20
+    g = z > 20.0f ? 1.0f : sigmoidf_fast(z);
+  } else {                                                             // GELU, erf form
+    const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
+    a = z * cdf; g = cdf + z * (0.39894228040143268f * expf(-0.5f * z * z));
+  }
+}
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float z) {
+  if (ACT == FFB_ACT_SILU) return z * sigmoidf_fast(z);
+  float a, g;
+  act_fwd_grad<ACT>(z, a, g);
+  return a;
+}
+// run fn(std::integral_constant<int, ACT>) for the run-time activation code (warp-uniform)
+#define FFB_ACT_DISPATCH(code, CALL)                                    \
+  switch (code) {                                                       \
+    case FFB_ACT_TANH: { constexpr int ACT = FFB_ACT_TANH; CALL; break; }         \
+    case FFB_ACT_RELU: { constexpr int ACT = FFB_ACT_RELU; CALL; break; }         \
+    case FFB_ACT_SOFTPLUS: { constexpr int ACT = FFB_ACT_SOFTPLUS; CALL; break; } \
+    case FFB_ACT_GELU: { constexpr int ACT = FFB_ACT_GELU; CALL; break; }         \
+    default: { constexpr int ACT = FFB_ACT_SILU; CALL; break; }                   \
+  }
 
 // ---------------------------------------------------------------------------------------------
 // per-CTA context

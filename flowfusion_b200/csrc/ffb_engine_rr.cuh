@@ -138,7 +138,10 @@ __host__ __device__ inline size_t smem_layout_rr(int SD, int CD, int nslot_smem,
   return o;
 }
 
-struct EngineRR {
+// GEN = false: SiLU networks (the hot instantiation, no activation dispatch in the epilogue);
+// GEN = true: the activation code of the network is dispatched at run time (FFB_ACT_*).
+template <bool GEN>
+struct EngineRR_ {
   static constexpr int NTHR = RR_NTHR;
 
   static __device__ __forceinline__ void init(CtxR& cx, const FieldDev& f, float* scratch, int nslot, int nbeff) {
@@ -352,6 +355,11 @@ struct EngineRR {
 
   // hidden layers: accumulator chunk -> + bias -> SiLU -> TF32 split -> next A operand chunk -> hand off
   static __device__ __forceinline__ void hidden(CtxR& cx, const NetDev& net, int c, const float* beff) {
+    if (GEN) { FFB_ACT_DISPATCH(net.act, hidden_act<ACT>(cx, net, c, beff)); }
+    else hidden_act<FFB_ACT_SILU>(cx, net, c, beff);
+  }
+  template <int ACT>
+  static __device__ __forceinline__ void hidden_act(CtxR& cx, const NetDev& net, int c, const float* beff) {
     for (int l = 0; l + 1 < net.n_layers; ++l) {
       const int nc = net.Np[l] / KC;
       const float* bias = (l == 0) ? beff : cx.sbias() + (c * FFB_MAX_LAYERS + l) * KMAX;
@@ -374,7 +382,7 @@ struct EngineRR {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float z = __uint_as_float(m[ci & 1][u]) + bb[u];
-            tf32_split(z * sigmoidf_fast(z), hi[u], lo[u]);
+            tf32_split(act_fwd<ACT>(z), hi[u], lo[u]);
           }
           tc_st8(cx.lane_addr + RR_COL_AHI + c0, hi);
           tc_st8(cx.lane_addr + RR_COL_ALO + c0, lo);
@@ -462,6 +470,7 @@ struct EngineRR {
     RR_TRACE(cx, 13);
   }
 };
+using EngineRR = EngineRR_<false>;
 
 // ---- row-local stage algebra helpers --------------------------------------------------------------
 // A thread owns, in its row, the state columns d with (d >> 3) & 3 == cg: blocks of 8 columns starting at

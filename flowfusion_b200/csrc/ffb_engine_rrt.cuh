@@ -92,7 +92,8 @@ __host__ __device__ inline size_t smem_layout_rrt(int SD, int CD, int ld, int hu
   return o;
 }
 
-struct EngineRRT {
+template <bool GEN>
+struct EngineRRT_ {
   static __device__ __forceinline__ void init(CtxR& cx, TanCtx& tc, const FieldDev& f, int nslot, int nbeff) {
     tc.exact = (f.div_mode == FFB_DIV_EXACT);
     tc.T = tc.exact ? f.net[0].x_dim : 1;
@@ -172,6 +173,11 @@ struct EngineRRT {
   }
 
   static __device__ __forceinline__ void hidden(CtxR& cx, const TanCtx& tc, const NetDev& net, const float* beff) {
+    if (GEN) { FFB_ACT_DISPATCH(net.act, hidden_act<ACT>(cx, tc, net, beff)); }
+    else hidden_act<FFB_ACT_SILU>(cx, tc, net, beff);
+  }
+  template <int ACT>
+  static __device__ __forceinline__ void hidden_act(CtxR& cx, const TanCtx& tc, const NetDev& net, const float* beff) {
     const bool prim = tc.primal(), tan = (tc.kind == RT_TAN);
     for (int l = 0; l + 1 < net.n_layers; ++l) {
       const int nc = net.Np[l] / KC;
@@ -200,8 +206,8 @@ struct EngineRRT {
               const float t = __shfl_sync(0xffffffffu, __uint_as_float(m[ci & 1][u]) + bb[u], tc.gsrc);
               zz = (tc.my_u == u) ? t : zz;
             }
-            const float sg = sigmoidf_fast(zz);
-            const float aval = zz * sg, gate = sg * (1.0f + zz * (1.0f - sg));
+            float aval, gate;
+            act_fwd_grad<ACT>(zz, aval, gate);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float g = __shfl_sync(0xffffffffu, gate, tc.pbase + u);
@@ -214,8 +220,9 @@ struct EngineRRT {
             for (int u = 0; u < 8; ++u) {
               const float d = __uint_as_float(m[ci & 1][u]);
               const float z = __shfl_sync(0xffffffffu, d + bb[u], tc.plane);      // z of this row's primal
-              const float sg = sigmoidf_fast(z);
-              const float a = prim ? z * sg : (tan ? d * (sg * (1.0f + z * (1.0f - sg))) : 0.0f);
+              float av, g;
+              act_fwd_grad<ACT>(z, av, g);
+              const float a = prim ? av : (tan ? d * g : 0.0f);
               tf32_split(a, hi[u], lo[u]);
             }
           }
@@ -309,6 +316,7 @@ struct EngineRRT {
     }
   }
 };
+using EngineRRT = EngineRRT_<false>;
 
 // ---- per-sample state helpers (the owner row's thread, 8 state columns at a time) -----------------------
 __device__ __forceinline__ void rt_load8(const CtxR& cx, const TanCtx& tc, const float* buf, int d0, float (&v)[8]) {
@@ -347,11 +355,13 @@ __device__ __forceinline__ void rt_store_rows(float* __restrict__ dst, const flo
 // =============================================================================================
 // k_field_eval_rrt: one evaluation with the divergence (+ torchdiffeq's initial-step norms)
 // =============================================================================================
+template <bool GEN>
 __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rrt(const __grid_constant__ ffb::FieldDev f,
         const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
   using namespace ffb;
+  using ENGT = EngineRRT_<GEN>;
   CtxR cx; TanCtx tc;
-  EngineRRT::init(cx, tc, f, 3, 1);
+  ENGT::init(cx, tc, f, 3, 1);
   const int SD = cx.SD, CD = cx.CD, S = tc.S, ld = tc.ld;
   const bool owner = (tc.kind == RT_OWNER);
   if (!cx.producer) {
@@ -361,9 +371,9 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rrt(const __grid
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * S;
     const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* F = EngineRRT::slot(cx, tc, 0);
-    float* Y0 = EngineRRT::slot(cx, tc, 1);
-    float* FB = EngineRRT::slot(cx, tc, 2);
+    float* F = ENGT::slot(cx, tc, 0);
+    float* Y0 = ENGT::slot(cx, tc, 1);
+    float* FB = ENGT::slot(cx, tc, 2);
     if (!cx.producer) {
       rt_load_rows(Y0, a.y, row0, nv, S, ld, SD, cx.tid);
       if (a.fbase) rt_load_rows(FB, a.fbase, row0, nv, S, ld, SD, cx.tid);
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rrt(const __grid
         }
       }
     }
-    EngineRRT::eval(cx, tc, f, a.ev.a, a.ev.c, a.ev.sigma, a.ev.sign, cx.beff(), 0);
+    ENGT::eval(cx, tc, f, a.ev.a, a.ev.c, a.ev.sigma, a.ev.sign, cx.beff(), 0);
     if (!cx.producer) {
       rr_bar();                                           // klp[0] of every sample is written
       double v[6] = {0, 0, 0, 0, 0, 0};   // x_y, x_f, x_df, lp_f, lp_df, c_y
@@ -441,11 +451,13 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rrt(const __grid
 // =============================================================================================
 // k_dopri5_rrt: one attempted Dormand-Prince step of (x, log-det)
 // =============================================================================================
+template <bool GEN>
 __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_constant__ ffb::FieldDev f,
         const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
   using namespace ffb;
+  using ENGT = EngineRRT_<GEN>;
   CtxR cx; TanCtx tc;
-  EngineRRT::init(cx, tc, f, NSLOT, 6);
+  ENGT::init(cx, tc, f, NSLOT, 6);
   const int SD = cx.SD, CD = cx.CD, S = tc.S, ld = tc.ld;
   const bool owner = (tc.kind == RT_OWNER);
   float* LP0 = tc.klp() + NSLOT * ld;
@@ -456,11 +468,11 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * S;
     const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* Y0 = EngineRRT::slot(cx, tc, SLOT_Y0);
+    float* Y0 = ENGT::slot(cx, tc, SLOT_Y0);
     double nonfinite = 0.0;
     if (!cx.producer) {
       rt_load_rows(Y0, a.y0, row0, nv, S, ld, SD, cx.tid);
-      rt_load_rows(EngineRRT::slot(cx, tc, 0), a.f0, row0, nv, S, ld, SD, cx.tid);
+      rt_load_rows(ENGT::slot(cx, tc, 0), a.f0, row0, nv, S, ld, SD, cx.tid);
       if (CD) rt_load_rows(cx.condb(), a.cond, row0, nv, S, ld, CD, cx.tid);
       if (!tc.exact) rt_load_rows(tc.prb(), a.probes, row0, nv, S, ld, SD, cx.tid);
       for (int s = cx.tid; s < S; s += RR_NCOMP) {
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
       rr_bar();
       if (owner) {
         const float c00 = a.cb[0][0];
-        const float* K1 = EngineRRT::slot(cx, tc, 0);
+        const float* K1 = ENGT::slot(cx, tc, 0);
         for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
           float y0v[8], kv[8], y[8];
           rt_load8(cx, tc, Y0, d0, y0v);
@@ -487,7 +499,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
     }
     for (int i = 1; i <= 6; ++i) {
       const ffb_eval_scalars& ev = a.ev[i - 1];
-      EngineRRT::eval(cx, tc, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * KMAX, i);
+      ENGT::eval(cx, tc, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * KMAX, i);
       if (!cx.producer && owner && i < 6) {
         float cbi[6];
 #pragma unroll
@@ -495,12 +507,12 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
         for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
           float y0v[8], kv[8], acc[8];
           rt_load8(cx, tc, Y0, d0, y0v);
-          rt_load8(cx, tc, EngineRRT::slot(cx, tc, 0), d0, kv);
+          rt_load8(cx, tc, ENGT::slot(cx, tc, 0), d0, kv);
 #pragma unroll
           for (int u = 0; u < 8; ++u) acc[u] = __fmul_rn(kv[u], cbi[0]);
 #pragma unroll
           for (int j = 1; j < 6; ++j) {
-            rt_load8_if(cx, tc, j <= i, EngineRRT::slot(cx, tc, j), d0, kv);
+            rt_load8_if(cx, tc, j <= i, ENGT::slot(cx, tc, j), d0, kv);
 #pragma unroll
             for (int u = 0; u < 8; ++u) acc[u] = fmaf(kv[u], cbi[j], acc[u]);
           }
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
     if (!cx.producer) {
       rr_bar();                                            // klp[6] of every sample is written
       double v[3] = {0.0, 0.0, nonfinite};
-      float* OUT = EngineRRT::slot(cx, tc, 1);              // K2 of an element is dead once its sums are formed
+      float* OUT = ENGT::slot(cx, tc, 1);              // K2 of an element is dead once its sums are formed
       if (owner && tc.smp < nv) {
         float ce[7], cm[7];
 #pragma unroll
@@ -522,12 +534,12 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
           float y0v[8], y1v[8], k0[8], kv[8], err[8], mid[8];
           rt_load8(cx, tc, Y0, d0, y0v);
           rt_load8(cx, tc, cx.ycur(), d0, y1v);
-          rt_load8(cx, tc, EngineRRT::slot(cx, tc, 0), d0, k0);
+          rt_load8(cx, tc, ENGT::slot(cx, tc, 0), d0, k0);
 #pragma unroll
           for (int u = 0; u < 8; ++u) { err[u] = __fmul_rn(k0[u], ce[0]); mid[u] = __fmul_rn(k0[u], cm[0]); }
 #pragma unroll
           for (int j = 1; j < 7; ++j) {
-            rt_load8(cx, tc, EngineRRT::slot(cx, tc, j), d0, kv);
+            rt_load8(cx, tc, ENGT::slot(cx, tc, j), d0, kv);
 #pragma unroll
             for (int u = 0; u < 8; ++u) { err[u] = fmaf(kv[u], ce[j], err[u]); mid[u] = fmaf(kv[u], cm[j], mid[u]); }
           }
@@ -565,7 +577,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
       }
       rr_bar();
       rt_store_rows(a.y1, cx.ycur(), row0, nv, ld, SD, cx.tid);
-      rt_store_rows(a.f1, EngineRRT::slot(cx, tc, 6), row0, nv, ld, SD, cx.tid);
+      rt_store_rows(a.f1, ENGT::slot(cx, tc, 6), row0, nv, ld, SD, cx.tid);
       if (a.final) rt_store_rows(a.y_out, OUT, row0, nv, ld, SD, cx.tid);
       const int slot[3] = {P_X_ERR, P_LP_ERR, P_NONFINITE};
       rr_block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);

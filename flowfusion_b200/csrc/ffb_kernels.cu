@@ -677,11 +677,13 @@ extern "C" int ffb_net_create(const ffb_net_desc* d, void* stream_, ffb_net** ou
   for (int l = 0; l < d->n_layers; ++l)
     if (d->widths[l] < 1 || d->widths[l] > FFB_MAX_WIDTH)
       return fail(FFB_ERR_ARG, "ffb_net_create: layer widths must be in 1..128");
+  if (d->activation < FFB_ACT_SILU || d->activation > FFB_ACT_GELU) return fail(FFB_ERR_ARG, "ffb_net_create: unknown activation");
   ffb_net* net = new ffb_net();
   NetDev& nd = net->dev;
   memset(&nd, 0, sizeof(nd));
   nd.n_layers = d->n_layers;
   nd.t_dim = d->t_dim; nd.x_dim = d->x_dim; nd.c_dim = d->c_dim;
+  nd.act = d->activation;
   net->flops = 0;
   int in_f = d->in_features;
   auto cleanup = [&]() { for (void* p : net->allocs) cudaFree(p); delete net; };
@@ -719,6 +721,7 @@ extern "C" int ffb_net_create(const ffb_net_desc* d, void* stream_, ffb_net** ou
   memset(&nt, 0, sizeof(nt));
   nt.n_layers = d->n_layers;
   nt.t_dim = d->t_dim; nt.x_dim = d->x_dim; nt.c_dim = d->c_dim;
+  nt.act = d->activation;
   in_f = d->in_features;
   for (int l = 0; l < d->n_layers; ++l) {
     const int N = d->widths[l], Np = (N + 31) & ~31;
@@ -858,6 +861,10 @@ template <typename Kern, typename Args>
 static int launch_tiles(Kern kern, int nthr, const char* name, const ffb_field* f, const FieldDev& fd, const Args& a,
                         int64_t batch, cudaStream_t stream) {
   const int T = tangents_of(f);
+  for (int c = 0; c < fd.n_calls; ++c)
+    if (fd.net[c].act != FFB_ACT_SILU)
+      return fail(FFB_ERR_ARG, std::string(name) + ": non-SiLU activations run on the chunk-pipelined tensor-core engines only "
+                  "(not on FFB_ENGINE=ffma / tc_tile, fixed grids with a divergence, or samples wider than a tile)");
   const size_t smem = field_smem(fd, T, fd.slots_smem);
   int dev = 0, optin = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -878,6 +885,11 @@ static int launch_tiles(Kern kern, int nthr, const char* name, const ffb_field* 
 // ---- row-resident tensor-core kernels (fields without tangent rows) -----------------------------
 // FFB_ENGINE=tc_tile (or ffb_set_engine(2)) keeps the older whole-layer hand-off tile engine for A/B runs
 static bool use_rr(const FieldDev& fd) { return engine() == 1 && fd.div_mode == FFB_DIV_NONE; }
+// true when a network of the field has a non-SiLU activation (selects the kernels with the run-time dispatch)
+static bool gen_act(const FieldDev& fd) {
+  for (int c = 0; c < fd.n_calls; ++c) if (fd.net[c].act != FFB_ACT_SILU) return true;
+  return false;
+}
 
 static int smem_optin() {
   static int v = 0;
@@ -942,11 +954,17 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
   if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
-  if (const size_t smt = rrt_smem(f, &fd, 3, 1)) return launch_rrt(k_field_eval_rrt, smt, "ffb_field_eval", fd, *a, a->batch, st_);
+  if (const size_t smt = rrt_smem(f, &fd, 3, 1))
+    return gen_act(fd) ? launch_rrt(k_field_eval_rrt<true>, smt, "ffb_field_eval", fd, *a, a->batch, st_)
+                       : launch_rrt(k_field_eval_rrt<false>, smt, "ffb_field_eval", fd, *a, a->batch, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, 3, 1);
-    if (fd.slots_smem) return launch_rr(k_field_eval_rr<true>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
-    return launch_rr(k_field_eval_rr<false>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
+    if (gen_act(fd)) {
+      if (fd.slots_smem) return launch_rr(k_field_eval_rr<true, true>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
+      return launch_rr(k_field_eval_rr<false, true>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
+    }
+    if (fd.slots_smem) return launch_rr(k_field_eval_rr<true, false>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
+    return launch_rr(k_field_eval_rr<false, false>, smem, "ffb_field_eval", fd, *a, a->batch, st_);
   }
   if (engine()) {
     if (fd.slots_smem) return launch_tiles(k_field_eval<EngineTC, true>, EngineTC::NTHR, "ffb_field_eval", f, fd, *a, a->batch, st_);
@@ -969,11 +987,17 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
-  if (const size_t smt = rrt_smem(f, &fd, NSLOT, 6)) return launch_rrt(k_dopri5_rrt, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+  if (const size_t smt = rrt_smem(f, &fd, NSLOT, 6))
+    return gen_act(fd) ? launch_rrt(k_dopri5_rrt<true>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_)
+                       : launch_rrt(k_dopri5_rrt<false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, NSLOT, 6);
-    if (fd.slots_smem) return launch_rr(k_dopri5_rr<true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
-    return launch_rr(k_dopri5_rr<false>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+    if (gen_act(fd)) {
+      if (fd.slots_smem) return launch_rr(k_dopri5_rr<true, true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+      return launch_rr(k_dopri5_rr<false, true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+    }
+    if (fd.slots_smem) return launch_rr(k_dopri5_rr<true, false>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+    return launch_rr(k_dopri5_rr<false, false>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
   }
   if (engine()) {
     if (fd.slots_smem) return launch_tiles(k_dopri5<EngineTC, true>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
@@ -998,8 +1022,12 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, rr_fixed_slots(a->method), 8);
-    if (fd.slots_smem) return launch_rr(k_fixed_rr<true>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
-    return launch_rr(k_fixed_rr<false>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
+    if (gen_act(fd)) {
+      if (fd.slots_smem) return launch_rr(k_fixed_rr<true, true>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
+      return launch_rr(k_fixed_rr<false, true>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
+    }
+    if (fd.slots_smem) return launch_rr(k_fixed_rr<true, false>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
+    return launch_rr(k_fixed_rr<false, false>, smem, "ffb_integrate_fixed", fd, *a, a->batch, st_);
   }
   if (engine()) {
     if (fd.slots_smem) return launch_tiles(k_fixed<EngineTC, true>, EngineTC::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);

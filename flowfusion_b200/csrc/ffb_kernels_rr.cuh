@@ -66,15 +66,16 @@ __host__ __device__ inline int rr_fixed_slots(int method) {
 // =============================================================================================
 // k_field_eval_rr: one evaluation (+ the norms of torchdiffeq's initial-step heuristic)
 // =============================================================================================
-template <bool SS>
+template <bool SS, bool GEN>
 __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rr(const __grid_constant__ ffb::FieldDev f,
         const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
   using namespace ffb;
+  using ENG = EngineRR_<GEN>;
   CtxR cx;
-  EngineRR::init(cx, f, reinterpret_cast<float*>(a.scratch), 3, 1);
+  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch), 3, 1);
   const int SD = cx.SD, CD = cx.CD;
   if (!cx.producer) {
-    EngineRR::prep_beff(cx, f, a.ev.tfeat, cx.beff());
+    ENG::prep_beff(cx, f, a.ev.tfeat, cx.beff());
     rr_bar();
   }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rr(const __grid_
         rr_store8(cx, cx.ycur(), d0, y0v);
       });
     }
-    EngineRR::eval<SS>(cx, f, a.ev.a, a.ev.c, a.ev.sigma, a.ev.sign, cx.beff(), 0);
+    ENG::template eval<SS>(cx, f, a.ev.a, a.ev.c, a.ev.sigma, a.ev.sign, cx.beff(), 0);
     if (!cx.producer) {
       double v[6] = {0, 0, 0, 0, 0, 0};   // x_y, x_f, x_df, lp_f, lp_df, c_y
       if (a.norms && cx.row < nv) {
@@ -139,22 +140,23 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rr(const __grid_
       }
     }
   }
-  EngineRR::fini(cx);
+  ENG::fini(cx);
 }
 
 // =============================================================================================
 // k_dopri5_rr
 // =============================================================================================
-template <bool SS>
+template <bool SS, bool GEN>
 __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_constant__ ffb::FieldDev f,
         const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
   using namespace ffb;
+  using ENG = EngineRR_<GEN>;
   CtxR cx;
-  EngineRR::init(cx, f, reinterpret_cast<float*>(a.scratch), NSLOT, 6);
+  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch), NSLOT, 6);
   const int SD = cx.SD, CD = cx.CD;
   const int bstride = f.n_calls * KMAX;
   if (!cx.producer) {
-    for (int s = 0; s < 6; ++s) EngineRR::prep_beff(cx, f, a.ev[s].tfeat, cx.beff() + s * bstride);
+    for (int s = 0; s < 6; ++s) ENG::prep_beff(cx, f, a.ev[s].tfeat, cx.beff() + s * bstride);
     rr_bar();
   }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
     }
     for (int i = 1; i <= 6; ++i) {
       const ffb_eval_scalars& ev = a.ev[i - 1];
-      EngineRR::eval<SS>(cx, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * bstride, i);
+      ENG::template eval<SS>(cx, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * bstride, i);
       if (!cx.producer && i < 6) {
         // input of stage i+1: y0 + sum_j cb[i][j] k_j  (the 7th stage input is y1: FSAL)
         float cbi[6];
@@ -249,19 +251,20 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
       if (cx.tid == 0) a.partials[tile * FFB_NPART + P_LP_ERR] = 0.0;
     }
   }
-  EngineRR::fini(cx);
+  ENG::fini(cx);
 }
 
 // =============================================================================================
 // k_fixed_rr
 // =============================================================================================
-template <bool SS>
+template <bool SS, bool GEN>
 __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_constant__ ffb::FieldDev f,
         const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
   using namespace ffb;
+  using ENG = EngineRR_<GEN>;
   CtxR cx;
   const int nslot = rr_fixed_slots(a.method);
-  EngineRR::init(cx, f, reinterpret_cast<float*>(a.scratch), nslot, 8);
+  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch), nslot, 8);
   const int SD = cx.SD, CD = cx.CD;
   const int nev = evals_per_step(a.method);
   const float third = (float)(1.0 / 3.0);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
           else if (step + 1 < a.nsteps) nxt = ev + nev + first_e;
           float ea = 0.f, ec = 0.f, es = 1.f, esg = 1.f;
           if (!cx.producer) { ea = ev[e].a; ec = ev[e].c; es = ev[e].sigma; esg = ev[e].sign; }
-          EngineRR::eval<SS>(cx, f, ea, ec, es, esg, beff_buf(nbuf), dst, mask,
+          ENG::template eval<SS>(cx, f, ea, ec, es, esg, beff_buf(nbuf), dst, mask,
                              [&]() { if (nxt) prep_q(nxt, beff_buf(nbuf + 1)); });
           ++nbuf;
         }
@@ -431,5 +434,5 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
       rr_bar();
     }
   }
-  EngineRR::fini(cx);
+  ENG::fini(cx);
 }

@@ -60,10 +60,9 @@ class MLP(torch.nn.Module):
         return 2 * self.W.shape[0]
 
     def _net(self) -> E.PackedNet:
-        if not isinstance(self.activation, torch.nn.SiLU):
-            raise NotImplementedError("only SiLU activations are implemented in the CUDA kernels")
+        act = E.activation_code(self.activation)
         lin = list(self.NN)
-        key = E.weights_fingerprint(lin)
+        key = E.weights_fingerprint(lin, act)
         if self._packed is None or self._packed[0] != key:
             emb, D, Cn = self.embedding_dimensions, self.n_dimensions, self.n_conditionals
             if emb + D + Cn != lin[0].in_features:
@@ -71,7 +70,7 @@ class MLP(torch.nn.Module):
             dev = lin[0].weight.device
             E.require_cuda_device(dev)
             self._packed = (key, E.PackedNet(lin, x_col=emb, x_dim=D, c_col=emb + D, c_dim=Cn, t_col=0,
-                                             t_dim=emb, device=dev))
+                                             t_dim=emb, device=dev, activation=act))
         return self._packed[1]
 
     def _time_features(self, t32: torch.Tensor, W_cpu=None, pi_cpu=None) -> torch.Tensor:

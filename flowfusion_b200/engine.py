@@ -82,10 +82,37 @@ def require_cuda_device(dev):
         raise L.FFBError("the model must be on a CUDA device (flowfusion_b200 has no CPU path)")
 
 
+def activation_code(act) -> int:
+    """FFB_ACT_* of an activation module (instance or class), or NotImplementedError."""
+    nn = torch.nn
+    m = act() if isinstance(act, type) else act
+    if isinstance(m, nn.SiLU):
+        return L.ACT_SILU
+    if isinstance(m, nn.Tanh):
+        return L.ACT_TANH
+    if isinstance(m, nn.ReLU):
+        return L.ACT_RELU
+    if isinstance(m, nn.Softplus) and m.beta == 1 and m.threshold == 20:
+        return L.ACT_SOFTPLUS
+    if isinstance(m, nn.GELU) and getattr(m, "approximate", "none") == "none":
+        return L.ACT_GELU
+    raise NotImplementedError(f"activation {type(m).__name__} is not implemented in the CUDA kernels "
+                              "(SiLU, Tanh, ReLU, Softplus(beta=1, threshold=20), GELU(erf) are)")
+
+
+def activation_of(modules) -> int:
+    """The one activation code used between the Linear layers of ``modules`` (default SiLU when there is none)."""
+    codes = {activation_code(m) for m in modules if not isinstance(m, torch.nn.Linear)}
+    if len(codes) > 1:
+        raise NotImplementedError("mixed hidden-layer activations are not implemented in the CUDA kernels")
+    return codes.pop() if codes else L.ACT_SILU
+
+
 class PackedNet:
     """One MLP, packed for the tile engine.  ``linears``: the nn.Linear modules in order."""
 
-    def __init__(self, linears: Sequence[torch.nn.Linear], x_col, x_dim, c_col, c_dim, t_col, t_dim, device):
+    def __init__(self, linears: Sequence[torch.nn.Linear], x_col, x_dim, c_col, c_dim, t_col, t_dim, device,
+                 activation: int = 0):
         lib = L.load()
         if len(linears) > L.MAX_LAYERS:
             raise NotImplementedError(f"at most {L.MAX_LAYERS} Linear layers are supported")
@@ -102,6 +129,8 @@ class PackedNet:
             d.weight[i] = w.data_ptr()
             d.bias[i] = b.data_ptr()
         d.x_col, d.x_dim, d.c_col, d.c_dim, d.t_col, d.t_dim = x_col, x_dim, c_col, c_dim, t_col, t_dim
+        d.activation = int(activation)
+        self.activation = int(activation)
         h = C.c_void_p()
         with torch.cuda.device(device):
             L.check(lib.ffb_net_create(C.byref(d), _stream(), C.byref(h)), "ffb_net_create")
@@ -122,9 +151,9 @@ class PackedNet:
             pass
 
 
-def weights_fingerprint(linears: Sequence[torch.nn.Linear]):
-    """Cheap change detector so trained / reloaded weights are re-packed."""
-    return tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version, str(l.weight.device))
+def weights_fingerprint(linears: Sequence[torch.nn.Linear], activation: int = 0):
+    """Cheap change detector so trained / reloaded weights (or a swapped activation) are re-packed."""
+    return (activation,) + tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version, str(l.weight.device))
                  for l in linears)
 
 

@@ -59,15 +59,14 @@ class _FlowBase(nn.Module):
 
     def _net(self) -> E.PackedNet:
         lin = [m for m in self.layers if isinstance(m, nn.Linear)]
-        for m in self.layers:
-            if not isinstance(m, (nn.Linear, nn.SiLU)):
-                raise NotImplementedError("only SiLU activations are implemented in the CUDA kernels")
-        key = E.weights_fingerprint(lin)
+        act = E.activation_of(self.layers)
+        key = E.weights_fingerprint(lin, act)
         if self._packed is None or self._packed[0] != key:
             D, Cn = self.target_dimension, self._cdim()
             dev = lin[0].weight.device
             E.require_cuda_device(dev)
-            self._packed = (key, E.PackedNet(lin, x_col=0, x_dim=D, c_col=D + 1, c_dim=Cn, t_col=D, t_dim=1, device=dev))
+            self._packed = (key, E.PackedNet(lin, x_col=0, x_dim=D, c_col=D + 1, c_dim=Cn, t_col=D, t_dim=1, device=dev,
+                                             activation=act))
         return self._packed[1]
 
     def _field(self, div_mode=L.DIV_NONE):

@@ -48,14 +48,13 @@ class SymplecticMLP(nn.Module):
         D, Cn, emb = self._dims
         lq = [m for m in self.mlp_q_dynamics if isinstance(m, nn.Linear)]
         lp = [m for m in self.mlp_p_dynamics if isinstance(m, nn.Linear)]
-        for m in list(self.mlp_q_dynamics) + list(self.mlp_p_dynamics):
-            if not isinstance(m, (nn.Linear, nn.SiLU)):
-                raise NotImplementedError("only SiLU activations are implemented in the CUDA kernels")
-        key = E.weights_fingerprint(lq + lp)
+        act = E.activation_of(list(self.mlp_q_dynamics) + list(self.mlp_p_dynamics))
+        key = E.weights_fingerprint(lq + lp, act)
         if self._packed is None or self._packed[0] != key:
             dev = lq[0].weight.device
             E.require_cuda_device(dev)
-            mk = lambda lin: E.PackedNet(lin, x_col=0, x_dim=D, c_col=D, c_dim=Cn, t_col=D + Cn, t_dim=emb, device=dev)  # noqa: E731
+            mk = lambda lin: E.PackedNet(lin, x_col=0, x_dim=D, c_col=D, c_dim=Cn, t_col=D + Cn, t_dim=emb, device=dev,  # noqa: E731
+                                         activation=act)
             self._packed = (key, (mk(lq), mk(lp)))
         return self._packed[1]
 

@@ -54,6 +54,16 @@ typedef enum {
 #define FFB_DIV_EXACT 1      /* D forward-mode tangents  (flow.py:157-161, diffusion.py:483-503) */
 #define FFB_DIV_HUTCH 2      /* one tangent along a fixed Rademacher probe (diffusion.py:327-334) */
 
+/* hidden-layer activations (ffb_net_desc.activation).  SiLU is the reference's default (diffusion.py:38,
+ * flow.py:41, symplectic.py:25); the others are what a user may pass as `activation=`.  Non-SiLU activations run
+ * on the chunk-pipelined tensor-core engines only (every dopri5 / single-evaluation path, fixed grids without a
+ * divergence); the remaining paths return FFB_ERR_ARG for them. */
+#define FFB_ACT_SILU 0
+#define FFB_ACT_TANH 1
+#define FFB_ACT_RELU 2
+#define FFB_ACT_SOFTPLUS 3   /* torch.nn.Softplus(beta=1, threshold=20) */
+#define FFB_ACT_GELU 4       /* torch.nn.GELU(approximate='none')       */
+
 /* fixed-grid methods */
 #define FFB_M_EULER 0        /* torchdiffeq 'euler'; also symplectic.py:192-197 */
 #define FFB_M_MIDPOINT 1     /* torchdiffeq 'midpoint'                          */
@@ -77,6 +87,7 @@ typedef struct {
   int32_t x_col, x_dim;
   int32_t c_col, c_dim;
   int32_t t_col, t_dim;
+  int32_t activation;                   /* FFB_ACT_*                                      */
 } ffb_net_desc;
 
 /* A vector field built from one or two networks acting on column blocks of the state. */

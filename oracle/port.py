@@ -37,7 +37,7 @@ silu = torch.nn.functional.silu
 # ------------------------------------------------------------------------------------
 # weights
 # ------------------------------------------------------------------------------------
-def net_from_state_dict(sd, prefix, stride=1):
+def net_from_state_dict(sd, prefix, stride=1, act=None):
     """Collect ``{prefix}{i*stride}.weight|bias`` into ``{"w": [...], "b": [...]}``.
 
     ``stride=1`` for ``diffusion.MLP.NN`` (`diffusion.py:67-72`), ``stride=2`` for the
@@ -50,14 +50,15 @@ def net_from_state_dict(sd, prefix, stride=1):
         i += 1
     if not w:
         raise KeyError(f"no layers under {prefix!r}")
-    return {"w": w, "b": b}
+    return {"w": w, "b": b, "act": act or silu}      # `act`: the activation callable the model was built with
 
 
 def _mlp(net, h):
-    """Linear -> SiLU -> ... -> Linear  (`diffusion.py:116-119`, `flow.py:118`, `symplectic.py:120`)."""
+    """Linear -> act -> ... -> Linear  (`diffusion.py:116-119`, `flow.py:118`, `symplectic.py:120`; act defaults to SiLU)."""
     n = len(net["w"])
+    act = net.get("act", silu)
     for i in range(n - 1):
-        h = silu(torch.nn.functional.linear(h, net["w"][i], net["b"][i]))
+        h = act(torch.nn.functional.linear(h, net["w"][i], net["b"][i]))
     return torch.nn.functional.linear(h, net["w"][-1], net["b"][-1])
 
 
@@ -353,14 +354,14 @@ def symplectic_log_prob(Sy, x, p0, cond=None, atol=1e-5, rtol=1e-5):
 # ------------------------------------------------------------------------------------
 # builders from state_dicts that use the reference's key layout
 # ------------------------------------------------------------------------------------
-def score_model_from_state_dict(sd, sde, no_sigma, prefix="model."):
-    P = {"net": net_from_state_dict(sd, prefix + "NN."), "W": sd[prefix + "W"].detach().float().cpu(),
+def score_model_from_state_dict(sd, sde, no_sigma, prefix="model.", act=None):
+    P = {"net": net_from_state_dict(sd, prefix + "NN.", act=act), "W": sd[prefix + "W"].detach().float().cpu(),
          "pi": sd[prefix + "pi"].detach().float().cpu()}
     return {"P": P, "sde": sde, "no_sigma": bool(no_sigma)}
 
 
-def flow_from_state_dict(sd):
-    Fl = {"net": net_from_state_dict(sd, "velocity.", 2),
+def flow_from_state_dict(sd, act=None):
+    Fl = {"net": net_from_state_dict(sd, "velocity.", 2, act=act),
           "shift": sd["target_shift"].float().cpu(), "scale": sd["target_scale"].float().cpu()}
     if "conditional_shift" in sd:
         Fl["cshift"] = sd["conditional_shift"].float().cpu()
@@ -368,9 +369,9 @@ def flow_from_state_dict(sd):
     return Fl
 
 
-def symplectic_from_state_dict(sd):
-    return {"net_q": net_from_state_dict(sd, "model.mlp_q_dynamics.", 2),
-            "net_p": net_from_state_dict(sd, "model.mlp_p_dynamics.", 2),
+def symplectic_from_state_dict(sd, act=None):
+    return {"net_q": net_from_state_dict(sd, "model.mlp_q_dynamics.", 2, act=act),
+            "net_p": net_from_state_dict(sd, "model.mlp_p_dynamics.", 2, act=act),
             "W": sd["model.W"].float().cpu(), "shift": sd["shift"].float().cpu(),
             "scale": sd["scale"].float().cpu(), "cshift": sd["conditional_shift"].float().cpu(),
             "cscale": sd["conditional_scale"].float().cpu()}

@@ -20,8 +20,12 @@ from flowfusion_b200 import engine as E
 silu = torch.nn.functional.silu
 
 
+_ACTS = {0: silu, 1: torch.tanh, 2: torch.relu, 3: torch.nn.functional.softplus, 4: torch.nn.functional.gelu}
+
+
 class FakePackedNet:
-    def __init__(self, linears, x_col, x_dim, c_col, c_dim, t_col, t_dim, device):
+    def __init__(self, linears, x_col, x_dim, c_col, c_dim, t_col, t_dim, device, activation=0):
+        self.act = _ACTS[activation]
         self.lin = [(l.weight.detach().float().cpu().clone(), l.bias.detach().float().cpu().clone()) for l in linears]
         self.x_col, self.x_dim, self.c_col, self.c_dim, self.t_col, self.t_dim = x_col, x_dim, c_col, c_dim, t_col, t_dim
         self.handle = C.c_void_p(0)
@@ -38,7 +42,7 @@ class FakePackedNet:
         for i, (w, b) in enumerate(self.lin):
             h = torch.nn.functional.linear(h, w, b)
             if i < len(self.lin) - 1:
-                h = silu(h)
+                h = self.act(h)
         return h
 
 

@@ -261,3 +261,41 @@ def test_maximum_sizes(cuda_dev):
     # a CPU tensor is refused: there is no CPU path
     with pytest.raises(_lib.FFBError):
         sm.sample_ode_from_base(base)
+
+
+@pytest.mark.parametrize("act_cls,act_fn", [(torch.nn.Tanh, torch.tanh), (torch.nn.ReLU, torch.relu),
+                                            (torch.nn.Softplus, torch.nn.functional.softplus),
+                                            (torch.nn.GELU, torch.nn.functional.gelu)])
+def test_non_silu_activations(cuda_dev, act_cls, act_fn):
+    """`activation=` is a pass-through constructor argument of every reference model."""
+    D, F, Sy = _mods()
+    from oracle import port
+    from flowfusion_b200 import _lib
+    torch.manual_seed(31)
+    sm = D.ScoreModel(D.MLP(16, 4, 8, [128, 96], activation=act_cls()), D.VPSDE(), no_sigma=True).eval()
+    base = torch.randn(300, 16, generator=gen(1)); cond = torch.randn(300, 4, generator=gen(2))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True, act=act_fn)
+    opts = {"step_t": torch.tensor([1e-3])}
+    ref = port.sample_ode_from_base(M, base, cond, 1e-5, 1e-5, options=opts)[0]
+    rs = port.last_stats()
+    ref4 = port.sample_ode_from_base(M, base, cond, method="rk4", options={"step_size": 1 / 8})[0]
+    sm.to(cuda_dev)
+    x, _ = sm.sample_ode_from_base(base.to(cuda_dev), cond.to(cuda_dev), atol=1e-5, rtol=1e-5, options=opts)
+    assert rel_row_err(ref, x) < SAMPLE_TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected) == (rs.accepted, rs.rejected)
+    x4, _ = sm.sample_ode_from_base(base.to(cuda_dev), cond.to(cuda_dev), method="rk4", options={"step_size": 1 / 8})
+    assert rel_row_err(ref4, x4) < SAMPLE_TOL
+    # exact-trace log-prob: the tangent rows use the activation's derivative
+    torch.manual_seed(32)
+    fl = F.ODEFlow(9, [64, 128], activation=act_cls).eval()
+    xs = torch.randn(90, 9, generator=gen(3))
+    ref_lp = port.flow_log_prob(port.flow_from_state_dict(fl.state_dict(), act=act_fn), xs)
+    rs = port.last_stats()
+    fl.to(cuda_dev)
+    lp = fl.log_prob(xs.to(cuda_dev))
+    assert float((lp.cpu() - ref_lp).abs().max()) < LP_TOL
+    if act_cls is not torch.nn.ReLU:      # ReLU's kinks make the step sequence sensitive to FP32 summation order
+        assert (fl.last_stats.accepted, fl.last_stats.rejected) == (rs.accepted, rs.rejected)
+    # paths that still run on the SiLU-only engines refuse the network instead of silently using SiLU
+    with pytest.raises(_lib.FFBError):
+        fl.log_prob(xs.to(cuda_dev), method="rk4", options={"step_size": 0.5})

@@ -150,3 +150,25 @@ def test_symplectic(name):
     assert lp.shape == outs["log_prob"].shape
     assert float((lp - outs["log_prob"]).abs().max()) < 1e-3
     check_stats(m.last_stats, meta["stats_logprob"])
+
+
+@pytest.mark.parametrize("act_cls,act_fn", [(torch.nn.Tanh, torch.tanh), (torch.nn.ReLU, torch.relu),
+                                            (torch.nn.Softplus, torch.nn.functional.softplus),
+                                            (torch.nn.GELU, torch.nn.functional.gelu)])
+def test_non_silu_activations_reach_the_kernels(act_cls, act_fn):
+    """The activation code travels from the model object to the packed network; unknown ones are refused."""
+    from oracle import port
+    torch.manual_seed(3)
+    m = F.ODEFlow(4, [24, 24], activation=act_cls).eval()
+    x = torch.randn(40, 4, generator=torch.Generator().manual_seed(2))
+    ref = port.flow_log_prob(port.flow_from_state_dict(m.state_dict(), act=act_fn), x)
+    with patched_engine():
+        lp = m.log_prob(x)
+        assert m._net().act is {torch.nn.Tanh: torch.tanh, torch.nn.ReLU: torch.relu}.get(act_cls, m._net().act)
+    assert float((lp - ref).abs().max()) < 1e-3
+    with pytest.raises(NotImplementedError):
+        with patched_engine():
+            F.ODEFlow(4, [8], activation=torch.nn.Sigmoid).eval().log_prob(x)
+    with pytest.raises(NotImplementedError):
+        with patched_engine():
+            D.ScoreModel(D.MLP(4, 0, 4, [8], activation=torch.nn.Softplus(beta=2.0)), D.VESDE()).eval().sample_ode_from_base(x)

@@ -251,3 +251,20 @@ def test_reference_population_wrappers_and_accelerate():
         assert set(obj.state_dict()) == set(tw.state_dict())
         for k, v in obj.state_dict().items():
             assert torch.equal(v, tw.state_dict()[k]), k
+
+
+@needs_ref
+@pytest.mark.parametrize("act_cls,act_fn", [(torch.nn.Tanh, torch.tanh), (torch.nn.GELU, torch.nn.functional.gelu)])
+def test_reference_non_silu_activations(act_cls, act_fn):
+    """`activation=` is a public constructor argument of every reference model: the port follows it."""
+    D, F, S = loader.load_reference()
+    torch.manual_seed(5)
+    m = F.ODEFlow(3, [24, 24], activation=act_cls).eval()
+    x = torch.randn(30, 3, generator=torch.Generator().manual_seed(1))
+    Fl = port.flow_from_state_dict(m.state_dict(), act=act_fn)
+    assert rel_row_err(m.sample(x).detach(), port.flow_sample(Fl, x)) < TIGHT
+    assert float((m.log_prob(x).detach() - port.flow_log_prob(Fl, x)).abs().max()) < 1e-5
+    sm = D.ScoreModel(D.MLP(3, 0, 4, [24], activation=act_cls()), D.VESDE(), no_sigma=True).eval()
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("ve"), True, act=act_fn)
+    assert rel_row_err(sm.sample_ode_from_base(x, atol=1e-5, rtol=1e-5)[0].detach(),
+                       port.sample_ode_from_base(M, x, None, 1e-5, 1e-5)[0]) < TIGHT
