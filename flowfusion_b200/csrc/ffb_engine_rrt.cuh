@@ -585,3 +585,112 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
   }
   EngineRR::fini(cx);
 }
+
+// =============================================================================================
+// k_fixed_rrt: fixed-grid integration of (x, log-det): euler / midpoint / rk4 (3/8 rule), whole trajectory on-chip
+// =============================================================================================
+template <bool GEN>
+__global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rrt(const __grid_constant__ ffb::FieldDev f,
+        const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
+  using namespace ffb;
+  using ENGT = EngineRRT_<GEN>;
+  CtxR cx; TanCtx tc;
+  const int nslot = rr_fixed_slots(a.method);
+  ENGT::init(cx, tc, f, nslot, 1);
+  const int SD = cx.SD, CD = cx.CD, S = tc.S, ld = tc.ld;
+  const bool owner = (tc.kind == RT_OWNER);
+  const int nev = evals_per_step(a.method);
+  const float third = (float)(1.0 / 3.0);
+  float* LPC = tc.klp() + (NSLOT + 1) * ld;          // running log-det
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * S;
+    const int nv = (int)min((int64_t)S, a.batch - row0);
+    float* Y0 = ENGT::slot(cx, tc, nslot - 1);
+    const float* K1 = ENGT::slot(cx, tc, 0);
+    const float* K2 = ENGT::slot(cx, tc, nslot > 1 ? 1 : 0);
+    const float* K3 = ENGT::slot(cx, tc, nslot > 2 ? 2 : 0);
+    const float* K4 = ENGT::slot(cx, tc, nslot > 3 ? 3 : 0);
+    if (!cx.producer) {
+      rt_load_rows(cx.ycur(), a.x0, row0, nv, S, ld, SD, cx.tid);
+      if (CD) rt_load_rows(cx.condb(), a.cond, row0, nv, S, ld, CD, cx.tid);
+      if (!tc.exact) rt_load_rows(tc.prb(), a.probes, row0, nv, S, ld, SD, cx.tid);
+      for (int s = cx.tid; s < S; s += RR_NCOMP) LPC[s] = (s < nv && a.lp0) ? a.lp0[row0 + s] : 0.0f;
+    }
+    for (int step = 0; step < a.nsteps; ++step) {
+      const float* st = a.step_table + (size_t)step * FFB_STEP_STRIDE;
+      const ffb_eval_scalars* ev = a.ev_table + (size_t)step * nev;
+      const float dt = st[0], half = st[3];
+      for (int e = 0; e < nev; ++e) {
+        float ea = 0.f, ec = 0.f, es = 1.f, esg = 1.f;
+        if (!cx.producer) {
+          ea = ev[e].a; ec = ev[e].c; es = ev[e].sigma; esg = ev[e].sign;
+          EngineRR::prep_beff(cx, f, ev[e].tfeat, cx.beff());      // made visible by the barrier that opens the evaluation
+        }
+        ENGT::eval(cx, tc, f, ea, ec, es, esg, cx.beff(), e);
+        if (cx.producer || !owner) continue;
+        float* y = cx.ycur();
+        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
+          float yv[8], y0v[8], k1[8], k2[8], k3[8], k4[8];
+          rt_load8(cx, tc, K1, d0, k1);
+          if (a.method == FFB_M_EULER) {
+            rt_load8(cx, tc, y, d0, yv);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(yv[u], __fmul_rn(dt, k1[u]));
+          } else if (a.method == FFB_M_MIDPOINT) {
+            if (e == 0) {
+              rt_load8(cx, tc, y, d0, yv);
+              rt_store8(cx, tc, Y0, d0, yv);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(yv[u], __fmul_rn(k1[u], half));
+            } else {
+              rt_load8(cx, tc, Y0, d0, yv); rt_load8(cx, tc, K2, d0, k2);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(yv[u], __fmul_rn(dt, k2[u]));
+            }
+          } else {                                                   // rk4, 3/8 rule
+            if (e == 0) {
+              rt_load8(cx, tc, y, d0, y0v);
+              rt_store8(cx, tc, Y0, d0, y0v);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(y0v[u], __fmul_rn(__fmul_rn(dt, k1[u]), third));
+            } else if (e == 1) {
+              rt_load8(cx, tc, Y0, d0, y0v); rt_load8(cx, tc, K2, d0, k2);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(y0v[u], __fmul_rn(dt, __fsub_rn(k2[u], __fmul_rn(k1[u], third))));
+            } else if (e == 2) {
+              rt_load8(cx, tc, Y0, d0, y0v); rt_load8(cx, tc, K2, d0, k2); rt_load8(cx, tc, K3, d0, k3);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) yv[u] = __fadd_rn(y0v[u], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[u], k2[u]), k3[u])));
+            } else {
+              rt_load8(cx, tc, Y0, d0, y0v); rt_load8(cx, tc, K2, d0, k2); rt_load8(cx, tc, K3, d0, k3); rt_load8(cx, tc, K4, d0, k4);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float sum = __fadd_rn(__fadd_rn(k1[u], __fmul_rn(3.0f, __fadd_rn(k2[u], k3[u]))), k4[u]);
+                yv[u] = __fadd_rn(y0v[u], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+              }
+            }
+          }
+          rt_store8(cx, tc, y, d0, yv);
+        }
+        if (cx.cg == 0) {                                          // the log-det column, same stage formulas
+          const int s = tc.smp;
+          const float* kl = tc.klp();
+          if (a.method == FFB_M_EULER) LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, kl[s]));
+          else if (a.method == FFB_M_MIDPOINT && e == 1) LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, kl[ld + s]));
+          else if (a.method == FFB_M_RK4 && e == 3) {
+            const float sum = __fadd_rn(__fadd_rn(kl[s], __fmul_rn(3.0f, __fadd_rn(kl[ld + s], kl[2 * ld + s]))), kl[3 * ld + s]);
+            LPC[s] = __fadd_rn(LPC[s], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+          }
+        }
+      }
+    }
+    if (!cx.producer) {
+      rr_bar();
+      rt_store_rows(a.x_out, cx.ycur(), row0, nv, ld, SD, cx.tid);
+      if (a.lp_out)
+        for (int s = cx.tid; s < nv; s += RR_NCOMP) a.lp_out[row0 + s] = LPC[s];
+      rr_bar();
+    }
+  }
+  EngineRR::fini(cx);
+}

@@ -1020,6 +1020,9 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (const size_t smt = rrt_smem(f, &fd, rr_fixed_slots(a->method), 1))
+    return gen_act(fd) ? launch_rrt(k_fixed_rrt<true>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_)
+                       : launch_rrt(k_fixed_rrt<false>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, rr_fixed_slots(a->method), 8);
     if (gen_act(fd)) {

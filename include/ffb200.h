@@ -56,8 +56,8 @@ typedef enum {
 
 /* hidden-layer activations (ffb_net_desc.activation).  SiLU is the reference's default (diffusion.py:38,
  * flow.py:41, symplectic.py:25); the others are what a user may pass as `activation=`.  Non-SiLU activations run
- * on the chunk-pipelined tensor-core engines only (every dopri5 / single-evaluation path, fixed grids without a
- * divergence); the remaining paths return FFB_ERR_ARG for them. */
+ * on the chunk-pipelined tensor-core engines only; the debug engines (ffb_set_engine(0) / (2)) and samples wider
+ * than a tile return FFB_ERR_ARG for them. */
 #define FFB_ACT_SILU 0
 #define FFB_ACT_TANH 1
 #define FFB_ACT_RELU 2

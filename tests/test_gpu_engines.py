@@ -296,6 +296,37 @@ def test_non_silu_activations(cuda_dev, act_cls, act_fn):
     assert float((lp.cpu() - ref_lp).abs().max()) < LP_TOL
     if act_cls is not torch.nn.ReLU:      # ReLU's kinks make the step sequence sensitive to FP32 summation order
         assert (fl.last_stats.accepted, fl.last_stats.rejected) == (rs.accepted, rs.rejected)
-    # paths that still run on the SiLU-only engines refuse the network instead of silently using SiLU
-    with pytest.raises(_lib.FFBError):
-        fl.log_prob(xs.to(cuda_dev), method="rk4", options={"step_size": 0.5})
+    # fixed grid with the divergence (tangent-row engine), vs the port
+    ref_rk = port.flow_log_prob(port.flow_from_state_dict(fl.state_dict(), act=act_fn), xs, method="rk4",
+                                options={"step_size": 0.25})
+    lp_rk = fl.log_prob(xs.to(cuda_dev), method="rk4", options={"step_size": 0.25})
+    assert float((lp_rk.cpu() - ref_rk).abs().max()) < LP_TOL
+    # the SiLU-only engines refuse the network instead of silently using SiLU
+    with engine(0):
+        with pytest.raises(_lib.FFBError):
+            fl.log_prob(xs.to(cuda_dev))
+
+
+@pytest.mark.parametrize("method,opts", [("euler", {"step_size": 1 / 16}), ("midpoint", {"step_size": 1 / 8}), ("rk4", {"step_size": 1 / 4})])
+def test_fixed_grid_logprob_on_tangent_engine(cuda_dev, method, opts):
+    """Fixed-grid solves of (x, log-det): k_fixed_rrt vs the port, vs the tile engine, exact and Hutchinson."""
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(41)
+    fl = F.ConditionalODEFlow(10, 3, [96, 128]).eval()
+    xs = torch.randn(77, 10, generator=gen(1)); c = torch.randn(77, 3, generator=gen(2))
+    ref = port.flow_log_prob(port.flow_from_state_dict(fl.state_dict()), xs, c, method=method, options=opts)
+    fl.to(cuda_dev)
+    lp = fl.log_prob(xs.to(cuda_dev), c.to(cuda_dev), method=method, options=opts)
+    assert float((lp.cpu() - ref).abs().max()) < LP_TOL
+    with engine(2):
+        lp2 = fl.log_prob(xs.to(cuda_dev), c.to(cuda_dev), method=method, options=opts)
+    assert float((lp2 - lp).abs().max()) < 2e-4
+    torch.manual_seed(42)
+    sm = D.ScoreModel(D.MLP(6, 0, 8, [64, 64]), D.VPSDE(), no_sigma=True, hutchinson=True).eval()
+    x0 = torch.randn(50, 6, generator=gen(3)); e = torch.sign(torch.randn(50, 6, generator=gen(4)))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    refh = port.score_log_prob(M, x0, None, method=method, options=opts, probes=e)
+    sm.to(cuda_dev)
+    lph = sm.log_prob(x0.to(cuda_dev), method=method, options=opts, probes=e.to(cuda_dev))
+    assert float((lph.cpu() - refh).abs().max()) < LP_TOL
