@@ -379,10 +379,33 @@ struct EngineRR_ {
           const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           uint32_t hi[8], lo[8];
+          if (ACT == FFB_ACT_SILU) {
+            // SiLU + TF32 split on packed FP32 pairs (add/mul/fma.f32x2): 6.5 issue slots per element instead of 11,
+            // which leaves the schedulers to the SFU (2 MUFU per element) and to the MMA warp
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float z = __uint_as_float(m[ci & 1][u]) + bb[u];
-            tf32_split(act_fwd<ACT>(z), hi[u], lo[u]);
+            for (int u = 0; u < 8; u += 2) {
+              const float2 z = __fadd2_rn(make_float2(__uint_as_float(m[ci & 1][u]), __uint_as_float(m[ci & 1][u + 1])),
+                                          make_float2(bb[u], bb[u + 1]));
+              const float2 x = __fmul2_rn(z, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+              float2 e, r;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+              const float2 s = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(s.x));
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(s.y));
+              const float2 a = __fmul2_rn(z, r);
+              hi[u] = (__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u;
+              hi[u + 1] = (__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u;
+              const float2 l = __ffma2_rn(make_float2(__uint_as_float(hi[u]), __uint_as_float(hi[u + 1])),
+                                          make_float2(-1.0f, -1.0f), a);            // a - hi, exact
+              lo[u] = __float_as_uint(l.x); lo[u + 1] = __float_as_uint(l.y);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float z = __uint_as_float(m[ci & 1][u]) + bb[u];
+              tf32_split(act_fwd<ACT>(z), hi[u], lo[u]);
+            }
           }
           tc_st8(cx.lane_addr + RR_COL_AHI + c0, hi);
           tc_st8(cx.lane_addr + RR_COL_ALO + c0, lo);
