@@ -14,9 +14,10 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "ffb_kernels.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
-                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh")] + \
+                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh")] + \
           [os.path.join(ROOT, "include", "ffb200.h")]
 
+ABI_VERSION = 2
 MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
 FIELD_NET, FIELD_SCORE = 0, 1
 DIV_NONE, DIV_EXACT, DIV_HUTCH = 0, 1, 2
@@ -67,7 +68,43 @@ class Dopri5Args(C.Structure):
                 ("lp_out", C.c_void_p), ("ev", EvalScalars * 6), ("cb", (C.c_float * 6) * 6),
                 ("ce", C.c_float * 7), ("cm", C.c_float * 7), ("dt", C.c_float), ("atol", C.c_float),
                 ("rtol", C.c_float), ("x_interp", C.c_float), ("final", C.c_int32),
-                ("partials", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p)]
+                ("partials", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p),
+                ("ctl", C.c_void_p)]
+
+
+# ---- device-side dopri5 controller (include/ffb200.h, csrc/ffb_control.cuh) ---------------------------
+PROG_RAW_T, PROG_FOURIER = 0, 1
+SDE_NONE, SDE_VP, SDE_VE, SDE_SUBVP = 0, 1, 2, 3
+MAX_FREQ = MAX_TFEAT // 2
+CTL_MAX_GRID, CTL_HIST = 16, 256
+CTL_RUNNING, CTL_FINISHED, CTL_NONFINITE, CTL_DT_UNDERFLOW, CTL_MAX_STEPS = 0, 1, -1, -2, -3
+
+
+class TimeProgram(C.Structure):
+    _fields_ = [("time_features", C.c_int32), ("n_freq", C.c_int32), ("W", C.c_float * MAX_FREQ), ("pi", C.c_float),
+                ("sde", C.c_int32), ("use_sigma", C.c_int32), ("sde_mode", C.c_int32), ("T", C.c_float),
+                ("beta_min", C.c_float), ("beta_diff", C.c_float), ("half_beta_diff", C.c_float),
+                ("m2_beta_min", C.c_float), ("sigma_min", C.c_float), ("sigma_ratio", C.c_float),
+                ("ve_gfac", C.c_float)]
+
+
+class CtlParams(C.Structure):
+    _fields_ = [("t_end", C.c_double), ("min_step", C.c_double), ("max_step", C.c_double), ("safety", C.c_double),
+                ("ifactor", C.c_double), ("dfactor", C.c_double), ("n_x", C.c_int64), ("n_lp", C.c_int64),
+                ("n_cond", C.c_int64), ("reverse", C.c_int32), ("max_num_steps", C.c_int32), ("n_grid", C.c_int32),
+                ("_pad", C.c_int32), ("grid", C.c_double * CTL_MAX_GRID), ("alpha", C.c_float * 6),
+                ("beta", (C.c_float * 6) * 6), ("c_err", C.c_float * 7), ("c_mid", C.c_float * 7),
+                ("prog", TimeProgram)]
+
+
+class Ctl(C.Structure):
+    _fields_ = [("ev", EvalScalars * 6), ("cb", (C.c_float * 6) * 6), ("ce", C.c_float * 7), ("cm", C.c_float * 7),
+                ("dt", C.c_float), ("x_interp", C.c_float), ("final", C.c_int32), ("cur", C.c_int32),
+                ("done", C.c_int32), ("grid_idx", C.c_int32), ("t", C.c_double), ("dt_next", C.c_double),
+                ("cur_t1", C.c_double), ("cur_dt", C.c_double), ("cur_on_grid", C.c_int32),
+                ("n_attempts", C.c_int32), ("n_accepted", C.c_int32), ("n_rejected", C.c_int32),
+                ("hist_dt", C.c_double * CTL_HIST), ("hist_ratio", C.c_float * CTL_HIST),
+                ("hist_accept", C.c_uint8 * CTL_HIST)]
 
 
 class FixedArgs(C.Structure):
@@ -91,6 +128,10 @@ SYMBOLS = {
     "ffb_field_eval": (C.c_int, [C.POINTER(Field), C.POINTER(EvalArgs), C.c_void_p]),
     "ffb_dopri5_attempt": (C.c_int, [C.POINTER(Field), C.POINTER(Dopri5Args), C.c_void_p]),
     "ffb_integrate_fixed": (C.c_int, [C.POINTER(Field), C.POINTER(FixedArgs), C.c_void_p]),
+    "ffb_dopri5_ctl_supported": (C.c_int, [C.POINTER(Field)]),
+    "ffb_dopri5_control": (C.c_int, [C.POINTER(CtlParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "ffb_dopri5_control_host": (C.c_int, [C.POINTER(CtlParams), C.c_void_p, C.POINTER(Ctl), C.c_int32]),
+    "ffb_time_program_rows": (C.c_int, [C.POINTER(TimeProgram), C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int32]),
     "ffb_reduce_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ffb_gaussian_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "ffb_philox_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]),
@@ -146,7 +187,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype, fn.argtypes = res, args
-    if lib.ffb_abi_version() != 1:
+    if lib.ffb_abi_version() != ABI_VERSION:
         raise FFBError("libffb200.so ABI version mismatch")
     _lib = lib
     return lib

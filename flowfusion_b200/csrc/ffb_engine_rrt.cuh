@@ -455,18 +455,22 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rrt(const __grid
 // =============================================================================================
 // k_dopri5_rrt: one attempted Dormand-Prince step of (x, log-det)
 // =============================================================================================
-template <bool GEN>
+template <bool GEN, bool DYN>      // DYN: step and buffer roles from the device-resident controller block (see k_dopri5_rr)
 __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_constant__ ffb::FieldDev f,
         const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
   using namespace ffb;
   using ENGT = EngineRRT_<GEN>;
+  if (DYN) { if (__ldg(&a.ctl->done) != 0) return; }
+  // controller values are re-read (L1 hits) where they are used so that none stays in a register across the evaluations
+#define FFB_STEP(x) (DYN ? __ldg(&a.ctl->x) : a.x)
+#define FFB_SWAPPED() (DYN && __ldg(&a.ctl->cur) != 0)
   CtxR cx; TanCtx tc;
   ENGT::init(cx, tc, f, NSLOT, 6);
   const int SD = cx.SD, CD = cx.CD, S = tc.S, ld = tc.ld;
   const bool owner = (tc.kind == RT_OWNER);
   float* LP0 = tc.klp() + NSLOT * ld;
   if (!cx.producer) {
-    for (int s = 0; s < 6; ++s) EngineRR::prep_beff(cx, f, a.ev[s].tfeat, cx.beff() + s * KMAX);
+    for (int s = 0; s < 6; ++s) EngineRR::prep_beff(cx, f, DYN ? a.ctl->ev[s].tfeat : a.ev[s].tfeat, cx.beff() + s * KMAX);
     rr_bar();
   }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -475,18 +479,21 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
     float* Y0 = ENGT::slot(cx, tc, SLOT_Y0);
     double nonfinite = 0.0;
     if (!cx.producer) {
-      rt_load_rows(Y0, a.y0, row0, nv, S, ld, SD, cx.tid);
-      rt_load_rows(ENGT::slot(cx, tc, 0), a.f0, row0, nv, S, ld, SD, cx.tid);
+      const bool sw = FFB_SWAPPED();
+      const float* __restrict__ in_lp = sw ? a.lp1 : a.lp0;
+      const float* __restrict__ in_dlp = sw ? a.dlp1 : a.dlp0;
+      rt_load_rows(Y0, sw ? a.y1 : a.y0, row0, nv, S, ld, SD, cx.tid);
+      rt_load_rows(ENGT::slot(cx, tc, 0), sw ? a.f1 : a.f0, row0, nv, S, ld, SD, cx.tid);
       if (CD) rt_load_rows(cx.condb(), a.cond, row0, nv, S, ld, CD, cx.tid);
       if (!tc.exact) rt_load_rows(tc.prb(), a.probes, row0, nv, S, ld, SD, cx.tid);
       for (int s = cx.tid; s < S; s += RR_NCOMP) {
-        LP0[s] = (s < nv) ? a.lp0[row0 + s] : 0.0f;
-        tc.klp()[s] = (s < nv) ? a.dlp0[row0 + s] : 0.0f;
+        LP0[s] = (s < nv) ? in_lp[row0 + s] : 0.0f;
+        tc.klp()[s] = (s < nv) ? in_dlp[row0 + s] : 0.0f;
         if (!is_finite_f(LP0[s])) nonfinite += 1.0;
       }
       rr_bar();
       if (owner) {
-        const float c00 = a.cb[0][0];
+        const float c00 = FFB_STEP(cb[0][0]);
         const float* K1 = ENGT::slot(cx, tc, 0);
         for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
           float y0v[8], kv[8], y[8];
@@ -502,12 +509,11 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
       }
     }
     for (int i = 1; i <= 6; ++i) {
-      const ffb_eval_scalars& ev = a.ev[i - 1];
-      ENGT::eval(cx, tc, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * KMAX, i);
+      ENGT::eval(cx, tc, f, FFB_STEP(ev[i - 1].a), FFB_STEP(ev[i - 1].c), FFB_STEP(ev[i - 1].sigma), FFB_STEP(ev[i - 1].sign), cx.beff() + (i - 1) * KMAX, i);
       if (!cx.producer && owner && i < 6) {
         float cbi[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) cbi[j] = a.cb[i][j];
+        for (int j = 0; j < 6; ++j) cbi[j] = FFB_STEP(cb[i][j]);
         for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
           float y0v[8], kv[8], acc[8];
           rt_load8(cx, tc, Y0, d0, y0v);
@@ -529,11 +535,14 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
     if (!cx.producer) {
       rr_bar();                                            // klp[6] of every sample is written
       double v[3] = {0.0, 0.0, nonfinite};
+      const int final_ = FFB_STEP(final);
+      const bool sw = FFB_SWAPPED();
       float* OUT = ENGT::slot(cx, tc, 1);              // K2 of an element is dead once its sums are formed
       if (owner && tc.smp < nv) {
         float ce[7], cm[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) { ce[j] = a.ce[j]; cm[j] = a.cm[j]; }
+        for (int j = 0; j < 7; ++j) { ce[j] = FFB_STEP(ce[j]); cm[j] = FFB_STEP(cm[j]); }
+        const float dt_ = FFB_STEP(dt), xi_ = FFB_STEP(x_interp);
         for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
           float y0v[8], y1v[8], k0[8], kv[8], err[8], mid[8];
           rt_load8(cx, tc, Y0, d0, y0v);
@@ -553,41 +562,43 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
             const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0v[u]), fabsf(y1v[u]))));
             const float q = __fdiv_rn(err[u], tol);
             if (d0 + u < SD) v[0] += (double)q * q;
-            out[u] = a.final ? dense_output(y0v[u], y1v[u], __fadd_rn(y0v[u], mid[u]), k0[u], kv[u], a.dt, a.x_interp) : 0.0f;
+            out[u] = final_ ? dense_output(y0v[u], y1v[u], __fadd_rn(y0v[u], mid[u]), k0[u], kv[u], dt_, xi_) : 0.0f;
           }
-          if (a.final) rt_store8(cx, tc, OUT, d0, out);
+          if (final_) rt_store8(cx, tc, OUT, d0, out);
         }
         if (cx.cg == 0) {
           // the log-det column: same formulas on (lp0, d(logp)/dt of the 7 stages)
           const int s = tc.smp;
           const float* kl = tc.klp();
           const float l0 = LP0[s];
-          float acc = __fmul_rn(kl[s], a.cb[5][0]);
-          for (int j = 1; j < 6; ++j) acc = fmaf(kl[j * ld + s], a.cb[5][j], acc);
+          float acc = __fmul_rn(kl[s], FFB_STEP(cb[5][0]));
+          for (int j = 1; j < 6; ++j) acc = fmaf(kl[j * ld + s], FFB_STEP(cb[5][j]), acc);
           const float l1 = __fadd_rn(l0, acc);
           float err = __fmul_rn(kl[s], ce[0]);
           for (int j = 1; j < 7; ++j) err = fmaf(kl[j * ld + s], ce[j], err);
           const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(l0), fabsf(l1))));
           const float q = __fdiv_rn(err, tol);
           v[1] += (double)q * q;
-          a.lp1[row0 + s] = l1;
-          a.dlp1[row0 + s] = kl[6 * ld + s];
-          if (a.final) {
+          (sw ? const_cast<float*>(a.lp0) : a.lp1)[row0 + s] = l1;
+          (sw ? const_cast<float*>(a.dlp0) : a.dlp1)[row0 + s] = kl[6 * ld + s];
+          if (final_) {
             float mid = __fmul_rn(kl[s], cm[0]);
             for (int j = 1; j < 7; ++j) mid = fmaf(kl[j * ld + s], cm[j], mid);
-            a.lp_out[row0 + s] = dense_output(l0, l1, __fadd_rn(l0, mid), kl[s], kl[6 * ld + s], a.dt, a.x_interp);
+            a.lp_out[row0 + s] = dense_output(l0, l1, __fadd_rn(l0, mid), kl[s], kl[6 * ld + s], dt_, xi_);
           }
         }
       }
       rr_bar();
-      rt_store_rows(a.y1, cx.ycur(), row0, nv, ld, SD, cx.tid);
-      rt_store_rows(a.f1, ENGT::slot(cx, tc, 6), row0, nv, ld, SD, cx.tid);
-      if (a.final) rt_store_rows(a.y_out, OUT, row0, nv, ld, SD, cx.tid);
+      rt_store_rows(sw ? const_cast<float*>(a.y0) : a.y1, cx.ycur(), row0, nv, ld, SD, cx.tid);
+      rt_store_rows(sw ? const_cast<float*>(a.f0) : a.f1, ENGT::slot(cx, tc, 6), row0, nv, ld, SD, cx.tid);
+      if (final_) rt_store_rows(a.y_out, OUT, row0, nv, ld, SD, cx.tid);
       const int slot[3] = {P_X_ERR, P_LP_ERR, P_NONFINITE};
       rr_block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
     }
   }
   EngineRR::fini(cx);
+#undef FFB_STEP
+#undef FFB_SWAPPED
 }
 
 // =============================================================================================

@@ -23,6 +23,7 @@
 #include "ffb200.h"
 #include "ffb_engine.cuh"
 #include "ffb_engine_tc.cuh"
+#include "ffb_control.cuh"
 
 using namespace ffb;
 
@@ -600,6 +601,19 @@ __global__ void k_pack_bias_tc(const float* __restrict__ b, int out_features, fl
 }
 
 // =============================================================================================
+// device-side dopri5 controller (ffb_control.cuh): one thread, between two attempt kernels
+// =============================================================================================
+__global__ void k_dopri5_control(const __grid_constant__ ffb_dopri5_ctl_params p, const double* __restrict__ sums,
+                                 ffb_dopri5_ctl* __restrict__ ctl, int after) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ffbctl::control_turn(p, sums, *ctl, after);
+}
+__global__ void k_time_program(const __grid_constant__ ffb_time_program prog, const float* __restrict__ times, int n,
+                               float sign, ffb_eval_scalars* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ffbctl::program_row(prog, times[i], sign, out + i);
+}
+
+// =============================================================================================
 // host side: C ABI
 // =============================================================================================
 struct ffb_net {
@@ -982,23 +996,28 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
     return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: y0, f0, y1, f1, partials, scratch are required");
   if (fd.div_mode != FFB_DIV_NONE && (!a->lp0 || !a->dlp0 || !a->lp1 || !a->dlp1))
     return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: log-det buffers are required with a divergence");
-  if (a->final && (!a->y_out || (fd.div_mode != FFB_DIV_NONE && !a->lp_out)))
+  if ((a->final || a->ctl) && (!a->y_out || (fd.div_mode != FFB_DIV_NONE && !a->lp_out)))
     return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: final step needs y_out (and lp_out)");
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
-  if (const size_t smt = rrt_smem(f, &fd, NSLOT, 6))
-    return gen_act(fd) ? launch_rrt(k_dopri5_rrt<true>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_)
-                       : launch_rrt(k_dopri5_rrt<false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+  const bool dyn = a->ctl != nullptr;
+  if (const size_t smt = rrt_smem(f, &fd, NSLOT, 6)) {
+    if (dyn) return gen_act(fd) ? launch_rrt(k_dopri5_rrt<true, true>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_)
+                                : launch_rrt(k_dopri5_rrt<false, true>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+    return gen_act(fd) ? launch_rrt(k_dopri5_rrt<true, false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_)
+                       : launch_rrt(k_dopri5_rrt<false, false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+  }
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, NSLOT, 6);
-    if (gen_act(fd)) {
-      if (fd.slots_smem) return launch_rr(k_dopri5_rr<true, true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
-      return launch_rr(k_dopri5_rr<false, true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
-    }
-    if (fd.slots_smem) return launch_rr(k_dopri5_rr<true, false>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
-    return launch_rr(k_dopri5_rr<false, false>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
+#define FFB_RR_DOPRI5(SS_, GEN_)                                                                                      \
+  (dyn ? launch_rr(k_dopri5_rr<SS_, GEN_, true>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_)                    \
+       : launch_rr(k_dopri5_rr<SS_, GEN_, false>, smem, "ffb_dopri5_attempt", fd, *a, a->batch, st_))
+    if (gen_act(fd)) return fd.slots_smem ? FFB_RR_DOPRI5(true, true) : FFB_RR_DOPRI5(false, true);
+    return fd.slots_smem ? FFB_RR_DOPRI5(true, false) : FFB_RR_DOPRI5(false, false);
+#undef FFB_RR_DOPRI5
   }
+  if (dyn) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: args->ctl needs the chunk-pipelined tensor-core engines (ffb_dopri5_ctl_supported)");
   if (engine()) {
     if (fd.slots_smem) return launch_tiles(k_dopri5<EngineTC, true>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
     return launch_tiles(k_dopri5<EngineTC, false>, EngineTC::NTHR, "ffb_dopri5_attempt", f, fd, *a, a->batch, st_);
@@ -1038,6 +1057,54 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
   }
   if (fd.slots_smem) return launch_tiles(k_fixed<EngineFFMA, true>, EngineFFMA::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);
   return launch_tiles(k_fixed<EngineFFMA, false>, EngineFFMA::NTHR, "ffb_integrate_fixed", f, fd, *a, a->batch, st_);
+}
+
+extern "C" int ffb_dopri5_ctl_supported(const ffb_field* f) {
+  FieldDev fd;
+  if (make_field(f, &fd)) return 0;
+  if (rrt_smem(f, &fd, NSLOT, 6)) return 1;
+  return use_rr(fd) ? 1 : 0;
+}
+
+extern "C" int ffb_dopri5_control(const ffb_dopri5_ctl_params* p, const double* sums, ffb_dopri5_ctl* ctl,
+                                  int32_t after_attempt, void* stream) {
+  if (!p || !ctl || (after_attempt && !sums)) return fail(FFB_ERR_ARG, "ffb_dopri5_control: null argument");
+  if (p->n_grid < 0 || p->n_grid > FFB_CTL_MAX_GRID) return fail(FFB_ERR_ARG, "ffb_dopri5_control: at most 16 step_t points");
+  if (p->prog.n_freq < 0 || p->prog.n_freq > FFB_MAX_FREQ) return fail(FFB_ERR_ARG, "ffb_dopri5_control: bad n_freq");
+  k_dopri5_control<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, sums, ctl, after_attempt);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+
+extern "C" int ffb_dopri5_control_host(const ffb_dopri5_ctl_params* p, const double* sums, ffb_dopri5_ctl* ctl,
+                                       int32_t after_attempt) {
+  if (!p || !ctl || (after_attempt && !sums)) return fail(FFB_ERR_ARG, "ffb_dopri5_control_host: null argument");
+  if (p->n_grid < 0 || p->n_grid > FFB_CTL_MAX_GRID) return fail(FFB_ERR_ARG, "ffb_dopri5_control_host: at most 16 step_t points");
+  if (p->prog.n_freq < 0 || p->prog.n_freq > FFB_MAX_FREQ) return fail(FFB_ERR_ARG, "ffb_dopri5_control_host: bad n_freq");
+  ffbctl::control_turn(*p, sums, *ctl, after_attempt);
+  return FFB_OK;
+}
+
+extern "C" int ffb_time_program_rows(const ffb_time_program* prog, const float* times, int32_t n, float sign,
+                                     ffb_eval_scalars* out, int32_t on_device) {
+  if (!prog || !times || !out || n < 0) return fail(FFB_ERR_ARG, "ffb_time_program_rows: bad argument");
+  if (prog->n_freq < 0 || prog->n_freq > FFB_MAX_FREQ) return fail(FFB_ERR_ARG, "ffb_time_program_rows: bad n_freq");
+  if (n == 0) return FFB_OK;
+  if (!on_device) {
+    for (int i = 0; i < n; ++i) ffbctl::program_row(*prog, times[i], sign, out + i);
+    return FFB_OK;
+  }
+  float* dt = nullptr; ffb_eval_scalars* dout = nullptr;
+  CUDA_TRY(cudaMalloc(&dt, sizeof(float) * n));
+  if (cudaMalloc(&dout, sizeof(ffb_eval_scalars) * n) != cudaSuccess) { cudaFree(dt); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
+  cudaMemcpy(dt, times, sizeof(float) * n, cudaMemcpyHostToDevice);
+  k_time_program<<<(n + 127) / 128, 128>>>(*prog, dt, n, sign, dout);
+  g_launches += 1;
+  cudaError_t e = cudaMemcpy(out, dout, sizeof(ffb_eval_scalars) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dt); cudaFree(dout);
+  if (e != cudaSuccess) return fail(FFB_ERR_CUDA, std::string("ffb_time_program_rows: ") + cudaGetErrorString(e));
+  return FFB_OK;
 }
 
 extern "C" int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream) {

@@ -146,17 +146,24 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rr(const __grid_
 // =============================================================================================
 // k_dopri5_rr
 // =============================================================================================
-template <bool SS, bool GEN>
+// DYN: the step (scalars, dt-scaled tableau, final flag) and the roles of the two state buffers come from the
+// device-resident controller block a.ctl (ffb_control.cuh) instead of the launch arguments; a finished solve
+// makes the kernel return at once.
+template <bool SS, bool GEN, bool DYN>
 __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_constant__ ffb::FieldDev f,
         const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
   using namespace ffb;
   using ENG = EngineRR_<GEN>;
+  if (DYN) { if (__ldg(&a.ctl->done) != 0) return; }
+  // controller values are re-read (L1 hits) where they are used so that none stays in a register across the evaluations
+#define FFB_STEP(x) (DYN ? __ldg(&a.ctl->x) : a.x)
+#define FFB_SWAPPED() (DYN && __ldg(&a.ctl->cur) != 0)
   CtxR cx;
   ENG::init(cx, f, reinterpret_cast<float*>(a.scratch), NSLOT, 6);
   const int SD = cx.SD, CD = cx.CD;
   const int bstride = f.n_calls * KMAX;
   if (!cx.producer) {
-    for (int s = 0; s < 6; ++s) ENG::prep_beff(cx, f, a.ev[s].tfeat, cx.beff() + s * bstride);
+    for (int s = 0; s < 6; ++s) ENG::prep_beff(cx, f, DYN ? a.ctl->ev[s].tfeat : a.ev[s].tfeat, cx.beff() + s * bstride);
     rr_bar();
   }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -165,12 +172,13 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
     float* Y0 = rr_slot<SS>(cx, SLOT_Y0);
     double nonfinite = 0.0;
     if (!cx.producer) {
-      load_rows_t<RR_NCOMP>(Y0, a.y0, row0, nv, TM, SD, cx.tid);
-      load_rows_t<RR_NCOMP>(rr_slot<SS>(cx, 0), a.f0, row0, nv, TM, SD, cx.tid);
+      const bool sw = FFB_SWAPPED();
+      load_rows_t<RR_NCOMP>(Y0, sw ? a.y1 : a.y0, row0, nv, TM, SD, cx.tid);
+      load_rows_t<RR_NCOMP>(rr_slot<SS>(cx, 0), sw ? a.f1 : a.f0, row0, nv, TM, SD, cx.tid);
       if (CD) load_rows_t<RR_NCOMP>(cx.condb(), a.cond, row0, nv, TM, CD, cx.tid);
       rr_bar();
       const float* K1 = rr_slot<SS>(cx, 0);
-      const float c00 = a.cb[0][0];
+      const float c00 = FFB_STEP(cb[0][0]);
       rr_for_blocks(cx, [&](int d0) {
         float y0v[8], kv[8], y[8];
         rr_load8(cx, Y0, d0, y0v);
@@ -184,13 +192,12 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
       });
     }
     for (int i = 1; i <= 6; ++i) {
-      const ffb_eval_scalars& ev = a.ev[i - 1];
-      ENG::template eval<SS>(cx, f, ev.a, ev.c, ev.sigma, ev.sign, cx.beff() + (i - 1) * bstride, i);
+      ENG::template eval<SS>(cx, f, FFB_STEP(ev[i - 1].a), FFB_STEP(ev[i - 1].c), FFB_STEP(ev[i - 1].sigma), FFB_STEP(ev[i - 1].sign), cx.beff() + (i - 1) * bstride, i);
       if (!cx.producer && i < 6) {
         // input of stage i+1: y0 + sum_j cb[i][j] k_j  (the 7th stage input is y1: FSAL)
         float cbi[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) cbi[j] = a.cb[i][j];
+        for (int j = 0; j < 6; ++j) cbi[j] = FFB_STEP(cb[i][j]);
         rr_for_blocks(cx, [&](int d0) {
           float y0v[8], kv[8], acc[8];
           rr_load8(cx, Y0, d0, y0v);
@@ -212,11 +219,13 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
     if (!cx.producer) {
       // cx.ycur() holds y1, slot 6 holds f1
       double v[2] = {0.0, nonfinite};
+      const int final_ = FFB_STEP(final);
       float* OUT = rr_slot<SS>(cx, 1);     // K2 of an element is dead once its error / mid sums are formed
       if (cx.row < nv) {
         float ce[7], cm[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) { ce[j] = a.ce[j]; cm[j] = a.cm[j]; }
+        for (int j = 0; j < 7; ++j) { ce[j] = FFB_STEP(ce[j]); cm[j] = FFB_STEP(cm[j]); }
+        const float dt_ = FFB_STEP(dt), xi_ = FFB_STEP(x_interp);
         rr_for_blocks(cx, [&](int d0) {
           float y0v[8], y1v[8], k0[8], kv[8], err[8], mid[8];
           rr_load8(cx, Y0, d0, y0v);
@@ -237,21 +246,24 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
             const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0v[u]), fabsf(y1v[u]))));
             const float q = __fdiv_rn(err[u], tol);
             if (d0 + u < SD) v[0] += (double)q * q;
-            out[u] = a.final ? dense_output(y0v[u], y1v[u], __fadd_rn(y0v[u], mid[u]), k0[u], kv[u], a.dt, a.x_interp) : 0.0f;
+            out[u] = final_ ? dense_output(y0v[u], y1v[u], __fadd_rn(y0v[u], mid[u]), k0[u], kv[u], dt_, xi_) : 0.0f;
           }
-          if (a.final) rr_store8(cx, OUT, d0, out);
+          if (final_) rr_store8(cx, OUT, d0, out);
         });
       }
       rr_bar();
-      store_rows_t<RR_NCOMP>(a.y1, cx.ycur(), row0, nv, SD, cx.tid);
-      store_rows_t<RR_NCOMP>(a.f1, rr_slot<SS>(cx, 6), row0, nv, SD, cx.tid);
-      if (a.final) store_rows_t<RR_NCOMP>(a.y_out, OUT, row0, nv, SD, cx.tid);
+      const bool sw = FFB_SWAPPED();
+      store_rows_t<RR_NCOMP>(sw ? const_cast<float*>(a.y0) : a.y1, cx.ycur(), row0, nv, SD, cx.tid);
+      store_rows_t<RR_NCOMP>(sw ? const_cast<float*>(a.f0) : a.f1, rr_slot<SS>(cx, 6), row0, nv, SD, cx.tid);
+      if (final_) store_rows_t<RR_NCOMP>(a.y_out, OUT, row0, nv, SD, cx.tid);
       const int slot[2] = {P_X_ERR, P_NONFINITE};
       rr_block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
       if (cx.tid == 0) a.partials[tile * FFB_NPART + P_LP_ERR] = 0.0;
     }
   }
   ENG::fini(cx);
+#undef FFB_STEP
+#undef FFB_SWAPPED
 }
 
 // =============================================================================================

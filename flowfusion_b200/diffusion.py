@@ -212,6 +212,47 @@ class SUBVPSDE(_BetaSDE):
         return torch.exp(-0.5 * lc), 1.0 - torch.exp(-lc)
 
 
+def fourier_program_spec(W_cpu: torch.Tensor, pi32: float):
+    """ffb_time_program of `sin|cos(((t*W)*2)*pi)` features, or None when there are too many frequencies."""
+    n = int(W_cpu.numel())
+    if n > L.MAX_FREQ:
+        return None
+    spec = L.TimeProgram()
+    spec.time_features, spec.n_freq, spec.pi = L.PROG_FOURIER, n, float(np.float32(pi32))
+    for k in range(n):
+        spec.W[k] = float(W_cpu.reshape(-1)[k])
+    spec.sde, spec.T = L.SDE_NONE, 1.0
+    return spec
+
+
+def _device_program(sde, W_cpu, pi_cpu, use_sigma, sde_mode):
+    """The same scalars as ``program`` for the device-side dopri5 controller (csrc/ffb_control.cuh), with every
+    Python scalar rounded to FP32 where the reference's eager ops would round it; None for an SDE class the
+    controller does not restate (the host loop is used then)."""
+    spec = fourier_program_spec(W_cpu.float(), float(pi_cpu))
+    if spec is None:
+        return None
+    f32 = lambda v: float(np.float32(v))
+    spec.use_sigma, spec.sde_mode = int(use_sigma), int(sde_mode)
+    # sigma(t) of VP / subVP and g(t) of subVP are 1 - exp(-small) near t = epsilon: one ulp of exp() is ~3e-4 of the
+    # result there (SURVEY Q11), so these stay on the host program, which uses the reference's own math library
+    if type(sde) is SUBVPSDE or (type(sde) is VPSDE and use_sigma):
+        return None
+    if type(sde) in (VPSDE, SUBVPSDE):
+        spec.sde = L.SDE_VP if type(sde) is VPSDE else L.SDE_SUBVP
+        bmin, bmax = float(sde.beta_min), float(sde.beta_max)
+        spec.T, spec.beta_min, spec.beta_diff = f32(sde.T), f32(bmin), f32(bmax - bmin)
+        spec.half_beta_diff, spec.m2_beta_min = f32(0.5 * (bmax - bmin)), f32(-2 * bmin)
+    elif type(sde) is VESDE:
+        spec.sde = L.SDE_VE
+        spec.T, spec.sigma_min = float(sde.T), float(sde.sigma_min)
+        spec.sigma_ratio = float(sde.sigma_max / sde.sigma_min)
+        spec.ve_gfac = float(torch.sqrt(2 * (torch.log(sde.sigma_max) - torch.log(sde.sigma_min)) / sde.T))
+    else:
+        return None
+    return spec
+
+
 # ----------------------------------------------------------------------------------------------
 # ScoreModel (`diffusion.py:124-815`)
 # ----------------------------------------------------------------------------------------------
@@ -264,6 +305,7 @@ class ScoreModel(torch.nn.Module):
             return rows
 
         program.g = lambda t: sde._g(t)
+        program.spec = _device_program(sde, W_cpu, pi_cpu, use_sigma, sde_mode)
         return program
 
     def _group(self):

@@ -322,6 +322,77 @@ class CudaBackend:
     def accept(self):
         self.cur = 1 - self.cur
 
+    # -- device-side controller (csrc/ffb_control.cuh): the host only enqueues and polls ----------------
+    def ctl_supported(self):
+        return self.B > 0 and bool(self.lib.ffb_dopri5_ctl_supported(C.byref(self.field.c)))
+
+    def ctl_begin(self, params: "L.CtlParams", t: float, dt_next: float, grid_idx: int, atol, rtol):
+        """Upload the controller block and let the device prepare the first attempt."""
+        self._ctl_params = params
+        host = L.Ctl()
+        host.t, host.dt_next, host.grid_idx = float(t), float(dt_next), int(grid_idx)
+        self.ctl_dev = torch.from_numpy(np.frombuffer(bytes(host), np.uint8).copy()).to(self.dev)
+        self._ctl_ptr = C.c_void_p(self.ctl_dev.data_ptr())
+        off = L.Ctl.done.offset
+        self._ctl_done_view = self.ctl_dev[off:off + 4].view(torch.int32)
+        self._ctl_flags = torch.zeros(64, dtype=torch.int32).pin_memory()
+        self._ctl_nflag = 0
+        L.check(self.lib.ffb_dopri5_control(C.byref(params), None, self._ctl_ptr, 0, self._stream), "ffb_dopri5_control")
+        a = self.dargs
+        c, n = self.cur, 1 - self.cur
+        a.batch = self.B
+        a.cond, a.probes = _ptr(self.cond), _ptr(self.probes)
+        a.y_out, a.lp_out = _ptr(self.y_out), _ptr(self.lp_out)
+        a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
+        a.y0, a.f0, a.lp0, a.dlp0 = _ptr(self.y[c]), _ptr(self.f[c]), _ptr(self.lp[c]), _ptr(self.dlp[c])
+        a.y1, a.f1, a.lp1, a.dlp1 = _ptr(self.y[n]), _ptr(self.f[n]), _ptr(self.lp[n]), _ptr(self.dlp[n])
+        a.atol, a.rtol, a.final = float(atol), float(rtol), 0
+        a.ctl = self._ctl_ptr
+        self._dargs_static = False                       # a later host-driven solve refills the block
+        self._ctl_first_record = len(profiler.records)
+        self._ctl_sums_ptr = _ptr(self.sums)
+
+    def ctl_attempt(self):
+        """attempt + tile reduction; the attempt returns at once when the solve has already finished"""
+        with _timed("dopri5_attempt", self.B):
+            L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(self.dargs), self._stream), "ffb_dopri5_attempt")
+        return self._reduce()
+
+    def ctl_control(self):
+        L.check(self.lib.ffb_dopri5_control(C.byref(self._ctl_params), self._ctl_sums_ptr, self._ctl_ptr, 1, self._stream),
+                "ffb_dopri5_control")
+
+    def ctl_flag_async(self):
+        """Start a device->host copy of `done`; returns a token for ctl_flag_wait."""
+        i = self._ctl_nflag % 64
+        self._ctl_nflag += 1
+        self._ctl_flags[i:i + 1].copy_(self._ctl_done_view, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return (i, ev)
+
+    def ctl_flag_wait(self, token):
+        i, ev = token
+        ev.synchronize()
+        return int(self._ctl_flags[i])
+
+    def ctl_finish(self) -> "L.Ctl":
+        """Synchronise and fetch the controller block (statistics, final state of the loop)."""
+        host = L.Ctl.from_buffer_copy(self.ctl_dev.cpu().numpy().tobytes())
+        self.dargs.ctl = None
+        if host.cur:
+            self.cur = 1 - self.cur
+        if profiler.enabled:       # launches enqueued after the solve had finished did no work: not attempts
+            keep, seen = [], 0
+            for idx, rec in enumerate(profiler.records):
+                if idx >= self._ctl_first_record and rec[0] == "dopri5_attempt":
+                    seen += 1
+                    if seen > host.n_attempts:
+                        continue
+                keep.append(rec)
+            profiler.records[:] = keep
+        return host
+
     def output(self):
         return self.y_out, self.lp_out
 

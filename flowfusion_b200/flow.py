@@ -37,6 +37,15 @@ def _raw_time_program(times32: np.ndarray) -> np.ndarray:
     return rows
 
 
+def _raw_time_spec():
+    spec = L.TimeProgram()
+    spec.time_features, spec.sde, spec.T = L.PROG_RAW_T, L.SDE_NONE, 1.0
+    return spec
+
+
+_raw_time_program.spec = _raw_time_spec()       # the same program for the device-side dopri5 controller
+
+
 class _FlowBase(nn.Module):
     def _build(self, target_dimension, conditional_dimension, hidden_units, activation, target_shift, target_scale):
         self.target_dimension = target_dimension

@@ -20,7 +20,9 @@ Semantics follow torchdiffeq 0.2.x (call sites: reference `diffusion.py:631-639,
 from __future__ import annotations
 
 import bisect
+import contextlib
 import dataclasses
+import os
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -64,6 +66,35 @@ class SolveStats:
     accept_history: List[bool] = dataclasses.field(default_factory=list)
     ratio_history: List[float] = dataclasses.field(default_factory=list)
     launches: int = 0
+    controller: str = "host"
+
+
+# Where torchdiffeq's accept / step-size loop runs: "device" = csrc/ffb_control.cuh between two attempt kernels
+# (the host enqueues ahead and polls a flag), "host" = the Python loop below (one device->host read per attempt).
+# Both evaluate the same statements; "device" is used whenever the backend and the scalar program support it.
+_CONTROLLER = os.environ.get("FFB_CONTROLLER", "device")
+_CTL_BATCH = 4        # attempts enqueued between two polls of the `done` flag
+
+
+def set_controller(mode: str):
+    global _CONTROLLER
+    if mode not in ("device", "host"):
+        raise ValueError("controller must be 'device' or 'host'")
+    _CONTROLLER = mode
+
+
+def get_controller() -> str:
+    return _CONTROLLER
+
+
+@contextlib.contextmanager
+def controller(mode: str):
+    prev = _CONTROLLER
+    set_controller(mode)
+    try:
+        yield
+    finally:
+        set_controller(prev)
 
 
 class SolverError(AssertionError):
@@ -173,6 +204,25 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
         grid = sorted(float(v) for v in g if v >= ts)
     grid_idx = min(bisect.bisect(grid, float(ts)), len(grid) - 1) if grid else 0
 
+    spec = getattr(program, "spec", None)
+    if (_CONTROLLER == "device" and spec is not None and len(grid) <= L.CTL_MAX_GRID and counts["x"] > 0
+            and getattr(backend, "ctl_supported", lambda: False)()):
+        p = L.CtlParams()
+        p.t_end, p.min_step, p.max_step = float(te), float(min_step), float(max_step)
+        p.safety, p.ifactor, p.dfactor = float(safety), float(ifactor), float(dfactor)
+        p.n_x, p.n_lp, p.n_cond = int(counts["x"]), int(counts.get("lp") or 0), int(counts.get("cond") or 0)
+        p.reverse, p.max_num_steps, p.n_grid = int(reverse), min(max_num_steps, 2 ** 31 - 1), len(grid)
+        for i, v in enumerate(grid):
+            p.grid[i] = v
+        for i in range(6):
+            p.alpha[i] = float(ALPHA32[i])
+            for j in range(6):
+                p.beta[i][j] = float(BETA32[i, j])
+        for j in range(7):
+            p.c_err[j], p.c_mid[j] = float(C_ERR32[j]), float(C_MID32[j])
+        p.prog = spec
+        return _dopri5_device(backend, p, st, float(ts), float(dt), grid_idx, atol32, rtol32, group)
+
     t = ts
     n_steps = 0
     done = False
@@ -236,6 +286,42 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
                 nxt_dt = dts * np.minimum(ifactor, np.maximum(safety / r ** f64(0.2), dfac))
             dt = f64(np.clip(nxt_dt, min_step, max_step)) if not np.isnan(nxt_dt) else f64(np.nan)
     assert done, "internal: integration loop ended without a final step"
+    return st
+
+
+def _dopri5_device(backend, params, st: SolveStats, ts: float, dt: float, grid_idx: int, atol32, rtol32, group) -> SolveStats:
+    """The adaptive loop with the controller on the device: per attempt the host enqueues
+    attempt -> tile reduction -> (all-reduce over ranks) -> control and never waits for the result; it polls the
+    controller's `done` flag once per _CTL_BATCH attempts, one batch behind what it has enqueued.  Every rank
+    sees bit-identical sums, hence identical flags, hence the same number of collectives."""
+    st.controller = "device"
+    backend.ctl_begin(params, ts, dt, grid_idx, atol32, rtol32)
+    st.launches += 1
+    pending = None
+    while True:
+        for _ in range(_CTL_BATCH):
+            _allreduce(backend.ctl_attempt(), group)
+            backend.ctl_control()
+            st.launches += 3
+        token = backend.ctl_flag_async()
+        if pending is not None and backend.ctl_flag_wait(pending) != L.CTL_RUNNING:
+            break
+        pending = token
+    c = backend.ctl_finish()
+    n = int(c.n_attempts)
+    st.nfe += 6 * n
+    st.accepted, st.rejected = int(c.n_accepted), int(c.n_rejected)
+    for i in range(min(n, L.CTL_HIST)):
+        st.dt_history.append(float(c.hist_dt[i]))
+        st.accept_history.append(bool(c.hist_accept[i]))
+        st.ratio_history.append(float(c.hist_ratio[i]))
+    if c.done == L.CTL_NONFINITE:
+        raise SolverError("non-finite values in state `y`")
+    if c.done == L.CTL_DT_UNDERFLOW:
+        raise SolverError("underflow in dt {}".format(float(c.dt_next)))
+    if c.done == L.CTL_MAX_STEPS:
+        raise SolverError("max_num_steps exceeded ({}>={})".format(n, int(params.max_num_steps)))
+    assert c.done == L.CTL_FINISHED, "internal: device controller ended in state {}".format(int(c.done))
     return st
 
 

@@ -76,6 +76,8 @@ class SymplecticMLP(nn.Module):
             rows[:, L.MAX_TFEAT + 3] = 1.0
             return rows
 
+        from .diffusion import fourier_program_spec
+        program.spec = fourier_program_spec(W, math.pi)      # device-side dopri5 controller
         return program
 
     def forward(self, t, state, conditional):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FFB_ABI_VERSION 1
+#define FFB_ABI_VERSION 2
 #define FFB_MAX_LAYERS 8    /* Linear layers per network                         */
 #define FFB_MAX_WIDTH 128   /* widest layer (input or output) the tile engine holds */
 #define FFB_MAX_TFEAT 32    /* time-feature columns (embedding_dimensions or 1)  */
@@ -152,7 +152,92 @@ typedef struct {
   double* partials;
   int32_t* status;
   void* scratch;
+  const struct ffb_dopri5_ctl* ctl;         /* NULL: the step is described by the fields above (host-driven loop);
+                                               else: device-resident step + controller state, see below            */
 } ffb_dopri5_args;
+
+/* ---- device-side dopri5 controller ------------------------------------------------------------
+ * torchdiffeq's adaptive loop (accept test, step-size controller, step_t clipping, stage times) and the
+ * per-evaluation scalars of the next attempt, evaluated by a one-block kernel between two attempts, so that
+ * the host never sits between two launches: it enqueues attempt -> reduce [-> all-reduce] -> control a few
+ * times ahead and only polls `done`.  Attempt kernels launched after the solve has finished return at once.
+ * The same code compiles for the host (ffb_dopri5_control_host) so that the controller is testable without a
+ * GPU.  Semantics: SURVEY.md section 8c T3-T12, identical to flowfusion_b200/solver.py::dopri5 (host loop). */
+#define FFB_PROG_RAW_T 0      /* tfeat[0] = t                                  flow.py:112-115             */
+#define FFB_PROG_FOURIER 1    /* tfeat = sin|cos(((t*W)*2)*pi)                 diffusion.py:109-110,
+                                                                               symplectic.py:103           */
+#define FFB_SDE_NONE 0        /* a = c = 0, sigma = 1 (flows, symplectic)                                  */
+#define FFB_SDE_VP 1          /* diffusion.py:1047-1156                                                    */
+#define FFB_SDE_VE 2          /* diffusion.py:852-905                                                      */
+#define FFB_SDE_SUBVP 3       /* diffusion.py:1223-1342                                                    */
+#define FFB_MAX_FREQ (FFB_MAX_TFEAT / 2)
+
+/* How ffb_eval_scalars derive from the (user) time of an evaluation.  Every constant is the FP32 value the
+ * reference's eager ops would use (Python scalars rounded to FP32 where they meet an FP32 tensor). */
+typedef struct {
+  int32_t time_features;        /* FFB_PROG_*                                                  */
+  int32_t n_freq;               /* FOURIER: embedding_dimensions / 2                           */
+  float W[FFB_MAX_FREQ];        /* FOURIER: frequencies                                         */
+  float pi;                     /* FOURIER: fl32(pi)                                            */
+  int32_t sde;                  /* FFB_SDE_*                                                    */
+  int32_t use_sigma;            /* fill ev.sigma with sigma(t) (else 1)                         */
+  int32_t sde_mode;             /* c = g^2 (reverse SDE) instead of 0.5*g^2 (PF-ODE)            */
+  float T;
+  float beta_min, beta_diff;    /* VP / subVP: fl32(beta_min), fl32(beta_max - beta_min)        */
+  float half_beta_diff;         /* fl32(0.5*(beta_max - beta_min))                              */
+  float m2_beta_min;            /* fl32(-2*beta_min)                                            */
+  float sigma_min, sigma_ratio; /* VE: sigma_min, fl32(sigma_max / sigma_min)                   */
+  float ve_gfac;                /* VE: fl32(sqrt(2*(log sigma_max - log sigma_min)/T))          */
+} ffb_time_program;
+
+#define FFB_CTL_MAX_GRID 16   /* options['step_t'] points                                       */
+#define FFB_CTL_HIST 256      /* attempts whose (dt, ratio, accept) are kept for SolveStats      */
+/* ffb_dopri5_ctl.done */
+#define FFB_CTL_RUNNING 0
+#define FFB_CTL_FINISHED 1
+#define FFB_CTL_NONFINITE (-1)      /* torchdiffeq: "non-finite values in state `y`"   */
+#define FFB_CTL_DT_UNDERFLOW (-2)   /* torchdiffeq: "underflow in dt"                   */
+#define FFB_CTL_MAX_STEPS (-3)      /* torchdiffeq: "max_num_steps exceeded"            */
+
+/* constants of one solve (passed by value to the control kernel) */
+typedef struct {
+  double t_end;                 /* solver time (negated for descending spans, T2)               */
+  double min_step, max_step, safety, ifactor, dfactor;
+  int64_t n_x, n_lp, n_cond;    /* GLOBAL element counts of the RMS norms (0 = component absent) */
+  int32_t reverse;              /* user time = -solver time, ev.sign = -1                        */
+  int32_t max_num_steps;
+  int32_t n_grid;
+  int32_t _pad;
+  double grid[FFB_CTL_MAX_GRID];/* ascending solver-time step_t points >= t0                     */
+  float alpha[6];               /* Dormand-Prince tableau rounded to FP32 as torchdiffeq does    */
+  float beta[6][6];
+  float c_err[7];
+  float c_mid[7];
+  ffb_time_program prog;
+} ffb_dopri5_ctl_params;
+
+/* device-resident block: the next attempt's step + the controller's state */
+typedef struct ffb_dopri5_ctl {
+  /* read by ffb_dopri5_attempt (same meaning as the same-named fields of ffb_dopri5_args) */
+  ffb_eval_scalars ev[6];
+  float cb[6][6];
+  float ce[7];
+  float cm[7];
+  float dt, x_interp;
+  int32_t final;
+  int32_t cur;                  /* 0: (y0,f0,lp0,dlp0) hold the current state and (y1,..) receive the
+                                   candidate; 1: the roles are swapped (flips on every accepted step)   */
+  int32_t done;                 /* FFB_CTL_*                                                             */
+  int32_t grid_idx;
+  /* controller state */
+  double t, dt_next;            /* initialise: t = t0, dt_next = first step                              */
+  double cur_t1, cur_dt;        /* the attempt in flight                                                 */
+  int32_t cur_on_grid;
+  int32_t n_attempts, n_accepted, n_rejected;
+  double hist_dt[FFB_CTL_HIST];
+  float hist_ratio[FFB_CTL_HIST];
+  uint8_t hist_accept[FFB_CTL_HIST];
+} ffb_dopri5_ctl;
 
 /* ---- fixed-grid integrators, whole trajectory on-chip ---------------------------------- */
 #define FFB_STEP_STRIDE 8   /* floats per step in step_table: dt, g, sqrt(-dt), then method constants */
@@ -193,6 +278,21 @@ size_t ffb_scratch_bytes(const ffb_field* field);
 int ffb_field_eval(const ffb_field* field, const ffb_eval_args* args, void* stream);
 int ffb_dopri5_attempt(const ffb_field* field, const ffb_dopri5_args* args, void* stream);
 int ffb_integrate_fixed(const ffb_field* field, const ffb_fixed_args* args, void* stream);
+
+/* 1 when ffb_dopri5_attempt accepts args->ctl for this field (the chunk-pipelined tensor-core engines) */
+int ffb_dopri5_ctl_supported(const ffb_field* field);
+/* One controller turn on the device (one block, enqueued on `stream`).  after_attempt = 0: prepare the first
+ * attempt from ctl->t / ctl->dt_next; 1: judge the attempt whose FFB_NPART sums are in `sums` (device, FP64,
+ * already reduced over tiles and ranks), update the state, prepare the next attempt or set ctl->done. */
+int ffb_dopri5_control(const ffb_dopri5_ctl_params* params, const double* sums, ffb_dopri5_ctl* ctl,
+                       int32_t after_attempt, void* stream);
+/* the same turn on the CPU (host pointers): test twin of the kernel above, no CUDA call */
+int ffb_dopri5_control_host(const ffb_dopri5_ctl_params* params, const double* sums, ffb_dopri5_ctl* ctl,
+                            int32_t after_attempt);
+/* rows of ffb_eval_scalars for n user times (host arrays); on_device != 0 evaluates them in a kernel on the
+ * current device (synchronous, for tests), else on the CPU twin */
+int ffb_time_program_rows(const ffb_time_program* prog, const float* times, int32_t n, float sign,
+                          ffb_eval_scalars* out, int32_t on_device);
 
 /* sums[FFB_NPART] = sum over tiles of partials, in tile order (deterministic) */
 int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream);

@@ -173,6 +173,44 @@ class FakeBackend:
     def output(self):
         return self.y_out, (self.lp_out if self.with_lp else None)
 
+    # -- device-side controller: the CPU twin of the control kernel (ffb_dopri5_control_host) drives this model ----
+    def ctl_supported(self):
+        return self.B > 0
+
+    def ctl_begin(self, params, t, dt_next, grid_idx, atol, rtol):
+        self._lib = L.load()
+        self._p, self._c = params, L.Ctl()
+        self._c.t, self._c.dt_next, self._c.grid_idx = float(t), float(dt_next), int(grid_idx)
+        self._tol = (atol, rtol)
+        self._sums = torch.zeros(L.NPART, dtype=torch.float64)
+        L.check(self._lib.ffb_dopri5_control_host(C.byref(self._p), None, C.byref(self._c), 0), "control_host")
+
+    def ctl_attempt(self):
+        c = self._c
+        if c.done == L.CTL_RUNNING:           # the CUDA attempt kernel returns at once otherwise
+            ev = np.frombuffer(bytes(c.ev), np.float32).reshape(6, L.EV_FLOATS).copy()
+            cb = np.frombuffer(bytes(c.cb), np.float32).reshape(6, 6).copy()
+            ce, cm = np.frombuffer(bytes(c.ce), np.float32).copy(), np.frombuffer(bytes(c.cm), np.float32).copy()
+            self._sums = self.attempt(ev, cb, ce, cm, np.float32(c.dt), self._tol[0], self._tol[1], bool(c.final),
+                                      np.float32(c.x_interp))
+        return self._sums
+
+    def ctl_control(self):
+        cur = self._c.cur
+        sums = np.ascontiguousarray(self._sums.numpy(), np.float64)
+        L.check(self._lib.ffb_dopri5_control_host(C.byref(self._p), sums.ctypes.data, C.byref(self._c), 1), "control_host")
+        if self._c.cur != cur:
+            self.accept()
+
+    def ctl_flag_async(self):
+        return int(self._c.done)
+
+    def ctl_flag_wait(self, token):
+        return token
+
+    def ctl_finish(self):
+        return self._c
+
 
 def _dense(y0, y1, ymid, f0, f1, dt, x):
     a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * ymid

@@ -30,7 +30,7 @@ def check_stats(stats, meta_stats):
 def test_library_loaded(cuda_dev):
     from flowfusion_b200 import _lib, engine
     lib = _lib.load()
-    assert lib.ffb_abi_version() == 1
+    assert lib.ffb_abi_version() == _lib.ABI_VERSION
     info = engine.device_info()
     assert info["cc_major"] == 10, info
 
