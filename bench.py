@@ -383,6 +383,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{name}: {w['desc']}", "rows_per_gpu": B, "nfe": nfe,
                        "dopri5_steps": None if stats is None else [stats.accepted, stats.rejected],
+                       "dopri5_controller": getattr(stats, "controller", None),
                        "l2": "working set (state + derivative ping-pong buffers) exceeds the 126 MB L2; no flush needed",
                        "weights": "random init, torch.manual_seed(1234), reference construction order"},
             "clocks": clk.summary(), "gpu_launches": launches, "roofline": roof}

@@ -76,7 +76,7 @@ class Dopri5Args(C.Structure):
 PROG_RAW_T, PROG_FOURIER = 0, 1
 SDE_NONE, SDE_VP, SDE_VE, SDE_SUBVP = 0, 1, 2, 3
 MAX_FREQ = MAX_TFEAT // 2
-CTL_MAX_GRID, CTL_HIST = 16, 256
+CTL_MAX_GRID, CTL_HIST, CTL_NOTIFY_SLOTS = 16, 256, 1024
 CTL_RUNNING, CTL_FINISHED, CTL_NONFINITE, CTL_DT_UNDERFLOW, CTL_MAX_STEPS = 0, 1, -1, -2, -3
 
 
@@ -103,6 +103,7 @@ class Ctl(C.Structure):
                 ("done", C.c_int32), ("grid_idx", C.c_int32), ("t", C.c_double), ("dt_next", C.c_double),
                 ("cur_t1", C.c_double), ("cur_dt", C.c_double), ("cur_on_grid", C.c_int32),
                 ("n_attempts", C.c_int32), ("n_accepted", C.c_int32), ("n_rejected", C.c_int32),
+                ("n_turns", C.c_int32), ("_pad", C.c_int32), ("notify", C.c_void_p),
                 ("hist_dt", C.c_double * CTL_HIST), ("hist_ratio", C.c_float * CTL_HIST),
                 ("hist_accept", C.c_uint8 * CTL_HIST)]
 
@@ -129,7 +130,7 @@ SYMBOLS = {
     "ffb_dopri5_attempt": (C.c_int, [C.POINTER(Field), C.POINTER(Dopri5Args), C.c_void_p]),
     "ffb_integrate_fixed": (C.c_int, [C.POINTER(Field), C.POINTER(FixedArgs), C.c_void_p]),
     "ffb_dopri5_ctl_supported": (C.c_int, [C.POINTER(Field)]),
-    "ffb_dopri5_control": (C.c_int, [C.POINTER(CtlParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "ffb_dopri5_control": (C.c_int, [C.POINTER(CtlParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "ffb_dopri5_control_host": (C.c_int, [C.POINTER(CtlParams), C.c_void_p, C.POINTER(Ctl), C.c_int32]),
     "ffb_time_program_rows": (C.c_int, [C.POINTER(TimeProgram), C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int32]),
     "ffb_reduce_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -183,8 +183,20 @@ FFB_HD void after_attempt(const ffb_dopri5_ctl_params& p, const double* s, ffb_d
   prepare_attempt(p, c);
 }
 
+// tell the host which turn has been taken and whether the solve goes on (pinned host memory, no stream operation)
+FFB_HD void notify_host(ffb_dopri5_ctl& c) {
+  c.n_turns += 1;
+  if (c.notify) {
+    volatile int32_t* slot = c.notify + ((c.n_turns - 1) & (FFB_CTL_NOTIFY_SLOTS - 1));
+    *slot = (int32_t)(((uint32_t)c.n_turns << 8) | ((uint32_t)c.done & 0xffu));
+#ifdef __CUDA_ARCH__
+    __threadfence_system();
+#endif
+  }
+}
+
 FFB_HD void control_turn(const ffb_dopri5_ctl_params& p, const double* sums, ffb_dopri5_ctl& c, int after) {
-  if (after) after_attempt(p, sums, c);
+  if (after) { after_attempt(p, sums, c); notify_host(c); }
   else if (c.done == FFB_CTL_RUNNING) prepare_attempt(p, c);
 }
 

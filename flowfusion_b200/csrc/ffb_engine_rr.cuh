@@ -77,6 +77,22 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
 #endif
 constexpr int RR_TRACE_CAP = 2048;
 
+// per-evaluation scalars by value (launch arguments) or read from the device-resident controller block when used
+struct EvVals {
+  float a_, c_, sigma_, sign_;
+  __device__ __forceinline__ float a() const { return a_; }
+  __device__ __forceinline__ float c() const { return c_; }
+  __device__ __forceinline__ float sigma() const { return sigma_; }
+  __device__ __forceinline__ float sign() const { return sign_; }
+};
+struct EvCtl {
+  const ffb_dopri5_ctl* ctl; int i;
+  __device__ __forceinline__ float a() const { return __ldg(&ctl->ev[i].a); }
+  __device__ __forceinline__ float c() const { return __ldg(&ctl->ev[i].c); }
+  __device__ __forceinline__ float sigma() const { return __ldg(&ctl->ev[i].sigma); }
+  __device__ __forceinline__ float sign() const { return __ldg(&ctl->ev[i].sign); }
+};
+
 struct CtxR {
   int tr_role, tr_n;
   uint32_t o_ring, o_ycur, o_cond, o_sbias, o_beff, o_wt, o_red, o_bar, o_slots;
@@ -450,6 +466,13 @@ struct EngineRR_ {
   static __device__ __forceinline__ void eval(CtxR& cx, const FieldDev& f, float ev_a, float ev_c, float ev_sigma,
                                               float ev_sign, const float* beff, int dst, unsigned call_mask = 3u,
                                               OV&& overlap = OV()) {
+    eval_ev<SS>(cx, f, EvVals{ev_a, ev_c, ev_sigma, ev_sign}, beff, dst, call_mask, static_cast<OV&&>(overlap));
+  }
+  // EV: where the per-evaluation scalars come from.  They are fetched where the last-layer epilogue uses them, so a
+  // source that costs a load (EvCtl: the device-resident controller block) holds no register across the hidden layers.
+  template <bool SS, class EV, class OV = NoOverlap>
+  static __device__ __forceinline__ void eval_ev(CtxR& cx, const FieldDev& f, const EV& ev, const float* beff, int dst,
+                                                 unsigned call_mask = 3u, OV&& overlap = OV()) {
     bool first = true;
     for (int c = 0; c < f.n_calls; ++c) {
       if (!((call_mask >> c) & 1u)) continue;
@@ -465,7 +488,6 @@ struct EngineRR_ {
       hidden(cx, net, c, beff + c * KMAX);
       float* kd = rr_slot<SS>(cx, dst) + cx.row;
       const float* yc = cx.ycur() + cx.row;
-      const float sgn = ev_sign * f.out_sign[c];
       const int ooff = f.out_off[c], Nreal = net.N[net.n_layers - 1];
       const bool score = (f.kind == FFB_FIELD_SCORE), use_sigma = f.use_sigma != 0, has_drift = f.has_drift != 0;
       last(cx, net, c, beff + c * KMAX, [&](int c0, const float (&o)[8]) {
@@ -473,6 +495,9 @@ struct EngineRR_ {
 #pragma unroll
         for (int u = 0; u < 8; ++u) yv[u] = (score && has_drift) ? yc[(ooff + min(c0 + u, Nreal - 1)) * LDA] : 0.0f;
         float xd_[8];
+        const float sgn = ev.sign() * f.out_sign[c];
+        const float ev_a = (score && has_drift) ? ev.a() : 0.0f, ev_c = score ? ev.c() : 0.0f;
+        const float ev_sigma = (score && use_sigma) ? ev.sigma() : 1.0f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (score) {

@@ -242,6 +242,12 @@ struct EngineRRT_ {
   // one evaluation at cx.ycur(): derivative -> slot dst, divergence -> klp[dst]
   static __device__ __forceinline__ void eval(CtxR& cx, const TanCtx& tc, const FieldDev& f, float ev_a, float ev_c,
                                               float ev_sigma, float ev_sign, const float* beff, int dst) {
+    eval_ev(cx, tc, f, EvVals{ev_a, ev_c, ev_sigma, ev_sign}, beff, dst);
+  }
+  // EV: source of the per-evaluation scalars, fetched where they are used (see EngineRR_::eval_ev)
+  template <class EV>
+  static __device__ __forceinline__ void eval_ev(CtxR& cx, const TanCtx& tc, const FieldDev& f, const EV& ev,
+                                                 const float* beff, int dst) {
     const NetDev& net = f.net[0];
     if (cx.warp == RR_WLOAD) { EngineRR::load_net(cx, net); return; }
     if (cx.warp == RR_WMMA) { EngineRR::mma_net(cx, net); return; }
@@ -267,6 +273,9 @@ struct EngineRRT_ {
       tc_ld8(dcol + (uint32_t)(c0 - 8 * cx.cg), m);
       tc_wait_ld();
       if (tc.kind == RT_OWNER) {
+        const float ev_sign = ev.sign();
+        const float ev_a = (score && has_drift) ? ev.a() : 0.0f, ev_c = score ? ev.c() : 0.0f;
+        const float ev_sigma = (score && use_sigma) ? ev.sigma() : 1.0f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int n = c0 + u;
@@ -310,13 +319,13 @@ struct EngineRRT_ {
       else { for (int g = 0; 8 * g < xd; ++g) tr += tc.diag()[s * 16 + g]; }
       float dv;
       if (score) {
-        const float trs = use_sigma ? __fdiv_rn(tr, ev_sigma) : tr;
-        const float lin = has_drift ? ev_a * (float)xd : 0.0f;
-        dv = lin - ev_c * trs;
+        const float trs = use_sigma ? __fdiv_rn(tr, ev.sigma()) : tr;
+        const float lin = has_drift ? ev.a() * (float)xd : 0.0f;
+        dv = lin - ev.c() * trs;
       } else {
         dv = tr;
       }
-      tc.klp()[dst * ld + s] = dv * ev_sign;
+      tc.klp()[dst * ld + s] = dv * ev.sign();
     }
   }
 };
@@ -509,7 +518,8 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
       }
     }
     for (int i = 1; i <= 6; ++i) {
-      ENGT::eval(cx, tc, f, FFB_STEP(ev[i - 1].a), FFB_STEP(ev[i - 1].c), FFB_STEP(ev[i - 1].sigma), FFB_STEP(ev[i - 1].sign), cx.beff() + (i - 1) * KMAX, i);
+      if constexpr (DYN) ENGT::eval_ev(cx, tc, f, EvCtl{a.ctl, i - 1}, cx.beff() + (i - 1) * KMAX, i);
+      else ENGT::eval(cx, tc, f, a.ev[i - 1].a, a.ev[i - 1].c, a.ev[i - 1].sigma, a.ev[i - 1].sign, cx.beff() + (i - 1) * KMAX, i);
       if (!cx.producer && owner && i < 6) {
         float cbi[6];
 #pragma unroll

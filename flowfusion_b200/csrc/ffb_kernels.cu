@@ -466,14 +466,31 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
 // =============================================================================================
 // helpers
 // =============================================================================================
-__global__ void k_reduce(const double* __restrict__ partials, int64_t ntiles, double* __restrict__ sums) {
-  // one warp per quantity; fixed strided order + shuffle tree => deterministic
-  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (q >= FFB_NPART) return;
-  double s = 0.0;
-  for (int64_t t = lane; t < ntiles; t += 32) s += partials[t * FFB_NPART + q];
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0) sums[q] = s;
+// sums[q] = sum over tiles of partials[tile][q], in a fixed order (deterministic).  Thread i owns quantity q = i & 15
+// of the tiles (i >> 4) + 64 k: a warp reads two whole 128-byte rows per load and keeps 8 loads in flight (the former
+// one-warp-per-quantity loop was a chain of dependent L2 reads: 80 us for the 7 813 tiles of 1 M rows).
+__device__ __forceinline__ void reduce_partials_block(const double* __restrict__ partials, int64_t ntiles, double* sh /*[1024]*/,
+                                                      double* out /*[FFB_NPART], shared or global*/) {
+  const int q = threadIdx.x & (FFB_NPART - 1);
+  const int64_t r = threadIdx.x >> 4;
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t t = r;
+  for (; t + 7 * 64 < ntiles; t += 8 * 64) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] += partials[(t + 64 * u) * FFB_NPART + q];
+  }
+  for (; t < ntiles; t += 64) s[0] += partials[t * FFB_NPART + q];
+  sh[threadIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  __syncthreads();
+  if (threadIdx.x < FFB_NPART) {
+    double a = 0.0;
+    for (int k = 0; k < 64; ++k) a += sh[k * FFB_NPART + threadIdx.x];
+    out[threadIdx.x] = a;
+  }
+}
+__global__ void __launch_bounds__(1024) k_reduce(const double* __restrict__ partials, int64_t ntiles, double* __restrict__ sums) {
+  __shared__ double sh[1024];
+  reduce_partials_block(partials, ntiles, sh, sums);
 }
 
 __global__ void k_gauss_logprob(const float* __restrict__ x, const float* __restrict__ add, float* __restrict__ out,
@@ -606,6 +623,20 @@ __global__ void k_pack_bias_tc(const float* __restrict__ b, int out_features, fl
 __global__ void k_dopri5_control(const __grid_constant__ ffb_dopri5_ctl_params p, const double* __restrict__ sums,
                                  ffb_dopri5_ctl* __restrict__ ctl, int after) {
   if (threadIdx.x == 0 && blockIdx.x == 0) ffbctl::control_turn(p, sums, *ctl, after);
+}
+// single-GPU shortcut: the tile reduction and the controller turn in one launch (sums is still written, for the caller)
+__global__ void __launch_bounds__(1024) k_dopri5_reduce_control(const __grid_constant__ ffb_dopri5_ctl_params p,
+        const double* __restrict__ partials, int64_t ntiles, double* __restrict__ sums, ffb_dopri5_ctl* __restrict__ ctl) {
+  __shared__ double sh[1024];
+  __shared__ double tot[FFB_NPART];
+  if (ctl->done != FFB_CTL_RUNNING) {                  // uniform: nothing in flight to judge, only the turn is counted
+    if (threadIdx.x == 0) ffbctl::notify_host(*ctl);
+    return;
+  }
+  reduce_partials_block(partials, ntiles, sh, tot);
+  __syncthreads();
+  if (threadIdx.x < FFB_NPART) sums[threadIdx.x] = tot[threadIdx.x];
+  if (threadIdx.x == 0) ffbctl::control_turn(p, tot, *ctl, 1);
 }
 __global__ void k_time_program(const __grid_constant__ ffb_time_program prog, const float* __restrict__ times, int n,
                                float sign, ffb_eval_scalars* __restrict__ out) {
@@ -1066,12 +1097,15 @@ extern "C" int ffb_dopri5_ctl_supported(const ffb_field* f) {
   return use_rr(fd) ? 1 : 0;
 }
 
-extern "C" int ffb_dopri5_control(const ffb_dopri5_ctl_params* p, const double* sums, ffb_dopri5_ctl* ctl,
-                                  int32_t after_attempt, void* stream) {
+extern "C" int ffb_dopri5_control(const ffb_dopri5_ctl_params* p, double* sums, const double* partials, int64_t n_tiles,
+                                  ffb_dopri5_ctl* ctl, int32_t after_attempt, void* stream) {
   if (!p || !ctl || (after_attempt && !sums)) return fail(FFB_ERR_ARG, "ffb_dopri5_control: null argument");
   if (p->n_grid < 0 || p->n_grid > FFB_CTL_MAX_GRID) return fail(FFB_ERR_ARG, "ffb_dopri5_control: at most 16 step_t points");
   if (p->prog.n_freq < 0 || p->prog.n_freq > FFB_MAX_FREQ) return fail(FFB_ERR_ARG, "ffb_dopri5_control: bad n_freq");
-  k_dopri5_control<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, sums, ctl, after_attempt);
+  if (after_attempt && partials)
+    k_dopri5_reduce_control<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, partials, n_tiles, sums, ctl);
+  else
+    k_dopri5_control<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, sums, ctl, after_attempt);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return FFB_OK;
@@ -1109,7 +1143,7 @@ extern "C" int ffb_time_program_rows(const ffb_time_program* prog, const float* 
 
 extern "C" int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream) {
   if (!partials || !sums) return fail(FFB_ERR_ARG, "ffb_reduce_partials: null argument");
-  k_reduce<<<1, 32 * FFB_NPART, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles, sums);
+  k_reduce<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(partials, n_tiles, sums);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return FFB_OK;

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rr(const __grid_cons
       });
     }
     for (int i = 1; i <= 6; ++i) {
-      ENG::template eval<SS>(cx, f, FFB_STEP(ev[i - 1].a), FFB_STEP(ev[i - 1].c), FFB_STEP(ev[i - 1].sigma), FFB_STEP(ev[i - 1].sign), cx.beff() + (i - 1) * bstride, i);
+      if constexpr (DYN) ENG::template eval_ev<SS>(cx, f, EvCtl{a.ctl, i - 1}, cx.beff() + (i - 1) * bstride, i);
+      else ENG::template eval<SS>(cx, f, a.ev[i - 1].a, a.ev[i - 1].c, a.ev[i - 1].sigma, a.ev[i - 1].sign, cx.beff() + (i - 1) * bstride, i);
       if (!cx.producer && i < 6) {
         // input of stage i+1: y0 + sum_j cb[i][j] k_j  (the 7th stage input is y1: FSAL)
         float cbi[6];

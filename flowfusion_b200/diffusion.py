@@ -73,6 +73,15 @@ class MLP(torch.nn.Module):
                                              t_dim=emb, device=dev, activation=act))
         return self._packed[1]
 
+    def _host_embedding(self):
+        """(W, pi) on the host; a device->host copy stalls the stream, so it is repeated only when W was modified."""
+        key = (self.W.data_ptr(), self.W._version, self.pi.data_ptr(), self.pi._version, str(self.W.device))
+        cached = getattr(self, "_emb_host", None)
+        if cached is None or cached[0] != key:
+            cached = (key, self.W.detach().cpu(), self.pi.detach().cpu())
+            self._emb_host = cached
+        return cached[1], cached[2]
+
     def _time_features(self, t32: torch.Tensor, W_cpu=None, pi_cpu=None) -> torch.Tensor:
         """(n,) float32 CPU times -> (n, emb) features, op order of `diffusion.py:109-110`.
         Solver loops pass host copies of W and pi (a device->host copy per call would stall the stream)."""
@@ -289,7 +298,7 @@ class ScoreModel(torch.nn.Module):
         (`diffusion.py:276-278` for the PF-ODE, `:552-553` for the reverse SDE)."""
         sde = copy.deepcopy(self.sde).cpu()
         model, emb = self.model, self.model.embedding_dimensions
-        W_cpu, pi_cpu = model.W.detach().cpu(), model.pi.detach().cpu()     # once per solve, not per step
+        W_cpu, pi_cpu = model._host_embedding()     # host copies, refreshed only when W changes
         use_sigma = not self.no_sigma
 
         def program(times32: np.ndarray) -> np.ndarray:

@@ -248,10 +248,12 @@ class CudaBackend:
 
     # -- counts for the RMS norms (global over ranks) -------------------------------------------
     def global_counts(self, group):
-        n = torch.tensor([self.B], dtype=torch.int64, device=self.dev)
-        if group is not None:
+        if group is None:
+            Bt = self.B                              # no device round trip for a single rank
+        else:
+            n = torch.tensor([self.B], dtype=torch.int64, device=self.dev)
             torch.distributed.all_reduce(n, group=group)
-        Bt = int(n.item())
+            Bt = int(n.item())
         out = {"x": Bt * self.D}
         if self.with_lp:
             out["lp"] = Bt
@@ -331,13 +333,13 @@ class CudaBackend:
         self._ctl_params = params
         host = L.Ctl()
         host.t, host.dt_next, host.grid_idx = float(t), float(dt_next), int(grid_idx)
+        # pinned host memory is device-accessible (UVA): the control kernel stores its progress there
+        self._ctl_notify = torch.zeros(L.CTL_NOTIFY_SLOTS, dtype=torch.int32).pin_memory()
+        self._ctl_notify_np = self._ctl_notify.numpy()
+        host.notify = self._ctl_notify.data_ptr()
         self.ctl_dev = torch.from_numpy(np.frombuffer(bytes(host), np.uint8).copy()).to(self.dev)
         self._ctl_ptr = C.c_void_p(self.ctl_dev.data_ptr())
-        off = L.Ctl.done.offset
-        self._ctl_done_view = self.ctl_dev[off:off + 4].view(torch.int32)
-        self._ctl_flags = torch.zeros(64, dtype=torch.int32).pin_memory()
-        self._ctl_nflag = 0
-        L.check(self.lib.ffb_dopri5_control(C.byref(params), None, self._ctl_ptr, 0, self._stream), "ffb_dopri5_control")
+        L.check(self.lib.ffb_dopri5_control(C.byref(params), None, None, 0, self._ctl_ptr, 0, self._stream), "ffb_dopri5_control")
         a = self.dargs
         c, n = self.cur, 1 - self.cur
         a.batch = self.B
@@ -352,29 +354,33 @@ class CudaBackend:
         self._ctl_first_record = len(profiler.records)
         self._ctl_sums_ptr = _ptr(self.sums)
 
-    def ctl_attempt(self):
-        """attempt + tile reduction; the attempt returns at once when the solve has already finished"""
+    def ctl_attempt(self, reduce=True):
+        """attempt (+ tile reduction when the sums go through an all-reduce first); the attempt returns at once when
+        the solve has already finished"""
         with _timed("dopri5_attempt", self.B):
             L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(self.dargs), self._stream), "ffb_dopri5_attempt")
-        return self._reduce()
+        return self._reduce() if reduce else self.sums
 
-    def ctl_control(self):
-        L.check(self.lib.ffb_dopri5_control(C.byref(self._ctl_params), self._ctl_sums_ptr, self._ctl_ptr, 1, self._stream),
-                "ffb_dopri5_control")
+    def ctl_control(self, reduce=False):
+        """controller turn; reduce=True folds the tile reduction into the same launch (no all-reduce in between)"""
+        L.check(self.lib.ffb_dopri5_control(C.byref(self._ctl_params), self._ctl_sums_ptr,
+                                            _ptr(self.partials) if reduce else None, self.ntiles, self._ctl_ptr, 1,
+                                            self._stream), "ffb_dopri5_control")
 
-    def ctl_flag_async(self):
-        """Start a device->host copy of `done`; returns a token for ctl_flag_wait."""
-        i = self._ctl_nflag % 64
-        self._ctl_nflag += 1
-        self._ctl_flags[i:i + 1].copy_(self._ctl_done_view, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        return (i, ev)
-
-    def ctl_flag_wait(self, token):
-        i, ev = token
-        ev.synchronize()
-        return int(self._ctl_flags[i])
+    def ctl_wait_turn(self, k: int) -> int:
+        """Block until the controller has taken turn k (1-based); returns its `done` code as of that turn."""
+        arr, i, want = self._ctl_notify_np, (k - 1) % L.CTL_NOTIFY_SLOTS, k & 0xFFFFFF
+        spins = 0
+        while True:
+            v = int(arr[i]) & 0xFFFFFFFF
+            if (v >> 8) == want:
+                d = v & 0xFF
+                return d - 256 if d > 127 else d
+            spins += 1
+            if spins % 4096 == 0 and torch.cuda.current_stream().query():
+                v = int(arr[i]) & 0xFFFFFFFF          # the stream has drained: the turn must have been announced
+                if (v >> 8) != want:
+                    raise L.FFBError("dopri5 controller: turn %d was never announced (kernel fault?)" % k)
 
     def ctl_finish(self) -> "L.Ctl":
         """Synchronise and fetch the controller block (statistics, final state of the loop)."""

@@ -73,7 +73,7 @@ class SolveStats:
 # (the host enqueues ahead and polls a flag), "host" = the Python loop below (one device->host read per attempt).
 # Both evaluate the same statements; "device" is used whenever the backend and the scalar program support it.
 _CONTROLLER = os.environ.get("FFB_CONTROLLER", "device")
-_CTL_BATCH = 4        # attempts enqueued between two polls of the `done` flag
+_CTL_AHEAD = 2        # attempts enqueued beyond the last controller turn whose outcome the host has seen
 
 
 def set_controller(mode: str):
@@ -291,22 +291,27 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
 
 def _dopri5_device(backend, params, st: SolveStats, ts: float, dt: float, grid_idx: int, atol32, rtol32, group) -> SolveStats:
     """The adaptive loop with the controller on the device: per attempt the host enqueues
-    attempt -> tile reduction -> (all-reduce over ranks) -> control and never waits for the result; it polls the
-    controller's `done` flag once per _CTL_BATCH attempts, one batch behind what it has enqueued.  Every rank
-    sees bit-identical sums, hence identical flags, hence the same number of collectives."""
+    attempt -> tile reduction -> (all-reduce over ranks) -> control and follows the controller's turns through
+    pinned host memory, _CTL_AHEAD attempts behind what it has enqueued.  The outcome of turn k is the same on
+    every rank (bit-identical sums), so every rank leaves the loop after the same number of collectives."""
     st.controller = "device"
     backend.ctl_begin(params, ts, dt, grid_idx, atol32, rtol32)
     st.launches += 1
-    pending = None
+    k = 0
     while True:
-        for _ in range(_CTL_BATCH):
-            _allreduce(backend.ctl_attempt(), group)
-            backend.ctl_control()
+        if group is None:                       # tile reduction folded into the controller's launch
+            backend.ctl_attempt(reduce=False)
+            backend.ctl_control(reduce=True)
+            st.launches += 2
+        else:
+            _allreduce(backend.ctl_attempt(reduce=True), group)
+            backend.ctl_control(reduce=False)
             st.launches += 3
-        token = backend.ctl_flag_async()
-        if pending is not None and backend.ctl_flag_wait(pending) != L.CTL_RUNNING:
+        k += 1
+        # stay _CTL_AHEAD attempts ahead of the last turn whose outcome is known: the device always has work queued
+        # and at most _CTL_AHEAD launches are wasted (they return at once) after the solve has ended
+        if k > _CTL_AHEAD and backend.ctl_wait_turn(k - _CTL_AHEAD) != L.CTL_RUNNING:
             break
-        pending = token
     c = backend.ctl_finish()
     n = int(c.n_attempts)
     st.nfe += 6 * n

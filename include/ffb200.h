@@ -192,6 +192,7 @@ typedef struct {
 
 #define FFB_CTL_MAX_GRID 16   /* options['step_t'] points                                       */
 #define FFB_CTL_HIST 256      /* attempts whose (dt, ratio, accept) are kept for SolveStats      */
+#define FFB_CTL_NOTIFY_SLOTS 1024
 /* ffb_dopri5_ctl.done */
 #define FFB_CTL_RUNNING 0
 #define FFB_CTL_FINISHED 1
@@ -234,6 +235,11 @@ typedef struct ffb_dopri5_ctl {
   double cur_t1, cur_dt;        /* the attempt in flight                                                 */
   int32_t cur_on_grid;
   int32_t n_attempts, n_accepted, n_rejected;
+  int32_t n_turns;              /* controller turns after an attempt, including those after the solve ended  */
+  int32_t _pad;
+  int32_t* notify;              /* optional: FFB_CTL_NOTIFY_SLOTS int32 of PINNED HOST memory (device-accessible);
+                                   turn k stores (k << 8) | (done & 0xff) into slot (k - 1) % slots, so the host
+                                   can follow the solve without any stream operation                          */
   double hist_dt[FFB_CTL_HIST];
   float hist_ratio[FFB_CTL_HIST];
   uint8_t hist_accept[FFB_CTL_HIST];
@@ -283,9 +289,11 @@ int ffb_integrate_fixed(const ffb_field* field, const ffb_fixed_args* args, void
 int ffb_dopri5_ctl_supported(const ffb_field* field);
 /* One controller turn on the device (one block, enqueued on `stream`).  after_attempt = 0: prepare the first
  * attempt from ctl->t / ctl->dt_next; 1: judge the attempt whose FFB_NPART sums are in `sums` (device, FP64,
- * already reduced over tiles and ranks), update the state, prepare the next attempt or set ctl->done. */
-int ffb_dopri5_control(const ffb_dopri5_ctl_params* params, const double* sums, ffb_dopri5_ctl* ctl,
-                       int32_t after_attempt, void* stream);
+ * already reduced over tiles and ranks), update the state, prepare the next attempt or set ctl->done.
+ * Single-GPU shortcut: with partials != NULL the same launch first reduces partials (n_tiles, FFB_NPART) into
+ * sums, like ffb_reduce_partials. */
+int ffb_dopri5_control(const ffb_dopri5_ctl_params* params, double* sums, const double* partials, int64_t n_tiles,
+                       ffb_dopri5_ctl* ctl, int32_t after_attempt, void* stream);
 /* the same turn on the CPU (host pointers): test twin of the kernel above, no CUDA call */
 int ffb_dopri5_control_host(const ffb_dopri5_ctl_params* params, const double* sums, ffb_dopri5_ctl* ctl,
                             int32_t after_attempt);

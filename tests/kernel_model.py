@@ -182,10 +182,11 @@ class FakeBackend:
         self._p, self._c = params, L.Ctl()
         self._c.t, self._c.dt_next, self._c.grid_idx = float(t), float(dt_next), int(grid_idx)
         self._tol = (atol, rtol)
+        self._done_at = []
         self._sums = torch.zeros(L.NPART, dtype=torch.float64)
         L.check(self._lib.ffb_dopri5_control_host(C.byref(self._p), None, C.byref(self._c), 0), "control_host")
 
-    def ctl_attempt(self):
+    def ctl_attempt(self, reduce=True):
         c = self._c
         if c.done == L.CTL_RUNNING:           # the CUDA attempt kernel returns at once otherwise
             ev = np.frombuffer(bytes(c.ev), np.float32).reshape(6, L.EV_FLOATS).copy()
@@ -195,18 +196,17 @@ class FakeBackend:
                                       np.float32(c.x_interp))
         return self._sums
 
-    def ctl_control(self):
+    def ctl_control(self, reduce=False):
         cur = self._c.cur
         sums = np.ascontiguousarray(self._sums.numpy(), np.float64)
         L.check(self._lib.ffb_dopri5_control_host(C.byref(self._p), sums.ctypes.data, C.byref(self._c), 1), "control_host")
         if self._c.cur != cur:
             self.accept()
+        self._done_at.append(int(self._c.done))
+        assert self._c.n_turns == len(self._done_at)
 
-    def ctl_flag_async(self):
-        return int(self._c.done)
-
-    def ctl_flag_wait(self, token):
-        return token
+    def ctl_wait_turn(self, k):
+        return int(self._done_at[k - 1])
 
     def ctl_finish(self):
         return self._c

@@ -197,7 +197,7 @@ def test_control_twin_rejects_bad_arguments():
     lib = L.load()
     p, c = L.CtlParams(), L.Ctl()
     assert lib.ffb_dopri5_control_host(None, None, C.byref(c), 0) == -1
-    assert lib.ffb_dopri5_control(None, None, None, 0, None) == -1
+    assert lib.ffb_dopri5_control(None, None, None, 0, None, 0, None) == -1
     p.n_grid = L.CTL_MAX_GRID + 1
     assert lib.ffb_dopri5_control_host(C.byref(p), None, C.byref(c), 0) == -1
     assert b"step_t" in lib.ffb_last_error()

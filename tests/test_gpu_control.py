@@ -170,8 +170,8 @@ def test_rejections_failures_and_ragged_batches(cuda_dev):
     bad = x.clone()
     bad[5, 1] = float("nan")
     with S.controller("device"), pytest.raises(S.SolverError) as e:
-        m._integrate(bad, None, None, 1.0, 0.0, 1e-6, 1e-6, "dopri5", None, L.DIV_NONE)
-    assert "non-finite" in str(e.value)
+        m._integrate(bad, None, None, 1.0, 0.0, 1e-6, 1e-6, "dopri5", {"first_step": 0.1}, L.DIV_NONE)
+    assert "non-finite" in str(e.value)      # (without first_step the NaN reaches dt first: "underflow in dt nan", as in torchdiffeq)
     lib = L.load()
     lib.ffb_set_engine(0)                            # FP32 FFMA2 debug engine: no controller block support
     try:
