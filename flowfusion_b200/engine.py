@@ -328,6 +328,10 @@ class CudaBackend:
     def ctl_supported(self):
         return self.B > 0 and bool(self.lib.ffb_dopri5_ctl_supported(C.byref(self.field.c)))
 
+    def ctl_attempt_ms_estimate(self):
+        """Rough duration of one attempted step (6 evaluations at ~140 TFLOP/s), for solver.py's "auto" choice."""
+        return 6.0 * self.B * self.field.flops_per_eval() / 140e12 * 1e3
+
     def ctl_begin(self, params: "L.CtlParams", t: float, dt_next: float, grid_idx: int, atol, rtol):
         """Upload the controller block and let the device prepare the first attempt."""
         self._ctl_params = params

@@ -177,6 +177,9 @@ class FakeBackend:
     def ctl_supported(self):
         return self.B > 0
 
+    def ctl_attempt_ms_estimate(self):
+        return 0.0
+
     def ctl_begin(self, params, t, dt_next, grid_idx, atol, rtol):
         self._lib = L.load()
         self._p, self._c = params, L.Ctl()
