@@ -12,6 +12,7 @@ tensor these classes raise.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -207,6 +208,19 @@ def ev_rows_to_struct(dst_array, rows: np.ndarray):
     C.memmove(C.addressof(dst_array), rows.ctypes.data, rows.nbytes)
 
 
+_ctl_tls = threading.local()
+
+
+def _ctl_pinned():
+    """(notify slots, controller-block staging) in pinned host memory, one pair per host thread."""
+    bufs = getattr(_ctl_tls, "bufs", None)
+    if bufs is None:
+        bufs = (torch.zeros(L.CTL_NOTIFY_SLOTS, dtype=torch.int32).pin_memory(),
+                torch.zeros(C.sizeof(L.Ctl), dtype=torch.uint8).pin_memory())
+        _ctl_tls.bufs = bufs
+    return bufs
+
+
 class CudaBackend:
     """Device state of ONE adaptive solve (this rank's shard of the batch)."""
 
@@ -337,11 +351,16 @@ class CudaBackend:
         self._ctl_params = params
         host = L.Ctl()
         host.t, host.dt_next, host.grid_idx = float(t), float(dt_next), int(grid_idx)
-        # pinned host memory is device-accessible (UVA): the control kernel stores its progress there
-        self._ctl_notify = torch.zeros(L.CTL_NOTIFY_SLOTS, dtype=torch.int32).pin_memory()
-        self._ctl_notify_np = self._ctl_notify.numpy()
-        host.notify = self._ctl_notify.data_ptr()
-        self.ctl_dev = torch.from_numpy(np.frombuffer(bytes(host), np.uint8).copy()).to(self.dev)
+        # pinned host memory is device-accessible (UVA): the control kernel stores its progress there.  The two pinned
+        # buffers are allocated once per host thread (cudaHostAlloc is slow and serialises against running copies);
+        # a solve owns them until ctl_finish() has synchronised, so the next solve of this thread may reuse them.
+        notify, staging = _ctl_pinned()
+        self._ctl_notify_np = notify.numpy()
+        self._ctl_notify_np[:] = 0
+        host.notify = notify.data_ptr()
+        staging.numpy()[:] = np.frombuffer(bytes(host), np.uint8)
+        self.ctl_dev = torch.empty(C.sizeof(L.Ctl), dtype=torch.uint8, device=self.dev)
+        self.ctl_dev.copy_(staging, non_blocking=True)
         self._ctl_ptr = C.c_void_p(self.ctl_dev.data_ptr())
         L.check(self.lib.ffb_dopri5_control(C.byref(params), None, None, 0, self._ctl_ptr, 0, self._stream), "ffb_dopri5_control")
         a = self.dargs
