@@ -67,6 +67,15 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
 #ifndef RR_EARLY
 #define RR_EARLY 0
 #endif
+// Narrow last layer with W_hi | W_lo stacked along N (NetDev::Wst): 2 MMAs per k-step instead of 3 (an MMA costs
+// ~51 cycles whatever N <= 64 is, csrc/tc_rate.cu); the last-layer epilogue adds the two accumulator halves.
+// Parity-green (all GPU tests) but 3-5 % SLOWER on cfg2-cfg5 (A/B), so it is off.
+#ifndef RR_STACK_LAST
+#define RR_STACK_LAST 0
+#endif
+__device__ __forceinline__ bool rr_stacked(const NetDev& net, int l) {
+  return RR_STACK_LAST && l == net.n_layers - 1 && net.Wst != nullptr;
+}
 
 // Debug timeline (compiled in with -DFFB_TRACE only): CTA 0 records clock64() at hand-off points, one
 // private region per role (0: compute warp 0, 1: MMA warp, 2: compute warp 15), no atomics.
@@ -246,7 +255,8 @@ struct EngineRR_ {
         ++cx.tr_n;
 #endif
         mbar_expect_tx(&cx.full()[cx.stage], bytes);
-        bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, net.W[l] + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
+        const float* src = rr_stacked(net, l) ? net.Wst : net.W[l];
+        bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, src + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
         advance(cx);
       }
     }
@@ -274,6 +284,8 @@ struct EngineRR_ {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t lbo = (uint32_t)Np * 16u;
       const uint64_t kstep = (uint64_t)(lbo >> 3);
+      const bool stacked = rr_stacked(net, l);
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * Np) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t d_acc = cx.tmem + cx.dbuf * 128u;
       cx.dbuf ^= 1u;
       uint32_t acc = 0;
@@ -290,7 +302,18 @@ struct EngineRR_ {
         uint64_t* ebar = &cx.empty()[cx.stage];
         const bool lastc = (k0 + KC >= K);
         if (elect_one()) {
-          if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
+          if (stacked) {
+            // [W_hi | W_lo] is one B operand of width 2 Np: D[0:Np) += A W_hi, D[Np:2Np) += A W_lo for A = A_hi, A_lo
+            const uint64_t ds0 = tc_desc(hi_base, 2u * lbo, 128u);
+#pragma unroll
+            for (int j = 0; j < KC / 8; ++j) {
+              if (j < nj) {
+                tc_mma_ts(d_acc, a_hi0 + 8u * j, ds0 + (uint64_t)j * (2u * kstep), idesc2, (j == 0) ? acc : 1u);
+                tc_mma_ts(d_acc, a_lo0 + 8u * j, ds0 + (uint64_t)j * (2u * kstep), idesc2, 1u);
+              }
+            }
+          }
+          else if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
           else issue_chunk<0>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
           if (ci < RR_EARLY) tc_commit(ebar);                   // frees the ring stage when these MMAs retire
           if (lastc) tc_commit(cx.d_ready());                   // the accumulator of this layer is complete
@@ -442,16 +465,20 @@ struct EngineRR_ {
     cx.dbuf ^= 1u;
     wait_d_ready(cx, net.K[nl - 1]);
     RR_TRACE(cx, 290);
+    const bool stacked = rr_stacked(net, nl - 1);
+    const uint32_t half = (uint32_t)net.Np[nl - 1];
     for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += KC) {              // warp-uniform trip count
-      uint32_t m[8];
+      uint32_t m[8], m2[8];
       tc_ld8(dcol + (uint32_t)(c0 - 8 * cx.cg), m);
+      if (stacked) tc_ld8(dcol + half + (uint32_t)(c0 - 8 * cx.cg), m2);
       const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
       const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       tc_wait_ld();
       float o[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(m[u]) + bb[u];
+      for (int u = 0; u < 8; ++u)
+        o[u] = (stacked ? __uint_as_float(m[u]) + __uint_as_float(m2[u]) : __uint_as_float(m[u])) + bb[u];
       fn(c0, o);
     }
     tc_fence_before();
