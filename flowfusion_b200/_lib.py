@@ -14,10 +14,10 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "ffb_kernels.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
-                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh")] + \
+                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh", "ffb_staged.cuh")] + \
           [os.path.join(ROOT, "include", "ffb200.h")]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
 FIELD_NET, FIELD_SCORE = 0, 1
 DIV_NONE, DIV_EXACT, DIV_HUTCH = 0, 1, 2
@@ -58,7 +58,7 @@ class EvalArgs(C.Structure):
                 ("f", C.c_void_p),
                 ("dlp", C.c_void_p), ("ev", EvalScalars), ("atol", C.c_float), ("rtol", C.c_float),
                 ("norms", C.c_int32), ("cond_in_state", C.c_int32), ("partials", C.c_void_p),
-                ("status", C.c_void_p), ("scratch", C.c_void_p)]
+                ("status", C.c_void_p), ("scratch", C.c_void_p), ("jac", C.c_void_p)]
 
 
 class Dopri5Args(C.Structure):
@@ -116,6 +116,32 @@ class FixedArgs(C.Structure):
                 ("ev_table", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p)]
 
 
+# ---- staged solves (Hutch++ / XTrace): include/ffb200.h, csrc/ffb_staged.cuh ----------------------------
+TRACE_HUTCHPP, TRACE_XTRACE = 1, 2
+TRACE_MAX_DIM, TRACE_MAX_RANK, STAGED_BLOCKS = 32, 8, 1024
+
+
+class TraceArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("dim", C.c_int32), ("kind", C.c_int32), ("rank", C.c_int32),
+                ("nvec", C.c_int32), ("jac", C.c_void_p), ("S", C.c_void_p), ("G", C.c_void_p),
+                ("score", C.c_int32), ("use_sigma", C.c_int32), ("has_drift", C.c_int32), ("a", C.c_float),
+                ("c", C.c_float), ("sigma", C.c_float), ("sign", C.c_float), ("dlp", C.c_void_p),
+                ("norms", C.c_int32), ("atol", C.c_float), ("dlpbase", C.c_void_p), ("partials", C.c_void_p)]
+
+
+class RkCombineArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_terms", C.c_int32), ("y0", C.c_void_p), ("k", C.c_void_p * 7),
+                ("coef", C.c_float * 7), ("out", C.c_void_p)]
+
+
+class RkFinishArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("dim", C.c_int32), ("final", C.c_int32), ("y0", C.c_void_p),
+                ("y1", C.c_void_p), ("k", C.c_void_p * 7), ("lp0", C.c_void_p), ("dlp", C.c_void_p * 7),
+                ("lp1", C.c_void_p), ("cl", C.c_float * 6), ("ce", C.c_float * 7), ("cm", C.c_float * 7),
+                ("dt", C.c_float), ("atol", C.c_float), ("rtol", C.c_float), ("x_interp", C.c_float),
+                ("y_out", C.c_void_p), ("lp_out", C.c_void_p), ("partials", C.c_void_p)]
+
+
 # every symbol include/ffb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ffb_abi_version": (C.c_int, []),
@@ -133,6 +159,10 @@ SYMBOLS = {
     "ffb_dopri5_control": (C.c_int, [C.POINTER(CtlParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "ffb_dopri5_control_host": (C.c_int, [C.POINTER(CtlParams), C.c_void_p, C.POINTER(Ctl), C.c_int32]),
     "ffb_time_program_rows": (C.c_int, [C.POINTER(TimeProgram), C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int32]),
+    "ffb_trace_estimate": (C.c_int, [C.POINTER(TraceArgs), C.c_void_p]),
+    "ffb_trace_estimate_host": (C.c_int, [C.POINTER(TraceArgs)]),
+    "ffb_rk_combine": (C.c_int, [C.POINTER(RkCombineArgs), C.c_void_p]),
+    "ffb_rk_finish": (C.c_int, [C.POINTER(RkFinishArgs), C.c_void_p]),
     "ffb_reduce_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ffb_gaussian_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "ffb_philox_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]),

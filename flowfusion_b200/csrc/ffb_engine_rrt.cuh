@@ -62,6 +62,8 @@ struct TanCtx {
   bool use_tr;
   int gsrc, my_u, pbase;        // lane of that primal row; i % 8; 8 * (index of THIS row's primal among the quarter's primal rows)
   uint32_t o_klp, o_diag, o_prb;
+  float* jac;                   // k_field_eval_rrt only: this tile's (sample, tangent j, output n) Jacobian rows, or nullptr
+  int jac_nv;                   // valid samples of the tile
   __device__ __forceinline__ float* klp() const { return reinterpret_cast<float*>(smem_base() + o_klp); }
   __device__ __forceinline__ float* diag() const { return reinterpret_cast<float*>(smem_base() + o_diag); }
   __device__ __forceinline__ float* prb() const { return reinterpret_cast<float*>(smem_base() + o_prb); }
@@ -96,6 +98,7 @@ template <bool GEN>
 struct EngineRRT_ {
   static __device__ __forceinline__ void init(CtxR& cx, TanCtx& tc, const FieldDev& f, int nslot, int nbeff) {
     tc.exact = (f.div_mode == FFB_DIV_EXACT);
+    tc.jac = nullptr; tc.jac_nv = 0;
     tc.T = tc.exact ? f.net[0].x_dim : 1;
     RowMap m;
     const int row = ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31);
@@ -309,6 +312,17 @@ struct EngineRRT_ {
           for (int u = 0; u < 8; ++u)
             if (c0 + u == tc.tj) { v = __uint_as_float(m[u]); mine = true; }
           if (mine) tc.diag()[s * tc.T + tc.tj] = v;                      // d f_j / d x_j
+          if (tc.jac != nullptr && s < tc.jac_nv) {                       // full row: d net_n / d x_tj, n = c0..c0+7
+            float* jr = tc.jac + ((size_t)s * tc.T + tc.tj) * tc.T + c0;
+            if (c0 + 8 <= Nreal && (tc.T & 3) == 0) {
+              *reinterpret_cast<float4*>(jr) = make_float4(__uint_as_float(m[0]), __uint_as_float(m[1]), __uint_as_float(m[2]), __uint_as_float(m[3]));
+              *reinterpret_cast<float4*>(jr + 4) = make_float4(__uint_as_float(m[4]), __uint_as_float(m[5]), __uint_as_float(m[6]), __uint_as_float(m[7]));
+            } else {
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (c0 + u < Nreal) jr[u] = __uint_as_float(m[u]);
+            }
+          }
         } else {
           float part = 0.0f;
 #pragma unroll
@@ -413,6 +427,8 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_field_eval_rrt(const __grid
         }
       }
     }
+    tc.jac = a.jac ? a.jac + (size_t)row0 * tc.T * tc.T : nullptr;
+    tc.jac_nv = nv;
     ENGT::eval(cx, tc, f, a.ev.a, a.ev.c, a.ev.sigma, a.ev.sign, cx.beff(), 0);
     if (!cx.producer) {
       rr_bar();                                           // klp[0] of every sample is written

@@ -1034,9 +1034,11 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
   if (a->norms == 2 && (!a->fbase || (fd.div_mode != FFB_DIV_NONE && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (a->jac && fd.div_mode != FFB_DIV_EXACT) return fail(FFB_ERR_ARG, "ffb_field_eval: jac needs div_mode FFB_DIV_EXACT");
   if (const size_t smt = rrt_smem(f, &fd, 3, 1))
     return gen_act(fd) ? launch_rrt(k_field_eval_rrt<true>, smt, "ffb_field_eval", fd, *a, a->batch, st_)
                        : launch_rrt(k_field_eval_rrt<false>, smt, "ffb_field_eval", fd, *a, a->batch, st_);
+  if (a->jac) return fail(FFB_ERR_ARG, "ffb_field_eval: jac is written by the tangent-row tensor-core engine only");
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, 3, 1);
     if (gen_act(fd)) {
@@ -1230,3 +1232,5 @@ extern "C" int ffb_ffma_peak(int32_t iters, float* tflops, void* stream_) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
   return FFB_OK;
 }
+
+#include "ffb_staged.cuh"

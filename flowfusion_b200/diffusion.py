@@ -15,7 +15,7 @@ this module                     reference                      kernel
 ==============================  =============================  ==================================
 
 Out of scope here (training side): the score-matching losses, adjoint
-back-propagation (``training=True``), Hutch++ and XTrace.  They raise ``NotImplementedError``.
+back-propagation (``training=True``).  It raises ``NotImplementedError``.
 Tensors must live on a CUDA device; there is no CPU path.
 """
 from __future__ import annotations
@@ -324,8 +324,6 @@ class ScoreModel(torch.nn.Module):
         if self.training:
             raise NotImplementedError("training=True selects odeint_adjoint (gradients through the solver): "
                                       "training side, out of scope -- call .eval() first")
-        if self.hutchpp or self.xtrace:
-            raise NotImplementedError("Hutch++ / XTrace estimators are not implemented yet (SURVEY 8f-1)")
 
     # -- reference API ------------------------------------------------------------------------
     def score(self, t, x, conditional=None):
@@ -353,9 +351,41 @@ class ScoreModel(torch.nn.Module):
         row = self._program()(tt.numpy())[0]
         if not self.prob:
             return _eval_once(self._field(), row, x, self.conditional)[0]
+        est = None if self.hutch else self._estimator(x, stored=True)
+        if est is not None:                 # Hutch++ / XTrace (`:336-481`): staged evaluation
+            be = E.StagedBackend(self._field(L.DIV_EXACT), x, est, cond=self.conditional)
+            f, d = be.single_eval(row)
+            return f, d.view(-1, 1)
         div = L.DIV_HUTCH if self.hutch else L.DIV_EXACT
         f, d = _eval_once(self._field(div), row, x, self.conditional, probes=self.e if self.hutch else None)
         return f, d.view(-1, 1)
+
+    def _estimator(self, x, stored=False, probes=None):
+        """The Hutch++ / XTrace estimator of this solve with its probes, or None (exact / Hutchinson).  Flag priority
+        and probe shapes follow `diffusion.py:327, 336, 402` and `:703-721`; ``stored=True`` reuses the probes of the
+        last solve when their shapes fit (`:346-354`, `:413-418`), else draws fresh ones."""
+        if self.hutch or not (self.hutchpp or self.xtrace):
+            return None
+        B, D = x.shape[0], x.reshape(x.shape[0], -1).shape[1]
+        rs = lambda n: torch.sign(torch.randn(n, B, D, device=x.device, dtype=x.dtype))     # noqa: E731
+        if self.hutchpp:
+            r, m = int(min(self.hpp_rank, D)), int(max(1, self.hpp_vector))
+            if probes is not None:
+                self.S, self.G = probes
+            elif not stored or getattr(self, "S", None) is None or self.S.shape != (r, B, D) \
+                    or getattr(self, "G", None) is None or self.G.shape != (m, B, D):
+                self.S, self.G = rs(r), rs(m)
+            if tuple(self.S.shape) != (r, B, D) or tuple(self.G.shape) != (m, B, D):
+                raise ValueError("Hutch++ probes must have shapes (min(hpp_rank, D), B, D) and (max(1, hpp_vecs), B, D)")
+            return E.TraceEstimator(L.TRACE_HUTCHPP, self.S, self.G)
+        m = int(min(max(1, self.xt_vector), D))      # `:410`; solve_odes_forward's own draw (`:718`) omits the min
+        if probes is not None:
+            self.O = probes
+        elif not stored or getattr(self, "O", None) is None or self.O.shape != (m, B, D):
+            self.O = rs(m)
+        if tuple(self.O.shape) != (m, B, D):
+            raise ValueError("XTrace probes must have shape (min(max(1, xt_vecs), D), B, D)")
+        return E.TraceEstimator(L.TRACE_XTRACE, self.O)
 
     @torch.no_grad()
     def sample_sde(self, shape, conditional=None, steps=100, *, x0=None, noise=None, seed=None):
@@ -435,9 +465,22 @@ class ScoreModel(torch.nn.Module):
         if self.hutch:
             self.e = probes if probes is not None else torch.sign(torch.randn(x0_samples.shape)).to(x0_samples.device)
         self.conditional = conditional
+        est = self._estimator(x0_samples, probes=probes)
+        if est is not None:
+            x, lp = self._solve_staged(x0_samples, conditional, est, float(self.sde.epsilon), 1.0, atol, rtol, method, options)
+            return x, lp.view(-1, 1)
         x, lp = self._solve(x0_samples, conditional, float(self.sde.epsilon), 1.0, atol, rtol, method, options,
                             L.DIV_HUTCH if self.hutch else L.DIV_EXACT, self.e if self.hutch else None)
         return x, lp.view(-1, 1)
+
+    def _solve_staged(self, y0, cond, est, t0, t1, atol, rtol, method, options):
+        """Hutch++ / XTrace solves: evaluation-at-a-time dopri5 (engine.StagedBackend), host controller."""
+        method = "dopri5" if method is None else method
+        if method != "dopri5":
+            raise NotImplementedError(f"Hutch++ / XTrace solves are implemented for dopri5 only (got {method!r})")
+        be = E.StagedBackend(self._field(L.DIV_EXACT), y0, est, cond=cond)
+        self.last_stats = S.dopri5(be, self._program(), t0, t1, rtol, atol, options, group=self._group())
+        return be.output()
 
     @torch.no_grad()
     def log_prob(self, x0_samples, conditional=None, atol=1e-4, rtol=1e-4, method="dopri5",

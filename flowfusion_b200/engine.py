@@ -426,6 +426,128 @@ class CudaBackend:
         return self.y_out, self.lp_out
 
 
+class TraceEstimator:
+    """Which stochastic trace estimator a staged solve uses, with its fixed probes (reference layout (n, B, D),
+    `diffusion.py:703-721`).  kind: L.TRACE_HUTCHPP (S, G) or L.TRACE_XTRACE (S = O)."""
+
+    def __init__(self, kind: int, S: torch.Tensor, G: Optional[torch.Tensor] = None):
+        self.kind, self.S, self.G = kind, S, G
+        if S.dim() != 3 or (G is not None and G.dim() != 3):
+            raise ValueError("probes must have shape (n_vectors, batch, dim)")
+        self.rank = int(S.shape[0])
+        self.nvec = int(G.shape[0]) if G is not None else 0
+        D = int(S.shape[2])
+        if D > L.TRACE_MAX_DIM or self.rank > L.TRACE_MAX_RANK:
+            raise NotImplementedError(f"Hutch++ / XTrace kernels hold D <= {L.TRACE_MAX_DIM} and rank <= "
+                                      f"{L.TRACE_MAX_RANK} (got D = {D}, rank = {self.rank})")
+        if self.rank > D:
+            raise ValueError("rank must not exceed the state dimension")
+
+
+class StagedBackend(CudaBackend):
+    """Adaptive solve with a Hutch++ / XTrace divergence (`diffusion.py:336-481`): every evaluation is
+    ``ffb_field_eval`` (tangent-row engine, full Jacobian out) + ``ffb_trace_estimate``; an attempt is six of them
+    between ``ffb_rk_combine`` launches plus ``ffb_rk_finish`` (csrc/ffb_staged.cuh).  Same interface and the same
+    partial sums as ``CudaBackend``, so ``solver.dopri5``'s host controller drives it unchanged."""
+
+    def __init__(self, field: FieldSpec, y0: torch.Tensor, estimator: TraceEstimator, cond=None):
+        if field.div_mode != L.DIV_EXACT or len(field.nets) != 1:
+            raise ValueError("staged solves run on a one-network field with div_mode DIV_EXACT")
+        super().__init__(field, y0, cond=cond, probes=None, with_lp=True)
+        dev, B, D = self.dev, self.B, self.D
+        if tuple(estimator.S.shape[1:]) != (B, D) or (estimator.G is not None and tuple(estimator.G.shape[1:]) != (B, D)):
+            raise ValueError("probe shapes do not match the state")
+        self.est = estimator
+        self.S = _dev_f32(estimator.S, dev)
+        self.G = None if estimator.G is None else _dev_f32(estimator.G, dev)
+        self.jac = torch.empty(B, D, D, device=dev)
+        self.ks = [torch.empty(B, D, device=dev) for _ in range(5)]       # k2..k6
+        self.dks = [torch.empty(B, device=dev) for _ in range(5)]
+        self.ystage = torch.empty(B, D, device=dev)
+        self.partials2 = torch.zeros(L.STAGED_BLOCKS, L.NPART, dtype=torch.float64, device=dev)
+        self.sums2 = torch.zeros(L.NPART, dtype=torch.float64, device=dev)
+        self.targs, self.cargs, self.fargs = L.TraceArgs(), L.RkCombineArgs(), L.RkFinishArgs()
+        t = self.targs
+        t.batch, t.dim, t.kind, t.rank, t.nvec = B, D, estimator.kind, estimator.rank, estimator.nvec
+        t.jac, t.S, t.G = _ptr(self.jac), _ptr(self.S), _ptr(self.G)
+        t.score, t.use_sigma, t.has_drift = int(field.kind == L.FIELD_SCORE), int(field.use_sigma), int(field.has_drift)
+        t.partials = _ptr(self.partials2)
+
+    def ctl_supported(self):
+        return False                      # the device controller drives the fused attempt kernel only
+
+    def _reduce2(self):
+        L.check(self.lib.ffb_reduce_partials(_ptr(self.partials2), L.STAGED_BLOCKS, _ptr(self.sums2), self._stream),
+                "ffb_reduce_partials")
+        return self.sums2
+
+    def _field_and_trace(self, y, ev_row, f_out, dlp_out, *, fbase=None, h=0.0, norms=0, atol=1.0, rtol=0.0, dlpbase=None):
+        a = self.eargs
+        a.batch = self.B
+        a.y, a.fbase, a.dlpbase, a.h = _ptr(y), _ptr(fbase), _ptr(dlpbase), float(h)
+        a.cond, a.probes, a.cond_state = _ptr(self.cond), None, None
+        a.f, a.dlp, a.jac = _ptr(f_out), _ptr(dlp_out), _ptr(self.jac)
+        ev_rows_to_struct(a.ev, ev_row[None, :])
+        a.atol, a.rtol, a.norms, a.cond_in_state = float(atol), float(rtol), int(norms), 0
+        a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
+        t = self.targs
+        t.a, t.c = float(ev_row[L.MAX_TFEAT + 0]), float(ev_row[L.MAX_TFEAT + 1])
+        t.sigma, t.sign = float(ev_row[L.MAX_TFEAT + 2]), float(ev_row[L.MAX_TFEAT + 3])
+        t.dlp, t.norms, t.atol, t.dlpbase = _ptr(dlp_out), int(norms), float(atol), _ptr(dlpbase)
+        if self.B:
+            with _timed("field_eval_jac", self.B):
+                L.check(self.lib.ffb_field_eval(C.byref(self.field.c), C.byref(a), self._stream), "ffb_field_eval")
+            # the estimator overwrites the exact trace the evaluation left in dlp_out
+            with _timed("trace_estimate", self.B):
+                L.check(self.lib.ffb_trace_estimate(C.byref(t), self._stream), "ffb_trace_estimate")
+
+    def _eval(self, ev_row, atol, rtol, norms, h=None):
+        c = self.cur
+        if norms == 1:
+            self._field_and_trace(self.y[c], ev_row, self.f[c], self.dlp[c], norms=1, atol=atol, rtol=rtol)
+        else:       # f(y + h f0) against f0: only the norms are kept (k7 scratch buffers take the outputs)
+            self._field_and_trace(self.y[c], ev_row, self.f[1 - c], self.dlp[1 - c], fbase=self.f[c], h=h, norms=2,
+                                  atol=atol, rtol=rtol, dlpbase=self.dlp[c])
+        sums = self._reduce()
+        sums2 = self._reduce2()
+        sums[L.P_LP_F:L.P_LP_DF + 1] = sums2[L.P_LP_F:L.P_LP_DF + 1]      # log-det norms come from the estimator
+        return sums
+
+    def attempt(self, ev, cb, ce, cm, dt32, atol, rtol, final, x_interp):
+        c, n = self.cur, 1 - self.cur
+        ks = [self.f[c]] + self.ks + [self.f[n]]            # k1 .. k7 (FSAL: k7 = f1)
+        dks = [self.dlp[c]] + self.dks + [self.dlp[n]]
+        cb = np.ascontiguousarray(cb, np.float32)
+        ca = self.cargs
+        ca.n, ca.y0 = self.B * self.D, _ptr(self.y[c])
+        for i in range(6):
+            out = self.y[n] if i == 5 else self.ystage          # the 7th stage's input is y1
+            ca.n_terms, ca.out = i + 1, _ptr(out)
+            for j in range(7):
+                ca.k[j] = ks[j].data_ptr() if j <= i else None
+                ca.coef[j] = float(cb[i, j]) if j <= i else 0.0
+            if self.B:
+                L.check(self.lib.ffb_rk_combine(C.byref(ca), self._stream), "ffb_rk_combine")
+                self._field_and_trace(out, ev[i], ks[i + 1], dks[i + 1])
+        fa = self.fargs
+        fa.batch, fa.dim, fa.final = self.B, self.D, int(final)
+        fa.y0, fa.y1, fa.lp0, fa.lp1 = _ptr(self.y[c]), _ptr(self.y[n]), _ptr(self.lp[c]), _ptr(self.lp[n])
+        for j in range(7):
+            fa.k[j], fa.dlp[j] = ks[j].data_ptr(), dks[j].data_ptr()
+            fa.ce[j], fa.cm[j] = float(ce[j]), float(cm[j])
+        for j in range(6):
+            fa.cl[j] = float(cb[5, j])
+        fa.dt, fa.atol, fa.rtol, fa.x_interp = float(dt32), float(atol), float(rtol), float(x_interp)
+        fa.y_out, fa.lp_out, fa.partials = _ptr(self.y_out), _ptr(self.lp_out), _ptr(self.partials2)
+        if self.B:
+            L.check(self.lib.ffb_rk_finish(C.byref(fa), self._stream), "ffb_rk_finish")
+        return self._reduce2()
+
+    def single_eval(self, ev_row):
+        self._field_and_trace(self.y[self.cur], ev_row, self.f[self.cur], self.dlp[self.cur])
+        return self.f[self.cur], self.dlp[self.cur]
+
+
 def run_fixed(field: FieldSpec, method: int, x0: torch.Tensor, step_table: np.ndarray, ev_table: np.ndarray,
               cond=None, probes=None, lp0=None, noise=None, philox=None, row_offset=0, want_lp=False):
     """Whole fixed-grid trajectory in one kernel.  ``step_table`` (nsteps, 8) and ``ev_table``

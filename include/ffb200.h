@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FFB_ABI_VERSION 2
+#define FFB_ABI_VERSION 3
 #define FFB_MAX_LAYERS 8    /* Linear layers per network                         */
 #define FFB_MAX_WIDTH 128   /* widest layer (input or output) the tile engine holds */
 #define FFB_MAX_TFEAT 32    /* time-feature columns (embedding_dimensions or 1)  */
@@ -133,6 +133,11 @@ typedef struct {
   double* partials;             /* (n_tiles, FFB_NPART)                                        */
   int32_t* status;
   void* scratch;
+  float* jac;                   /* optional out (B, x_dim, x_dim), FFB_DIV_EXACT on the tensor-core engine only:
+                                   jac[b][j][n] = d net_n / d x_j of the NETWORK output (before a*x - c*score);
+                                   row j is what a reverse sweep seeded with e_n collects for x_j, i.e. the
+                                   matrix a VJP multiplies by (diffusion.py:361-374), consumed by
+                                   ffb_trace_estimate                                              */
 } ffb_eval_args;
 
 /* ---- one attempted dopri5 step (6 fused evaluations + error norm + dense output) ------- */
@@ -301,6 +306,72 @@ int ffb_dopri5_control_host(const ffb_dopri5_ctl_params* params, const double* s
  * current device (synchronous, for tests), else on the CPU twin */
 int ffb_time_program_rows(const ffb_time_program* prog, const float* times, int32_t n, float sign,
                           ffb_eval_scalars* out, int32_t on_device);
+
+/* ---- staged solves: Hutch++ / XTrace divergence estimators (diffusion.py:336-481) ---------------
+ * Both estimators need a per-sample thin QR BETWEEN two rounds of Jacobian products, so one evaluation is
+ * staged over two launches instead of living inside the fused attempt kernel:
+ *   ffb_field_eval(div_mode = FFB_DIV_EXACT, jac = J)   field + the full network Jacobian (D tangent rows)
+ *   ffb_trace_estimate(J, probes)                        the reference's estimator algebra, one thread per sample
+ * and a dopri5 attempt is 6 x (ffb_rk_combine, ffb_field_eval, ffb_trace_estimate) + ffb_rk_finish, which leaves
+ * the same FFB_NPART partial sums the fused attempt kernel does (the host controller does not change).      */
+#define FFB_TRACE_HUTCHPP 1   /* diffusion.py:336-400 */
+#define FFB_TRACE_XTRACE 2    /* diffusion.py:402-481 */
+#define FFB_TRACE_MAX_DIM 32  /* state columns D                                   */
+#define FFB_TRACE_MAX_RANK 8  /* Hutch++ r = min(hpp_rank, D); XTrace m = xt_vecs  */
+#define FFB_STAGED_BLOCKS 1024 /* rows of the `partials` buffer the staged kernels write (caller zero-fills once) */
+typedef struct {
+  int64_t batch;
+  int32_t dim;                  /* D                                                             */
+  int32_t kind;                 /* FFB_TRACE_*                                                   */
+  int32_t rank;                 /* Hutch++: rows of S (r);  XTrace: rows of O (m <= D)            */
+  int32_t nvec;                 /* Hutch++: rows of G (m >= 1); XTrace: unused                    */
+  const float* jac;             /* (B, D, D) from ffb_field_eval                                  */
+  const float* S;               /* (rank, B, D): Hutch++ S / XTrace O, reference layout (diffusion.py:710, 721) */
+  const float* G;               /* (nvec, B, D): Hutch++ G (diffusion.py:711)                     */
+  int32_t score;                /* field kind FFB_FIELD_SCORE: J_f = a I - c J_net [/ sigma]      */
+  int32_t use_sigma;
+  int32_t has_drift;
+  float a, c, sigma, sign;      /* the evaluation's ffb_eval_scalars                              */
+  float* dlp;                   /* out (B,): sign * estimated divergence                          */
+  /* optional norms of torchdiffeq's initial-step heuristic on the log-det column (as ffb_eval_args.norms) */
+  int32_t norms;                /* 0 none; 1: sum (dlp/atol)^2 -> P_LP_F; 2: sum ((dlp - dlpbase)/atol)^2 -> P_LP_DF */
+  float atol;
+  const float* dlpbase;
+  double* partials;             /* (FFB_STAGED_BLOCKS, FFB_NPART), required when norms != 0        */
+} ffb_trace_args;
+int ffb_trace_estimate(const ffb_trace_args* args, void* stream);
+/* the same algebra on the CPU (host pointers, no CUDA call; norms ignored): test twin of the kernel */
+int ffb_trace_estimate_host(const ffb_trace_args* args);
+
+/* out = y0 + sum_{j < n_terms} coef[j] * k[j] over n flat elements: the stage input of torchdiffeq's
+ * `y0 + k[..., :i+1] @ (beta_i * dt)` */
+typedef struct {
+  int64_t n;
+  int32_t n_terms;
+  const float* y0;
+  const float* k[7];
+  float coef[7];
+  float* out;
+} ffb_rk_combine_args;
+int ffb_rk_combine(const ffb_rk_combine_args* args, void* stream);
+
+/* end of one staged dopri5 attempt: log-det column of y1, error partial sums (P_X_ERR, P_LP_ERR,
+ * P_NONFINITE), and the dense output at t_end when `final` (same statements as the fused attempt kernel) */
+typedef struct {
+  int64_t batch;
+  int32_t dim;
+  int32_t final;
+  const float* y0; const float* y1;       /* (B, D): y1 is the 7th stage's input            */
+  const float* k[7];                      /* k1..k7, (B, D) each                            */
+  const float* lp0; const float* dlp[7];  /* log-det column and its 7 stage derivatives, or NULL */
+  float* lp1;
+  float cl[6];                            /* fl32(beta_6j * dt)                             */
+  float ce[7], cm[7];
+  float dt, atol, rtol, x_interp;
+  float* y_out; float* lp_out;
+  double* partials;                       /* (FFB_STAGED_BLOCKS, FFB_NPART)                 */
+} ffb_rk_finish_args;
+int ffb_rk_finish(const ffb_rk_finish_args* args, void* stream);
 
 /* sums[FFB_NPART] = sum over tiles of partials, in tile order (deterministic) */
 int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream);

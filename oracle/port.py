@@ -148,10 +148,64 @@ def ode_drift(M, t, x, cond=None):
     return f - 0.5 * g ** 2 * score(M, t, x, cond)
 
 
+def _batched_vjp(M, t, x, cond):
+    """`diffusion.py:359-374`: v (n, B, D) -> J^T v, J = d x_dot / d x, through torch.func.vjp + vmap."""
+    x_dot, vjp_fn = torch.func.vjp(lambda x_: ode_drift(M, t, x_, cond), x)
+    return x_dot, torch.func.vmap(lambda v: vjp_fn(v.reshape_as(x))[0].reshape(x.shape[0], -1))
+
+
+def hutchpp_divergence(M, t, x, cond, S, G):
+    """`diffusion.py:336-400`.  S (r, B, D), G (m, B, D): the probes drawn once per solve (`:703-711`)."""
+    m = G.shape[0]
+    x_dot, bvjp = _batched_vjp(M, t, x, cond)
+    Y = bvjp(S).permute(1, 2, 0).detach()                    # (B, D, r)              `:367-369`
+    Q, _ = torch.linalg.qr(Y, mode="reduced")                #                         `:372`
+    AQ = bvjp(Q.permute(2, 0, 1)).permute(1, 2, 0).detach()  #                         `:376-379`
+    trace_lr = torch.einsum("bdk,bdk->b", Q, AQ)             #                         `:380`
+    Gp = G.permute(1, 2, 0)
+    U = Gp - torch.einsum("bdk,bkm->bdm", Q, torch.einsum("bdk,bdm->bkm", Q, Gp))     # `:383-387`
+    AU = bvjp(U.permute(2, 0, 1)).permute(1, 2, 0).detach()  #                         `:389-392`
+    trace_res = torch.einsum("bdm,bdm->b", U, AU)
+    return x_dot, trace_lr + trace_res / float(m)            #                         `:395`
+
+
+def xtrace_divergence(M, t, x, cond, O):
+    """`diffusion.py:402-481`.  O (m, B, D), m <= D."""
+    x_dot, bvjp = _batched_vjp(M, t, x, cond)
+    Y = bvjp(O).permute(1, 2, 0).detach()                    # (B, D, m)               `:433-435`
+    Q, R = torch.linalg.qr(Y, mode="reduced")                #                          `:438`
+    k = Q.shape[2]
+    AQ = bvjp(Q.permute(2, 0, 1)).permute(1, 2, 0).detach()  #                          `:443-445`
+    H = torch.einsum("bdi,bdj->bij", Q, AQ)                  #                          `:447`
+    W = torch.einsum("bdk,mbd->bkm", Q, O)                   #                          `:449`
+    T = torch.einsum("bdk,mbd->bkm", AQ, O)                  #                          `:451`
+    St = torch.linalg.solve_triangular(R, torch.eye(k), upper=True)                   # `:453`
+    St = St / torch.linalg.vector_norm(St, dim=-1, keepdim=True)                      # `:455`
+    S = St.permute(0, 2, 1)
+    trace_H = torch.diagonal(H, 0, 1, 2).sum(dim=-1)         #                          `:459`
+    X = W - torch.sum(S * W, dim=1, keepdim=True) * S        #                          `:463`
+    SHS = torch.sum(S * torch.einsum("bim,bmk->bik", H, S), dim=1)
+    XHX = torch.sum(X * torch.einsum("bim,bmk->bik", H, X), dim=1)
+    WS = torch.sum(W * S, dim=1)
+    SR = torch.sum(S * R, dim=1)
+    TX = torch.sum(T * X, dim=1)
+    ests = trace_H[:, None] - SHS + WS * SR - TX + XHX       #                          `:475`
+    return x_dot, torch.mean(ests, dim=1)                    #                          `:477`
+
+
 def score_field(M, t, states, cond=None, prob=False, probes=None):
-    """`diffusion.py:313-508` -- exact trace (`:483-503`) or Hutchinson (`:327-334`)."""
+    """`diffusion.py:313-508` -- exact trace (`:483-503`), Hutchinson (`:327-334`), Hutch++ (`:336-400`) or
+    XTrace (`:402-481`).  ``probes``: None (exact), a (B, D) tensor (Hutchinson), ("hutchpp", S, G) or ("xtrace", O)."""
     x = states[0]
     B = x.shape[0]
+    if prob and isinstance(probes, tuple):
+        with torch.set_grad_enabled(True):
+            xg = x.detach().requires_grad_(True)
+            if probes[0] == "hutchpp":
+                x_dot, div = hutchpp_divergence(M, t, xg, cond, probes[1], probes[2])
+            else:
+                x_dot, div = xtrace_divergence(M, t, xg, cond, probes[1])
+        return x_dot.detach(), div.detach().view(B, 1)
     if not prob:
         # the reference returns the bare tensor (`:508`), which torchdiffeq then re-flattens
         # row by row (SURVEY H8), and keeps autograd on; a detached 1-tuple gives bit-identical

@@ -90,8 +90,11 @@ class FakeBackend:
         self.lp = torch.zeros(self.B) if with_lp else None
         self.f = self.dlp = None
 
+    def _fe(self, ev_row, y):
+        return field_eval(self.field, ev_row, y, self.cond, self.probes)
+
     def single_eval(self, ev_row):
-        return field_eval(self.field, ev_row, self.y, self.cond, self.probes)
+        return self._fe(ev_row, self.y)
 
     def global_counts(self, group):
         n = torch.tensor([self.B], dtype=torch.int64)
@@ -111,7 +114,7 @@ class FakeBackend:
 
     def eval0(self, ev_row, atol, rtol):
         atol, rtol = torch.tensor(float(atol)), torch.tensor(float(rtol))
-        self.f, self.dlp = field_eval(self.field, ev_row, self.y, self.cond, self.probes)
+        self.f, self.dlp = self._fe(ev_row, self.y)
         s = torch.zeros(L.NPART, dtype=torch.float64)
         sc = atol + self.y.abs() * rtol
         s[L.P_X_Y], s[L.P_X_F] = self._ss(self.y / sc), self._ss(self.f / sc)
@@ -124,7 +127,7 @@ class FakeBackend:
 
     def eval1(self, h0, ev_row, atol, rtol):
         atol, rtol, h0 = torch.tensor(float(atol)), torch.tensor(float(rtol)), torch.tensor(float(h0))
-        f1, dlp1 = field_eval(self.field, ev_row, self.y + h0 * self.f, self.cond, self.probes)
+        f1, dlp1 = self._fe(ev_row, self.y + h0 * self.f)
         s = torch.zeros(L.NPART, dtype=torch.float64)
         sc = atol + self.y.abs() * rtol
         s[L.P_X_DF] = self._ss((f1 - self.f) / sc)
@@ -142,7 +145,7 @@ class FakeBackend:
         yi = self.y
         for i in range(6):
             yi = self.y + sum(k[j] * cb[i, j] for j in range(i + 1))
-            f, d = field_eval(self.field, ev[i], yi, self.cond, self.probes)
+            f, d = self._fe(ev[i], yi)
             k.append(f); kl.append(d)
         y1, f1 = yi, k[6]
         err = sum(k[j] * ce[j] for j in range(7))
@@ -213,6 +216,44 @@ class FakeBackend:
 
     def ctl_finish(self):
         return self._c
+
+
+class FakeStagedBackend(FakeBackend):
+    """Model of engine.StagedBackend: the field from the torch model, the network Jacobian by autograd, and the
+    Hutch++ / XTrace algebra from the C twin of the estimator kernel (ffb_trace_estimate_host)."""
+
+    def __init__(self, field, y0, estimator, cond=None):
+        super().__init__(field, y0, cond=cond, probes=None, with_lp=True)
+        self.est = estimator
+
+    def ctl_supported(self):
+        return False
+
+    def _fe(self, ev_row, y):
+        field, net = self.field, self.field.nets[0]
+        f, _ = field_eval(field.with_div(L.DIV_NONE) if hasattr(field, "with_div") else field, ev_row, y, self.cond, None)
+        tfeat = ev_row[: L.MAX_TFEAT]
+
+        with torch.enable_grad():
+            yy = y.detach().clone().requires_grad_(True)
+            o = net(yy, self.cond, tfeat)
+            J = torch.stack([torch.autograd.grad(o[:, n].sum(), yy, retain_graph=True)[0] for n in range(o.shape[1])], dim=1)
+        J = J.detach()                                                            # [b][n][j]
+        jac = np.ascontiguousarray(J.permute(0, 2, 1).numpy(), np.float32)        # [b][j][n] = d net_n / d x_j
+        S = np.ascontiguousarray(self.est.S.detach().float().numpy())
+        G = None if self.est.G is None else np.ascontiguousarray(self.est.G.detach().float().numpy())
+        out = np.zeros(self.B, np.float32)
+        a = L.TraceArgs()
+        a.batch, a.dim, a.kind, a.rank, a.nvec = self.B, self.D, self.est.kind, self.est.rank, self.est.nvec
+        a.jac, a.S, a.G = jac.ctypes.data, S.ctypes.data, None if G is None else G.ctypes.data
+        a.score, a.use_sigma, a.has_drift = int(field.kind == L.FIELD_SCORE), int(field.use_sigma), int(field.has_drift)
+        a.a, a.c, a.sigma, a.sign = (float(ev_row[L.MAX_TFEAT + i]) for i in range(4))
+        a.dlp = out.ctypes.data
+        L.check(L.load().ffb_trace_estimate_host(C.byref(a)), "ffb_trace_estimate_host")
+        return f, torch.from_numpy(out)
+
+    def single_eval(self, ev_row):
+        return self._fe(ev_row, self.y)
 
 
 def _dense(y0, y1, ymid, f0, f1, dt, x):
@@ -296,9 +337,10 @@ def fake_gaussian_logprob(x, add, sigma=1.0):
 @contextlib.contextmanager
 def patched_engine():
     """Route the package's device plumbing to the torch-CPU model (tests only)."""
-    saved = {k: getattr(E, k) for k in ("CudaBackend", "run_fixed", "gaussian_logprob", "PackedNet", "require_cuda",
+    saved = {k: getattr(E, k) for k in ("CudaBackend", "StagedBackend", "run_fixed", "gaussian_logprob", "PackedNet", "require_cuda",
                                         "require_cuda_device")}
     E.CudaBackend = FakeBackend
+    E.StagedBackend = FakeStagedBackend
     E.run_fixed = fake_run_fixed
     E.gaussian_logprob = fake_gaussian_logprob
     E.PackedNet = FakePackedNet

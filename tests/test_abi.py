@@ -44,7 +44,7 @@ def test_exports_are_plain_c(lib):
 
 
 def test_abi_version_and_error_paths(lib):
-    assert lib.ffb_abi_version() == L.ABI_VERSION == 2
+    assert lib.ffb_abi_version() == L.ABI_VERSION == 3
     # null arguments are reported through the status code + ffb_last_error, no CUDA call is made
     assert lib.ffb_net_create(None, None, None) == -1
     assert b"null" in lib.ffb_last_error()
@@ -52,20 +52,23 @@ def test_abi_version_and_error_paths(lib):
     assert lib.ffb_gaussian_logprob(None, None, None, 0, 0, 1.0, None) == -1
     assert lib.ffb_num_tiles(None, 10) == -1
     lib.ffb_net_destroy(None)                     # must be a no-op
+    assert lib.ffb_trace_estimate(None, None) == -1 and lib.ffb_rk_combine(None, None) == -1
+    assert lib.ffb_rk_finish(None, None) == -1
 
 
 def test_struct_sizes_match_the_header(lib, tmp_path):
     """Compile a 10-line C program against include/ffb200.h and compare sizeof() with the ctypes mirrors."""
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "ffb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "ffb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(ffb_net_desc),sizeof(ffb_field),sizeof(ffb_eval_scalars),sizeof(ffb_eval_args),"
                    "sizeof(ffb_dopri5_args),sizeof(ffb_fixed_args),sizeof(ffb_time_program),"
-                   "sizeof(ffb_dopri5_ctl_params),sizeof(ffb_dopri5_ctl));return 0;}\n")
+                   "sizeof(ffb_dopri5_ctl_params),sizeof(ffb_dopri5_ctl),sizeof(ffb_trace_args),sizeof(ffb_rk_combine_args),"
+                   "sizeof(ffb_rk_finish_args));return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(t) for t in (L.NetDesc, L.Field, L.EvalScalars, L.EvalArgs, L.Dopri5Args, L.FixedArgs,
-                                  L.TimeProgram, L.CtlParams, L.Ctl)]
+                                  L.TimeProgram, L.CtlParams, L.Ctl, L.TraceArgs, L.RkCombineArgs, L.RkFinishArgs)]
     assert got == want
 
 
