@@ -476,8 +476,12 @@ class ScoreModel(torch.nn.Module):
     def _solve_staged(self, y0, cond, est, t0, t1, atol, rtol, method, options):
         """Hutch++ / XTrace solves: evaluation-at-a-time dopri5 (engine.StagedBackend), host controller."""
         method = "dopri5" if method is None else method
+        if method in _METHODS:
+            be = E.StagedBackend(self._field(L.DIV_EXACT), y0, est, cond=cond)
+            dt, ev = _fixed_tables(self._program(), method, t0, t1, options)
+            return E.staged_fixed(be, method, dt, ev)
         if method != "dopri5":
-            raise NotImplementedError(f"Hutch++ / XTrace solves are implemented for dopri5 only (got {method!r})")
+            raise NotImplementedError(f"method {method!r} is not implemented (dopri5, rk4, euler, midpoint)")
         be = E.StagedBackend(self._field(L.DIV_EXACT), y0, est, cond=cond)
         self.last_stats = S.dopri5(be, self._program(), t0, t1, rtol, atol, options, group=self._group())
         return be.output()
@@ -506,7 +510,8 @@ class ScoreModel(torch.nn.Module):
         raise NotImplementedError(f"method {method!r} is not implemented (dopri5, rk4, euler, midpoint)")
 
 
-def _solve_fixed(field, prog, method, y0, cond, probes, t0, t1, options, with_lp):
+def _fixed_tables(prog, method, t0, t1, options):
+    """Step sizes (n,) and evaluation scalars (n, evaluations per step, EV_FLOATS) of a torchdiffeq fixed grid."""
     opts = dict(options or {})
     for k in ("norm", "min_step", "max_step"):
         opts.pop(k, None)
@@ -522,9 +527,14 @@ def _solve_fixed(field, prog, method, y0, cond, probes, t0, t1, options, with_lp
     user = (-times if reverse else times).reshape(-1).numpy().astype(np.float32)
     ev = prog(user).reshape(n, nev, L.EV_FLOATS)
     ev[:, :, L.MAX_TFEAT + 3] = -1.0 if reverse else 1.0
-    step_table = np.zeros((n, L.STEP_STRIDE), np.float32)
-    step_table[:, 0] = dt.numpy()
-    step_table[:, 3] = (0.5 * dt).numpy()
+    return dt.numpy().astype(np.float32), ev
+
+
+def _solve_fixed(field, prog, method, y0, cond, probes, t0, t1, options, with_lp):
+    dt, ev = _fixed_tables(prog, method, t0, t1, options)
+    step_table = np.zeros((dt.shape[0], L.STEP_STRIDE), np.float32)
+    step_table[:, 0] = dt
+    step_table[:, 3] = np.float32(0.5) * dt
     x, lp, _ = E.run_fixed(field, _METHODS[method], y0, step_table, ev, cond=cond, probes=probes,
                            want_lp=with_lp)
     return x, lp

@@ -547,6 +547,54 @@ class StagedBackend(CudaBackend):
         self._field_and_trace(self.y[self.cur], ev_row, self.f[self.cur], self.dlp[self.cur])
         return self.f[self.cur], self.dlp[self.cur]
 
+    # -- primitives of the fixed-grid driver (staged_fixed) ------------------------------------------------
+    def state(self):
+        return self.y[self.cur], self.lp[self.cur]
+
+    def feval(self, y, ev_row):
+        """(f, d log p / dt) at ``y`` into fresh buffers."""
+        f, d = torch.empty(self.B, self.D, device=self.dev), torch.empty(self.B, device=self.dev)
+        self._field_and_trace(y, ev_row, f, d)
+        return f, d
+
+    def combine(self, y0, ks, coefs):
+        """y0 + sum_j coefs[j] * ks[j]  (ffb_rk_combine)."""
+        out = torch.empty_like(y0)
+        ca = self.cargs
+        ca.n, ca.n_terms, ca.y0, ca.out = y0.numel(), len(ks), _ptr(y0), _ptr(out)
+        for j in range(7):
+            ca.k[j] = ks[j].data_ptr() if j < len(ks) else None
+            ca.coef[j] = float(coefs[j]) if j < len(ks) else 0.0
+        if y0.numel():
+            L.check(self.lib.ffb_rk_combine(C.byref(ca), self._stream), "ffb_rk_combine")
+        return out
+
+
+def staged_fixed(be, method: str, dts: np.ndarray, ev: np.ndarray):
+    """torchdiffeq's fixed-grid steppers (euler, midpoint, rk4 = 3/8 rule) on a staged backend: one
+    ``feval`` per stage, stage inputs and the step itself through ``combine``.  ``dts`` (n,) float32 step sizes,
+    ``ev`` (n, evaluations per step, EV_FLOATS).  Returns (x, log-det column) at the end of the grid."""
+    third, half, eighth = np.float32(1.0 / 3.0), np.float32(0.5), np.float32(0.125)
+    y, lp = be.state()
+    for s in range(int(dts.shape[0])):
+        dt = np.float32(dts[s])
+        k1, d1 = be.feval(y, ev[s, 0])
+        if method == "euler":
+            ks, ds, cf = [k1], [d1], [dt]
+        elif method == "midpoint":
+            k2, d2 = be.feval(be.combine(y, [k1], [half * dt]), ev[s, 1])
+            ks, ds, cf = [k2], [d2], [dt]
+        elif method == "rk4":
+            k2, d2 = be.feval(be.combine(y, [k1], [dt * third]), ev[s, 1])
+            k3, d3 = be.feval(be.combine(y, [k1, k2], [-(dt * third), dt]), ev[s, 2])
+            k4, d4 = be.feval(be.combine(y, [k1, k2, k3], [dt, -dt, dt]), ev[s, 3])
+            e = dt * eighth
+            ks, ds, cf = [k1, k2, k3, k4], [d1, d2, d3, d4], [e, np.float32(3) * e, np.float32(3) * e, e]
+        else:
+            raise ValueError(method)
+        y, lp = be.combine(y, ks, cf), be.combine(lp, ds, cf)
+    return y, lp
+
 
 def run_fixed(field: FieldSpec, method: int, x0: torch.Tensor, step_table: np.ndarray, ev_table: np.ndarray,
               cond=None, probes=None, lp0=None, noise=None, philox=None, row_offset=0, want_lp=False):

@@ -255,6 +255,18 @@ class FakeStagedBackend(FakeBackend):
     def single_eval(self, ev_row):
         return self._fe(ev_row, self.y)
 
+    def state(self):
+        return self.y, self.lp
+
+    def feval(self, y, ev_row):
+        return self._fe(ev_row, y)
+
+    def combine(self, y0, ks, coefs):
+        acc = ks[0] * torch.tensor(float(coefs[0]))
+        for k, c in zip(ks[1:], coefs[1:]):
+            acc = acc + k * torch.tensor(float(c))
+        return y0 + acc
+
 
 def _dense(y0, y1, ymid, f0, f1, dt, x):
     a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * ymid

@@ -167,6 +167,21 @@ def test_host_logic_reproduces_reference_golden(name):
         assert (sm.last_stats.accepted, sm.last_stats.rejected) == (meta["stats_xt"]["accepted"], meta["stats_xt"]["rejected"])
 
 
+@pytest.mark.parametrize("method,h", [("euler", 1 / 64), ("midpoint", 1 / 32), ("rk4", 1 / 16)])
+def test_host_logic_fixed_grid_methods_vs_oracle(method, h):
+    meta, sd, ins, outs = load_golden("score_logprob_hpp_xt_vp")
+    fl, cond = meta["flags"], ins["cond"]
+    M = port.score_model_from_state_dict(sd, port.make_sde(meta["sde"]), meta["no_sigma"])
+    opts = {"step_size": h}
+    rx, rl = port.solve_odes_forward(M, ins["x0"], cond, method=method, options=opts, probes=("hutchpp", ins["S"], ins["G"]))
+    with patched_engine():
+        sm = _model(meta, sd, hutchpp=True, hpp_rank=fl["hpp_rank"], hpp_vecs=fl["hpp_vecs"])
+        x, lp = sm.solve_odes_forward(ins["x0"], cond, method=method, options=opts, probes=(ins["S"], ins["G"]))
+    assert lp.shape == rl.shape
+    assert float((x - rx).abs().max()) <= 1e-4 * max(1.0, float(rx.abs().max()))
+    assert float((lp - rl).abs().max()) < 1e-3
+
+
 def test_flag_priority_probe_shapes_and_refusals():
     meta, sd, ins, outs = load_golden("score_logprob_hpp_xt_ve")
     x0 = ins["x0"]
@@ -187,7 +202,7 @@ def test_flag_priority_probe_shapes_and_refusals():
         with pytest.raises(ValueError):
             sm.solve_odes_forward(x0, probes=torch.ones(2, B, Dn))
         with pytest.raises(NotImplementedError):
-            sm.solve_odes_forward(x0, method="rk4", options={"step_size": 0.1})
+            sm.solve_odes_forward(x0, method="bosh3")
         sm = _model(meta, sd, hutchpp=True, hpp_rank=1)
         sm.train()
         with pytest.raises(NotImplementedError):
@@ -262,21 +277,35 @@ def test_gpu_jacobian_and_estimators_vs_oracle(kind, no_sigma, Dn, Cn, B, cuda_d
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("method,h", [("euler", 1 / 64), ("midpoint", 1 / 32), ("rk4", 1 / 16)])
+def test_gpu_fixed_grid_methods_vs_oracle(method, h, cuda_dev):
+    meta, sd, ins, outs = load_golden("score_logprob_hpp_xt_vp")
+    fl, cond = meta["flags"], ins["cond"]
+    M = port.score_model_from_state_dict(sd, port.make_sde(meta["sde"]), meta["no_sigma"])
+    opts = {"step_size": h}
+    rx, rl = port.solve_odes_forward(M, ins["x0"], cond, method=method, options=opts, probes=("xtrace", ins["O"]))
+    sm = _model(meta, sd, xtrace=True, xt_vecs=fl["xt_vecs"]).to(cuda_dev)
+    x, lp = sm.solve_odes_forward(ins["x0"].to(cuda_dev), cond.to(cuda_dev), method=method, options=opts, probes=ins["O"].to(cuda_dev))
+    assert float((x.cpu() - rx).abs().max()) <= 1e-4 * max(1.0, float(rx.abs().max()))
+    assert float((lp.cpu() - rl).abs().max()) < 1e-3
+
+
+@pytest.mark.gpu
 def test_gpu_staged_solve_ragged_empty_and_partition_invariance(cuda_dev):
     torch.manual_seed(3)
     sm = D.ScoreModel(D.MLP(16, 0, 8, [128] * 2), D.VPSDE(), no_sigma=True, hutchpp=True, hpp_rank=2, hpp_vecs=2).eval().to(cuda_dev)
     B = 300
     x = torch.randn(B, 16, device=cuda_dev)
     S, G = full_rank_probes(2, B, 16, 41).to(cuda_dev), torch.sign(torch.randn(2, B, 16)).to(cuda_dev)
-    opts = {"first_step": 0.05, "min_step": 1e-6}
-    lp = sm.log_prob(x, probes=(S, G), options=opts)
+    lp = sm.log_prob(x, probes=(S, G), options={"first_step": 0.05, "min_step": 1e-6})
     assert lp.shape == (B, 1) and torch.isfinite(lp).all()
-    # per-sample results do not depend on the batch they ride in when the step sequence is pinned by the tolerance
-    # being loose enough to accept every attempt of the same first_step sequence: compare with a fixed split
-    a = sm.log_prob(x[:130], probes=(S[:, :130].contiguous(), G[:, :130].contiguous()), atol=1.0, rtol=1.0, options=opts)
-    b = sm.log_prob(x, probes=(S, G), atol=1.0, rtol=1.0, options=opts)
-    assert float((a - b[:130]).abs().max()) < 1e-4
-    e = sm.log_prob(x[:0], probes=(S[:, :0].contiguous(), G[:, :0].contiguous()), options={"first_step": 0.05})
+    # a sample's result does not depend on the batch it rides in once the step sequence is pinned (fixed grid)
+    opts = {"step_size": 0.125}
+    for method in ("rk4", "midpoint"):
+        a = sm.log_prob(x[:130], probes=(S[:, :130].contiguous(), G[:, :130].contiguous()), method=method, options=opts)
+        b = sm.log_prob(x, probes=(S, G), method=method, options=opts)
+        assert torch.equal(a, b[:130])
+    e = sm.log_prob(x[:0], probes=(S[:, :0].contiguous(), G[:, :0].contiguous()), method="euler", options={"step_size": 0.25})
     assert e.shape == (0, 1)
     with pytest.raises(NotImplementedError):
         D.ScoreModel(D.MLP(16, 0, 8, [64]), D.VPSDE(), xtrace=True, xt_vecs=9).eval().to(cuda_dev).log_prob(x)
