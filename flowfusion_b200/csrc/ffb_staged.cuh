@@ -25,8 +25,10 @@
 
 namespace ffb {
 
-constexpr int TR_MAXD = FFB_TRACE_MAX_DIM;
-constexpr int TR_MAXK = FFB_TRACE_MAX_RANK;
+// The per-sample algebra is templated on the padded sizes of its work arrays (DMAX >= D, KMAX >= rank): the arrays
+// are indexed at run time, so they live in local memory, and with one [32][8] size for all (~4.4 KB per thread) the
+// footprint of a resident block set overflowed L1 and the kernel ran at L2 latency (6.4 ms per 10^6 samples at
+// D = 16, rank 1).  Sized to the rank it stays in L1.
 
 // A v = J_f^T v for x_dot = a x - c net(x) [/ sigma]  (diffusion.py:233-238, 276-279), or = J_net^T v
 struct TraceOp {
@@ -50,6 +52,7 @@ struct TraceOp {
 
 // Householder QR in place (LAPACK geqrf conventions): R in the upper triangle of Y (D x k, row stride TR_MAXK),
 // the reflectors below the diagonal (v_jj = 1 implicit), their scales in tau.
+template <int TR_MAXK>
 __host__ __device__ inline void tr_qr(float* Y, float* tau, int D, int k) {
   for (int j = 0; j < k; ++j) {
     const float alpha = Y[j * TR_MAXK + j];
@@ -76,6 +79,7 @@ __host__ __device__ inline void tr_qr(float* Y, float* tau, int D, int k) {
   }
 }
 // thin Q (D x k) = H_0 ... H_{k-1} [I_k; 0]  (LAPACK orgqr)
+template <int TR_MAXK>
 __host__ __device__ inline void tr_formq(const float* Y, const float* tau, float* Q, int D, int k) {
   for (int d = 0; d < D; ++d)
     for (int i = 0; i < k; ++i) Q[d * TR_MAXK + i] = (d == i) ? 1.0f : 0.0f;
@@ -92,6 +96,7 @@ __host__ __device__ inline void tr_formq(const float* Y, const float* tau, float
 }
 
 // Hutch++ (diffusion.py:336-400): Y = A S, Q = qr(Y), tr(Q^T A Q) + mean_l u_l^T A u_l, u_l = (I - Q Q^T) g_l
+template <int TR_MAXD, int TR_MAXK>
 __host__ __device__ inline float hutchpp_one(const ffb_trace_args& a, const TraceOp& op, int64_t b) {
   const int D = a.dim, k = a.rank;
   float Y[TR_MAXD * TR_MAXK], Q[TR_MAXD * TR_MAXK], tau[TR_MAXK], v[TR_MAXD], w[TR_MAXD], qg[TR_MAXK];
@@ -101,8 +106,8 @@ __host__ __device__ inline float hutchpp_one(const ffb_trace_args& a, const Trac
     op.apply(v, w);
     for (int d = 0; d < D; ++d) Y[d * TR_MAXK + i] = w[d];
   }
-  tr_qr(Y, tau, D, k);
-  tr_formq(Y, tau, Q, D, k);
+  tr_qr<TR_MAXK>(Y, tau, D, k);
+  tr_formq<TR_MAXK>(Y, tau, Q, D, k);
   float trace_lr = 0.0f;
   for (int i = 0; i < k; ++i) {                                   // sum_i q_i^T A q_i   (:376-381)
     for (int d = 0; d < D; ++d) v[d] = Q[d * TR_MAXK + i];
@@ -129,6 +134,7 @@ __host__ __device__ inline float hutchpp_one(const ffb_trace_args& a, const Trac
 }
 
 // XTrace (diffusion.py:402-481), index for index; k = m (m <= D is enforced by the caller as in :410)
+template <int TR_MAXD, int TR_MAXK>
 __host__ __device__ inline float xtrace_one(const ffb_trace_args& a, const TraceOp& op, int64_t b) {
   const int D = a.dim, k = a.rank;
   constexpr int K = TR_MAXK;
@@ -140,8 +146,8 @@ __host__ __device__ inline float xtrace_one(const ffb_trace_args& a, const Trace
     op.apply(v, w);
     for (int d = 0; d < D; ++d) Y[d * K + i] = w[d];
   }
-  tr_qr(Y, tau, D, k);                                            // R = upper triangle of Y (:438)
-  tr_formq(Y, tau, Q, D, k);
+  tr_qr<TR_MAXK>(Y, tau, D, k);                                            // R = upper triangle of Y (:438)
+  tr_formq<TR_MAXK>(Y, tau, Q, D, k);
   for (int i = 0; i < k; ++i) {                                   // Z = A Q (:443-445)
     for (int d = 0; d < D; ++d) v[d] = Q[d * K + i];
     op.apply(v, w);
@@ -201,12 +207,13 @@ __host__ __device__ inline float xtrace_one(const ffb_trace_args& a, const Trace
   return total / (float)k;                                        // :477
 }
 
+template <int TR_MAXD, int TR_MAXK>
 __host__ __device__ inline float trace_estimate_one(const ffb_trace_args& a, const float* A, int64_t b) {
   TraceOp op;
   op.A = A; op.D = a.dim;
   op.score = a.score != 0; op.use_sigma = a.use_sigma != 0; op.has_drift = a.has_drift != 0;
   op.a = a.a; op.c = a.c; op.sigma = a.sigma;
-  const float v = (a.kind == FFB_TRACE_HUTCHPP) ? hutchpp_one(a, op, b) : xtrace_one(a, op, b);
+  const float v = (a.kind == FFB_TRACE_HUTCHPP) ? hutchpp_one<TR_MAXD, TR_MAXK>(a, op, b) : xtrace_one<TR_MAXD, TR_MAXK>(a, op, b);
   return v * a.sign;
 }
 
@@ -227,6 +234,7 @@ __device__ __forceinline__ double st_block_sum(double v, double* red) {
 }  // namespace ffb
 
 // one thread per sample; the block's Jacobians go through shared memory (stride D*D + 1: conflict-free)
+template <int DMAX, int KMAX>
 __global__ void k_trace_estimate(const __grid_constant__ ffb_trace_args a, const int64_t ntiles) {
   using namespace ffb;
   extern __shared__ float sA[];
@@ -245,7 +253,7 @@ __global__ void k_trace_estimate(const __grid_constant__ ffb_trace_args a, const
     __syncthreads();
     if ((int)threadIdx.x < nv) {
       const int64_t b = row0 + threadIdx.x;
-      const float dv = trace_estimate_one(a, sA + threadIdx.x * stride, b);
+      const float dv = trace_estimate_one<DMAX, KMAX>(a, sA + threadIdx.x * stride, b);
       a.dlp[b] = dv;
       if (a.norms == 1) {
         const float q = dv / a.atol;
@@ -349,26 +357,49 @@ static int staged_grid(int64_t work_items, int threads) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, std::min(FFB_STAGED_BLOCKS, 8 * num_sms())));
 }
 
+template <int DMAX, int KMAX>
+static int launch_trace(const ffb_trace_args* a, cudaStream_t stream) {
+  const int threads = (sizeof(float) * 64 * (a->dim * a->dim + 1) <= 200 * 1024) ? 64 : 32;
+  const size_t smem = sizeof(float) * threads * (a->dim * a->dim + 1);
+  CUDA_TRY(cudaFuncSetAttribute(k_trace_estimate<DMAX, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (a->batch + threads - 1) / threads;
+  k_trace_estimate<DMAX, KMAX><<<staged_grid(a->batch, threads), threads, smem, stream>>>(*a, ntiles);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+template <int DMAX, int KMAX>
+static void host_trace(const ffb_trace_args* a) {
+  const int DD = a->dim * a->dim;
+  for (int64_t b = 0; b < a->batch; ++b) a->dlp[b] = ffb::trace_estimate_one<DMAX, KMAX>(*a, a->jac + b * DD, b);
+}
+// work-array sizes: DMAX in {16, 32}, KMAX in {1, 2, 4, 8}
+#define TRACE_DISPATCH(CALL)                                                          \
+  do {                                                                                \
+    const int kk = a->rank <= 1 ? 1 : (a->rank <= 2 ? 2 : (a->rank <= 4 ? 4 : 8));    \
+    if (a->dim <= 16) {                                                               \
+      if (kk == 1) CALL(16, 1); else if (kk == 2) CALL(16, 2); else if (kk == 4) CALL(16, 4); else CALL(16, 8); \
+    } else {                                                                          \
+      if (kk == 1) CALL(32, 1); else if (kk == 2) CALL(32, 2); else if (kk == 4) CALL(32, 4); else CALL(32, 8); \
+    }                                                                                 \
+  } while (0)
+
 extern "C" int ffb_trace_estimate(const ffb_trace_args* a, void* stream) {
   if (int rc = trace_args_ok(a, "ffb_trace_estimate")) return rc;
   if (a->norms && (!a->partials || (a->norms == 2 && !a->dlpbase)))
     return fail(FFB_ERR_ARG, "ffb_trace_estimate: norms need partials (and dlpbase for norms = 2)");
   if (a->batch <= 0) return FFB_OK;
-  const int threads = (sizeof(float) * 64 * (a->dim * a->dim + 1) <= 200 * 1024) ? 64 : 32;
-  const size_t smem = sizeof(float) * threads * (a->dim * a->dim + 1);
-  CUDA_TRY(cudaFuncSetAttribute(k_trace_estimate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t ntiles = (a->batch + threads - 1) / threads;
-  const int grid = staged_grid(a->batch, threads);
-  k_trace_estimate<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*a, ntiles);
-  g_launches += 1;
-  CUDA_TRY(cudaGetLastError());
+#define TRACE_LAUNCH(DM, KK) return launch_trace<DM, KK>(a, reinterpret_cast<cudaStream_t>(stream))
+  TRACE_DISPATCH(TRACE_LAUNCH);
+#undef TRACE_LAUNCH
   return FFB_OK;
 }
 
 extern "C" int ffb_trace_estimate_host(const ffb_trace_args* a) {
   if (int rc = trace_args_ok(a, "ffb_trace_estimate_host")) return rc;
-  const int DD = a->dim * a->dim;
-  for (int64_t b = 0; b < a->batch; ++b) a->dlp[b] = ffb::trace_estimate_one(*a, a->jac + b * DD, b);
+#define TRACE_HOST(DM, KK) host_trace<DM, KK>(a)
+  TRACE_DISPATCH(TRACE_HOST);
+#undef TRACE_HOST
   return FFB_OK;
 }
 

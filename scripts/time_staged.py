@@ -15,9 +15,12 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 torch.manual_seed(1234)
 x = torch.randn(B, 16, device=dev) 
 out = {}
+only = os.environ.get("FFB_STAGED_ONLY")
 for name, flags in (("exact", {}), ("hutchinson", dict(hutchinson=True)), ("hutchpp_r1_m1", dict(hutchpp=True)),
                     ("hutchpp_r4_m4", dict(hutchpp=True, hpp_rank=4, hpp_vecs=4)), ("xtrace_m1", dict(xtrace=True)),
                     ("xtrace_m4", dict(xtrace=True, xt_vecs=4))):
+    if only and name != only:
+        continue
     torch.manual_seed(1234)
     sm = D.ScoreModel(D.MLP(16, 0, 8, [128] * 4), D.VPSDE(), no_sigma=True, **flags).eval().to(dev)
     for it in range(2):

@@ -55,6 +55,21 @@ def _worker(rank, world, port, q):
         out["lp_err"] = float((lp_full - outs["log_prob"]).abs().max())
         out["lp_steps"] = (m.last_stats.accepted, m.last_stats.rejected)
         out["lp_want"] = (meta["stats"]["accepted"], meta["stats"]["rejected"])
+        # ---- Hutch++ log-prob (staged attempts): probes are sharded with the rows ------------------------------
+        meta, sd, ins, outs = load_golden("score_logprob_hpp_xt_vp")
+        fl = meta["flags"]
+        sm = D.ScoreModel(D.MLP(**meta["ctor"]), D.VPSDE(), no_sigma=True, hutchpp=True, hpp_rank=fl["hpp_rank"],
+                          hpp_vecs=fl["hpp_vecs"]).eval()
+        sm.load_state_dict(sd)
+        from flowfusion_b200.dist import shard_bounds
+        lo, hi = shard_bounds(ins["x0"].shape[0], rank, world)
+        with patched_engine(), fd.use_group(td.group.WORLD):
+            lp = sm.log_prob(ins["x0"][lo:hi], ins["cond"][lo:hi],
+                             probes=(ins["S"][:, lo:hi].contiguous(), ins["G"][:, lo:hi].contiguous()))
+            lp_full = fd.gather_rows(lp)
+        out["hpp_err"] = float((lp_full - outs["lp_hpp"]).abs().max())
+        out["hpp_steps"] = (sm.last_stats.accepted, sm.last_stats.rejected)
+        out["hpp_want"] = (meta["stats_hpp"]["accepted"], meta["stats_hpp"]["rejected"])
         # ---- uneven shards, an empty shard, and the row offsets Philox streams are keyed on -----------------
         t = torch.arange(7, dtype=torch.float32)[:, None]
         mine = fd.shard_rows(t, rank, world)
@@ -84,6 +99,7 @@ def test_two_rank_sharded_solves_match_single_process_golden():
         assert o["pf_err"] < 1e-4 and o["lp_err"] < 1e-3
         assert o["pf_steps"] == o["pf_want"], "sharded dopri5 must take the reference's steps"
         assert o["lp_steps"] == o["lp_want"]
+        assert o["hpp_err"] < 1e-3 and o["hpp_steps"] == o["hpp_want"]
         assert o["gather_ok"] and o["gather_empty_ok"]
     assert res[0]["pf_dt"] == res[1]["pf_dt"], "every rank must take bit-identical step sizes"
     assert (res[0]["offset"], res[1]["offset"]) == (0, 4)       # 7 rows over 2 ranks: 4 + 3
