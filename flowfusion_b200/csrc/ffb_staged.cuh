@@ -233,8 +233,12 @@ __device__ __forceinline__ double st_block_sum(double v, double* red) {
 
 }  // namespace ffb
 
-// one thread per sample; the block's Jacobians go through shared memory (stride D*D + 1: conflict-free)
-template <int DMAX, int KMAX>
+// One thread per sample.  STAGE = false (default): every thread streams its own contiguous D*D Jacobian straight from
+// global memory (each 32-byte sector is fetched once per pass and then served by L1), no shared memory, so the
+// occupancy is set by registers alone.  STAGE = true (FFB_TRACE_STAGE=1, kept for A/B): the block's Jacobians go
+// through shared memory first (coalesced load, row stride D*D + 1: conflict-free reads) -- 1 KB of shared memory per
+// thread at D = 16 caps an SM at 192 threads and every latency of the serial per-sample algebra is exposed.
+template <int DMAX, int KMAX, bool STAGE>
 __global__ void k_trace_estimate(const __grid_constant__ ffb_trace_args a, const int64_t ntiles) {
   using namespace ffb;
   extern __shared__ float sA[];
@@ -244,16 +248,19 @@ __global__ void k_trace_estimate(const __grid_constant__ ffb_trace_args a, const
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * blockDim.x;
     const int nv = (int)min((int64_t)blockDim.x, a.batch - row0);
-    const float* __restrict__ src = a.jac + row0 * DD;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nv * DD; idx += blockDim.x) {
-      const int s = idx / DD, e = idx - s * DD;
-      sA[s * stride + e] = src[idx];
+    if (STAGE) {
+      const float* __restrict__ src = a.jac + row0 * DD;
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nv * DD; idx += blockDim.x) {
+        const int s = idx / DD, e = idx - s * DD;
+        sA[s * stride + e] = src[idx];
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if ((int)threadIdx.x < nv) {
       const int64_t b = row0 + threadIdx.x;
-      const float dv = trace_estimate_one<DMAX, KMAX>(a, sA + threadIdx.x * stride, b);
+      const float* A = STAGE ? sA + threadIdx.x * stride : a.jac + b * DD;
+      const float dv = trace_estimate_one<DMAX, KMAX>(a, A, b);
       a.dlp[b] = dv;
       if (a.norms == 1) {
         const float q = dv / a.atol;
@@ -357,13 +364,24 @@ static int staged_grid(int64_t work_items, int threads) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, std::min(FFB_STAGED_BLOCKS, 8 * num_sms())));
 }
 
+static bool trace_stage() {
+  static const bool on = [] { const char* e = getenv("FFB_TRACE_STAGE"); return e && e[0] == '1'; }();
+  return on;
+}
 template <int DMAX, int KMAX>
 static int launch_trace(const ffb_trace_args* a, cudaStream_t stream) {
-  const int threads = (sizeof(float) * 64 * (a->dim * a->dim + 1) <= 200 * 1024) ? 64 : 32;
-  const size_t smem = sizeof(float) * threads * (a->dim * a->dim + 1);
-  CUDA_TRY(cudaFuncSetAttribute(k_trace_estimate<DMAX, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t ntiles = (a->batch + threads - 1) / threads;
-  k_trace_estimate<DMAX, KMAX><<<staged_grid(a->batch, threads), threads, smem, stream>>>(*a, ntiles);
+  if (trace_stage()) {
+    const int threads = (sizeof(float) * 64 * (a->dim * a->dim + 1) <= 200 * 1024) ? 64 : 32;
+    const size_t smem = sizeof(float) * threads * (a->dim * a->dim + 1);
+    CUDA_TRY(cudaFuncSetAttribute(k_trace_estimate<DMAX, KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t ntiles = (a->batch + threads - 1) / threads;
+    k_trace_estimate<DMAX, KMAX, true><<<staged_grid(a->batch, threads), threads, smem, stream>>>(*a, ntiles);
+  } else {
+    const int threads = 128;
+    const int64_t ntiles = (a->batch + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, FFB_STAGED_BLOCKS));
+    k_trace_estimate<DMAX, KMAX, false><<<grid, threads, 0, stream>>>(*a, ntiles);
+  }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return FFB_OK;

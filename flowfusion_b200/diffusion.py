@@ -366,7 +366,7 @@ class ScoreModel(torch.nn.Module):
         last solve when their shapes fit (`:346-354`, `:413-418`), else draws fresh ones."""
         if self.hutch or not (self.hutchpp or self.xtrace):
             return None
-        B, D = x.shape[0], x.reshape(x.shape[0], -1).shape[1]
+        B, D = x.shape[0], int(np.prod(x.shape[1:]))
         rs = lambda n: torch.sign(torch.randn(n, B, D, device=x.device, dtype=x.dtype))     # noqa: E731
         if self.hutchpp:
             r, m = int(min(self.hpp_rank, D)), int(max(1, self.hpp_vector))
