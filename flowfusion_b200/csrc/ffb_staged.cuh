@@ -133,13 +133,60 @@ __host__ __device__ inline float hutchpp_one(const ffb_trace_args& a, const Trac
   return trace_lr + trace_res / (float)a.nvec;                    // :398
 }
 
+// The k x k tail of XTrace (diffusion.py:453-477) on H = Q^T Z, W = Q^T O, T = Z^T O and the upper-triangular R
+// (row stride K): shared by the per-sample path and the cooperative kernel.
+template <int K>
+__host__ __device__ inline float xtrace_tail(const float* H, const float* W, const float* T, const float* R, int k) {
+  float St[K * K], X[K * K];
+  // St = inv(R) by back substitution (:453), rows scaled to unit 2-norm (:455)
+  for (int j = 0; j < k; ++j) {
+    for (int i = k - 1; i >= 0; --i) {
+      if (i > j) { St[i * K + j] = 0.0f; continue; }
+      float acc = (i == j) ? 1.0f : 0.0f;
+      for (int l = i + 1; l <= j; ++l) acc = fmaf(-R[i * K + l], St[l * K + j], acc);
+      St[i * K + j] = acc / R[i * K + i];
+    }
+  }
+  for (int i = 0; i < k; ++i) {
+    float ss = 0.0f;
+    for (int j = 0; j < k; ++j) ss = fmaf(St[i * K + j], St[i * K + j], ss);
+    const float nrm = sqrtf(ss);
+    for (int j = 0; j < k; ++j) St[i * K + j] /= nrm;
+  }
+  // S = St^T (:456): S[p][q] = St[q][p]
+  float trace_H = 0.0f;
+  for (int i = 0; i < k; ++i) trace_H += H[i * K + i];            // :459
+  float total = 0.0f;
+  for (int q = 0; q < k; ++q) {                                   // one estimate per probe (:461-477)
+    float ws = 0.0f, sr = 0.0f;
+    for (int p = 0; p < k; ++p) {
+      const float s = St[q * K + p];
+      ws = fmaf(s, W[p * K + q], ws);                             // WS = sum_p W[p][q] S[p][q]
+      if (p <= q) sr = fmaf(s, R[p * K + q], sr);                 // SR = sum_p S[p][q] R[p][q]  (R upper triangular)
+    }
+    for (int p = 0; p < k; ++p) X[p * K + q] = W[p * K + q] - ws * St[q * K + p];    // :463
+    float shs = 0.0f, xhx = 0.0f, tx = 0.0f;
+    for (int i = 0; i < k; ++i) {
+      float hs = 0.0f, hx = 0.0f;
+      for (int p = 0; p < k; ++p) {
+        hs = fmaf(H[i * K + p], St[q * K + p], hs);
+        hx = fmaf(H[i * K + p], X[p * K + q], hx);
+      }
+      shs = fmaf(St[q * K + i], hs, shs);                         // :465
+      xhx = fmaf(X[i * K + q], hx, xhx);                          // :467
+      tx = fmaf(T[i * K + q], X[i * K + q], tx);                  // :473
+    }
+    total += trace_H - shs + ws * sr - tx + xhx;                  // :475
+  }
+  return total / (float)k;                                        // :477
+}
 // XTrace (diffusion.py:402-481), index for index; k = m (m <= D is enforced by the caller as in :410)
 template <int TR_MAXD, int TR_MAXK>
 __host__ __device__ inline float xtrace_one(const ffb_trace_args& a, const TraceOp& op, int64_t b) {
   const int D = a.dim, k = a.rank;
   constexpr int K = TR_MAXK;
   float Y[TR_MAXD * K], Q[TR_MAXD * K], Z[TR_MAXD * K], tau[K], v[TR_MAXD], w[TR_MAXD];
-  float H[K * K], W[K * K], T[K * K], St[K * K], X[K * K];
+  float H[K * K], W[K * K], T[K * K];
   for (int i = 0; i < k; ++i) {                                   // Y = A O (:433-435)
     const float* o = a.S + ((int64_t)i * a.batch + b) * D;
     for (int d = 0; d < D; ++d) v[d] = o[d];
@@ -164,47 +211,10 @@ __host__ __device__ inline float xtrace_one(const ffb_trace_args& a, const Trace
       }
       H[i * K + j] = h; W[i * K + j] = wq; T[i * K + j] = tz;
     }
-  // St = inv(R) by back substitution (:453), rows scaled to unit 2-norm (:455)
-  for (int j = 0; j < k; ++j) {
-    for (int i = k - 1; i >= 0; --i) {
-      if (i > j) { St[i * K + j] = 0.0f; continue; }
-      float acc = (i == j) ? 1.0f : 0.0f;
-      for (int l = i + 1; l <= j; ++l) acc = fmaf(-Y[i * K + l], St[l * K + j], acc);
-      St[i * K + j] = acc / Y[i * K + i];
-    }
-  }
-  for (int i = 0; i < k; ++i) {
-    float ss = 0.0f;
-    for (int j = 0; j < k; ++j) ss = fmaf(St[i * K + j], St[i * K + j], ss);
-    const float nrm = sqrtf(ss);
-    for (int j = 0; j < k; ++j) St[i * K + j] /= nrm;
-  }
-  // S = St^T (:456): S[p][q] = St[q][p]
-  float trace_H = 0.0f;
-  for (int i = 0; i < k; ++i) trace_H += H[i * K + i];            // :459
-  float total = 0.0f;
-  for (int q = 0; q < k; ++q) {                                   // one estimate per probe (:461-477)
-    float ws = 0.0f, sr = 0.0f;
-    for (int p = 0; p < k; ++p) {
-      const float s = St[q * K + p];
-      ws = fmaf(s, W[p * K + q], ws);                             // WS = sum_p W[p][q] S[p][q]
-      if (p <= q) sr = fmaf(s, Y[p * K + q], sr);                 // SR = sum_p S[p][q] R[p][q]  (R upper triangular)
-    }
-    for (int p = 0; p < k; ++p) X[p * K + q] = W[p * K + q] - ws * St[q * K + p];    // :463
-    float shs = 0.0f, xhx = 0.0f, tx = 0.0f;
-    for (int i = 0; i < k; ++i) {
-      float hs = 0.0f, hx = 0.0f;
-      for (int p = 0; p < k; ++p) {
-        hs = fmaf(H[i * K + p], St[q * K + p], hs);
-        hx = fmaf(H[i * K + p], X[p * K + q], hx);
-      }
-      shs = fmaf(St[q * K + i], hs, shs);                         // :465
-      xhx = fmaf(X[i * K + q], hx, xhx);                          // :467
-      tx = fmaf(T[i * K + q], X[i * K + q], tx);                  // :473
-    }
-    total += trace_H - shs + ws * sr - tx + xhx;                  // :475
-  }
-  return total / (float)k;                                        // :477
+  float R[K * K];
+  for (int p = 0; p < k; ++p)
+    for (int q = 0; q < k; ++q) R[p * K + q] = (p <= q) ? Y[p * K + q] : 0.0f;
+  return xtrace_tail<K>(H, W, T, R, k);
 }
 
 template <int TR_MAXD, int TR_MAXK>
@@ -235,7 +245,7 @@ __device__ __forceinline__ double st_block_sum(double v, double* red) {
 
 // One thread per sample.  STAGE = false (default): every thread streams its own contiguous D*D Jacobian straight from
 // global memory (each 32-byte sector is fetched once per pass and then served by L1), no shared memory, so the
-// occupancy is set by registers alone.  STAGE = true (FFB_TRACE_STAGE=1, kept for A/B): the block's Jacobians go
+// occupancy is set by registers alone.  STAGE = true (first version, measured 6.4 ms per 10^6 rows against 3.0 ms): the block's Jacobians go
 // through shared memory first (coalesced load, row stride D*D + 1: conflict-free reads) -- 1 KB of shared memory per
 // thread at D = 16 caps an SM at 192 threads and every latency of the serial per-sample algebra is exposed.
 template <int DMAX, int KMAX, bool STAGE>
@@ -261,6 +271,170 @@ __global__ void k_trace_estimate(const __grid_constant__ ffb_trace_args a, const
       const int64_t b = row0 + threadIdx.x;
       const float* A = STAGE ? sA + threadIdx.x * stride : a.jac + b * DD;
       const float dv = trace_estimate_one<DMAX, KMAX>(a, A, b);
+      a.dlp[b] = dv;
+      if (a.norms == 1) {
+        const float q = dv / a.atol;
+        q2 += (double)q * q;
+      } else if (a.norms == 2) {
+        const float q = (dv - a.dlpbase[b]) / a.atol;
+        q2 += (double)q * q;
+      }
+    }
+  }
+  if (a.norms) {
+    const double s = st_block_sum(q2, red);
+    if (threadIdx.x == 0) a.partials[(int64_t)blockIdx.x * FFB_NPART + (a.norms == 1 ? P_LP_F : P_LP_DF)] = s;
+  }
+}
+
+// =============================================================================================
+// Cooperative estimator kernel (the default): LANES = 16 or 32 lanes per sample.
+// Lane j keeps ROW j of A = J^T in registers (the group reads one contiguous D*D block: coalesced, once), vectors
+// are distributed one element per lane, A v = D shuffles + D FMAs per lane, inner products are butterfly
+// reductions (every lane gets the same bits), the Householder QR runs on distributed columns and the k x k XTrace
+// tail redundantly on every lane.  Same mathematics as trace_estimate_one with tree- instead of serially-ordered
+// sums; tests compare both with the oracle.  The thread-per-sample kernel re-read each Jacobian once per pass from
+// DRAM (3.7 KB / row against 1.2 KB algorithmic, ncu) behind dependent 32-byte loads: 3.0 ms per 10^6 rows.
+// =============================================================================================
+namespace ffb {
+
+template <int LANES>
+__device__ __forceinline__ float co_sum(float v) {
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LANES);
+  return v;
+}
+
+template <int LANES>
+struct CoOp {
+  float row[LANES];       // A[lane][n]
+  bool score, use_sigma, has_drift;
+  float a, c, sigma;
+  __device__ __forceinline__ float apply(float v) const {
+    float acc = 0.0f;
+#pragma unroll
+    for (int n = 0; n < LANES; ++n) acc = fmaf(row[n], __shfl_sync(0xffffffffu, v, n, LANES), acc);
+    if (!score) return acc;
+    const float s = use_sigma ? acc / sigma : acc;
+    return (has_drift ? a * v : 0.0f) - c * s;
+  }
+};
+
+// Householder QR of the distributed columns Y[0..k) (lane d holds row d), LAPACK conventions as tr_qr; then the thin Q
+template <int LANES, int K>
+__device__ __forceinline__ void co_qr(float (&Y)[K], float (&Q)[K], int k, int lane) {
+  float tau[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    tau[j] = 0.0f;
+    if (j < k) {
+      const float alpha = __shfl_sync(0xffffffffu, Y[j], j, LANES);
+      const float ss = co_sum<LANES>(lane > j ? Y[j] * Y[j] : 0.0f);
+      const bool on = ss != 0.0f;
+      const float beta = -copysignf(sqrtf(fmaf(alpha, alpha, ss)), alpha);
+      const float t = on ? (beta - alpha) / beta : 0.0f;
+      const float scal = on ? 1.0f / (alpha - beta) : 1.0f;
+      if (lane > j) Y[j] *= scal;
+      if (lane == j && on) Y[j] = beta;
+      tau[j] = t;
+#pragma unroll
+      for (int c = j + 1; c < K; ++c) {
+        if (c < k) {
+          const float w = t * co_sum<LANES>(lane > j ? Y[j] * Y[c] : (lane == j ? Y[c] : 0.0f));
+          if (lane == j) Y[c] -= w;
+          if (lane > j) Y[c] = fmaf(-w, Y[j], Y[c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) Q[i] = (lane == i) ? 1.0f : 0.0f;
+#pragma unroll
+  for (int j = K - 1; j >= 0; --j) {
+    if (j < k) {
+#pragma unroll
+      for (int c = j; c < K; ++c) {
+        if (c < k) {
+          const float w = tau[j] * co_sum<LANES>(lane > j ? Y[j] * Q[c] : (lane == j ? Q[c] : 0.0f));
+          if (lane == j) Q[c] -= w;
+          if (lane > j) Q[c] = fmaf(-w, Y[j], Q[c]);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace ffb
+
+template <int LANES, int K>
+__global__ void __launch_bounds__(128) k_trace_coop(const __grid_constant__ ffb_trace_args a, const int64_t ngroups) {
+  using namespace ffb;
+  __shared__ double red[32];
+  constexpr int GPB = 128 / LANES;                  // samples per block and pass
+  const int D = a.dim, k = a.rank, lane = threadIdx.x % LANES, grp = threadIdx.x / LANES;
+  const bool row_on = lane < D;
+  double q2 = 0.0;
+  for (int64_t g0 = (int64_t)blockIdx.x * GPB; g0 < ngroups; g0 += (int64_t)gridDim.x * GPB) {
+    const int64_t bb = g0 + grp;
+    const bool live = bb < a.batch;
+    const int64_t b = live ? bb : a.batch - 1;      // idle groups shadow the last sample: every lane runs every shuffle
+    CoOp<LANES> op;
+    op.score = a.score != 0; op.use_sigma = a.use_sigma != 0; op.has_drift = a.has_drift != 0;
+    op.a = a.a; op.c = a.c; op.sigma = a.sigma;
+    const float* __restrict__ ar = a.jac + (b * D + (row_on ? lane : 0)) * D;
+    if ((D & 3) == 0) {
+#pragma unroll
+      for (int n = 0; n < LANES; n += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_on && n < D) v = *reinterpret_cast<const float4*>(ar + n);
+        op.row[n] = v.x; op.row[n + 1] = v.y; op.row[n + 2] = v.z; op.row[n + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < LANES; ++n) op.row[n] = (row_on && n < D) ? ar[n] : 0.0f;
+    }
+    float P[K], Y[K], Q[K];                          // probes (S or O), A P, thin Q: lane d holds row d
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      P[i] = (i < k && row_on) ? a.S[((int64_t)i * a.batch + b) * D + lane] : 0.0f;
+      Y[i] = 0.0f;
+      if (i < k) Y[i] = op.apply(P[i]);
+    }
+    co_qr<LANES, K>(Y, Q, k, lane);
+    float est;
+    if (a.kind == FFB_TRACE_HUTCHPP) {
+      float trace_lr = 0.0f, trace_res = 0.0f;
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+        if (i < k) trace_lr += co_sum<LANES>(Q[i] * op.apply(Q[i]));
+      for (int l = 0; l < a.nvec; ++l) {
+        const float gv = row_on ? a.G[((int64_t)l * a.batch + b) * D + lane] : 0.0f;
+        float u = gv;
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+          if (i < k) u = fmaf(-Q[i], co_sum<LANES>(Q[i] * gv), u);
+        trace_res += co_sum<LANES>(u * op.apply(u));
+      }
+      est = trace_lr + trace_res / (float)a.nvec;
+    } else {
+      float Z[K], H[K * K], W[K * K], T[K * K], R[K * K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) Z[i] = (i < k) ? op.apply(Q[i]) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const bool in = i < k && j < k;            // uniform
+          H[i * K + j] = in ? co_sum<LANES>(Q[i] * Z[j]) : 0.0f;
+          W[i * K + j] = in ? co_sum<LANES>(Q[i] * P[j]) : 0.0f;
+          T[i * K + j] = in ? co_sum<LANES>(Z[i] * P[j]) : 0.0f;
+          R[i * K + j] = (in && i <= j) ? __shfl_sync(0xffffffffu, Y[j], i, LANES) : 0.0f;
+        }
+      }
+      est = xtrace_tail<K>(H, W, T, R, k);
+    }
+    if (live && lane == 0) {
+      const float dv = est * a.sign;
       a.dlp[b] = dv;
       if (a.norms == 1) {
         const float q = dv / a.atol;
@@ -364,18 +538,24 @@ static int staged_grid(int64_t work_items, int threads) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, std::min(FFB_STAGED_BLOCKS, 8 * num_sms())));
 }
 
-static bool trace_stage() {
-  static const bool on = [] { const char* e = getenv("FFB_TRACE_STAGE"); return e && e[0] == '1'; }();
-  return on;
+// FFB_TRACE_KERNEL=thread : the thread-per-sample kernel (same statements as the CPU twin), kept for A/B.
+// Default: the cooperative kernel.  (The STAGE = true variant of the thread kernel is no longer instantiated.)
+static int trace_kernel_choice() {
+  static const int c = [] {
+    const char* e = getenv("FFB_TRACE_KERNEL");
+    if (!e) return 0;
+    return !strcmp(e, "thread") ? 1 : 0;
+  }();
+  return c;
 }
 template <int DMAX, int KMAX>
 static int launch_trace(const ffb_trace_args* a, cudaStream_t stream) {
-  if (trace_stage()) {
-    const int threads = (sizeof(float) * 64 * (a->dim * a->dim + 1) <= 200 * 1024) ? 64 : 32;
-    const size_t smem = sizeof(float) * threads * (a->dim * a->dim + 1);
-    CUDA_TRY(cudaFuncSetAttribute(k_trace_estimate<DMAX, KMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t ntiles = (a->batch + threads - 1) / threads;
-    k_trace_estimate<DMAX, KMAX, true><<<staged_grid(a->batch, threads), threads, smem, stream>>>(*a, ntiles);
+  const int choice = trace_kernel_choice();
+  if (choice == 0) {
+    constexpr int GPB = 128 / DMAX;
+    const int64_t blocks = (a->batch + GPB - 1) / GPB;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, FFB_STAGED_BLOCKS));
+    k_trace_coop<DMAX, KMAX><<<grid, 128, 0, stream>>>(*a, a->batch);
   } else {
     const int threads = 128;
     const int64_t ntiles = (a->batch + threads - 1) / threads;

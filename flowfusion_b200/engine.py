@@ -639,6 +639,8 @@ def gaussian_logprob(x: torch.Tensor, add: Optional[torch.Tensor], sigma: float 
     x = _dev_f32(x, x.device)
     B, D = x.shape
     out = torch.empty(B, device=x.device)
+    if B == 0:
+        return out
     add_c = None if add is None else _dev_f32(add, x.device)
     L.check(L.load().ffb_gaussian_logprob(_ptr(x), _ptr(add_c), _ptr(out), B, D, float(sigma), _stream()),
             "ffb_gaussian_logprob")
