@@ -12,10 +12,11 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "ffb_kernels.cu")]
-HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
-                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh", "ffb_staged.cuh")] + \
+SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu")]
+HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_common.cuh", "ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
+                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh")] + \
           [os.path.join(ROOT, "include", "ffb200.h")]
+OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 ABI_VERSION = 3
 MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
@@ -179,30 +180,63 @@ class FFBError(RuntimeError):
     pass
 
 
+_NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(_HERE, "csrc"), "-Xcompiler", "-fPIC"]
+# (-split-compile 0 would cut the build time further but the kernels it produces are 7 % slower)
+
+
+def _obj(src):
+    return os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+
+
+def nvcc_commands(out=LIB_PATH):
+    """One compile command per translation unit (run in parallel) and the link command."""
+    compiles = [["nvcc"] + _NVCC_FLAGS + ["-c", src, "-o", _obj(src)] for src in SOURCES]
+    link = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [_obj(src) for src in SOURCES]
+    return compiles, link
+
+
 def nvcc_command(out=LIB_PATH):
-    # (-split-compile 0 would cut the 2-minute build to 40 s but the kernels it produces are 7 % slower)
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-            "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(_HERE, "csrc"), "-shared",
-            "-Xcompiler", "-fPIC", "-o", out] + SOURCES
+    """The single-command equivalent (documentation, scripts/gpu_ab.sh)."""
+    return ["nvcc"] + _NVCC_FLAGS + ["-shared", "-o", out] + SOURCES
+
+
+def _stale(target, deps):
+    if not os.path.isfile(target):
+        return True
+    mt = os.path.getmtime(target)
+    return any(os.path.getmtime(p) > mt for p in deps)
 
 
 def needs_build():
-    if not os.path.isfile(LIB_PATH):
-        return True
-    mt = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > mt for p in SOURCES + HEADERS)
+    return _stale(LIB_PATH, SOURCES + HEADERS)
 
 
 def build(force=False, verbose=False):
-    """Compile libffb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile libffb200.so in-tree for sm_100a (nvcc cross-compiles without a GPU): the translation units are
+    compiled in parallel into build/obj (only the stale ones), then linked."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = nvcc_command()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    compiles, link = nvcc_commands()
+    procs = []
+    for src, cmd in zip(SOURCES, compiles):
+        if force or _stale(_obj(src), [src] + HEADERS):
+            if verbose:
+                print(" ".join(cmd))
+            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    errors = []
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            errors.append(" ".join(cmd) + "\n" + out)
+    if errors:
+        raise FFBError("nvcc failed:\n" + "\n".join(errors))
     if verbose:
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        print(" ".join(link))
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise FFBError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise FFBError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "ffb200.h"
+#include "ffb_common.cuh"
 #include "ffb_engine.cuh"
 #include "ffb_engine_tc.cuh"
 #include "ffb_control.cuh"
@@ -30,8 +31,6 @@ using namespace ffb;
 // =============================================================================================
 // small device helpers
 // =============================================================================================
-enum { P_X_Y = 0, P_X_F = 1, P_X_DF = 2, P_X_ERR = 3, P_LP_Y = 4, P_LP_F = 5, P_LP_DF = 6, P_LP_ERR = 7,
-       P_C_Y = 8, P_NONFINITE = 9 };
 
 // idx / D for D in 1..128 and idx < 2^25 without the ~25-instruction integer division sequence
 __device__ __forceinline__ int fast_div(int idx, int D) {
@@ -79,32 +78,6 @@ __device__ __forceinline__ void block_reduce_store(CTX& cx, double (&v)[NV], dou
     }
   }
   bar_compute();
-}
-
-__device__ __forceinline__ bool is_finite_f(float x) { return fabsf(x) <= 3.402823466e38f; }
-
-// torchdiffeq's dense-output polynomial (interp.py): coefficients then Horner-like evaluation,
-// every product and sum rounded separately as the eager PyTorch ops do
-__device__ __forceinline__ float dense_output(float y0, float y1, float ymid, float f0, float f1, float dt, float x) {
-  const float A = __fadd_rn(__fsub_rn(__fmul_rn(2.0f * dt, __fsub_rn(f1, f0)), __fmul_rn(8.0f, __fadd_rn(y1, y0))),
-                            __fmul_rn(16.0f, ymid));
-  const float B = __fsub_rn(
-      __fadd_rn(__fadd_rn(__fmul_rn(dt, __fsub_rn(__fmul_rn(5.0f, f0), __fmul_rn(3.0f, f1))), __fmul_rn(18.0f, y0)),
-                __fmul_rn(14.0f, y1)),
-      __fmul_rn(32.0f, ymid));
-  const float C = __fadd_rn(
-      __fsub_rn(__fsub_rn(__fmul_rn(dt, __fsub_rn(f1, __fmul_rn(4.0f, f0))), __fmul_rn(11.0f, y0)),
-                __fmul_rn(5.0f, y1)),
-      __fmul_rn(16.0f, ymid));
-  const float D = __fmul_rn(dt, f0);
-  float total = __fadd_rn(y0, __fmul_rn(x, D));
-  float xp = __fmul_rn(x, x);
-  total = __fadd_rn(total, __fmul_rn(xp, C));
-  xp = __fmul_rn(xp, x);
-  total = __fadd_rn(total, __fmul_rn(xp, B));
-  xp = __fmul_rn(xp, x);
-  total = __fadd_rn(total, __fmul_rn(xp, A));
-  return total;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -713,6 +686,10 @@ static int fail(int code, const std::string& msg) {
       return fail(FFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
   } while (0)
 
+// helpers shared with the other translation unit (csrc/ffb_staged.cu), declared in ffb_common.cuh
+int ffb_fail(int code, const std::string& msg) { return fail(code, msg); }
+void ffb_count_launches(int n) { g_launches += n; }
+
 extern "C" int ffb_abi_version(void) { return FFB_ABI_VERSION; }
 extern "C" const char* ffb_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t ffb_launch_count(void) { return g_launches.load(); }
@@ -931,6 +908,7 @@ static int num_sms() {
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
   return n > 0 ? n : 148;
 }
+int ffb_num_sms() { return num_sms(); }
 
 extern "C" size_t ffb_scratch_bytes(const ffb_field* f) {
   if (!f) return 0;
@@ -1233,4 +1211,3 @@ extern "C" int ffb_ffma_peak(int32_t iters, float* tflops, void* stream_) {
   return FFB_OK;
 }
 
-#include "ffb_staged.cuh"

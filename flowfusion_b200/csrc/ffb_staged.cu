@@ -1,4 +1,4 @@
-// ffb_staged.cuh -- staged (evaluation-at-a-time) solves for the Hutch++ and XTrace divergence estimators
+// ffb_staged.cu -- staged (evaluation-at-a-time) solves for the Hutch++ and XTrace divergence estimators
 // (reference diffusion.py:336-400 and :402-481).
 //
 // Why staged.  Both estimators multiply by the transposed field Jacobian A = (d x_dot / d x)^T twice with a
@@ -21,7 +21,22 @@
 // The per-sample algebra (trace_estimate_one) is __host__ __device__: ffb_trace_estimate_host runs the same
 // statements on the CPU (tests/test_trace_estimators.py checks it against the reference's torch code here,
 // without a GPU).
-#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+
+#include "ffb200.h"
+#include "ffb_common.cuh"
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ffb_fail(FFB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
 
 namespace ffb {
 
@@ -524,18 +539,18 @@ __global__ void k_rk_finish(const __grid_constant__ ffb_rk_finish_args a) {
 // C ABI
 // =============================================================================================
 static int trace_args_ok(const ffb_trace_args* a, const char* who) {
-  if (!a || !a->jac || !a->S || !a->dlp) return fail(FFB_ERR_ARG, std::string(who) + ": jac, S and dlp are required");
-  if (a->kind != FFB_TRACE_HUTCHPP && a->kind != FFB_TRACE_XTRACE) return fail(FFB_ERR_ARG, std::string(who) + ": unknown kind");
-  if (a->dim < 1 || a->dim > FFB_TRACE_MAX_DIM) return fail(FFB_ERR_ARG, std::string(who) + ": dim must be 1..FFB_TRACE_MAX_DIM");
+  if (!a || !a->jac || !a->S || !a->dlp) return ffb_fail(FFB_ERR_ARG, std::string(who) + ": jac, S and dlp are required");
+  if (a->kind != FFB_TRACE_HUTCHPP && a->kind != FFB_TRACE_XTRACE) return ffb_fail(FFB_ERR_ARG, std::string(who) + ": unknown kind");
+  if (a->dim < 1 || a->dim > FFB_TRACE_MAX_DIM) return ffb_fail(FFB_ERR_ARG, std::string(who) + ": dim must be 1..FFB_TRACE_MAX_DIM");
   if (a->rank < 1 || a->rank > FFB_TRACE_MAX_RANK || a->rank > a->dim)
-    return fail(FFB_ERR_ARG, std::string(who) + ": rank must be 1..min(dim, FFB_TRACE_MAX_RANK)");
-  if (a->kind == FFB_TRACE_HUTCHPP && (a->nvec < 1 || !a->G)) return fail(FFB_ERR_ARG, std::string(who) + ": Hutch++ needs G and nvec >= 1");
+    return ffb_fail(FFB_ERR_ARG, std::string(who) + ": rank must be 1..min(dim, FFB_TRACE_MAX_RANK)");
+  if (a->kind == FFB_TRACE_HUTCHPP && (a->nvec < 1 || !a->G)) return ffb_fail(FFB_ERR_ARG, std::string(who) + ": Hutch++ needs G and nvec >= 1");
   return FFB_OK;
 }
 
 static int staged_grid(int64_t work_items, int threads) {
   const int64_t blocks = (work_items + threads - 1) / threads;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, std::min(FFB_STAGED_BLOCKS, 8 * num_sms())));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, std::min(FFB_STAGED_BLOCKS, 8 * ffb_num_sms())));
 }
 
 // FFB_TRACE_KERNEL=thread : the thread-per-sample kernel (same statements as the CPU twin), kept for A/B.
@@ -562,7 +577,7 @@ static int launch_trace(const ffb_trace_args* a, cudaStream_t stream) {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, FFB_STAGED_BLOCKS));
     k_trace_estimate<DMAX, KMAX, false><<<grid, threads, 0, stream>>>(*a, ntiles);
   }
-  g_launches += 1;
+  ffb_count_launches(1);
   CUDA_TRY(cudaGetLastError());
   return FFB_OK;
 }
@@ -585,7 +600,7 @@ static void host_trace(const ffb_trace_args* a) {
 extern "C" int ffb_trace_estimate(const ffb_trace_args* a, void* stream) {
   if (int rc = trace_args_ok(a, "ffb_trace_estimate")) return rc;
   if (a->norms && (!a->partials || (a->norms == 2 && !a->dlpbase)))
-    return fail(FFB_ERR_ARG, "ffb_trace_estimate: norms need partials (and dlpbase for norms = 2)");
+    return ffb_fail(FFB_ERR_ARG, "ffb_trace_estimate: norms need partials (and dlpbase for norms = 2)");
   if (a->batch <= 0) return FFB_OK;
 #define TRACE_LAUNCH(DM, KK) return launch_trace<DM, KK>(a, reinterpret_cast<cudaStream_t>(stream))
   TRACE_DISPATCH(TRACE_LAUNCH);
@@ -602,28 +617,28 @@ extern "C" int ffb_trace_estimate_host(const ffb_trace_args* a) {
 }
 
 extern "C" int ffb_rk_combine(const ffb_rk_combine_args* a, void* stream) {
-  if (!a || !a->y0 || !a->out || a->n_terms < 1 || a->n_terms > 7) return fail(FFB_ERR_ARG, "ffb_rk_combine: bad arguments");
+  if (!a || !a->y0 || !a->out || a->n_terms < 1 || a->n_terms > 7) return ffb_fail(FFB_ERR_ARG, "ffb_rk_combine: bad arguments");
   ffb_rk_combine_args c = *a;
   for (int j = 0; j < 7; ++j) {
-    if (j < c.n_terms && !c.k[j]) return fail(FFB_ERR_ARG, "ffb_rk_combine: missing stage derivative");
+    if (j < c.n_terms && !c.k[j]) return ffb_fail(FFB_ERR_ARG, "ffb_rk_combine: missing stage derivative");
     if (j >= c.n_terms) { c.k[j] = c.k[0]; c.coef[j] = 0.0f; }
   }
   if (c.n <= 0) return FFB_OK;
   k_rk_combine<<<staged_grid(c.n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(c);
-  g_launches += 1;
+  ffb_count_launches(1);
   CUDA_TRY(cudaGetLastError());
   return FFB_OK;
 }
 
 extern "C" int ffb_rk_finish(const ffb_rk_finish_args* a, void* stream) {
-  if (!a || !a->y0 || !a->y1 || !a->partials) return fail(FFB_ERR_ARG, "ffb_rk_finish: y0, y1 and partials are required");
+  if (!a || !a->y0 || !a->y1 || !a->partials) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: y0, y1 and partials are required");
   for (int j = 0; j < 7; ++j)
-    if (!a->k[j] || (a->lp0 && !a->dlp[j])) return fail(FFB_ERR_ARG, "ffb_rk_finish: missing stage derivative");
-  if (a->lp0 && !a->lp1) return fail(FFB_ERR_ARG, "ffb_rk_finish: lp1 is required with lp0");
-  if (a->final && (!a->y_out || (a->lp0 && !a->lp_out))) return fail(FFB_ERR_ARG, "ffb_rk_finish: final needs y_out (and lp_out)");
+    if (!a->k[j] || (a->lp0 && !a->dlp[j])) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: missing stage derivative");
+  if (a->lp0 && !a->lp1) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: lp1 is required with lp0");
+  if (a->final && (!a->y_out || (a->lp0 && !a->lp_out))) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: final needs y_out (and lp_out)");
   if (a->batch <= 0) return FFB_OK;
   k_rk_finish<<<staged_grid(a->batch * a->dim, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*a);
-  g_launches += 1;
+  ffb_count_launches(1);
   CUDA_TRY(cudaGetLastError());
   return FFB_OK;
 }
