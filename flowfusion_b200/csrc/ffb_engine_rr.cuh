@@ -70,6 +70,10 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
 // Narrow last layer with W_hi | W_lo stacked along N (NetDev::Wst): 2 MMAs per k-step instead of 3 (an MMA costs
 // ~51 cycles whatever N <= 64 is, csrc/tc_rate.cu); the last-layer epilogue adds the two accumulator halves.
 // Parity-green (all GPU tests) but 3-5 % SLOWER on cfg2-cfg5 (A/B), so it is off.
+// Reciprocal of the SiLU epilogue on the FMA pipe instead of MUFU.RCP (A/B: DESIGN.md section 9)
+#ifndef RR_RCP_FMA
+#define RR_RCP_FMA 0
+#endif
 #ifndef RR_STACK_LAST
 #define RR_STACK_LAST 0
 #endif
@@ -430,8 +434,18 @@ struct EngineRR_ {
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
               const float2 s = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+#if RR_RCP_FMA
+              // 1 / s on the FMA pipe: magic-constant seed (12 % off), three Newton steps r <- r + r (1 - s r) on packed
+              // pairs: 6 FFMA2 + 2 IADD per pair instead of 2 MUFU.RCP (8 XU cycles each per warp)
+              const float sx = fminf(s.x, 1.0e30f), sy = fminf(s.y, 1.0e30f);      // e = +inf (z << 0): keep the seed finite
+              r = make_float2(__uint_as_float(0x7EF311C7u - __float_as_uint(sx)), __uint_as_float(0x7EF311C7u - __float_as_uint(sy)));
+              const float2 ns = make_float2(-sx, -sy), one = make_float2(1.0f, 1.0f);
+#pragma unroll
+              for (int it = 0; it < 3; ++it) r = __ffma2_rn(r, __ffma2_rn(ns, r, one), r);
+#else
               asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(s.x));
               asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(s.y));
+#endif
               const float2 a = __fmul2_rn(z, r);
               hi[u] = (__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u;
               hi[u + 1] = (__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u;
