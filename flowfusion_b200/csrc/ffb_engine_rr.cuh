@@ -70,6 +70,27 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
 // Narrow last layer with W_hi | W_lo stacked along N (NetDev::Wst): 2 MMAs per k-step instead of 3 (an MMA costs
 // ~51 cycles whatever N <= 64 is, csrc/tc_rate.cu); the last-layer epilogue adds the two accumulator halves.
 // Parity-green (all GPU tests) but 3-5 % SLOWER on cfg2-cfg5 (A/B), so it is off.
+// TF32 hi/lo split of a packed pair.  RR_SPLIT_FP = 1: Veltkamp split on the FMA pipe, c = 8193 a, hi = c - 8192 a
+// (one FMA: exact, a multiple of 2^13 ulp(a), i.e. a rounded to TF32's 11 significant bits), lo = a - hi (exact):
+// 3 packed instructions per pair.  RR_SPLIT_FP = 0: integer round-half-away ((bits + 0x1000) & ~0x1FFF), 4 integer
+// + 1 packed instruction per pair.  Same |lo| <= 2^-11 |a|; the two differ on ties only.  |a| must stay below
+// FLT_MAX / 8193 (4e34) in the FP form.
+#ifndef RR_SPLIT_FP
+#define RR_SPLIT_FP 0
+#endif
+__device__ __forceinline__ void tf32_split2(const float2 a, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0, uint32_t& lo1) {
+#if RR_SPLIT_FP
+  const float2 c = __fmul2_rn(a, make_float2(8193.0f, 8193.0f));
+  const float2 h = __ffma2_rn(a, make_float2(-8192.0f, -8192.0f), c);
+  const float2 l = __ffma2_rn(h, make_float2(-1.0f, -1.0f), a);
+  hi0 = __float_as_uint(h.x); hi1 = __float_as_uint(h.y);
+#else
+  hi0 = (__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u;
+  hi1 = (__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u;
+  const float2 l = __ffma2_rn(make_float2(__uint_as_float(hi0), __uint_as_float(hi1)), make_float2(-1.0f, -1.0f), a);   // a - hi, exact
+#endif
+  lo0 = __float_as_uint(l.x); lo1 = __float_as_uint(l.y);
+}
 // Reciprocal of the SiLU epilogue on the FMA pipe instead of MUFU.RCP (A/B: DESIGN.md section 9)
 #ifndef RR_RCP_FMA
 #define RR_RCP_FMA 0
@@ -447,11 +468,7 @@ struct EngineRR_ {
               asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(s.y));
 #endif
               const float2 a = __fmul2_rn(z, r);
-              hi[u] = (__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u;
-              hi[u + 1] = (__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u;
-              const float2 l = __ffma2_rn(make_float2(__uint_as_float(hi[u]), __uint_as_float(hi[u + 1])),
-                                          make_float2(-1.0f, -1.0f), a);            // a - hi, exact
-              lo[u] = __float_as_uint(l.x); lo[u + 1] = __float_as_uint(l.y);
+              tf32_split2(a, hi[u], hi[u + 1], lo[u], lo[u + 1]);
             }
           } else {
 #pragma unroll

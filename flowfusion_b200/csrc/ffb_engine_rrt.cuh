@@ -217,10 +217,7 @@ struct EngineRRT_ {
               const float av0 = __shfl_sync(0xffffffffu, aval, tc.pbase + u), av1 = __shfl_sync(0xffffffffu, aval, tc.pbase + u + 1);
               const float2 t = __fmul2_rn(make_float2(__uint_as_float(m[ci & 1][u]), __uint_as_float(m[ci & 1][u + 1])), make_float2(g0, g1));
               const float2 a = make_float2(prim ? av0 : (tan ? t.x : 0.0f), prim ? av1 : (tan ? t.y : 0.0f));
-              hi[u] = (__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u;
-              hi[u + 1] = (__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u;
-              const float2 l = __ffma2_rn(make_float2(__uint_as_float(hi[u]), __uint_as_float(hi[u + 1])), make_float2(-1.0f, -1.0f), a);
-              lo[u] = __float_as_uint(l.x); lo[u + 1] = __float_as_uint(l.y);
+              tf32_split2(a, hi[u], hi[u + 1], lo[u], lo[u + 1]);
             }
           } else {
 #pragma unroll
