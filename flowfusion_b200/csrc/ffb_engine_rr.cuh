@@ -76,7 +76,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
 // + 1 packed instruction per pair.  Same |lo| <= 2^-11 |a|; the two differ on ties only.  |a| must stay below
 // FLT_MAX / 8193 (4e34) in the FP form.
 #ifndef RR_SPLIT_FP
-#define RR_SPLIT_FP 0
+#define RR_SPLIT_FP 1
 #endif
 __device__ __forceinline__ void tf32_split2(const float2 a, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0, uint32_t& lo1) {
 #if RR_SPLIT_FP
