@@ -75,6 +75,13 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
 // 3 packed instructions per pair.  RR_SPLIT_FP = 0: integer round-half-away ((bits + 0x1000) & ~0x1FFF), 4 integer
 // + 1 packed instruction per pair.  Same |lo| <= 2^-11 |a|; the two differ on ties only.  |a| must stay below
 // FLT_MAX / 8193 (4e34) in the FP form.
+// MMA warp waits for the next chunk's barrier before the last RR_PREWAIT_TAIL MMAs of the current chunk (A/B)
+#ifndef RR_PREWAIT
+#define RR_PREWAIT 0
+#endif
+#ifndef RR_PREWAIT_TAIL
+#define RR_PREWAIT_TAIL 2
+#endif
 #ifndef RR_SPLIT_FP
 #define RR_SPLIT_FP 1
 #endif
@@ -303,6 +310,22 @@ struct EngineRR_ {
     for (int j = 0; j < KC / 8; ++j)
       if ((NJ > 0) ? (j < NJ) : (j < nj)) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
   }
+  // a full chunk in two parts (RR_PREWAIT): the first 10 MMAs, then -- after the MMA warp has waited for the NEXT
+  // chunk's barrier behind the backlog of the tensor queue -- the last 2
+  static __device__ __forceinline__ void issue_chunk_head(uint32_t d_acc, uint32_t a_hi0, uint32_t a_lo0, uint64_t dh0, uint64_t dl0,
+                                                          uint64_t kstep, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+    for (int j = 0; j < KC / 8; ++j) {
+      tc_mma_ts(d_acc, a_hi0 + 8u * j, dl0 + (uint64_t)j * kstep, idesc, (j == 0) ? acc0 : 1u);
+      tc_mma_ts(d_acc, a_lo0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+    }
+#pragma unroll
+    for (int j = 0; j < KC / 8 - RR_PREWAIT_TAIL; ++j) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+  }
+  static __device__ __forceinline__ void issue_chunk_tail(uint32_t d_acc, uint32_t a_hi0, uint64_t dh0, uint64_t kstep, uint32_t idesc) {
+#pragma unroll
+    for (int j = KC / 8 - RR_PREWAIT_TAIL; j < KC / 8; ++j) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
+  }
   static __device__ __forceinline__ void mma_net(CtxR& cx, const NetDev& net) {
     for (int l = 0; l < net.n_layers; ++l) {
       const int K = net.K[l], Np = net.Np[l];
@@ -315,10 +338,18 @@ struct EngineRR_ {
       cx.dbuf ^= 1u;
       uint32_t acc = 0;
       int ci = 0;
+#if RR_PREWAIT
+      bool prewaited = false;
+#endif
       for (int k0 = 0; k0 < K; k0 += KC, ++ci) {
         const int nj = min(KC, K - k0) >> 3;
-        mbar_wait(&cx.full()[cx.stage], cx.phase);              // W chunk landed AND A columns [k0, k0+32) written
-        tc_fence_after();
+#if RR_PREWAIT
+        if (!prewaited)
+#endif
+        {
+          mbar_wait(&cx.full()[cx.stage], cx.phase);            // W chunk landed AND A columns [k0, k0+32) written
+          tc_fence_after();
+        }
         RR_TRACE(cx, 100 + 10 * l + ci);
         const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
         const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
@@ -338,12 +369,36 @@ struct EngineRR_ {
               }
             }
           }
+#if RR_PREWAIT
+          else if (nj == KC / 8 && !lastc) issue_chunk_head(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc);
+#endif
           else if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
           else issue_chunk<0>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
+#if !RR_PREWAIT
           if (ci < RR_EARLY) tc_commit(ebar);                   // frees the ring stage when these MMAs retire
           if (lastc) tc_commit(cx.d_ready());                   // the accumulator of this layer is complete
+#endif
         }
         __syncwarp();
+#if RR_PREWAIT
+        // the next chunk of the SAME layer: wait for its barrier now, while the tensor queue still holds the MMAs just
+        // issued (a successful wait + fence costs ~280 cycles during which the queue used to drain), then the tail
+        prewaited = false;
+        if (!stacked && nj == KC / 8 && !lastc) {
+          const int ns = (cx.stage + 1 == TC_NSTAGE) ? 0 : cx.stage + 1;
+          const uint32_t np = (cx.stage + 1 == TC_NSTAGE) ? (cx.phase ^ 1u) : cx.phase;
+          mbar_wait(&cx.full()[ns], np);
+          tc_fence_after();
+          prewaited = true;
+          if (elect_one()) issue_chunk_tail(d_acc, a_hi0, dh0, kstep, idesc);
+          __syncwarp();
+        }
+        if (elect_one()) {
+          if (ci < RR_EARLY) tc_commit(ebar);
+          if (lastc) tc_commit(cx.d_ready());
+        }
+        __syncwarp();
+#endif
         RR_TRACE(cx, 300 + ci);
         acc = 1u;
         advance(cx);
