@@ -117,7 +117,7 @@ class FixedArgs(C.Structure):
                 ("ev_table", C.c_void_p), ("status", C.c_void_p), ("scratch", C.c_void_p)]
 
 
-# ---- staged solves (Hutch++ / XTrace): include/ffb200.h, csrc/ffb_staged.cuh ----------------------------
+# ---- staged solves (Hutch++ / XTrace): include/ffb200.h, csrc/ffb_staged.cu ----------------------------
 TRACE_HUTCHPP, TRACE_XTRACE = 1, 2
 TRACE_MAX_DIM, TRACE_MAX_RANK, STAGED_BLOCKS = 32, 8, 1024
 

@@ -7,20 +7,20 @@
 // Instead one evaluation is
 //     ffb_field_eval(FFB_DIV_EXACT, jac = J)   the tangent-row tensor-core engine writes the field AND the full
 //                                               network Jacobian (its D tangent rows, 4 D^2 bytes per sample)
-//     k_trace_estimate                          the estimator algebra, ONE THREAD PER SAMPLE, J staged through
-//                                               shared memory (coalesced load, conflict-free per-thread reads)
-// and a dopri5 attempt is 6 x (k_rk_combine, field_eval, k_trace_estimate) + k_rk_finish.  The Jacobian round
-// trip (2 x 4 D^2 B per sample and evaluation, 2 KB at D = 16) costs ~3 % of the evaluation's tensor time; the
-// algebra runs at full-GPU parallelism instead of on the 7 owner threads of a tangent tile.
+//     k_trace_coop                              the estimator algebra, 16 or 32 LANES PER SAMPLE: lane j holds row j of
+//                                               J^T in registers, vectors are distributed over the lanes (see below)
+// and a dopri5 attempt is 6 x (k_rk_combine, field_eval, k_trace_coop) + k_rk_finish.  The Jacobian round trip
+// (2 x 4 D^2 B per sample and evaluation, 2 KB at D = 16) costs ~3 % of the evaluation's tensor time; the algebra
+// runs at full-GPU parallelism instead of on the 7 owner threads of a tangent tile.
 //
 // With the whole Jacobian on hand every product A v is a D x D mat-vec, so the estimators cost one exact-trace
 // evaluation plus O(D^2 (r + m)) flops -- they reproduce the reference's numbers for given probes (parity), they
 // are not cheaper than the exact trace at these D.  A reverse-mode engine (r + m sweeps instead of D tangents)
 // is the follow-up for D >> 32.
 //
-// The per-sample algebra (trace_estimate_one) is __host__ __device__: ffb_trace_estimate_host runs the same
-// statements on the CPU (tests/test_trace_estimators.py checks it against the reference's torch code here,
-// without a GPU).
+// A one-thread-per-sample version of the algebra (trace_estimate_one) is __host__ __device__:
+// ffb_trace_estimate_host runs it on the CPU (tests/test_trace_estimators.py checks it against the oracle here,
+// without a GPU) and FFB_TRACE_KERNEL=thread launches it on the GPU (A/B; 8x slower than the cooperative kernel).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>

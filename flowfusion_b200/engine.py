@@ -447,7 +447,7 @@ class TraceEstimator:
 class StagedBackend(CudaBackend):
     """Adaptive solve with a Hutch++ / XTrace divergence (`diffusion.py:336-481`): every evaluation is
     ``ffb_field_eval`` (tangent-row engine, full Jacobian out) + ``ffb_trace_estimate``; an attempt is six of them
-    between ``ffb_rk_combine`` launches plus ``ffb_rk_finish`` (csrc/ffb_staged.cuh).  Same interface and the same
+    between ``ffb_rk_combine`` launches plus ``ffb_rk_finish`` (csrc/ffb_staged.cu).  Same interface and the same
     partial sums as ``CudaBackend``, so ``solver.dopri5``'s host controller drives it unchanged."""
 
     def __init__(self, field: FieldSpec, y0: torch.Tensor, estimator: TraceEstimator, cond=None):
