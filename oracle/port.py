@@ -5,7 +5,8 @@ Why it exists: the reference is Python and lives only in the build container
 (``/root/reference``); GPU boxes have neither it nor ``torchdiffeq``.  This port carries the
 same arithmetic (same op order where FP32 rounding is observable) on top of the restated
 solver in ``oracle/torchdiffeq``, and is pinned against the UNMODIFIED reference by
-``oracle/make_golden.py`` (golden vectors in ``tests/golden``) and by
+``oracle/make_golden.py`` / ``oracle/make_golden_trace.py`` (golden vectors in ``tests/golden``; the latter covers the
+Hutch++ / XTrace estimators, which this port reproduces bit for bit) and by
 ``tests/test_oracle.py`` (golden vectors always; the live reference whenever ``/root/reference`` is present).
 PARITY NOTE: the field definitions are pinned by the real reference; the ODE driver is the
 restated third-party ``torchdiffeq`` (parity unpinned upstream -- see its docstring).
