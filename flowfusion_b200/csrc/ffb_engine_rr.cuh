@@ -82,6 +82,10 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
 #ifndef RR_PREWAIT_TAIL
 #define RR_PREWAIT_TAIL 2
 #endif
+// The whole MMA issue loop of an evaluation in one elected thread (A/B)
+#ifndef RR_ONE_THREAD
+#define RR_ONE_THREAD 0
+#endif
 #ifndef RR_SPLIT_FP
 #define RR_SPLIT_FP 1
 #endif
@@ -326,6 +330,39 @@ struct EngineRR_ {
 #pragma unroll
     for (int j = KC / 8 - RR_PREWAIT_TAIL; j < KC / 8; ++j) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
   }
+#if RR_ONE_THREAD
+  // One elected thread of the MMA warp runs the whole evaluation (wait, fence, issue, commit); the other lanes only
+  // keep their copies of the ring position and the accumulator toggle in step and park at the closing __syncwarp.
+  static __device__ __forceinline__ void mma_net(CtxR& cx, const NetDev& net) {
+    const bool leader = elect_one();
+    for (int l = 0; l < net.n_layers; ++l) {
+      const int K = net.K[l], Np = net.Np[l];
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t lbo = (uint32_t)Np * 16u;
+      const uint64_t kstep = (uint64_t)(lbo >> 3);
+      const uint32_t d_acc = cx.tmem + cx.dbuf * 128u;
+      cx.dbuf ^= 1u;
+      uint32_t acc = 0;
+      for (int k0 = 0; k0 < K; k0 += KC) {
+        if (leader) {
+          const int nj = min(KC, K - k0) >> 3;
+          mbar_wait(&cx.full()[cx.stage], cx.phase);
+          tc_fence_after();
+          const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
+          const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
+          const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
+          const uint32_t a_hi0 = cx.tmem + RR_COL_AHI + (uint32_t)k0, a_lo0 = cx.tmem + RR_COL_ALO + (uint32_t)k0;
+          if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
+          else issue_chunk<0>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
+          if (k0 + KC >= K) tc_commit(cx.d_ready());
+        }
+        acc = 1u;
+        advance(cx);
+      }
+    }
+    __syncwarp();
+  }
+#else
   static __device__ __forceinline__ void mma_net(CtxR& cx, const NetDev& net) {
     for (int l = 0; l < net.n_layers; ++l) {
       const int K = net.K[l], Np = net.Np[l];
@@ -406,6 +443,7 @@ struct EngineRR_ {
       RR_TRACE(cx, 190 + l);
     }
   }
+#endif
 
   // ---- compute warps ---------------------------------------------------------------------------
   // "my part of the next A chunk is in tensor memory": arrive on the ring stage that chunk will use
