@@ -61,6 +61,18 @@ def accelerate(obj, device="cuda"):
         lin = [l for l in seq if isinstance(l, torch.nn.Linear)]
         return [l.out_features for l in lin[:-1]]
 
+    def act_modules_of(seq):
+        """The activation modules between the Linear layers (`flow.py:41, 63-70`, `symplectic.py:25, 52-60`)."""
+        acts = [m for m in seq if not isinstance(m, torch.nn.Linear)]
+        if len({type(m) for m in acts}) > 1:
+            raise NotImplementedError("mixed hidden-layer activations are not implemented in the CUDA kernels")
+        return acts
+
+    def act_class_of(seq):
+        """Flows take the activation CLASS and instantiate it per layer with its defaults (`flow.py:67`)."""
+        acts = act_modules_of(seq)
+        return type(acts[0]) if acts else torch.nn.SiLU
+
     if name in ("VESDE", "VPSDE", "SUBVPSDE"):
         new = sde_of(obj)
     elif name == "MLP":
@@ -78,16 +90,20 @@ def accelerate(obj, device="cuda"):
             mlp_of(obj.model), sde_of(obj.sde), obj.shift.clone(), obj.scale.clone(), obj.conditional_shift.clone(),
             obj.conditional_scale.clone(), no_sigma=obj.score_model.no_sigma, method=obj.method, options=obj.options)
     elif name == "ODEFlow":
-        new = F.ODEFlow(obj.target_dimension, hidden_of(obj.layers))
+        new = F.ODEFlow(obj.target_dimension, hidden_of(obj.layers), activation=act_class_of(obj.layers))
         new.load_state_dict(obj.state_dict())
     elif name == "ConditionalODEFlow":
-        new = F.ConditionalODEFlow(obj.target_dimension, obj.conditional_dimension, hidden_of(obj.layers))
+        new = F.ConditionalODEFlow(obj.target_dimension, obj.conditional_dimension, hidden_of(obj.layers),
+                                   activation=act_class_of(obj.layers))
         new.load_state_dict(obj.state_dict())
     elif name == "SymplecticMLP":
         lin = [l for l in obj.mlp_q_dynamics if isinstance(l, torch.nn.Linear)]
         emb = 2 * obj.W.shape[0]
         D_ = lin[-1].out_features
-        new = Sy.SymplecticMLP(D_, lin[0].in_features - D_ - emb, emb, hidden_of(obj.mlp_q_dynamics))
+        acts = act_modules_of(list(obj.mlp_q_dynamics) + list(obj.mlp_p_dynamics))
+        import copy
+        new = Sy.SymplecticMLP(D_, lin[0].in_features - D_ - emb, emb, hidden_of(obj.mlp_q_dynamics),
+                               activation=copy.deepcopy(acts[0]) if acts else torch.nn.SiLU())   # an INSTANCE, `symplectic.py:25`
         new.load_state_dict(obj.state_dict())
     elif name == "SymplecticFlowModel":
         new = Sy.SymplecticFlowModel(accelerate(obj.model, device="cpu"), obj.shift.clone(), obj.scale.clone(),

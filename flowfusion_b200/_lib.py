@@ -12,9 +12,10 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
-SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu", "ffb_rd.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_common.cuh", "ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
-                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh")] + \
+                                                     "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh", "ffb_engine_rd.cuh",
+                                                     "ffb_kernels_rd.cuh", "ffb_rd.h")] + \
           [os.path.join(ROOT, "include", "ffb200.h")]
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 

@@ -35,6 +35,47 @@ __device__ __forceinline__ float dense_output(float y0, float y1, float ymid, fl
   return total;
 }
 
+// idx / D for D in 1..128 and idx < 2^25 without the ~25-instruction integer division sequence
+__device__ __forceinline__ int fast_div(int idx, int D) {
+  return D == 1 ? idx : (int)__umulhi((unsigned)idx, (unsigned)((0x100000000ull + (unsigned)D - 1u) / (unsigned)D));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (throughput-mode noise of the Euler-Maruyama kernel)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+// 4 standard normals for (global row, step, group of 4 columns)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset, int64_t grow, int step, int grp) {
+  const uint64_t c1 = offset + (uint64_t)(uint32_t)step;
+  uint4 ctr = make_uint4((uint32_t)grow, (uint32_t)((uint64_t)grow >> 32) ^ ((uint32_t)grp << 8), (uint32_t)c1,
+                         (uint32_t)(c1 >> 32));
+  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = ((float)r.x + 1.0f) * k, u1 = (float)r.y * k;   // (0,1], [0,1)
+  const float u2 = ((float)r.z + 1.0f) * k, u3 = (float)r.w * k;
+  const float r0 = sqrtf(-2.0f * __logf(fminf(u0, 1.0f))), r1 = sqrtf(-2.0f * __logf(fminf(u2, 1.0f)));
+  float s0, c0, s1, c1f;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1f);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1f, r1 * s1);
+}
+
+
+// network evaluations per step of a fixed-grid method
+__device__ __forceinline__ int evals_per_step(int method) {
+  return method == FFB_M_RK4 ? 4 : (method == FFB_M_MIDPOINT ? 2 : (method == FFB_M_LEAPFROG ? 3 : 1));
+}
+
 #define FFB_HIDDEN __attribute__((visibility("hidden")))
 FFB_HIDDEN int ffb_fail(int code, const std::string& msg);   // stores the thread's ffb_last_error() text, returns code
 FFB_HIDDEN void ffb_count_launches(int n);                    // ffb_launch_count()

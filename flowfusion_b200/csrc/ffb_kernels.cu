@@ -25,6 +25,7 @@
 #include "ffb_engine.cuh"
 #include "ffb_engine_tc.cuh"
 #include "ffb_control.cuh"
+#include "ffb_rd.h"
 
 using namespace ffb;
 
@@ -32,10 +33,6 @@ using namespace ffb;
 // small device helpers
 // =============================================================================================
 
-// idx / D for D in 1..128 and idx < 2^25 without the ~25-instruction integer division sequence
-__device__ __forceinline__ int fast_div(int idx, int D) {
-  return D == 1 ? idx : (int)__umulhi((unsigned)idx, (unsigned)((0x100000000ull + (unsigned)D - 1u) / (unsigned)D));
-}
 // k-major tile buffer <- row-major global rows [row0, row0+nv); rows nv..S-1 are zero filled
 __device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ src, int64_t row0, int nv, int S,
                                           int D, int tid) {
@@ -78,36 +75,6 @@ __device__ __forceinline__ void block_reduce_store(CTX& cx, double (&v)[NV], dou
     }
   }
   bar_compute();
-}
-
-// ---------------------------------------------------------------------------------------------
-// Philox4x32-10 + Box-Muller (throughput-mode noise of the Euler-Maruyama kernel)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
-  }
-  return ctr;
-}
-// 4 standard normals for (global row, step, group of 4 columns)
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset, int64_t grow, int step, int grp) {
-  const uint64_t c1 = offset + (uint64_t)(uint32_t)step;
-  uint4 ctr = make_uint4((uint32_t)grow, (uint32_t)((uint64_t)grow >> 32) ^ ((uint32_t)grp << 8), (uint32_t)c1,
-                         (uint32_t)(c1 >> 32));
-  const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const float k = 2.3283064365386963e-10f;  // 2^-32
-  const float u0 = ((float)r.x + 1.0f) * k, u1 = (float)r.y * k;   // (0,1], [0,1)
-  const float u2 = ((float)r.z + 1.0f) * k, u3 = (float)r.w * k;
-  const float r0 = sqrtf(-2.0f * __logf(fminf(u0, 1.0f))), r1 = sqrtf(-2.0f * __logf(fminf(u2, 1.0f)));
-  float s0, c0, s1, c1f;
-  sincospif(2.0f * u1, &s0, &c0);
-  sincospif(2.0f * u3, &s1, &c1f);
-  return make_float4(r0 * c0, r0 * s0, r1 * c1f, r1 * s1);
 }
 
 // =============================================================================================
@@ -294,9 +261,6 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_dopri5(const __grid_constant__
 // =============================================================================================
 // k_fixed: fixed-grid integrators, the whole trajectory of a tile on-chip
 // =============================================================================================
-__device__ __forceinline__ int evals_per_step(int method) {
-  return method == FFB_M_RK4 ? 4 : (method == FFB_M_MIDPOINT ? 2 : (method == FFB_M_LEAPFROG ? 3 : 1));
-}
 
 template <class ENG, bool SS>
 __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ FieldDev f,
@@ -653,15 +617,21 @@ struct ffb_net {
   int64_t flops;
 };
 
-// engine selection: 1 = tensor cores (default), 0 = FP32 FFMA2 (FFB_ENGINE=ffma or ffb_set_engine(0))
+// engine selection: 1 = tensor cores (default: dual-tile engine for fields without tangent rows, tangent-row engine
+// for the log-likelihood paths), 3 = the same with the single-tile chunk-pipelined engine instead of the dual-tile one
+// (FFB_ENGINE=rr), 2 = the older whole-layer hand-off tile engine (FFB_ENGINE=tc_tile), 0 = FP32 FFMA2 (FFB_ENGINE=ffma)
 static int g_engine = -1;
 static int engine() {
   if (g_engine < 0) {
     const char* e = getenv("FFB_ENGINE");
-    g_engine = (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) ? 0 : ((e && (!strcmp(e, "tc_tile") || !strcmp(e, "2"))) ? 2 : 1);
+    if (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) g_engine = 0;
+    else if (e && (!strcmp(e, "tc_tile") || !strcmp(e, "2"))) g_engine = 2;
+    else if (e && (!strcmp(e, "rr") || !strcmp(e, "3"))) g_engine = 3;
+    else g_engine = 1;
   }
   return g_engine;
 }
+static bool chunk_engines() { return engine() == 1 || engine() == 3; }
 // debug: timeline trace buffer (2 * 4096 int64) or NULL to disable
 extern "C" int ffb_debug_trace(long long* buf) {
   int zero = 0;
@@ -669,7 +639,7 @@ extern "C" int ffb_debug_trace(long long* buf) {
   cudaMemcpyToSymbol(ffb::g_trace_pos, &zero, sizeof(zero));
   return 0;
 }
-extern "C" int ffb_set_engine(int e) { g_engine = (e == 2) ? 2 : (e ? 1 : 0); return g_engine; }
+extern "C" int ffb_set_engine(int e) { g_engine = (e == 2 || e == 3) ? e : (e ? 1 : 0); return g_engine; }
 extern "C" int ffb_get_engine(void) { return engine(); }
 
 static thread_local std::string g_err;
@@ -912,7 +882,7 @@ int ffb_num_sms() { return num_sms(); }
 
 extern "C" size_t ffb_scratch_bytes(const ffb_field* f) {
   if (!f) return 0;
-  return (size_t)num_sms() * NSLOT * f->state_dim * LDA * sizeof(float);
+  return std::max((size_t)num_sms() * NSLOT * f->state_dim * LDA * sizeof(float), rd_scratch_bytes(f->state_dim, f->cond_dim));
 }
 
 template <typename Kern, typename Args>
@@ -942,7 +912,9 @@ static int launch_tiles(Kern kern, int nthr, const char* name, const ffb_field* 
 
 // ---- row-resident tensor-core kernels (fields without tangent rows) -----------------------------
 // FFB_ENGINE=tc_tile (or ffb_set_engine(2)) keeps the older whole-layer hand-off tile engine for A/B runs
-static bool use_rr(const FieldDev& fd) { return engine() == 1 && fd.div_mode == FFB_DIV_NONE; }
+static bool use_rr(const FieldDev& fd) { return chunk_engines() && fd.div_mode == FFB_DIV_NONE; }
+// the dual-tile engine (two resident tiles per SM) serves every field without tangent rows by default
+static bool use_rd(const FieldDev& fd) { return engine() == 1 && fd.div_mode == FFB_DIV_NONE; }
 // true when a network of the field has a non-SiLU activation (selects the kernels with the run-time dispatch)
 static bool gen_act(const FieldDev& fd) {
   for (int c = 0; c < fd.n_calls; ++c) if (fd.net[c].act != FFB_ACT_SILU) return true;
@@ -979,7 +951,7 @@ static int launch_rr(Kern kern, size_t smem, const char* name, const FieldDev& f
 // ---- tangent-row engine (log-likelihood paths) ------------------------------------------------------------
 // returns 0 when the field cannot run on it; otherwise sets fd->rrt_cap and returns the shared-memory size
 static size_t rrt_smem(const ffb_field* f, FieldDev* fd, int nslot, int nbeff) {
-  if (engine() != 1 || fd->div_mode == FFB_DIV_NONE) return 0;
+  if (!chunk_engines() || fd->div_mode == FFB_DIV_NONE) return 0;
   size_t smem = 0;
   const int S = rrt_plan(f, fd->state_dim, fd->cond_dim, field_tdim(*fd), nslot, nbeff, &smem);
   if (S <= 0) return 0;
@@ -1017,6 +989,7 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
     return gen_act(fd) ? launch_rrt(k_field_eval_rrt<true>, smt, "ffb_field_eval", fd, *a, a->batch, st_)
                        : launch_rrt(k_field_eval_rrt<false>, smt, "ffb_field_eval", fd, *a, a->batch, st_);
   if (a->jac) return fail(FFB_ERR_ARG, "ffb_field_eval: jac is written by the tangent-row tensor-core engine only");
+  if (use_rd(fd)) return rd_launch_eval(fd, *a, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, 3, 1);
     if (gen_act(fd)) {
@@ -1054,6 +1027,7 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
     return gen_act(fd) ? launch_rrt(k_dopri5_rrt<true, false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_)
                        : launch_rrt(k_dopri5_rrt<false, false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
   }
+  if (use_rd(fd)) return rd_launch_dopri5(fd, *a, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, NSLOT, 6);
 #define FFB_RR_DOPRI5(SS_, GEN_)                                                                                      \
@@ -1088,6 +1062,7 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
   if (const size_t smt = rrt_smem(f, &fd, rr_fixed_slots(a->method), 1))
     return gen_act(fd) ? launch_rrt(k_fixed_rrt<true>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_)
                        : launch_rrt(k_fixed_rrt<false>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_);
+  if (use_rd(fd)) return rd_launch_fixed(fd, *a, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, rr_fixed_slots(a->method), 8);
     if (gen_act(fd)) {

@@ -254,6 +254,29 @@ def test_reference_population_wrappers_and_accelerate():
 
 
 @needs_ref
+@pytest.mark.parametrize("act_cls", [torch.nn.Tanh, torch.nn.GELU, torch.nn.ReLU, torch.nn.Softplus])
+def test_accelerate_keeps_activation(act_cls):
+    """accelerate() must rebuild the twin with the reference object's hidden activation (`flow.py:41, 478`,
+    `symplectic.py:25`, `diffusion.py:38`): same module types in the same order, same state_dict."""
+    import flowfusion_b200 as ffb
+    D, F, S = loader.load_reference()
+    torch.manual_seed(3)
+    objs = [F.ODEFlow(3, [16, 16], activation=act_cls), F.ConditionalODEFlow(3, 2, [16, 8], activation=act_cls),
+            S.SymplecticMLP(4, 1, 4, [16, 16], activation=act_cls()),
+            S.SymplecticFlowModel(S.SymplecticMLP(4, 1, 4, [16], activation=act_cls()), torch.zeros(4), torch.ones(4),
+                                  torch.zeros(1), torch.ones(1)),
+            D.ScoreModel(D.MLP(3, 0, 4, [16, 16], activation=act_cls()), D.VPSDE(), no_sigma=True)]
+    seqs = [lambda o: o.layers, lambda o: o.layers, lambda o: list(o.mlp_q_dynamics) + list(o.mlp_p_dynamics),
+            lambda o: list(o.model.mlp_q_dynamics) + list(o.model.mlp_p_dynamics), lambda o: [o.model.activation]]
+    for obj, seq in zip(objs, seqs):
+        tw = ffb.accelerate(obj.eval(), device="cpu")
+        assert [type(m).__name__ for m in seq(obj)] == [type(m).__name__ for m in seq(tw)], type(obj).__name__
+        assert any(isinstance(m, act_cls) for m in seq(tw))
+        for k, v in obj.state_dict().items():
+            assert torch.equal(v, tw.state_dict()[k]), k
+
+
+@needs_ref
 @pytest.mark.parametrize("act_cls,act_fn", [(torch.nn.Tanh, torch.tanh), (torch.nn.GELU, torch.nn.functional.gelu)])
 def test_reference_non_silu_activations(act_cls, act_fn):
     """`activation=` is a public constructor argument of every reference model: the port follows it."""
