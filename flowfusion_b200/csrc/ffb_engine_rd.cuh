@@ -35,14 +35,23 @@ constexpr int RD_NGROUP = 2;
 constexpr int RD_GWARPS = 8;                          // compute warps per group
 constexpr int RD_GTHR = RD_GWARPS * 32;               // compute threads per group
 constexpr int RD_NCOMP = RD_NGROUP * RD_GTHR;         // 512
-constexpr int RD_NTHR = RD_NCOMP + 64;                // + loader warp + MMA warp
+#ifndef RD_MMA_WARPS
+#define RD_MMA_WARPS 2                                 // MMA-issuing warps: 1, or 2 that take the ring stages (chunks) in turn
+#endif
+constexpr int RD_NTHR = RD_NCOMP + 32 + 32 * RD_MMA_WARPS;   // + loader warp + MMA warp(s)
 constexpr int RD_WLOAD = RD_NCOMP / 32;
-constexpr int RD_WMMA = RD_NCOMP / 32 + 1;
+constexpr int RD_WMMA = RD_NCOMP / 32 + 1;            // first MMA warp (owns the tensor-memory allocation)
 #ifndef RD_KC
 #define RD_KC 32                                       // weight rows (k) per ring stage: 32 or 16
 #endif
 #ifndef RD_NSTAGE
 #define RD_NSTAGE (64 / RD_KC)                         // 64 KB ring
+#endif
+#ifndef RD_CLUSTER
+#define RD_CLUSTER 2                                   // CTAs per cluster: every weight chunk is read from L2 once per cluster
+#endif                                                 // (each CTA loads 1 / RD_CLUSTER of it and multicasts the piece to all)
+#ifndef RD_TURN
+#define RD_TURN (32 / RD_KC)                           // ring stages one MMA warp issues before it passes the turn (32 k-rows)
 #endif
 constexpr int RD_STAGE_FLOATS = 2 * RD_KC * KMAX;     // W_hi | W_lo rows of one stage
 constexpr uint32_t RD_ALO_LBO = TM * 16u;             // bytes between two K core matrices of the A_lo image
@@ -63,6 +72,26 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// ---- thread-block cluster helpers (RD_CLUSTER > 1) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> shared bulk copy delivered to the same offset of every CTA in `mask`; each destination's mbarrier (same
+// offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset of every CTA in `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 struct CtxD {
   uint32_t o_ring, o_alo, o_ycur, o_cond, o_sbias, o_beff, o_red, o_bar, o_slots;   // o_alo, o_ycur, o_cond, o_red, o_slots: this group's
   uint32_t alo_gstride;             // bytes between the A_lo images of the two groups (special warps address both)
@@ -75,7 +104,7 @@ struct CtxD {
   __device__ __forceinline__ uint64_t* a_ready() const { return full() + 2 * RD_NSTAGE; }
   __device__ __forceinline__ uint64_t* d_ready() const { return full() + 2 * RD_NSTAGE + RD_NGROUP; }
   __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(full() + 2 * RD_NSTAGE + 2 * RD_NGROUP); }
-  float* scr;                       // this group's global scratch: [NSLOT + 1][SD][LDA] + [CD][LDA]
+  float* scr;                       // this group's global scratch: [RD_SCR_SLOTS][SD][LDA] + [CD][LDA]
   int SD, CD, maxl, ncalls;
   int tid, lane, warp;              // tid: index inside the group (compute warps)
   int g, q, cg, row;                // group, lane quarter, column parity, tile row (= TMEM lane)
@@ -86,7 +115,29 @@ struct CtxD {
   int stage; uint32_t phase;        // ring position (loader / MMA warp)
   uint32_t ph_d;                    // compute warps: parity of d_ready[g]
   uint32_t ph_a0, ph_a1;            // MMA warp: parity of a_ready[0], a_ready[1]
+  int mw; uint32_t cctr, tctr;      // MMA warps: index of this MMA warp, ring stages (chunks) / turns visited so far
+  uint32_t crank;                   // rank of this CTA in its cluster
+  int tr_role, tr_n;                // debug timeline (-DFFB_TRACE)
 };
+
+// Debug timeline (compiled in with -DFFB_TRACE only): CTA 0 records clock64() at hand-off points, one private
+// region per role (0: compute warp 0 of group 0, 1: MMA warp 0, 2: compute warp 0 of group 1, 3: loader, 4: MMA warp 1), no atomics.
+#if defined(FFB_TRACE) && defined(FFB_TRACE_ROUNDS)      // only the per-tile markers (tags >= 900): a whole launch fits the buffer
+#define RD_TRACE(cx, tag) do { if ((tag) >= 900) rd_trace(cx, tag); } while (0)
+#elif defined(FFB_TRACE)
+#define RD_TRACE(cx, tag) rd_trace(cx, tag)
+#else
+#define RD_TRACE(cx, tag) do {} while (0)
+#endif
+__device__ __forceinline__ void rd_trace(CtxD& cx, int tag) {
+  if (cx.tr_role >= 0 && g_trace && cx.tr_n < RR_TRACE_CAP) {
+    long long* p = g_trace + 2 * (cx.tr_role * RR_TRACE_CAP + cx.tr_n);
+    long long t = clock64();
+    if (tag >= 950) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));      // wall-clock nanoseconds
+    p[0] = t; p[1] = tag;
+    ++cx.tr_n;
+  }
+}
 
 __device__ __forceinline__ void rd_gbar(const CtxD& cx) { asm volatile("bar.sync %0, 256;" ::"r"(1 + cx.g) : "memory"); }
 __device__ __forceinline__ void rd_qbar(const CtxD& cx) { asm volatile("bar.sync %0, 64;" ::"r"(3 + 4 * cx.g + cx.q) : "memory"); }
@@ -101,14 +152,18 @@ __device__ __forceinline__ float* rd_ycur(const CtxD& cx) {
   if (MEM < 2) return reinterpret_cast<float*>(smem_base() + cx.o_ycur);
   return cx.scr + (size_t)NSLOT * cx.SD * LDA;
 }
+// slots beyond the integrator's K / Y0 slots: NSLOT = stage input (global copy, MEM == 2), RD_XSLOT .. = partial sums
+constexpr int RD_XSLOT = NSLOT + 1;
+constexpr int RD_NXSLOT = 2;
+constexpr int RD_SCR_SLOTS = RD_XSLOT + RD_NXSLOT;
 template <int MEM>
 __device__ __forceinline__ float* rd_cond(const CtxD& cx) {
   if (MEM < 2) return reinterpret_cast<float*>(smem_base() + cx.o_cond);
-  return cx.scr + (size_t)(NSLOT + 1) * cx.SD * LDA;
+  return cx.scr + (size_t)RD_SCR_SLOTS * cx.SD * LDA;
 }
 // floats of one group's global scratch
 __host__ __device__ inline size_t rd_scratch_floats(int SD, int CD) {
-  return (size_t)(NSLOT + 1) * SD * LDA + (size_t)(CD > 0 ? CD : 1) * LDA;
+  return (size_t)RD_SCR_SLOTS * SD * LDA + (size_t)(CD > 0 ? CD : 1) * LDA;
 }
 
 // ka: widest A operand (max K over every layer of every call, a multiple of 8); maxl: most layers of a call;
@@ -177,9 +232,14 @@ struct EngineRD_ {
     cx.stage = 0;
     cx.phase = (cx.warp == RD_WLOAD) ? 1u : 0u;      // the loader starts with every stage free
     cx.ph_d = 0; cx.ph_a0 = 0; cx.ph_a1 = 0;
+    cx.mw = cx.warp - RD_WMMA; cx.cctr = 0; cx.tctr = 0;
     cx.active = 0;
+    cx.tr_n = 0;
+    cx.tr_role = (blockIdx.x != 0 || cx.lane != 0) ? -1
+               : (cx.warp == RD_WMMA ? 1 : (cx.warp == RD_WMMA + 1 ? 4 : (cx.warp == RD_WLOAD ? 3 : (cx.warp == 0 ? 0 : (cx.warp == RD_GWARPS ? 2 : -1)))));
     if (threadIdx.x == 0) {
-      for (int s = 0; s < RD_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], 1); }
+      // a ring stage is refilled (by multicast from every CTA of the cluster) once EVERY CTA's MMAs have retired from it
+      for (int s = 0; s < RD_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], RD_CLUSTER); }
       for (int g = 0; g < RD_NGROUP; ++g) { mbar_init(&cx.a_ready()[g], RD_GWARPS); mbar_init(&cx.d_ready()[g], 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -193,6 +253,8 @@ struct EngineRD_ {
           cx.sbias()[(c * cx.maxl + l) * KMAX + n] = (n < f.net[c].Np[l]) ? f.net[c].b[l][n] : 0.0f;
     tc_fence_before();
     __syncthreads();
+    cx.crank = 0;
+    if (RD_CLUSTER > 1) { cx.crank = cluster_ctarank(); cluster_sync_all(); }    // every CTA's mbarriers exist before any remote arrive
     tc_fence_after();
     cx.tmem = *cx.tmem_slot();
     cx.lane_addr = cx.tmem + ((uint32_t)(cx.q << 5) << 16) + 256u * (uint32_t)cx.g;
@@ -200,8 +262,10 @@ struct EngineRD_ {
   }
 
   static __device__ __forceinline__ void fini(CtxD& cx) {
+    mma_drain(cx);
     tc_fence_before();
     __syncthreads();
+    if (RD_CLUSTER > 1) cluster_sync_all();        // no CTA leaves while a peer may still multicast into it / arrive on its barriers
     if (cx.warp == RD_WMMA) {
       tc_fence_after();
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(cx.tmem), "r"(512));
@@ -237,6 +301,7 @@ struct EngineRD_ {
         for (int k0 = 0; k0 < K; k0 += RD_KC) {
           const int rows = min(RD_KC, K - k0);
           mbar_wait(&cx.empty()[cx.stage], cx.phase);
+          RD_TRACE(cx, 500 + 10 * l + g);
           const uint32_t bytes = (uint32_t)(rows * Np) * sizeof(float);        // of one half (hi or lo)
           mbar_expect_tx(&cx.full()[cx.stage], 2u * bytes);
           float* dst = cx.ring() + cx.stage * RD_STAGE_FLOATS;
@@ -244,8 +309,16 @@ struct EngineRD_ {
           const int kc0 = k0 & ~(KC - 1), crow = min(KC, K - kc0);              // the 32-row chunk this stage is part of
           const float* hi = net.W[l] + (size_t)2 * kc0 * Np + (size_t)(k0 - kc0) * Np;
           const float* lo = hi + (size_t)crow * Np;
-          bulk_g2s(dst, hi, bytes, &cx.full()[cx.stage]);
-          bulk_g2s(dst + rows * Np, lo, bytes, &cx.full()[cx.stage]);
+          if (RD_CLUSTER == 1) {
+            bulk_g2s(dst, hi, bytes, &cx.full()[cx.stage]);
+            bulk_g2s(dst + rows * Np, lo, bytes, &cx.full()[cx.stage]);
+          } else {
+            // this CTA's share of the stage: piece `crank` of the hi block and of the lo block, delivered to every CTA
+            const uint32_t pf = (uint32_t)(rows * Np) / RD_CLUSTER;             // floats per piece (rows * Np is a multiple of 256)
+            const uint16_t mask = (uint16_t)((1u << RD_CLUSTER) - 1u);
+            bulk_g2s_mc(dst + cx.crank * pf, hi + cx.crank * pf, pf * 4u, &cx.full()[cx.stage], mask);
+            bulk_g2s_mc(dst + rows * Np + cx.crank * pf, lo + cx.crank * pf, pf * 4u, &cx.full()[cx.stage], mask);
+          }
           advance(cx);
         }
       }
@@ -254,6 +327,8 @@ struct EngineRD_ {
 
   // ---- MMA warp: (layer l, group 0), (layer l, group 1), (layer l+1, group 0) ... ------------------------------
   // one ring stage: NJ k-steps (compile-time when > 0), cross products first
+  // one ring stage: NJ k-steps (compile-time when > 0); per k-step the two cross products (A_hi W_lo from tensor memory,
+  // A_lo W_hi from shared memory), then the main products -- the order of the single-tile engine (csrc/tc_probe.cu)
   template <int NJ>
   static __device__ __forceinline__ void issue_stage(uint32_t d_acc, uint32_t a_hi0, uint64_t da_lo0, uint64_t dh0, uint64_t dl0,
                                                      uint64_t kstep, uint32_t idesc, uint32_t acc0, int nj) {
@@ -269,6 +344,14 @@ struct EngineRD_ {
     for (int j = 0; j < RD_KC / 8; ++j)
       if ((NJ > 0) ? (j < NJ) : (j < nj)) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
   }
+  // RD_MMA_WARPS == 2: the two MMA warps alternate ring stages.  Warp w issues the MMAs of every chunk that lands in
+  // stage w: while one warp's 12 MMAs run, the other has already waited for its weights (and for a_ready when its chunk
+  // opens a layer) and prepared its descriptors, so the hand-over costs one named-barrier wake-up instead of the whole
+  // wait + fence + descriptor sequence (measured with -DFFB_TRACE: ~300 cycles per chunk on a single issuing warp).
+  // The issue ORDER stays the order of the chunks (a turn token goes back and forth on named barriers 12 / 13), so the
+  // accumulation order -- and therefore every bit of the result -- is the same as with one warp.
+  static __device__ __forceinline__ void turn_wait(int mw) { asm volatile("bar.sync %0, 64;" ::"r"(12 + mw) : "memory"); }
+  static __device__ __forceinline__ void turn_pass(int mw) { asm volatile("bar.arrive %0, 64;" ::"r"(12 + (mw ^ 1)) : "memory"); }
   static __device__ __forceinline__ void mma_net(CtxD& cx, const NetDev& net) {
     const uint32_t alo0 = smem_u32(smem_base() + cx.o_alo);       // group 0's image (the special warps have g = 0)
     for (int l = 0; l < net.n_layers; ++l) {
@@ -282,32 +365,62 @@ struct EngineRD_ {
         const uint32_t a_hi = d_acc + 128u;
         const uint32_t alo = alo0 + (uint32_t)g * cx.alo_gstride;
         uint32_t& ph = g ? cx.ph_a1 : cx.ph_a0;
-        mbar_wait(&cx.a_ready()[g], ph);                          // the group's A operand of this layer is complete
-        ph ^= 1u;
-        tc_fence_after();
-        uint32_t acc = 0;
-        for (int k0 = 0; k0 < K; k0 += RD_KC) {
-          const int nj = min(RD_KC, K - k0) >> 3;
-          mbar_wait(&cx.full()[cx.stage], cx.phase);              // the weight rows [k0, k0 + RD_KC) have landed
+        // a TURN = RD_TURN consecutive ring stages issued by one warp
+        for (int k0 = 0; k0 < K; k0 += RD_KC * RD_TURN, ++cx.tctr) {
+          const int nsub = min(RD_TURN, (K - k0 + RD_KC - 1) / RD_KC);
+          const uint32_t c0 = cx.cctr;                                           // ring position of the turn's first stage
+          cx.cctr += (uint32_t)nsub;
+          if (RD_MMA_WARPS == 2 && (int)(cx.tctr & 1u) != cx.mw) continue;      // the other MMA warp's turn
+#pragma unroll
+          for (int u = 0; u < RD_TURN; ++u)
+            if (u < nsub) mbar_wait(&cx.full()[(c0 + u) % RD_NSTAGE], ((c0 + u) / RD_NSTAGE) & 1u);   // weight rows landed
+          RD_TRACE(cx, 300 + (k0 >> 4));
+          if (RD_MMA_WARPS == 2) {
+            // named barriers count WARPS: make sure the warp executes bar.sync in one piece
+            __syncwarp();
+            if (cx.tctr > 0) turn_wait(cx.mw);                    // the previous turn's MMAs have been issued
+          }
+          // The group's A operand of this layer is complete.  With two MMA warps this wait must come AFTER the turn token:
+          // a warp opens only some of the layers, so it skips phases of a_ready[g], and a parity wait is only unambiguous
+          // when the phase before the awaited one is known to be over -- which the token guarantees (the other warp
+          // waited for that phase before it issued the turn that precedes this one).
+          if (k0 == 0) { mbar_wait(&cx.a_ready()[g], ph); RD_TRACE(cx, 100 + 10 * l + g); }
           tc_fence_after();
-          const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * RD_STAGE_FLOATS);
-          const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
-          const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
-          const uint64_t da0 = tc_desc(alo + (uint32_t)(k0 >> 2) * RD_ALO_LBO, RD_ALO_LBO, 128u);
-          uint64_t* ebar = &cx.empty()[cx.stage];
-          const bool lastc = (k0 + RD_KC >= K);
           if (elect_one()) {
-            if (nj == RD_KC / 8) issue_stage<RD_KC / 8>(d_acc, a_hi + (uint32_t)k0, da0, dh0, dl0, kstep, idesc, acc, nj);
-            else issue_stage<0>(d_acc, a_hi + (uint32_t)k0, da0, dh0, dl0, kstep, idesc, acc, nj);
-            tc_commit(ebar);                                      // frees the ring stage when these MMAs retire
-            if (lastc) tc_commit(&cx.d_ready()[g]);               // the group's accumulator of this layer is complete
+#pragma unroll
+            for (int u = 0; u < RD_TURN; ++u) {
+              if (u < nsub) {
+                const int ks = k0 + u * RD_KC;
+                const int nj = min(RD_KC, K - ks) >> 3;
+                const uint32_t stage = (c0 + u) % RD_NSTAGE;
+                const uint32_t hi_base = smem_u32(cx.ring() + stage * RD_STAGE_FLOATS);
+                const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
+                const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
+                const uint64_t da0 = tc_desc(alo + (uint32_t)(ks >> 2) * RD_ALO_LBO, RD_ALO_LBO, 128u);
+                const uint32_t acc = ks ? 1u : 0u;
+                if (nj == RD_KC / 8) issue_stage<RD_KC / 8>(d_acc, a_hi + (uint32_t)ks, da0, dh0, dl0, kstep, idesc, acc, nj);
+                else issue_stage<0>(d_acc, a_hi + (uint32_t)ks, da0, dh0, dl0, kstep, idesc, acc, nj);
+                // frees the ring stage (in every CTA of the cluster) when these MMAs retire
+                if (RD_CLUSTER == 1) tc_commit(&cx.empty()[stage]);
+                else tc_commit_mc(&cx.empty()[stage], (uint16_t)((1u << RD_CLUSTER) - 1u));
+                if (ks + RD_KC >= K) tc_commit(&cx.d_ready()[g]);                // the group's accumulator of this layer is complete
+              }
+            }
           }
           __syncwarp();
-          acc = 1u;
-          advance(cx);
+          if (RD_MMA_WARPS == 2) {
+            tc_fence_before();
+            turn_pass(cx.mw);
+          }
+          RD_TRACE(cx, 400 + (k0 >> 4));
         }
+        ph ^= 1u;
       }
     }
+  }
+  // with two MMA warps: consume the turn token the last chunk handed over (keeps the named barriers balanced)
+  static __device__ __forceinline__ void mma_drain(CtxD& cx) {
+    if (RD_MMA_WARPS == 2 && cx.warp >= RD_WMMA && cx.tctr > 0 && (int)(cx.tctr & 1u) == cx.mw) { __syncwarp(); turn_wait(cx.mw); }
   }
 
   // ---- compute warps ---------------------------------------------------------------------------
@@ -368,6 +481,7 @@ struct EngineRD_ {
       store_a8(cx, k8, hi, lo);
     }
     signal_a(cx);
+    RD_TRACE(cx, 11);
   }
 
   // hidden layers: accumulator block -> + bias -> activation -> TF32 split -> next A operand; hand-off per layer
@@ -382,6 +496,7 @@ struct EngineRD_ {
       const float* bias = ((l == 0) ? beff : cx.sbias() + (c * cx.maxl + l) * KMAX) + 8 * cx.cg;
       const uint32_t dcol = cx.lane_addr + 8u * (uint32_t)cx.cg;
       wait_d(cx);
+      RD_TRACE(cx, 200 + 10 * l);
       uint32_t m[2][8];
       tc_ld8(dcol, m[0]);
 #pragma unroll
@@ -421,6 +536,7 @@ struct EngineRD_ {
         }
       }
       signal_a(cx);
+      RD_TRACE(cx, 201 + 10 * l);
     }
   }
 
@@ -431,6 +547,7 @@ struct EngineRD_ {
     const int nl = net.n_layers, Nreal = net.N[nl - 1];
     const float* bias = (nl == 1) ? beff : cx.sbias() + (c * cx.maxl + nl - 1) * KMAX;
     wait_d(cx);
+    RD_TRACE(cx, 290);
     for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += 16) {             // warp-uniform trip count
       uint32_t m[8];
       tc_ld8(cx.lane_addr + (uint32_t)c0, m);
@@ -464,8 +581,9 @@ struct EngineRD_ {
       if (!((call_mask >> c) & 1u)) continue;
       const NetDev& net = f.net[c];
       if (cx.warp == RD_WLOAD) { load_net(cx, net); continue; }
-      if (cx.warp == RD_WMMA) { mma_net(cx, net); continue; }
+      if (cx.warp >= RD_WMMA) { mma_net(cx, net); continue; }
       rd_qbar(cx);                           // the stage input of this lane quarter is final
+      RD_TRACE(cx, 10);
       build_A(cx, f, c);
       if (first) { overlap(); first = false; }
       hidden(cx, net, c, beff + c * KMAX);
@@ -496,7 +614,9 @@ struct EngineRD_ {
           if (c0 + u < Nreal) kd[(ooff + c0 + u) * LDA] = xd_[u];
       });
     }
+    RD_TRACE(cx, 12);
     if (!cx.producer) rd_qbar(cx);
+    RD_TRACE(cx, 13);
   }
 };
 

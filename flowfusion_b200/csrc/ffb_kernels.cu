@@ -619,7 +619,8 @@ struct ffb_net {
 
 // engine selection: 1 = tensor cores (default: dual-tile engine for fields without tangent rows, tangent-row engine
 // for the log-likelihood paths), 3 = the same with the single-tile chunk-pipelined engine instead of the dual-tile one
-// (FFB_ENGINE=rr), 2 = the older whole-layer hand-off tile engine (FFB_ENGINE=tc_tile), 0 = FP32 FFMA2 (FFB_ENGINE=ffma)
+// (FFB_ENGINE=rr), 4 = the same with the dual-tile engine for every dopri5 attempt it can hold, whatever the batch
+// (FFB_ENGINE=rd; tests), 2 = the older whole-layer hand-off tile engine (FFB_ENGINE=tc_tile), 0 = FP32 FFMA2 (FFB_ENGINE=ffma)
 static int g_engine = -1;
 static int engine() {
   if (g_engine < 0) {
@@ -627,11 +628,12 @@ static int engine() {
     if (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) g_engine = 0;
     else if (e && (!strcmp(e, "tc_tile") || !strcmp(e, "2"))) g_engine = 2;
     else if (e && (!strcmp(e, "rr") || !strcmp(e, "3"))) g_engine = 3;
+    else if (e && (!strcmp(e, "rd") || !strcmp(e, "4"))) g_engine = 4;
     else g_engine = 1;
   }
   return g_engine;
 }
-static bool chunk_engines() { return engine() == 1 || engine() == 3; }
+static bool chunk_engines() { return engine() == 1 || engine() == 3 || engine() == 4; }
 // debug: timeline trace buffer (2 * 4096 int64) or NULL to disable
 extern "C" int ffb_debug_trace(long long* buf) {
   int zero = 0;
@@ -639,7 +641,7 @@ extern "C" int ffb_debug_trace(long long* buf) {
   cudaMemcpyToSymbol(ffb::g_trace_pos, &zero, sizeof(zero));
   return 0;
 }
-extern "C" int ffb_set_engine(int e) { g_engine = (e == 2 || e == 3) ? e : (e ? 1 : 0); return g_engine; }
+extern "C" int ffb_set_engine(int e) { g_engine = (e == 2 || e == 3 || e == 4) ? e : (e ? 1 : 0); return g_engine; }
 extern "C" int ffb_get_engine(void) { return engine(); }
 
 static thread_local std::string g_err;
@@ -913,8 +915,13 @@ static int launch_tiles(Kern kern, int nthr, const char* name, const ffb_field* 
 // ---- row-resident tensor-core kernels (fields without tangent rows) -----------------------------
 // FFB_ENGINE=tc_tile (or ffb_set_engine(2)) keeps the older whole-layer hand-off tile engine for A/B runs
 static bool use_rr(const FieldDev& fd) { return chunk_engines() && fd.div_mode == FFB_DIV_NONE; }
-// the dual-tile engine (two resident tiles per SM) serves every field without tangent rows by default
-static bool use_rd(const FieldDev& fd) { return engine() == 1 && fd.div_mode == FFB_DIV_NONE; }
+// The dual-tile engine (two resident tiles per SM) takes the dopri5 attempts of fields without tangent rows when there
+// are at least two tiles per SM (below that the single-tile engine spreads the tiles over more SMs) and the stage input
+// fits shared memory beside its operand images.  Both engines issue the same MMAs in the same order: same bits.
+static bool use_rd(const FieldDev& fd, int64_t batch) {
+  if (fd.div_mode != FFB_DIV_NONE || !(engine() == 1 || engine() == 4) || !rd_dopri5_fits(fd)) return false;
+  return engine() == 4 || (batch + TM - 1) / TM >= 2 * (int64_t)num_sms();
+}
 // true when a network of the field has a non-SiLU activation (selects the kernels with the run-time dispatch)
 static bool gen_act(const FieldDev& fd) {
   for (int c = 0; c < fd.n_calls; ++c) if (fd.net[c].act != FFB_ACT_SILU) return true;
@@ -989,7 +996,6 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
     return gen_act(fd) ? launch_rrt(k_field_eval_rrt<true>, smt, "ffb_field_eval", fd, *a, a->batch, st_)
                        : launch_rrt(k_field_eval_rrt<false>, smt, "ffb_field_eval", fd, *a, a->batch, st_);
   if (a->jac) return fail(FFB_ERR_ARG, "ffb_field_eval: jac is written by the tangent-row tensor-core engine only");
-  if (use_rd(fd)) return rd_launch_eval(fd, *a, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, 3, 1);
     if (gen_act(fd)) {
@@ -1027,7 +1033,7 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
     return gen_act(fd) ? launch_rrt(k_dopri5_rrt<true, false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_)
                        : launch_rrt(k_dopri5_rrt<false, false>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
   }
-  if (use_rd(fd)) return rd_launch_dopri5(fd, *a, st_);
+  if (use_rd(fd, a->batch)) return rd_launch_dopri5(fd, *a, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, NSLOT, 6);
 #define FFB_RR_DOPRI5(SS_, GEN_)                                                                                      \
@@ -1062,7 +1068,6 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
   if (const size_t smt = rrt_smem(f, &fd, rr_fixed_slots(a->method), 1))
     return gen_act(fd) ? launch_rrt(k_fixed_rrt<true>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_)
                        : launch_rrt(k_fixed_rrt<false>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_);
-  if (use_rd(fd)) return rd_launch_fixed(fd, *a, st_);
   if (use_rr(fd)) {
     const size_t smem = rr_pick_smem(&fd, rr_fixed_slots(a->method), 8);
     if (gen_act(fd)) {

@@ -18,6 +18,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t a, uint64_t da, uint64_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5,%5,%5,%5}, p;\n\t}"
                  ::"r"(d), "r"(a), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
 }
+__device__ int g_bstride = 16;     // descriptor step between the B operands of consecutive MMAs (16-byte units)
 template <int N, int NACC, bool SS>
 __global__ void rate(int reps, long long* out, int bg, int commit_every) {
   __shared__ uint64_t bar2;
@@ -87,11 +88,12 @@ __global__ void rate(int reps, long long* out, int bg, int commit_every) {
     const uint32_t sb = smem_u32(smem);
     const uint64_t db = make_desc(sb, N * 16, 128);
     const uint64_t da = make_desc(sb + 16384, 128 * 16, 128);
+    const int bstr = g_bstride;
     long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
 #pragma unroll
       for (int i = 0; i < 12; ++i)
-        mma<SS>(tb + (uint32_t)(i % NACC) * 128u, tb + 384u + (uint32_t)i * 8u, da, db + (uint64_t)(i * 16), idesc, (r | (i >= NACC)) ? 1u : 0u);
+        mma<SS>(tb + (uint32_t)(i % NACC) * 128u, tb + 384u + (uint32_t)i * 8u, da, db + (uint64_t)(i * bstr), idesc, (r | (i >= NACC)) ? 1u : 0u);
       if (commit_every && (r % commit_every) == commit_every - 1)
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
     }
@@ -119,8 +121,40 @@ void run(long long* d, int grid = 1, int bgwarps = 0, int bg = 0, int ce = 0, in
                     reps * 12, (double)h[1] / (reps * 12), cudaGetErrorString(e));
   }
 }
-int main() {
+// long runs on every SM: does the MMA rate (cycles per MMA) or the SM clock give way under sustained load?
+template <int N, bool SS>
+static void run_long(long long* d, int bgwarps, int bg, int reps) {
+  cudaFuncSetAttribute(rate<N, 1, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  long long h[2];
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    rate<N, 1, SS><<<148, 64 + 32 * bgwarps, 64 * 1024>>>(reps, d, bg, 0);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("LONG grid=148 bgwarps=%2d bg=%d N=%3d %s reps=%d: %.1f cyc/MMA, kernel %.3f ms -> SM clock %.0f MHz (%s)\n", bgwarps, bg, N, SS ? "SS" : "TS",
+           reps, (double)h[1] / (reps * 12.0), ms, (double)h[1] / (ms * 1e3), cudaGetErrorString(e));
+  }
+}
+int main(int argc, char** argv) {
   long long* d; cudaMalloc(&d, 16);
+  if (argc > 1 && argv[1][0] == 'B') {      // B operands of consecutive MMAs 256 B apart (overlapping windows) vs 4 KB apart (distinct)
+    for (int st : {16, 256}) {
+      cudaMemcpyToSymbol(g_bstride, &st, sizeof(st));
+      printf("B-operand stride %d bytes\n", st * 16);
+      run<128, 1, false>(d, 148, 0, 0, 0, 512); run<128, 1, true>(d, 148, 0, 0, 0, 512); run<64, 1, false>(d, 148, 0, 0, 0, 512);
+    }
+    return 0;
+  }
+  if (argc > 1 && argv[1][0] == 'L') {
+    run_long<128, false>(d, 0, 0, 16384);
+    run_long<128, false>(d, 16, 3, 16384);
+    run_long<128, false>(d, 16, 1, 16384);
+    run_long<128, true>(d, 16, 3, 16384);
+    return 0;
+  }
   run<128, 1, false>(d); run<128, 2, false>(d); run<128, 3, false>(d);
   run<128, 1, false>(d, 148); run<128, 1, false>(d, 1, 16, 1); run<128, 1, false>(d, 1, 16, 2); run<128, 1, false>(d, 1, 16, 3);
   run<128, 1, false>(d, 1, 4, 0, 0, 64); run<128, 1, false>(d, 148, 4, 0, 0, 64); run<128, 1, false>(d, 1, 4, 8, 0, 64); run<128, 1, false>(d, 148, 4, 8, 0, 64); run<128, 1, false>(d, 148, 4, 8, 0, 512);

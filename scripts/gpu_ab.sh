@@ -5,7 +5,7 @@ W=${1:-cfg2}; shift
 mkdir -p gpurun_out
 for so in build/lib_*.so; do
   tag=$(basename $so .so)
-  FFB_LIB=$PWD/$so timeout 300 python bench.py --workload $W --steps 2 --warmup 2 --no-cpu-baseline --no-e2e "$@" > gpurun_out/ab_${W}_$tag.log 2>&1
+  FFB_LIB=$PWD/$so timeout 100 python bench.py --workload $W --steps 2 --warmup 2 --no-cpu-baseline --no-e2e "$@" > gpurun_out/ab_${W}_$tag.log 2>&1
   python - "$tag" gpurun_out/ab_${W}_$tag.log <<'PY'
 import json, sys
 tag, p = sys.argv[1:3]

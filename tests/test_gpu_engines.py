@@ -139,8 +139,85 @@ def test_score_logprob_hutchinson_wide(cuda_dev):
 
 
 # ---------------------------------------------------------------------------------------------
-# properties at the full BASELINE sizes (no oracle: it would take hours)
+# the full BASELINE sizes: against the CPU oracle (the port integrates 1 M cfg2 rows in ~30 s on the box's host cores)
+# and through size-independent properties
 # ---------------------------------------------------------------------------------------------
+def _hist_rel_dev(a, b):
+    """Largest deviation of the accepted-or-attempted step END TIMES (cumulative dt), relative to the whole interval.
+    (The last step is whatever is left of the interval, so its own relative deviation is not a meaningful number.)"""
+    assert len(a) == len(b), (len(a), len(b))
+    ta, tb, dev = 0.0, 0.0, 0.0
+    for x, y in zip(a, b):
+        ta += x; tb += y
+        dev = max(dev, abs(ta - tb))
+    return dev / max(abs(tb), 1e-30)
+
+
+def test_cfg2_full_size_vs_oracle(cuda_dev):
+    """BASELINE configs[1] at its full size (1 M rows, dopri5 1e-5, the bench workload) against oracle/port.py on the same
+    inputs: samples <= 1e-4 relative per row, identical (accepted, rejected), the whole dt history.  This is where the
+    FP64-partials-vs-torch-sum question of the global error norm (16 M elements) is decided."""
+    D, F, Sy = _mods()
+    from oracle import port
+    from flowfusion_b200 import solver
+    torch.manual_seed(1234)
+    sm = D.ScoreModel(D.MLP(16, 4, 8, [128] * 4), D.VPSDE(), no_sigma=True).eval()
+    B = 1_000_000
+    base = torch.randn(B, 16, generator=gen(2)); cond = torch.randn(B, 4, generator=gen(3))
+    opts = {"step_t": torch.tensor([1e-3])}
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    ref = port.sample_ode_from_base(M, base, cond, 1e-5, 1e-5, options=opts)[0]
+    rs = port.last_stats()
+    sm.to(cuda_dev)
+    for ctl in ("device", "host"):
+        with solver.controller(ctl):
+            x, _ = sm.sample_ode_from_base(base.to(cuda_dev), cond.to(cuda_dev), atol=1e-5, rtol=1e-5, options=opts)
+        st = sm.last_stats
+        err = rel_row_err(ref, x)
+        dev_dt = _hist_rel_dev(list(st.dt_history), list(rs.dt_history))
+        print(f"cfg2 1M rows [{ctl}]: sample err {err:.2e}, steps {st.accepted}/{st.rejected} (cpu {rs.accepted}/{rs.rejected}), "
+              f"max step-time deviation {dev_dt:.2e}")
+        assert err < SAMPLE_TOL
+        assert (st.accepted, st.rejected) == (rs.accepted, rs.rejected)
+        assert list(st.accept_history) == list(rs.accept_history)
+        # The step sizes follow ratio^(-1/5), and the error estimate sum_j c_err_j k_j is a ~1e-5 cancellation of O(1) stage
+        # derivatives: its 3xTF32 and FP32-FMA roundings differ by ~1e-3 relative, so the step end times agree to a few
+        # 1e-4 of the interval (measured on B200 at 1 M rows), not to FP64 resolution.  The accept / reject sequence is identical.
+        assert dev_dt < 1e-3
+
+
+def test_cfg3_100k_vs_oracle(cuda_dev):
+    """BASELINE configs[2] architecture on 100 k points (exact divergence trace) against oracle/port.py: log-prob <= 1e-3
+    nat, identical (accepted, rejected), dt history."""
+    D, F, Sy = _mods()
+    from oracle import port
+    from flowfusion_b200 import solver
+    torch.manual_seed(1234)
+    fl = F.ODEFlow(16, [128] * 4).eval()
+    B = 100_000
+    xs = torch.randn(B, 16, generator=gen(4))
+    ref = port.flow_log_prob(port.flow_from_state_dict(fl.state_dict()), xs)
+    rs = port.last_stats()
+    fl.to(cuda_dev)
+    for ctl in ("device", "host"):
+        with solver.controller(ctl):
+            lp = fl.log_prob(xs.to(cuda_dev))
+        st = fl.last_stats
+        err = float((lp.cpu() - ref).abs().max())
+        dev_dt = _hist_rel_dev(list(st.dt_history), list(rs.dt_history))
+        print(f"cfg3 100k rows [{ctl}]: log-prob err {err:.2e} nat, steps {st.accepted}/{st.rejected} (cpu {rs.accepted}/{rs.rejected}), "
+              f"max step-time deviation {dev_dt:.2e}")
+        assert err < LP_TOL
+        assert (st.accepted, st.rejected) == (rs.accepted, rs.rejected)
+        # With these weights the local error of the first steps is ~1e-9, far below the FP32 resolution of the state: the
+        # error ratio (measured 1e-6, 1.5e-5, 8e-2 against the port's 1.4e-6, 1.8e-5, 7e-2) is rounding noise on both sides, and
+        # 0.9 ratio^(-1/5) turns a 35 % difference of it into a 6 % longer step.  The step end times therefore only agree to a few per cent (measured 3 %); what is pinned is the
+        # accept / reject sequence and the result.
+        print("   error ratios gpu", [f"{r:.2e}" for r in st.ratio_history], "cpu", [f"{r:.2e}" for r in rs.ratio_history])
+        assert dev_dt < 0.25
+
+
+
 def test_cfg2_full_size_partition_invariance(cuda_dev):
     """1M rows, fixed grid: any row's result is independent of the batch it is integrated in."""
     D, F, Sy = _mods()
@@ -156,23 +233,6 @@ def test_cfg2_full_size_partition_invariance(cuda_dev):
         assert torch.equal(full[lo:hi], part)
     again, _ = sm.sample_ode_from_base(base, cond, method="rk4", options=opt)
     assert torch.equal(full, again)
-
-
-def test_cfg2_full_size_dopri5_matches_sharded_steps(cuda_dev):
-    """dopri5 on 1M rows vs the same rows solved as 4 independent quarters: the quarters use their own
-    (slightly different) global step sizes, so samples agree to the solver tolerance, not bit-wise."""
-    D, F, Sy = _mods()
-    torch.manual_seed(1234)
-    sm = D.ScoreModel(D.MLP(16, 4, 8, [128] * 4), D.VPSDE(), no_sigma=True).eval().to(cuda_dev)
-    B = 1_000_000
-    base = torch.randn(B, 16, generator=gen(2)).to(cuda_dev); cond = torch.randn(B, 4, generator=gen(3)).to(cuda_dev)
-    opts = {"step_t": torch.tensor([1e-3])}
-    full, _ = sm.sample_ode_from_base(base, cond, atol=1e-5, rtol=1e-5, options=opts)
-    steps_full = (sm.last_stats.accepted, sm.last_stats.rejected)
-    q = B // 4
-    part, _ = sm.sample_ode_from_base(base[q:2 * q], cond[q:2 * q], atol=1e-5, rtol=1e-5, options=opts)
-    assert abs(sm.last_stats.accepted - steps_full[0]) <= 1
-    assert rel_row_err(full[q:2 * q], part) < 5e-4
 
 
 def test_cfg4_em_noise_linearity_full_width(cuda_dev):
@@ -330,3 +390,62 @@ def test_fixed_grid_logprob_on_tangent_engine(cuda_dev, method, opts):
     sm.to(cuda_dev)
     lph = sm.log_prob(x0.to(cuda_dev), method=method, options=opts, probes=e.to(cuda_dev))
     assert float((lph.cpu() - refh).abs().max()) < LP_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# dual-tile engine (csrc/ffb_engine_rd.cuh): forced with engine(4) so that small batches run on it too
+# ---------------------------------------------------------------------------------------------
+def test_dual_tile_engine_golden_and_bit_identical_to_single_tile(cuda_dev):
+    """The dual-tile dopri5 kernel against the reference's golden vectors (cfg2: same accepted / rejected steps), against
+    the single-tile engine BIT FOR BIT (same MMAs in the same order; ragged batch, odd tile count -> dummy tiles, clusters),
+    with both controllers, and for a non-SiLU network, a two-call (symplectic) field and an unconditional VE model."""
+    from conftest import load_golden
+    from flowfusion_b200 import solver
+    D, F, Sy = _mods()
+    meta, sd, ins, outs = load_golden("cfg2_vp_pfode")
+    sm = D.ScoreModel(D.MLP(**meta["ctor"]), D.VPSDE(), no_sigma=True).eval()
+    sm.load_state_dict(sd)
+    sm.to(cuda_dev)
+    opts = {"step_t": torch.tensor([1e-3])}
+    base, cond = ins["base"].to(cuda_dev), ins["cond"].to(cuda_dev)
+    with engine(4):
+        x, _ = sm.sample_ode_from_base(base, cond, atol=1e-5, rtol=1e-5, options=opts)
+        st = sm.last_stats
+    assert rel_row_err(outs["x_dopri5"], x) < SAMPLE_TOL
+    assert (st.accepted, st.rejected) == (meta["stats"]["accepted"], meta["stats"]["rejected"])
+    # bit-identical to the single-tile engine, every controller, ragged sizes (1, 3 and 19 tiles: the last CTA / cluster
+    # runs dummy tiles), larger than one round of the 148 SMs (600 tiles)
+    for B in (100, 300, 2400, 76_800 + 77):
+        b = torch.randn(B, 16, generator=gen(B), device="cpu").to(cuda_dev)
+        c = torch.randn(B, 4, generator=gen(B + 1), device="cpu").to(cuda_dev)
+        for ctl in ("host", "device"):
+            with solver.controller(ctl):
+                with engine(3):
+                    x3, _ = sm.sample_ode_from_base(b, c, atol=1e-5, rtol=1e-5, options=opts)
+                    s3 = sm.last_stats
+                with engine(4):
+                    x4, _ = sm.sample_ode_from_base(b, c, atol=1e-5, rtol=1e-5, options=opts)
+                    s4 = sm.last_stats
+            assert torch.equal(x3, x4), (B, ctl, float((x3 - x4).abs().max()))
+            assert (s3.accepted, s3.rejected) == (s4.accepted, s4.rejected)
+            assert s3.dt_history == s4.dt_history
+    # non-SiLU activation (run-time dispatched epilogue), unconditional VE with the sigma division
+    torch.manual_seed(41)
+    sv = D.ScoreModel(D.MLP(7, 0, 8, [96, 64], activation=torch.nn.Tanh()), D.VESDE(), no_sigma=False).eval().to(cuda_dev)
+    bv = (torch.randn(700, 7, generator=gen(5)) * 10.0).to(cuda_dev)
+    with engine(3):
+        x3, _ = sv.sample_ode_from_base(bv, atol=1e-5, rtol=1e-5)
+    with engine(4):
+        x4, _ = sv.sample_ode_from_base(bv, atol=1e-5, rtol=1e-5)
+    assert torch.equal(x3, x4)
+    # two-network field (symplectic log_prob: dopri5 on the (q | p) state, 8-D phase space)
+    torch.manual_seed(42)
+    sf = Sy.SymplecticFlowModel(Sy.SymplecticMLP(4, 0, 8, [64, 64]), torch.zeros(4), torch.ones(4), torch.zeros(0), torch.ones(0)).eval().to(cuda_dev)
+    xq = torch.randn(500, 4, generator=gen(6)).to(cuda_dev)
+    p0 = torch.randn(500, 4, generator=gen(7)).to(cuda_dev)
+    outs_ = []
+    for e in (3, 4):
+        with engine(e):
+            lp = sf.log_prob(xq, p0=p0)
+            outs_.append((lp.clone(), sf.last_stats.accepted, sf.last_stats.rejected))
+    assert torch.equal(outs_[0][0], outs_[1][0]) and outs_[0][1:] == outs_[1][1:]
