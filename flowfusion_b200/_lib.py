@@ -19,7 +19,7 @@ HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_common.cuh", "ffb_engin
           [os.path.join(ROOT, "include", "ffb200.h")]
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
 FIELD_NET, FIELD_SCORE = 0, 1
 DIV_NONE, DIV_EXACT, DIV_HUTCH = 0, 1, 2
@@ -170,6 +170,8 @@ SYMBOLS = {
     "ffb_philox_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]),
     "ffb_ffma_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_float), C.c_void_p]),
     "ffb_set_engine": (C.c_int, [C.c_int]),
+    "ffb_debug_trace": (C.c_int, [C.c_void_p]),
+    "ffb_debug_trace_rd": (C.c_int, [C.c_void_p]),
     "ffb_get_engine": (C.c_int, []),
     "ffb_launch_count": (C.c_int64, []),
 }

@@ -45,7 +45,6 @@ struct NetDev {
   const float* b[FFB_MAX_LAYERS];   // packed [Np]
   const float* Wt;                  // packed time rows [t_dim][Np[0]]
   int act;                          // FFB_ACT_* of the hidden layers
-  const float* Wst;                 // tensor-core image only: last layer with W_hi | W_lo stacked along N (or NULL)
 };
 
 struct FieldDev {

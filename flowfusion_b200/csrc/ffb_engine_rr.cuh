@@ -30,20 +30,10 @@
 namespace ffb {
 
 constexpr int RR_NCOMP = 512;
-// Warp roles.  With -DRR_SPECIAL_FIRST the MMA warp is warp 0 and the loader warp 1 (two spare warps keep the
-// compute warps' index a multiple of 4 so that warp & 3 is still the TMEM lane quarter): the oldest warp of a
-// scheduler is favoured when several are ready, and the MMA warp must not starve behind 4 busy epilogue warps.
-#ifdef RR_SPECIAL_FIRST
-constexpr int RR_CW0 = 4;                      // first compute warp
-constexpr int RR_NTHR = RR_NCOMP + 128;
-constexpr int RR_WMMA = 0;
-constexpr int RR_WLOAD = 1;
-#else
-constexpr int RR_CW0 = 0;
+constexpr int RR_CW0 = 0;                      // first compute warp
 constexpr int RR_NTHR = RR_NCOMP + 64;
 constexpr int RR_WLOAD = RR_NCOMP / 32;
 constexpr int RR_WMMA = RR_NCOMP / 32 + 1;
-#endif
 constexpr int RR_NCHUNK = KMAX / KC;
 constexpr uint32_t RR_COL_AHI = 256, RR_COL_ALO = 384;     // D0 = 0, D1 = 128
 // Synchronisation of one ring stage (= one 32-row K chunk of one layer): ONE mbarrier `full[s]` collects
@@ -60,57 +50,18 @@ __device__ __forceinline__ void tc_ld8(uint32_t addr, uint32_t (&v)[8]) {
                : "r"(addr));
 }
 
-// Ring-stage release: a tcgen05.commit costs the tensor pipe 60-190 cycles (csrc/tc_rate.cu), so only the
-// stages of the first RR_EARLY chunks of a layer are released by a commit as soon as their MMAs retire (the
-// next layer's first weight chunks are then prefetched while this layer still runs); the stages of the
-// remaining chunks are released by compute thread 0 when it sees the layer's d_ready.
-#ifndef RR_EARLY
-#define RR_EARLY 0
-#endif
-// Narrow last layer with W_hi | W_lo stacked along N (NetDev::Wst): 2 MMAs per k-step instead of 3 (an MMA costs
-// ~51 cycles whatever N <= 64 is, csrc/tc_rate.cu); the last-layer epilogue adds the two accumulator halves.
-// Parity-green (all GPU tests) but 3-5 % SLOWER on cfg2-cfg5 (A/B), so it is off.
-// TF32 hi/lo split of a packed pair.  RR_SPLIT_FP = 1: Veltkamp split on the FMA pipe, c = 8193 a, hi = c - 8192 a
-// (one FMA: exact, a multiple of 2^13 ulp(a), i.e. a rounded to TF32's 11 significant bits), lo = a - hi (exact):
-// 3 packed instructions per pair.  RR_SPLIT_FP = 0: integer round-half-away ((bits + 0x1000) & ~0x1FFF), 4 integer
-// + 1 packed instruction per pair.  Same |lo| <= 2^-11 |a|; the two differ on ties only.  |a| must stay below
-// FLT_MAX / 8193 (4e34) in the FP form.
-// MMA warp waits for the next chunk's barrier before the last RR_PREWAIT_TAIL MMAs of the current chunk (A/B)
-#ifndef RR_PREWAIT
-#define RR_PREWAIT 0
-#endif
-#ifndef RR_PREWAIT_TAIL
-#define RR_PREWAIT_TAIL 2
-#endif
-// The whole MMA issue loop of an evaluation in one elected thread (A/B)
-#ifndef RR_ONE_THREAD
-#define RR_ONE_THREAD 0
-#endif
-#ifndef RR_SPLIT_FP
-#define RR_SPLIT_FP 1
-#endif
+// Ring-stage release: the stages of a layer are released by compute thread 0 when it sees the layer's d_ready (a
+// tcgen05.commit per stage was measured slower).
+// TF32 hi/lo split of a packed pair on the FMA pipe (Veltkamp): c = 8193 a, hi = c - 8192 a (one FMA: exact, a multiple of
+// 2^13 ulp(a), i.e. a rounded to TF32's 11 significant bits), lo = a - hi (exact): 3 packed instructions per pair.
+// |lo| <= 2^-11 |a|; differs from the integer round-half-away of tf32_split on ties only.  |a| must stay below
+// FLT_MAX / 8193 (4e34).
 __device__ __forceinline__ void tf32_split2(const float2 a, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0, uint32_t& lo1) {
-#if RR_SPLIT_FP
   const float2 c = __fmul2_rn(a, make_float2(8193.0f, 8193.0f));
   const float2 h = __ffma2_rn(a, make_float2(-8192.0f, -8192.0f), c);
   const float2 l = __ffma2_rn(h, make_float2(-1.0f, -1.0f), a);
   hi0 = __float_as_uint(h.x); hi1 = __float_as_uint(h.y);
-#else
-  hi0 = (__float_as_uint(a.x) + 0x1000u) & 0xFFFFE000u;
-  hi1 = (__float_as_uint(a.y) + 0x1000u) & 0xFFFFE000u;
-  const float2 l = __ffma2_rn(make_float2(__uint_as_float(hi0), __uint_as_float(hi1)), make_float2(-1.0f, -1.0f), a);   // a - hi, exact
-#endif
   lo0 = __float_as_uint(l.x); lo1 = __float_as_uint(l.y);
-}
-// Reciprocal of the SiLU epilogue on the FMA pipe instead of MUFU.RCP (A/B: DESIGN.md section 9)
-#ifndef RR_RCP_FMA
-#define RR_RCP_FMA 0
-#endif
-#ifndef RR_STACK_LAST
-#define RR_STACK_LAST 0
-#endif
-__device__ __forceinline__ bool rr_stacked(const NetDev& net, int l) {
-  return RR_STACK_LAST && l == net.n_layers - 1 && net.Wst != nullptr;
 }
 
 // Debug timeline (compiled in with -DFFB_TRACE only): CTA 0 records clock64() at hand-off points, one
@@ -286,13 +237,8 @@ struct EngineRR_ {
         const int rows = min(KC, K - k0);
         mbar_wait(&cx.empty()[cx.stage], cx.phase);
         const uint32_t bytes = (uint32_t)(2 * rows * Np) * sizeof(float);
-#ifdef FFB_ABL_NOLOAD   // ablation (wrong results): stop streaming weights after the first pass over the ring
-        if (cx.tr_n >= TC_NSTAGE) { mbar_arrive(&cx.full()[cx.stage]); advance(cx); continue; }
-        ++cx.tr_n;
-#endif
         mbar_expect_tx(&cx.full()[cx.stage], bytes);
-        const float* src = rr_stacked(net, l) ? net.Wst : net.W[l];
-        bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, src + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
+        bulk_g2s(cx.ring() + cx.stage * TC_STAGE_FLOATS, net.W[l] + (size_t)2 * k0 * Np, bytes, &cx.full()[cx.stage]);
         advance(cx);
       }
     }
@@ -314,128 +260,32 @@ struct EngineRR_ {
     for (int j = 0; j < KC / 8; ++j)
       if ((NJ > 0) ? (j < NJ) : (j < nj)) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
   }
-  // a full chunk in two parts (RR_PREWAIT): the first 10 MMAs, then -- after the MMA warp has waited for the NEXT
-  // chunk's barrier behind the backlog of the tensor queue -- the last 2
-  static __device__ __forceinline__ void issue_chunk_head(uint32_t d_acc, uint32_t a_hi0, uint32_t a_lo0, uint64_t dh0, uint64_t dl0,
-                                                          uint64_t kstep, uint32_t idesc, uint32_t acc0) {
-#pragma unroll
-    for (int j = 0; j < KC / 8; ++j) {
-      tc_mma_ts(d_acc, a_hi0 + 8u * j, dl0 + (uint64_t)j * kstep, idesc, (j == 0) ? acc0 : 1u);
-      tc_mma_ts(d_acc, a_lo0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
-    }
-#pragma unroll
-    for (int j = 0; j < KC / 8 - RR_PREWAIT_TAIL; ++j) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
-  }
-  static __device__ __forceinline__ void issue_chunk_tail(uint32_t d_acc, uint32_t a_hi0, uint64_t dh0, uint64_t kstep, uint32_t idesc) {
-#pragma unroll
-    for (int j = KC / 8 - RR_PREWAIT_TAIL; j < KC / 8; ++j) tc_mma_ts(d_acc, a_hi0 + 8u * j, dh0 + (uint64_t)j * kstep, idesc, 1u);
-  }
-#if RR_ONE_THREAD
-  // One elected thread of the MMA warp runs the whole evaluation (wait, fence, issue, commit); the other lanes only
-  // keep their copies of the ring position and the accumulator toggle in step and park at the closing __syncwarp.
-  static __device__ __forceinline__ void mma_net(CtxR& cx, const NetDev& net) {
-    const bool leader = elect_one();
-    for (int l = 0; l < net.n_layers; ++l) {
-      const int K = net.K[l], Np = net.Np[l];
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      const uint32_t lbo = (uint32_t)Np * 16u;
-      const uint64_t kstep = (uint64_t)(lbo >> 3);
-      const uint32_t d_acc = cx.tmem + cx.dbuf * 128u;
-      cx.dbuf ^= 1u;
-      uint32_t acc = 0;
-      for (int k0 = 0; k0 < K; k0 += KC) {
-        if (leader) {
-          const int nj = min(KC, K - k0) >> 3;
-          mbar_wait(&cx.full()[cx.stage], cx.phase);
-          tc_fence_after();
-          const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
-          const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
-          const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
-          const uint32_t a_hi0 = cx.tmem + RR_COL_AHI + (uint32_t)k0, a_lo0 = cx.tmem + RR_COL_ALO + (uint32_t)k0;
-          if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
-          else issue_chunk<0>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
-          if (k0 + KC >= K) tc_commit(cx.d_ready());
-        }
-        acc = 1u;
-        advance(cx);
-      }
-    }
-    __syncwarp();
-  }
-#else
   static __device__ __forceinline__ void mma_net(CtxR& cx, const NetDev& net) {
     for (int l = 0; l < net.n_layers; ++l) {
       const int K = net.K[l], Np = net.Np[l];
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t lbo = (uint32_t)Np * 16u;
       const uint64_t kstep = (uint64_t)(lbo >> 3);
-      const bool stacked = rr_stacked(net, l);
-      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * Np) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t d_acc = cx.tmem + cx.dbuf * 128u;
       cx.dbuf ^= 1u;
       uint32_t acc = 0;
       int ci = 0;
-#if RR_PREWAIT
-      bool prewaited = false;
-#endif
       for (int k0 = 0; k0 < K; k0 += KC, ++ci) {
         const int nj = min(KC, K - k0) >> 3;
-#if RR_PREWAIT
-        if (!prewaited)
-#endif
-        {
-          mbar_wait(&cx.full()[cx.stage], cx.phase);            // W chunk landed AND A columns [k0, k0+32) written
-          tc_fence_after();
-        }
+        mbar_wait(&cx.full()[cx.stage], cx.phase);            // W chunk landed AND A columns [k0, k0+32) written
+        tc_fence_after();
         RR_TRACE(cx, 100 + 10 * l + ci);
         const uint32_t hi_base = smem_u32(cx.ring() + cx.stage * TC_STAGE_FLOATS);
         const uint64_t dh0 = tc_desc(hi_base, lbo, 128u);
         const uint64_t dl0 = tc_desc(hi_base + (uint32_t)(nj * 8 * Np) * 4u, lbo, 128u);
         const uint32_t a_hi0 = cx.tmem + RR_COL_AHI + (uint32_t)k0, a_lo0 = cx.tmem + RR_COL_ALO + (uint32_t)k0;
-        uint64_t* ebar = &cx.empty()[cx.stage];
         const bool lastc = (k0 + KC >= K);
         if (elect_one()) {
-          if (stacked) {
-            // [W_hi | W_lo] is one B operand of width 2 Np: D[0:Np) += A W_hi, D[Np:2Np) += A W_lo for A = A_hi, A_lo
-            const uint64_t ds0 = tc_desc(hi_base, 2u * lbo, 128u);
-#pragma unroll
-            for (int j = 0; j < KC / 8; ++j) {
-              if (j < nj) {
-                tc_mma_ts(d_acc, a_hi0 + 8u * j, ds0 + (uint64_t)j * (2u * kstep), idesc2, (j == 0) ? acc : 1u);
-                tc_mma_ts(d_acc, a_lo0 + 8u * j, ds0 + (uint64_t)j * (2u * kstep), idesc2, 1u);
-              }
-            }
-          }
-#if RR_PREWAIT
-          else if (nj == KC / 8 && !lastc) issue_chunk_head(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc);
-#endif
-          else if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
+          if (nj == KC / 8) issue_chunk<KC / 8>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
           else issue_chunk<0>(d_acc, a_hi0, a_lo0, dh0, dl0, kstep, idesc, acc, nj);
-#if !RR_PREWAIT
-          if (ci < RR_EARLY) tc_commit(ebar);                   // frees the ring stage when these MMAs retire
           if (lastc) tc_commit(cx.d_ready());                   // the accumulator of this layer is complete
-#endif
         }
         __syncwarp();
-#if RR_PREWAIT
-        // the next chunk of the SAME layer: wait for its barrier now, while the tensor queue still holds the MMAs just
-        // issued (a successful wait + fence costs ~280 cycles during which the queue used to drain), then the tail
-        prewaited = false;
-        if (!stacked && nj == KC / 8 && !lastc) {
-          const int ns = (cx.stage + 1 == TC_NSTAGE) ? 0 : cx.stage + 1;
-          const uint32_t np = (cx.stage + 1 == TC_NSTAGE) ? (cx.phase ^ 1u) : cx.phase;
-          mbar_wait(&cx.full()[ns], np);
-          tc_fence_after();
-          prewaited = true;
-          if (elect_one()) issue_chunk_tail(d_acc, a_hi0, dh0, kstep, idesc);
-          __syncwarp();
-        }
-        if (elect_one()) {
-          if (ci < RR_EARLY) tc_commit(ebar);
-          if (lastc) tc_commit(cx.d_ready());
-        }
-        __syncwarp();
-#endif
         RR_TRACE(cx, 300 + ci);
         acc = 1u;
         advance(cx);
@@ -443,7 +293,6 @@ struct EngineRR_ {
       RR_TRACE(cx, 190 + l);
     }
   }
-#endif
 
   // ---- compute warps ---------------------------------------------------------------------------
   // "my part of the next A chunk is in tensor memory": arrive on the ring stage that chunk will use
@@ -459,9 +308,8 @@ struct EngineRR_ {
     mbar_wait(cx.d_ready(), cx.ph_d);
     cx.ph_d ^= 1u;
     tc_fence_after();
-    int ci = 0;
-    for (int k0 = 0; k0 < K; k0 += KC, ++ci) {
-      if (ci >= RR_EARLY && cx.tid == 0) mbar_arrive(&cx.empty()[cx.rstage]);
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      if (cx.tid == 0) mbar_arrive(&cx.empty()[cx.rstage]);
       if (++cx.rstage == TC_NSTAGE) cx.rstage = 0;
     }
   }
@@ -548,18 +396,8 @@ struct EngineRR_ {
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
               asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
               const float2 s = __fadd2_rn(e, make_float2(1.0f, 1.0f));
-#if RR_RCP_FMA
-              // 1 / s on the FMA pipe: magic-constant seed (12 % off), three Newton steps r <- r + r (1 - s r) on packed
-              // pairs: 6 FFMA2 + 2 IADD per pair instead of 2 MUFU.RCP (8 XU cycles each per warp)
-              const float sx = fminf(s.x, 1.0e30f), sy = fminf(s.y, 1.0e30f);      // e = +inf (z << 0): keep the seed finite
-              r = make_float2(__uint_as_float(0x7EF311C7u - __float_as_uint(sx)), __uint_as_float(0x7EF311C7u - __float_as_uint(sy)));
-              const float2 ns = make_float2(-sx, -sy), one = make_float2(1.0f, 1.0f);
-#pragma unroll
-              for (int it = 0; it < 3; ++it) r = __ffma2_rn(r, __ffma2_rn(ns, r, one), r);
-#else
               asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(s.x));
               asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(s.y));
-#endif
               const float2 a = __fmul2_rn(z, r);
               tf32_split2(a, hi[u], hi[u + 1], lo[u], lo[u + 1]);
             }
@@ -589,20 +427,16 @@ struct EngineRR_ {
     cx.dbuf ^= 1u;
     wait_d_ready(cx, net.K[nl - 1]);
     RR_TRACE(cx, 290);
-    const bool stacked = rr_stacked(net, nl - 1);
-    const uint32_t half = (uint32_t)net.Np[nl - 1];
     for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += KC) {              // warp-uniform trip count
-      uint32_t m[8], m2[8];
+      uint32_t m[8];
       tc_ld8(dcol + (uint32_t)(c0 - 8 * cx.cg), m);
-      if (stacked) tc_ld8(dcol + half + (uint32_t)(c0 - 8 * cx.cg), m2);
       const float4 b0 = *reinterpret_cast<const float4*>(bias + c0);
       const float4 b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       tc_wait_ld();
       float o[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        o[u] = (stacked ? __uint_as_float(m[u]) + __uint_as_float(m2[u]) : __uint_as_float(m[u])) + bb[u];
+      for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(m[u]) + bb[u];
       fn(c0, o);
     }
     tc_fence_before();

@@ -268,18 +268,9 @@ struct EngineRRT_ {
     float* kd = slot(cx, tc, dst) + s;
     const float* yc = cx.ycur() + s;
     const bool score = (f.kind == FFB_FIELD_SCORE), use_sigma = f.use_sigma != 0, has_drift = f.has_drift != 0;
-    const bool stacked = rr_stacked(net, nl - 1);
-    const uint32_t half = (uint32_t)net.Np[nl - 1];
     for (int c0 = 8 * cx.cg; c0 < Nreal; c0 += KC) {
       uint32_t m[8];
       tc_ld8(dcol + (uint32_t)(c0 - 8 * cx.cg), m);
-      if (stacked) {                                                     // W_hi | W_lo halves of the accumulator
-        uint32_t m2[8];
-        tc_ld8(dcol + half + (uint32_t)(c0 - 8 * cx.cg), m2);
-        tc_wait_ld();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) m[u] = __float_as_uint(__uint_as_float(m[u]) + __uint_as_float(m2[u]));
-      }
       tc_wait_ld();
       if (tc.kind == RT_OWNER) {
         const float ev_sign = ev.sign();

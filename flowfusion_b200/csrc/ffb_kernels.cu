@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
     const float* K2 = slot_ptr_t<SS>(cx, 1);
     const float* K3 = slot_ptr_t<SS>(cx, 2);
     const float* K4 = slot_ptr_t<SS>(cx, 3);
-    bool saw_nan = false;
+    int nan_step = 0x7fffffff;            // first Euler-Maruyama step of this thread's rows that produced a NaN
     if (!cx.producer) {
       load_rows(cx.ycur(), a.x0, row0, nv, S, SD, cx.tid);
       if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
               const float xn = __fadd_rn(xm, __fmul_rn(g, dw));
               Y0[i] = xm;
               y[i] = xn;
-              saw_nan |= (xn != xn);
+              if (xn != xn) nan_step = min(nan_step, step);
             }
           } else {
             const int ng = (SD + 3) >> 2;
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
                 const float xn = __fadd_rn(xm, __fmul_rn(g, __fmul_rn(zz[q], sq)));
                 Y0[i] = xm;
                 y[i] = xn;
-                saw_nan |= (xn != xn);
+                if (xn != xn) nan_step = min(nan_step, step);
               }
             }
           }
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ 
       store_rows(a.x_out, (a.method == FFB_M_EM) ? Y0 : cx.ycur(), row0, nv, SD, cx.tid);
       if (prob && a.lp_out)
         for (int s = cx.tid; s < nv; s += NCOMP) a.lp_out[row0 + s] = LPC[s];
-      if (saw_nan) atomicOr(a.status, FFB_ST_NAN_SAMPLE);
+      if (nan_step != 0x7fffffff) { atomicOr(a.status, FFB_ST_NAN_SAMPLE); atomicMin(a.status + 1, nan_step); }
       bar_compute();
     }
   }
@@ -540,32 +540,6 @@ __global__ void k_pack_weight_tc(const float* __restrict__ W, int in_features, i
   const size_t off = (size_t)(kk >> 2) * (Np * 4) + (size_t)(n >> 3) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
   dst[base + off] = __uint_as_float(hi);
   dst[base + (size_t)rows * Np + off] = __uint_as_float(lo);
-}
-// Last layer, stacked: per chunk of 32 k-rows ONE K-major image of width 2 Np holding [W_hi | W_lo] side by side
-// (element (n, k) of W_hi at column n, of W_lo at column Np + n).  A narrow last layer (N = 16: an MMA costs ~51
-// cycles whatever N <= 64 is) then needs two instructions per k-step, A_hi x [W_hi | W_lo] and A_lo x [W_hi | W_lo],
-// instead of three; the epilogue adds the two accumulator halves.
-__global__ void k_pack_weight_tc_stacked(const float* __restrict__ W, int in_features, int out_features,
-                                         float* __restrict__ dst, int K, int Np, int x_col, int x_dim, int c_col,
-                                         int c_dim, int layer0) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= K * Np) return;
-  const int k = idx / Np, n = idx - k * Np;
-  int col = -1;
-  if (layer0) {
-    if (k < x_dim) col = x_col + k;
-    else if (k < x_dim + c_dim) col = c_col + (k - x_dim);
-  } else if (k < in_features) {
-    col = k;
-  }
-  const float w = (n < out_features && col >= 0) ? W[(size_t)n * in_features + col] : 0.0f;
-  uint32_t hi, lo;
-  tf32_split_rn(w, hi, lo);
-  const int c = k / KC, kk = k - c * KC;
-  const size_t base = (size_t)c * 2 * KC * Np;
-  const int N2 = 2 * Np, nl = Np + n;
-  dst[base + (size_t)(kk >> 2) * (N2 * 4) + (size_t)(n >> 3) * 32 + (size_t)(n & 7) * 4 + (kk & 3)] = __uint_as_float(hi);
-  dst[base + (size_t)(kk >> 2) * (N2 * 4) + (size_t)(nl >> 3) * 32 + (size_t)(nl & 7) * 4 + (kk & 3)] = __uint_as_float(lo);
 }
 __global__ void k_pack_time_tc(const float* __restrict__ W, int in_features, int out_features, float* __restrict__ dst,
                                int t_dim, int Np, int t_col) {
@@ -758,15 +732,6 @@ extern "C" int ffb_net_create(const ffb_net_desc* d, void* stream_, ffb_net** ou
     k_pack_bias_tc<<<1, 128, 0, stream>>>(d->bias[l], N, b, Np);
     g_launches += 2;
     nt.W[l] = w; nt.b[l] = b;
-    if (RR_STACK_LAST && l == d->n_layers - 1 && 2 * Np <= KMAX) {   // stacked image: both halves fit one 128-column accumulator
-      float* ws = nullptr;
-      if (cudaMalloc(&ws, sizeof(float) * 2 * K * Np) != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
-      net->allocs.push_back(ws);
-      k_pack_weight_tc_stacked<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, ws, K, Np, d->x_col, d->x_dim,
-                                                                        d->c_col, d->c_dim, l == 0);
-      g_launches += 1;
-      nt.Wst = ws;
-    }
     if (l == 0) {
       float* wt = nullptr;
       const int td = d->t_dim > 0 ? d->t_dim : 1;

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
     const float* K2 = rr_slot<SS>(cx, nslot > 1 ? 1 : 0);
     const float* K3 = rr_slot<SS>(cx, nslot > 2 ? 2 : 0);
     const float* K4 = rr_slot<SS>(cx, nslot > 3 ? 3 : 0);
-    bool saw_nan = false;
+    int nan_step = 0x7fffffff;            // first Euler-Maruyama step of this thread's row that produced a NaN
     if (!cx.producer) {
       load_rows_t<RR_NCOMP>(cx.ycur(), a.x0, row0, nv, TM, SD, cx.tid);
       if (CD) load_rows_t<RR_NCOMP>(cx.condb(), a.cond, row0, nv, TM, CD, cx.tid);
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
                 for (int u = 0; u < 8; ++u) {
                   xm[u] = __fadd_rn(yv[u], __fmul_rn(k1[u], dt));
                   yv[u] = __fadd_rn(xm[u], __fmul_rn(g, __fmul_rn(zz[u], sq)));
-                  if (d0 + u < SD) saw_nan |= (yv[u] != yv[u]);
+                  if (d0 + u < SD && yv[u] != yv[u]) nan_step = min(nan_step, step);
                 }
                 rr_store8(cx, Y0, d0, xm);
                 rr_store8(cx, y, d0, yv);
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
     if (!cx.producer) {
       rr_bar();
       store_rows_t<RR_NCOMP>(a.x_out, (a.method == FFB_M_EM) ? Y0 : cx.ycur(), row0, nv, SD, cx.tid);
-      if (saw_nan) atomicOr(a.status, FFB_ST_NAN_SAMPLE);
+      if (nan_step != 0x7fffffff) { atomicOr(a.status, FFB_ST_NAN_SAMPLE); atomicMin(a.status + 1, nan_step); }
       rr_bar();
     }
   }

@@ -429,19 +429,41 @@ class ScoreModel(torch.nn.Module):
             philox = (seed, 0)
         else:
             noise = noise[:n_eff]
-        rank_off = _dist.row_offset(batch, self._group())
-        x, _, status = E.run_fixed(self._field(), L.M_EM, x0.reshape(batch, -1), step_table,
-                                   ev.reshape(n_eff, 1, L.EV_FLOATS), cond=conditional, noise=noise,
-                                   philox=philox, row_offset=rank_off)
+        if n_eff == 0:
+            # the reference's loop breaks before the first assignment of x_mean and `return x_mean` raises (`:548-563`)
+            raise UnboundLocalError("cannot access local variable 'x_mean' where it is not associated with a value")
+        group = self._group()
+        rank_off = _dist.row_offset(batch, group)
+        field = self._field()
+
+        def run(n):
+            return E.run_fixed(field, L.M_EM, x0.reshape(batch, -1), step_table[:n], ev[:n].reshape(n, 1, L.EV_FLOATS),
+                               cond=conditional, noise=None if noise is None else noise[:n], philox=philox,
+                               row_offset=rank_off)
+
+        x, _, status = run(n_eff)
+        # `diffusion.py:560-563`: the reference stops the WHOLE batch after the first step that left a NaN anywhere in x and
+        # returns that step's x_mean.  The kernel integrates every tile to the end and records the first such step; the
+        # (rare) unstable case is then integrated again up to that step -- the noise is a function of (seed, row, step)
+        # or the caller's tensor, so the second pass reproduces the first.
+        flags, first_nan = (int(v) for v in status.cpu())
+        if group is not None:                         # "anywhere in x" is global: every rank stops at the same step
+            t = torch.tensor([first_nan if flags & L.ST_NAN_SAMPLE else 2 ** 31 - 1], dtype=torch.int64, device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=group)
+            first_nan = int(t.item())
+            flags |= L.ST_NAN_SAMPLE if first_nan < 2 ** 31 - 1 else 0
         self._status = status
+        self.stopped_at_step = None
+        if flags & L.ST_NAN_SAMPLE:
+            print("Diffusion is not stable, NaN were produced. Stopped sampling.")
+            self.stopped_at_step = first_nan
+            if first_nan + 1 < n_eff:
+                x, _, _ = run(first_nan + 1)
         return x.reshape(batch, *dims)
 
     def check_stability(self):
-        """Host-side read of the status word of the last ``sample_sde`` (`diffusion.py:560-562`)."""
-        st = int(self._status.item())
-        if st & L.ST_NAN_SAMPLE:
-            print("Diffusion is not stable, NaN were produced. Stopped sampling.")
-        return st == 0
+        """True when the last ``sample_sde`` produced no NaN (it prints the reference's message itself, `diffusion.py:560-562`)."""
+        return not (int(self._status[0].item()) & L.ST_NAN_SAMPLE)
 
     def sample_ode_from_base(self, base_samples, conditional=None, atol=1e-4, rtol=1e-4, method="dopri5",
                              options=None):

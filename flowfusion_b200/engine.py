@@ -64,8 +64,16 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The current torch stream of ``device`` (default: the current device) as a ``cudaStream_t``."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(device):
+    """Context manager: make ``device`` the current CUDA device.  The C ABI launches on the current device with raw
+    pointers, so every entry point runs under the device of its state tensor (a model on cuda:1 works while
+    cuda:0 is current, as it does in the reference)."""
+    return torch.cuda.device(torch.device(device))
 
 
 def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:
@@ -141,6 +149,7 @@ class PackedNet:
         self.flops = int(lib.ffb_net_flops(h))
         self.dims = [linears[0].in_features] + [l.out_features for l in linears]
         self.x_dim, self.c_dim, self.t_dim = x_dim, c_dim, t_dim
+        self.device = torch.device(device)
         self._lib = lib
 
     def __del__(self):
@@ -172,6 +181,14 @@ class FieldSpec:
         f.state_dim, f.cond_dim, f.kind = state_dim, cond_dim, kind
         f.use_sigma, f.has_drift, f.div_mode = int(use_sigma), int(has_drift), div_mode
         self.c = f
+        self.device = getattr(nets[0], "device", None)
+        if any(getattr(n, "device", self.device) != self.device for n in nets):
+            raise L.FFBError("the networks of a field must live on one CUDA device")
+
+    def check_device(self, t: torch.Tensor, what="state"):
+        """The packed weights are raw pointers of ONE device: the state must live there too."""
+        if self.device is not None and t.device != self.device:
+            raise L.FFBError(f"{what} is on {t.device} but the model's weights are on {self.device}: move them to one device")
 
     def with_div(self, div_mode):
         return FieldSpec(self.nets, self.state_dim, self.cond_dim, self.kind, self.use_sigma, self.has_drift,
@@ -227,6 +244,7 @@ class CudaBackend:
     def __init__(self, field: FieldSpec, y0: torch.Tensor, cond=None, probes=None, with_lp=False,
                  cond_in_state=False, cond_state=None):
         require_cuda(y0, "state")
+        field.check_device(y0)
         self.lib = L.load()
         self.field = field
         dev = y0.device
@@ -257,7 +275,7 @@ class CudaBackend:
         self.cur = 0
         self.dargs = L.Dopri5Args()
         self._dargs_static = False
-        self._stream = _stream()           # torch.cuda.current_stream() costs ~20 us per call: once per solve
+        self._stream = _stream(dev)        # torch.cuda.current_stream() costs ~20 us per call: once per solve
         self.eargs = L.EvalArgs()
 
     # -- counts for the RMS norms (global over ranks) -------------------------------------------
@@ -305,7 +323,8 @@ class CudaBackend:
 
     def single_eval(self, ev_row):
         """One field evaluation at the current state -> (f, dlp or None)."""
-        self._eval(ev_row, 1.0, 0.0, 1)
+        with on_device(self.dev):
+            self._eval(ev_row, 1.0, 0.0, 1)
         return self.f[self.cur], self.dlp[self.cur]
 
     def eval1(self, h0, ev_row, atol, rtol):
@@ -340,11 +359,15 @@ class CudaBackend:
 
     # -- device-side controller (csrc/ffb_control.cuh): the host only enqueues and polls ----------------
     def ctl_supported(self):
-        return self.B > 0 and bool(self.lib.ffb_dopri5_ctl_supported(C.byref(self.field.c)))
+        """A property of the FIELD (not of this rank's shard): every rank of a sharded solve must take the same controller,
+        or their sequences of collectives differ.  A rank with an empty shard runs the same loop with no-op attempts."""
+        return bool(self.lib.ffb_dopri5_ctl_supported(C.byref(self.field.c)))
 
-    def ctl_attempt_ms_estimate(self):
-        """Rough duration of one attempted step (6 evaluations at ~140 TFLOP/s), for solver.py's "auto" choice."""
-        return 6.0 * self.B * self.field.flops_per_eval() / 140e12 * 1e3
+    def ctl_attempt_ms_estimate(self, rows=None):
+        """Rough duration of one attempted step (6 evaluations at ~140 TFLOP/s), for solver.py's "auto" choice.
+        ``rows``: rows per rank to assume (solver.py passes the GLOBAL batch / world size so that all ranks agree)."""
+        rows = self.B if rows is None else rows
+        return 6.0 * rows * self.field.flops_per_eval() / 140e12 * 1e3
 
     def ctl_begin(self, params: "L.CtlParams", t: float, dt_next: float, grid_idx: int, atol, rtol):
         """Upload the controller block and let the device prepare the first attempt."""
@@ -380,8 +403,9 @@ class CudaBackend:
     def ctl_attempt(self, reduce=True):
         """attempt (+ tile reduction when the sums go through an all-reduce first); the attempt returns at once when
         the solve has already finished"""
-        with _timed("dopri5_attempt", self.B):
-            L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(self.dargs), self._stream), "ffb_dopri5_attempt")
+        if self.B:                      # a rank with an empty shard only takes part in the reductions
+            with _timed("dopri5_attempt", self.B):
+                L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(self.dargs), self._stream), "ffb_dopri5_attempt")
         return self._reduce() if reduce else self.sums
 
     def ctl_control(self, reduce=False):
@@ -400,7 +424,7 @@ class CudaBackend:
                 d = v & 0xFF
                 return d - 256 if d > 127 else d
             spins += 1
-            if spins % 4096 == 0 and torch.cuda.current_stream().query():
+            if spins % 4096 == 0 and torch.cuda.current_stream(self.dev).query():
                 v = int(arr[i]) & 0xFFFFFFFF          # the stream has drained: the turn must have been announced
                 if (v >> 8) != want:
                     raise L.FFBError("dopri5 controller: turn %d was never announced (kernel fault?)" % k)
@@ -575,6 +599,14 @@ def staged_fixed(be, method: str, dts: np.ndarray, ev: np.ndarray):
     ``feval`` per stage, stage inputs and the step itself through ``combine``.  ``dts`` (n,) float32 step sizes,
     ``ev`` (n, evaluations per step, EV_FLOATS).  Returns (x, log-det column) at the end of the grid."""
     third, half, eighth = np.float32(1.0 / 3.0), np.float32(0.5), np.float32(0.125)
+    dev = getattr(be, "dev", None)
+    if dev is None or torch.device(dev).type != "cuda":      # the CPU model of the kernels (tests/kernel_model.py)
+        return _staged_fixed(be, method, dts, ev, third, half, eighth)
+    with on_device(dev):
+        return _staged_fixed(be, method, dts, ev, third, half, eighth)
+
+
+def _staged_fixed(be, method, dts, ev, third, half, eighth):
     y, lp = be.state()
     for s in range(int(dts.shape[0])):
         dt = np.float32(dts[s])
@@ -601,6 +633,7 @@ def run_fixed(field: FieldSpec, method: int, x0: torch.Tensor, step_table: np.nd
     """Whole fixed-grid trajectory in one kernel.  ``step_table`` (nsteps, 8) and ``ev_table``
     (nsteps, nev, EV_FLOATS) are host float32 arrays computed in the reference's op order."""
     require_cuda(x0, "state")
+    field.check_device(x0)
     lib = L.load()
     dev = x0.device
     x0 = _dev_f32(x0, dev)
@@ -610,7 +643,7 @@ def run_fixed(field: FieldSpec, method: int, x0: torch.Tensor, step_table: np.nd
     ev = torch.from_numpy(np.ascontiguousarray(ev_table, np.float32).reshape(-1)).to(dev)
     x_out = torch.empty_like(x0)
     lp_out = torch.empty(B, device=dev) if want_lp else None
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    status = torch.tensor([0, 2 ** 31 - 1], dtype=torch.int32, device=dev)      # [FFB_ST_* bits, first NaN step of EM]
     scratch = field.scratch(dev)
     a = L.FixedArgs()
     a.batch, a.method, a.nsteps = B, method, nsteps
@@ -627,7 +660,8 @@ def run_fixed(field: FieldSpec, method: int, x0: torch.Tensor, step_table: np.nd
     a.status, a.scratch = _ptr(status), _ptr(scratch)
     if B and nsteps:
         with _timed("integrate_fixed", B):
-            L.check(lib.ffb_integrate_fixed(C.byref(field.c), C.byref(a), _stream()), "ffb_integrate_fixed")
+            with on_device(dev):
+                L.check(lib.ffb_integrate_fixed(C.byref(field.c), C.byref(a), _stream(dev)), "ffb_integrate_fixed")
     elif B:
         x_out.copy_(x0)
     return x_out, lp_out, status
@@ -642,15 +676,17 @@ def gaussian_logprob(x: torch.Tensor, add: Optional[torch.Tensor], sigma: float 
     if B == 0:
         return out
     add_c = None if add is None else _dev_f32(add, x.device)
-    L.check(L.load().ffb_gaussian_logprob(_ptr(x), _ptr(add_c), _ptr(out), B, D, float(sigma), _stream()),
-            "ffb_gaussian_logprob")
+    with on_device(x.device):
+        L.check(L.load().ffb_gaussian_logprob(_ptr(x), _ptr(add_c), _ptr(out), B, D, float(sigma), _stream(x.device)),
+                "ffb_gaussian_logprob")
     return out
 
 
 def philox_normal(batch, dim, seed, offset, step, row_offset=0, device="cuda"):
     out = torch.empty(batch, dim, device=device)
-    L.check(L.load().ffb_philox_normal(_ptr(out), batch, dim, int(seed), int(offset), int(step), int(row_offset),
-                                       _stream()), "ffb_philox_normal")
+    with on_device(out.device):
+        L.check(L.load().ffb_philox_normal(_ptr(out), batch, dim, int(seed), int(offset), int(step), int(row_offset),
+                                           _stream(out.device)), "ffb_philox_normal")
     return out
 
 

@@ -132,7 +132,16 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
 
     ``program(times32)`` maps float32 *user* times, shape (n,), to the (n, EV_FLOATS) rows of
     host-computed evaluation scalars (time features, SDE coefficients).  The result is left in
-    the backend (``backend.output()``)."""
+    the backend (``backend.output()``).  Every launch of the solve is made with the backend's device current
+    (the C ABI launches on the current device with raw pointers)."""
+    dev = getattr(backend, "dev", None)
+    if dev is None or torch.device(dev).type != "cuda":          # the CPU model of the kernels (tests/kernel_model.py)
+        return _dopri5(backend, program, t0, t1, rtol, atol, options, group)
+    with torch.cuda.device(dev):
+        return _dopri5(backend, program, t0, t1, rtol, atol, options, group)
+
+
+def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None) -> SolveStats:
     opts = dict(options or {})
     for k in ("norm", "dtype"):
         opts.pop(k, None)
@@ -211,7 +220,10 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
     spec = getattr(program, "spec", None)
     if (_CONTROLLER != "host" and spec is not None and len(grid) <= L.CTL_MAX_GRID and counts["x"] > 0
             and getattr(backend, "ctl_supported", lambda: False)()
-            and (_CONTROLLER == "device" or backend.ctl_attempt_ms_estimate() < _CTL_AUTO_MAX_ATTEMPT_MS)):
+            and (_CONTROLLER == "device" or backend.ctl_attempt_ms_estimate(_rows_per_rank(counts, backend, group))
+                 < _CTL_AUTO_MAX_ATTEMPT_MS)):
+        # every term of this condition is the same on all ranks of a sharded solve (global counts, the field, the grid,
+        # the process-wide controller mode): the ranks must agree, their sequences of collectives differ otherwise
         p = L.CtlParams()
         p.t_end, p.min_step, p.max_step = float(te), float(min_step), float(max_step)
         p.safety, p.ifactor, p.dfactor = float(safety), float(ifactor), float(dfactor)
@@ -292,6 +304,12 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
             dt = f64(np.clip(nxt_dt, min_step, max_step)) if not np.isnan(nxt_dt) else f64(np.nan)
     assert done, "internal: integration loop ended without a final step"
     return st
+
+
+def _rows_per_rank(counts, backend, group) -> float:
+    """Global batch / world size: what the "auto" controller choice is based on, identical on every rank."""
+    world = torch.distributed.get_world_size(group) if group is not None else 1
+    return counts["x"] / max(1, getattr(backend, "D", 1)) / world
 
 
 def _dopri5_device(backend, params, st: SolveStats, ts: float, dt: float, grid_idx: int, atol32, rtol32, group) -> SolveStats:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FFB_ABI_VERSION 3
+#define FFB_ABI_VERSION 4
 #define FFB_MAX_LAYERS 8    /* Linear layers per network                         */
 #define FFB_MAX_WIDTH 128   /* widest layer (input or output) the tile engine holds */
 #define FFB_MAX_TFEAT 32    /* time-feature columns (embedding_dimensions or 1)  */
@@ -268,7 +268,9 @@ typedef struct {
   float* lp_out;
   const float* step_table;       /* device (nsteps, FFB_STEP_STRIDE)                            */
   const ffb_eval_scalars* ev_table; /* device (nsteps, evals_per_step)                          */
-  int32_t* status;
+  int32_t* status;               /* device, TWO words: [0] FFB_ST_* bits (atomicOr); [1] index of the first
+                                    Euler-Maruyama step after which any element of x was NaN (atomicMin; the
+                                    caller initialises it to INT32_MAX) -- diffusion.py:560-563 stops there      */
   void* scratch;
 } ffb_fixed_args;
 
@@ -383,10 +385,17 @@ int ffb_philox_normal(float* out, int64_t batch, int32_t dim, uint64_t seed, uin
                       int32_t step, int64_t row_offset, void* stream);
 /* FP32 FFMA2 peak probe: returns achieved TFLOP/s through *tflops (roofline denominator) */
 int ffb_ffma_peak(int32_t iters, float* tflops, void* stream);
-/* contraction engine: 1 = tcgen05 tensor cores, 3xTF32 (default); 0 = FP32 FFMA2 (debug / A-B checks).
- * The environment variable FFB_ENGINE=ffma selects 0 at load time. */
+/* contraction engine: 1 = tcgen05 tensor cores, 3xTF32 (default: the dual-tile engine takes the dopri5 attempts of
+ * fields without a divergence when the batch holds at least two tiles per SM, the single-tile engine everything else);
+ * 3 = single-tile engine only; 4 = dual-tile engine for every dopri5 attempt it can hold (tests); 2 = the older
+ * whole-layer hand-off tile engine; 0 = FP32 FFMA2 (debug / A-B checks).  Engines 1, 3 and 4 give the same bits.
+ * The environment variable FFB_ENGINE = ffma | tc_tile | rr | rd selects 0 | 2 | 3 | 4 at load time. */
 int ffb_set_engine(int engine);
 int ffb_get_engine(void);
+/* debug: hand-off timelines of CTA 0 (libraries built with -DFFB_TRACE only; scripts/trace_rr.py, scripts/trace_rd.py).
+ * buf: device buffer of 3 (single-tile engines) / 5 (dual-tile engine) roles x 2048 x 2 int64, or NULL to stop. */
+int ffb_debug_trace(long long* buf);
+int ffb_debug_trace_rd(long long* buf);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t ffb_launch_count(void);
 

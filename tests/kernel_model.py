@@ -178,9 +178,9 @@ class FakeBackend:
 
     # -- device-side controller: the CPU twin of the control kernel (ffb_dopri5_control_host) drives this model ----
     def ctl_supported(self):
-        return self.B > 0
+        return True                    # a property of the field, not of this rank's shard (engine.CudaBackend)
 
-    def ctl_attempt_ms_estimate(self):
+    def ctl_attempt_ms_estimate(self, rows=None):
         return 0.0
 
     def ctl_begin(self, params, t, dt_next, grid_idx, atol, rtol):
@@ -289,7 +289,7 @@ def fake_run_fixed(field, method, x0, step_table, ev_table, cond=None, probes=No
     third = torch.tensor(1 / 3, dtype=torch.float32)
     st = torch.from_numpy(np.asarray(step_table, np.float32))
     x_mean = x
-    status = torch.zeros(1, dtype=torch.int32)
+    status = torch.tensor([0, 2 ** 31 - 1], dtype=torch.int32)      # like the kernel: flags, first NaN step of EM
     D = field.state_dim
 
     def F(ev_row, y):
@@ -328,8 +328,9 @@ def fake_run_fixed(field, method, x0, step_table, ev_table, cond=None, probes=No
             f, _ = F(ev[0], x)
             x_mean = x + f * dt
             x = x_mean + st[n, 1] * (noise[n] * st[n, 2])
-            if torch.isnan(x).any():
+            if torch.isnan(x).any():          # the kernel keeps integrating and records the first such step
                 status[0] |= L.ST_NAN_SAMPLE
+                status[1] = min(int(status[1]), n)
         elif method == L.M_LEAPFROG:
             half = st[n, 3]
             if kick is None:

@@ -44,7 +44,7 @@ def test_exports_are_plain_c(lib):
 
 
 def test_abi_version_and_error_paths(lib):
-    assert lib.ffb_abi_version() == L.ABI_VERSION == 3
+    assert lib.ffb_abi_version() == L.ABI_VERSION == 4
     # null arguments are reported through the status code + ffb_last_error, no CUDA call is made
     assert lib.ffb_net_create(None, None, None) == -1
     assert b"null" in lib.ffb_last_error()

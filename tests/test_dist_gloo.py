@@ -70,6 +70,22 @@ def _worker(rank, world, port, q):
         out["hpp_err"] = float((lp_full - outs["lp_hpp"]).abs().max())
         out["hpp_steps"] = (sm.last_stats.accepted, sm.last_stats.rejected)
         out["hpp_want"] = (meta["stats_hpp"]["accepted"], meta["stats_hpp"]["rejected"])
+        # ---- an EMPTY shard on rank 1, every controller: all ranks must run the same sequence of collectives ----------
+        # (the device-vs-host controller choice is made from global quantities only; a rank without rows runs the same
+        # loop with no-op attempts), and a collective issued right after the solve must pair up correctly
+        from flowfusion_b200 import solver
+        meta, sd, ins, outs = load_golden("cfg2_vp_pfode")
+        sm = D.ScoreModel(D.MLP(**meta["ctor"]), D.VPSDE(), no_sigma=True).eval()
+        sm.load_state_dict(sd)
+        nb = ins["base"].shape[0]
+        lo, hi = (0, nb) if rank == 0 else (nb, nb)
+        for mode in ("device", "auto", "host"):
+            with patched_engine(), fd.use_group(td.group.WORLD), solver.controller(mode):
+                x, _ = sm.sample_ode_from_base(ins["base"][lo:hi], ins["cond"][lo:hi], atol=1e-5, rtol=1e-5,
+                                               options={"step_t": torch.tensor([1e-3])})
+                full = fd.gather_rows(x)
+            out["empty_" + mode] = (rel_row_err(outs["x_dopri5"], full), sm.last_stats.accepted, sm.last_stats.rejected,
+                                    sm.last_stats.controller)
         # ---- uneven shards, an empty shard, and the row offsets Philox streams are keyed on -----------------
         t = torch.arange(7, dtype=torch.float32)[:, None]
         mine = fd.shard_rows(t, rank, world)
@@ -101,6 +117,11 @@ def test_two_rank_sharded_solves_match_single_process_golden():
         assert o["lp_steps"] == o["lp_want"]
         assert o["hpp_err"] < 1e-3 and o["hpp_steps"] == o["hpp_want"]
         assert o["gather_ok"] and o["gather_empty_ok"]
+        for mode in ("device", "auto", "host"):
+            err, acc, rej, ctl = o["empty_" + mode]
+            assert err < 1e-4 and (acc, rej) == o["pf_want"][:2], (mode, o["empty_" + mode])
+            assert ctl == res[0]["empty_" + mode][3], "every rank must pick the same controller"
+        assert o["empty_device"][3] == "device" and o["empty_host"][3] == "host"
     assert res[0]["pf_dt"] == res[1]["pf_dt"], "every rank must take bit-identical step sizes"
     assert (res[0]["offset"], res[1]["offset"]) == (0, 4)       # 7 rows over 2 ranks: 4 + 3
 

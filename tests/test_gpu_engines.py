@@ -449,3 +449,85 @@ def test_dual_tile_engine_golden_and_bit_identical_to_single_tile(cuda_dev):
             lp = sf.log_prob(xq, p0=p0)
             outs_.append((lp.clone(), sf.last_stats.accepted, sf.last_stats.rejected))
     assert torch.equal(outs_[0][0], outs_[1][0]) and outs_[0][1:] == outs_[1][1:]
+
+
+# ---------------------------------------------------------------------------------------------
+# accelerate(): the documented drop-in entry point must keep the reference object's hidden activation
+# ---------------------------------------------------------------------------------------------
+def _reference_like_flow(meta, sd, act_cls, conditional):
+    """A stand-in with the attribute surface of the reference's ODEFlow / ConditionalODEFlow (`flow.py:37-86, 473-551`):
+    `/root/reference` does not exist on the GPU box, the golden vectors below were produced there by the real class."""
+    c = meta["ctor"]
+    D_, hidden = c["target_dimension"], c["hidden_units"]
+    Cn = c.get("conditional_dimension", 0)
+
+    class _Flow(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.target_dimension = D_
+            if conditional:
+                self.conditional_dimension = Cn
+            self.layers = torch.nn.ModuleList()
+            arch = [D_ + 1 + Cn] + list(hidden) + [D_]
+            for i in range(len(arch) - 2):
+                self.layers.append(torch.nn.Linear(arch[i], arch[i + 1]))
+                self.layers.append(act_cls())
+            self.layers.append(torch.nn.Linear(arch[-2], arch[-1]))
+            self.velocity = torch.nn.Sequential(*self.layers)
+            for k, v in sd.items():
+                if k not in self.state_dict():
+                    self.register_buffer(k, torch.zeros_like(v))
+
+    _Flow.__name__ = "ConditionalODEFlow" if conditional else "ODEFlow"
+    m = _Flow().eval()
+    m.load_state_dict(sd)
+    return m
+
+
+@pytest.mark.parametrize("name,act_cls,conditional", [("flow_tanh", torch.nn.Tanh, False), ("cflow_gelu", torch.nn.GELU, True)])
+def test_accelerate_non_silu_flow_matches_reference_golden(cuda_dev, name, act_cls, conditional):
+    """`flowfusion_b200.accelerate(ref_obj)` on a Tanh / GELU flow, then sample and log_prob against golden vectors
+    produced by the UNMODIFIED reference (oracle/make_golden_act.py)."""
+    from conftest import load_golden
+    import flowfusion_b200 as ffb
+    meta, sd, ins, outs = load_golden(name)
+    ref_like = _reference_like_flow(meta, sd, act_cls, conditional)
+    tw = ffb.accelerate(ref_like, device=cuda_dev)
+    assert [type(m).__name__ for m in tw.layers] == [type(m).__name__ for m in ref_like.layers]
+    args = (ins["cond"].to(cuda_dev),) if conditional else ()
+    x = tw.sample(ins["xT"].to(cuda_dev), *args)
+    assert rel_row_err(outs["x"], x) < SAMPLE_TOL
+    lp = tw.log_prob(outs["x"].to(cuda_dev), *args, atol=1e-6, rtol=1e-6)
+    assert float((lp.cpu() - outs["log_prob"]).abs().max()) < LP_TOL
+    st = meta["stats_logprob"]
+    assert (tw.last_stats.accepted, tw.last_stats.rejected) == (st["accepted"], st["rejected"])
+
+
+# ---------------------------------------------------------------------------------------------
+# more than one device in the process (these need 2 GPUs: `gpurun --gpus 2`)
+# ---------------------------------------------------------------------------------------------
+def test_model_on_a_device_that_is_not_current(cuda_dev):
+    """The reference works with a model on cuda:1 while cuda:0 is current; the C ABI launches on the current device with
+    raw pointers, so every entry point switches to the device of its state (engine.on_device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    D, F, Sy = _mods()
+    from flowfusion_b200 import _lib
+    torch.manual_seed(5)
+    sm = D.ScoreModel(D.MLP(6, 2, 8, [64, 64]), D.VPSDE(), no_sigma=True).eval()
+    base = torch.randn(300, 6, generator=gen(1)); cond = torch.randn(300, 2, generator=gen(2))
+    opts = {"step_t": torch.tensor([1e-3])}
+    outs_ = []
+    for d in ("cuda:0", "cuda:1"):
+        sm.to(d)
+        torch.cuda.set_device(0)                                    # cuda:0 stays current
+        x, _ = sm.sample_ode_from_base(base.to(d), cond.to(d), atol=1e-5, rtol=1e-5, options=opts)
+        x4, _ = sm.sample_ode_from_base(base.to(d), cond.to(d), method="rk4", options={"step_size": 0.25})
+        xs = sm.sample_sde((300, 6), cond.to(d), steps=20, x0=base.to(d), noise=torch.randn(20, 300, 6, generator=gen(3)).to(d))
+        lp = sm.log_prob(base.to(d), cond.to(d))
+        assert x.device == torch.device(d)
+        outs_.append([t.cpu() for t in (x, x4, xs, lp)])
+    for a, b in zip(*outs_):
+        assert torch.equal(a, b)
+    with pytest.raises(_lib.FFBError):                              # weights on cuda:1, state on cuda:0
+        sm.sample_ode_from_base(base.to("cuda:0"), cond.to("cuda:0"), atol=1e-5, rtol=1e-5, options=opts)

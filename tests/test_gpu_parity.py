@@ -140,6 +140,27 @@ def test_cfg4_euler_maruyama(cuda_dev):
         assert sm.check_stability()
 
 
+def test_em_stops_at_first_nan_like_the_reference(cuda_dev, capsys):
+    """`diffusion.py:560-563` on the GPU: a NaN planted in the caller's noise at (step 5, row 7) stops the whole batch (3
+    tiles) after step 5 and that step's x_mean comes back; same with the in-kernel engines' status words."""
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(11)
+    sm = D.ScoreModel(D.MLP(5, 0, 8, [32, 32]), D.VPSDE(), no_sigma=True).eval()
+    x0 = torch.randn(300, 5, generator=torch.Generator().manual_seed(1))
+    dw = torch.randn(20, 300, 5, generator=torch.Generator().manual_seed(2))
+    dw[5, 7, 2] = float("nan")
+    ref = port.sample_sde(port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True), x0, dw)
+    assert torch.isfinite(ref).all()
+    sm.to(cuda_dev)
+    x = sm.sample_sde((300, 5), steps=20, x0=x0.to(cuda_dev), noise=dw.to(cuda_dev))
+    assert rel_row_err(ref, x) < SAMPLE_TOL
+    assert sm.stopped_at_step == 5 and not sm.check_stability()
+    assert "Diffusion is not stable, NaN were produced. Stopped sampling." in capsys.readouterr().out
+    x = sm.sample_sde((300, 5), steps=20, x0=x0.to(cuda_dev), noise=torch.nan_to_num(dw).to(cuda_dev))
+    assert sm.stopped_at_step is None and sm.check_stability() and torch.isfinite(x).all()
+
+
 def test_em_ve_conditional(cuda_dev):
     meta, sd, ins, outs = load_golden("ve_em_cond")
     sm = _score_model(meta, sd, cuda_dev)

@@ -127,6 +127,27 @@ def test_cfg4_euler_maruyama():
         assert rel_row_err(outs[f"x_{run['steps']}"], x) < TOL
 
 
+def test_em_stops_at_first_nan_like_the_reference(capsys):
+    """`diffusion.py:560-563`: the first step that leaves a NaN anywhere in x stops the WHOLE batch and that step's x_mean
+    is returned.  A NaN planted in the caller's noise at (step 5, row 7) makes the step deterministic."""
+    from oracle import port
+    torch.manual_seed(11)
+    sm = D.ScoreModel(D.MLP(5, 0, 8, [32, 32]), D.VPSDE(), no_sigma=True).eval()
+    x0 = torch.randn(40, 5, generator=torch.Generator().manual_seed(1))
+    dw = torch.randn(20, 40, 5, generator=torch.Generator().manual_seed(2))
+    dw[5, 7, 2] = float("nan")
+    ref = port.sample_sde(port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True), x0, dw)
+    assert torch.isfinite(ref).all()                                     # x_mean of step 5: the NaN has not entered it yet
+    with patched_engine():
+        x = sm.sample_sde((40, 5), steps=20, x0=x0, noise=dw)
+    assert rel_row_err(ref, x) < TOL
+    assert sm.stopped_at_step == 5 and not sm.check_stability()
+    assert "Diffusion is not stable, NaN were produced. Stopped sampling." in capsys.readouterr().out
+    with patched_engine():
+        with pytest.raises(UnboundLocalError):                           # T < epsilon: the reference returns an unbound x_mean
+            D.ScoreModel(D.MLP(5, 0, 8, [32]), D.VPSDE(T=0.5, epsilon=0.9), no_sigma=True).eval().sample_sde((4, 5), steps=3, x0=x0[:4], noise=dw[:3, :4])
+
+
 def test_em_ve_conditional():
     meta, sd, ins, outs = load_golden("ve_em_cond")
     sm = _score_model(meta, sd)
