@@ -242,13 +242,85 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore its pinned-host allocations, first touch) to the CPUs of the NUMA node the GPU hangs
+    off: with 8 ranks on one box the host <-> device copies of the e2e leg otherwise cross the socket interconnect."""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus                      # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return None
+
+
+def tf32_gemm_tflops(dev):
+    """Measured dense TF32 GEMM rate (cuBLAS through torch.matmul, 8192^3, best of 5): the tensor pipe's own ceiling for
+    one of the three products of a 3xTF32 MAC."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev); b = torch.randn(n, n, device=dev)
+        best = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def shard_check(name, model, inp, out, rows=4096):
+    """After the timed region: the first `rows` rows of this rank's result against the CPU oracle (oracle/port.py) driven
+    with the step sequence the GPU solve recorded -- at N > 1 those steps came from the all-reduced global error norm, so
+    this is the data-plane check of the sharded solve.  Returns the largest per-row relative deviation."""
+    from oracle import port
+    st = getattr(model, "last_stats", None)
+    n = min(rows, out.shape[0])
+    if n == 0:
+        return None
+    sub = {k: v[:n].cpu() for k, v in inp.items()}
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}
+    replay = None if st is None else (list(st.dt_history), list(st.accept_history))
+    if name == "cfg2":
+        M = port.score_model_from_state_dict(sd, port.make_sde("vp"), True)
+        ref = port.sample_ode_from_base(M, sub["base"], sub["cond"], 1e-5, 1e-5,
+                                        options={"step_t": torch.tensor([1e-3]), "_replay": replay})[0]
+    elif name == "cfg4":
+        return None                                   # in-kernel Philox noise: covered by the golden-vector tests
+    elif name == "cfg5":
+        ref = port.symplectic_sample(port.symplectic_from_state_dict(sd), sub["z0"], None, 100)
+    else:
+        return None                                   # cfg1 / cfg3: the solve's first step size comes from a global norm too
+    got = out[:n].float().cpu()
+    num = (ref - got).abs().reshape(n, -1).amax(dim=1)
+    den = ref.abs().reshape(n, -1).amax(dim=1).clamp(min=1.0)
+    return {"rows": n, "max_rel_err": float((num / den).max()), "oracle": "oracle/port.py replaying the recorded step sequence"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=None, help="rows per GPU (default: the workload's size)")
+    ap.add_argument("--batch", type=int, default=None, help="rows per GPU (weak) / in total (strong); default: the workload's size")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank integrates its own batch; strong: ONE batch of the workload's size is sharded over the ranks")
+    ap.add_argument("--no-shard-check", action="store_true", help="skip the oracle check of a 4096-row slice after the timed region")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-scale", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -275,7 +347,12 @@ def main():
     _lib.load()
     name = args.workload
     w = WORKLOADS[name]
-    B = args.batch or w["B"]
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None        # before the pinned buffers are allocated
+    if args.scaling == "strong":
+        lo, hi = fdist.shard_bounds(args.batch or w["B"], rank, world)
+        B = hi - lo
+    else:
+        B = args.batch or w["B"]
     model = make_model(name, types.SimpleNamespace(D=D, F=F, Sy=Sy)).to(dev)
     host = {k: v.pin_memory() for k, v in make_inputs(name, B, rank).items()}
     inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -352,14 +429,29 @@ def main():
             e2e_pass(min(args.warmup, 2))      # untimed: the two-stream pattern warms the caching allocator's pools
             e2e_s = e2e_pass(args.steps)
     tmax = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    rows_all = torch.tensor([B], dtype=torch.int64, device=dev)
+    steps_identical = None
     if world > 1:
         td.all_reduce(tmax, op=td.ReduceOp.MAX)
+        td.all_reduce(rows_all, op=td.ReduceOp.SUM)
+        if stats is not None and stats.dt_history:
+            # every rank must have taken bit-identical step sizes and accept decisions (reference-exact dopri5: the
+            # FP64 partial sums of the error norm are all-reduced): gather the histories and compare them on rank 0
+            h = torch.zeros(2 * 256 + 2, dtype=torch.float64, device=dev)
+            n = min(len(stats.dt_history), 256)
+            h[0], h[1] = len(stats.dt_history), stats.accepted * 65536 + stats.rejected
+            h[2:2 + n] = torch.tensor(stats.dt_history[:n], dtype=torch.float64)
+            h[258:258 + n] = torch.tensor([float(a) for a in stats.accept_history[:n]], dtype=torch.float64)
+            allh = [torch.empty_like(h) for _ in range(world)]
+            td.all_gather(allh, h)
+            steps_identical = all(torch.equal(allh[0], x) for x in allh[1:])
     ms, e2e_ms = float(tmax[0]), float(tmax[1])
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
         return
-    total_rows = B * world * args.steps
+    check = None if args.no_shard_check else shard_check(name, model, inp, out)
+    total_rows = int(rows_all.item()) * args.steps
     value = total_rows / (ms * 1e-3)
     peaks, peak_src = measured_peaks()
     # ---- roofline of the dominant kernel: algorithmic FLOPs per launch / mean launch time ---------
@@ -373,6 +465,12 @@ def main():
         achieved = flop_per_launch / (k_ms / n_l * 1e-3) / 1e12
         ffma_peak = engine.ffma_peak_tflops()
         tensor_fp32_equiv = peaks["bf16_tflops"] / 6.0
+        tf32_gemm = tf32_gemm_tflops(dev)
+        clk_now = clk.summary().get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        # the tensor pipe's own rate: one kind::tf32 M128 N128 K8 MMA per 64 cycles per SM (csrc/tc_rate.cu,
+        # profiles/r02_tcgen05_rate_sustained.txt), three products per FP32-faithful MAC
+        sms = engine.device_info()["sm_count"]
+        instr_rate = 128 * 128 * 8 * 2 / 64.0 * sms * clk_now * 1e6 / 3.0 / 1e12
         # DRAM bytes of the dominant kernel from the committed ncu --set full capture, scaled to this launch's rows
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -385,11 +483,14 @@ def main():
                 "kernel": kname, "launches": n_l, "avg_launch_ms": k_ms / n_l, "share_of_step": k_ms / ms,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}) / 6 = 3xTF32 FP32-equivalent tensor peak",
                 "fp32_ffma2_peak_measured": ffma_peak, "frac_of_ffma2_peak": achieved / ffma_peak,
+                "tf32_gemm_tflops_measured": tf32_gemm, "frac_of_tf32_gemm_over_3": achieved / (tf32_gemm / 3.0),
+                "tcgen05_3xtf32_instruction_rate_tflops": instr_rate, "frac_of_instruction_rate": achieved / instr_rate,
                 "flop_per_launch": flop_per_launch}
     line = {"metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{name}: {w['desc']}", "rows_per_gpu": B, "nfe": nfe,
+            "config": {"workload": f"{name}: {w['desc']}", "rows_per_gpu": B, "global_rows": int(rows_all.item()), "nfe": nfe,
+                       "steps_identical_across_ranks": steps_identical, "shard_check": check, "numa": numa,
                        "dopri5_steps": None if stats is None else [stats.accepted, stats.rejected],
                        "dopri5_controller": getattr(stats, "controller", None),
                        "l2": "working set (state + derivative ping-pong buffers) exceeds the 126 MB L2; no flush needed",

@@ -144,9 +144,13 @@ class _Dopri5:
 
     def __init__(self, func, y0, rtol, atol, norm, stats, min_step=0, max_step=float("inf"),
                  first_step=None, step_t=None, jump_t=None, safety=0.9, ifactor=10.0,
-                 dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=torch.float64, **unused):
+                 dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=torch.float64, _replay=None, **unused):
         for k in unused:
             warnings.warn(f"dopri5: unexpected option {k!r}")
+        # TEST INFRASTRUCTURE (not a torchdiffeq option): `_replay = (dt_history, accept_history)` replays a recorded step
+        # sequence instead of running the controller.  bench.py uses it to check a slice of one rank's shard of a
+        # multi-GPU solve against this oracle: the step sizes of that solve came from the GLOBAL error norm.
+        self.replay = _replay
         if jump_t is not None:
             raise NotImplementedError("jump_t is outside the restated path (SURVEY 8f-4)")
         tdt = torch.promote_types(dtype, y0.dtype)
@@ -236,6 +240,10 @@ class _Dopri5:
             if on_grid:
                 t1 = nxt
                 dt = t1 - t0
+        if self.replay is not None:              # recorded (already clipped) step size of this attempt
+            i = len(self.stats.dt_history)
+            dt = torch.as_tensor(self.replay[0][i], dtype=self.tdtype, device=y0.device)
+            t1 = self.grid[self.grid_idx] if on_grid else t0 + dt
         y1, f1, err, k = self._rk_step(y0, f0, t0, dt, t1)
         tol = self.atol + self.rtol * torch.max(y0.abs(), y1.abs())
         ratio = self.norm(err / tol).abs()
@@ -244,6 +252,8 @@ class _Dopri5:
             accept = False
         if dt <= self.min_step:
             accept = True
+        if self.replay is not None:
+            accept = bool(self.replay[1][len(self.stats.dt_history)])
         st = self.stats
         st.dt_history.append(float(dt)); st.t_history.append(float(t0))
         st.accept_history.append(accept); st.ratio_history.append(float(ratio))
