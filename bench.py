@@ -51,7 +51,8 @@ WORKLOADS = {
                  B=1_000_000, cpu_B=400_000, metric="samples/s", unit="samples/s"),
     "cfg3": dict(desc="ODEFlow(16,[128]*4).log_prob, exact divergence trace, dopri5 atol=rtol=1e-5", B=4_000_000,
                  cpu_B=20_000, metric="log_prob evals/s", unit="evals/s"),
-    "cfg4": dict(desc="MLP(32,0,8,[128]*4)+VPSDE no_sigma: reverse-SDE Euler-Maruyama, 1000 steps, in-kernel Philox",
+    "cfg4": dict(B_strong=10_000_000,
+                 desc="MLP(32,0,8,[128]*4)+VPSDE no_sigma: reverse-SDE Euler-Maruyama, 1000 steps, in-kernel Philox",
                  B=1_250_000, cpu_B=20_000, metric="samples/s", unit="samples/s"),
     "cfg5": dict(desc="SymplecticMLP(32,0,8,[128]*4): forward-Euler sampling, 100 steps, 64-D phase space",
                  B=4_000_000, cpu_B=200_000, metric="samples/s", unit="samples/s"),
@@ -251,7 +252,7 @@ def bind_to_gpu_numa_node(index):
         bus = bus[-12:] if len(bus) > 12 else bus                      # 00000000:1b:00.0 -> 0000:1b:00.0
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
-            return None
+            return {"numa_node": node, "note": "the kernel reports no NUMA affinity for this GPU: nothing to bind"}
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
@@ -260,8 +261,8 @@ def bind_to_gpu_numa_node(index):
         if allowed:
             os.sched_setaffinity(0, allowed)
             return {"numa_node": node, "cpus": len(allowed)}
-    except Exception:
-        pass
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:160]}
     return None
 
 
@@ -348,8 +349,8 @@ def main():
     name = args.workload
     w = WORKLOADS[name]
     numa = bind_to_gpu_numa_node(local) if world > 1 else None        # before the pinned buffers are allocated
-    if args.scaling == "strong":
-        lo, hi = fdist.shard_bounds(args.batch or w["B"], rank, world)
+    if args.scaling == "strong":          # ONE batch of the BASELINE.json size (cfg3: 4 M points, cfg4: 10 M samples) over all ranks
+        lo, hi = fdist.shard_bounds(args.batch or w.get("B_strong", w["B"]), rank, world)
         B = hi - lo
     else:
         B = args.batch or w["B"]

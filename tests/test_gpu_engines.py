@@ -531,3 +531,42 @@ def test_model_on_a_device_that_is_not_current(cuda_dev):
         assert torch.equal(a, b)
     with pytest.raises(_lib.FFBError):                              # weights on cuda:1, state on cuda:0
         sm.sample_ode_from_base(base.to("cuda:0"), cond.to("cuda:0"), atol=1e-5, rtol=1e-5, options=opts)
+
+
+# ---------------------------------------------------------------------------------------------
+# repeatability stress (compute-sanitizer is closed on the GPU pool, profiles/r02_sanitizer_unavailable.txt): a data race in
+# the mbarrier / tensor-memory hand-offs of any engine shows as a bit difference between runs on the same inputs
+# ---------------------------------------------------------------------------------------------
+def test_repeatability_stress(cuda_dev):
+    D, F, Sy = _mods()
+    from flowfusion_b200 import solver
+    torch.manual_seed(1234)
+    sm = D.ScoreModel(D.MLP(16, 4, 8, [128] * 4), D.VPSDE(), no_sigma=True).eval().to(cuda_dev)
+    B = 148 * 128 * 2 + 333                                       # three rounds of the dual-tile engine, ragged last tile
+    base = torch.randn(B, 16, generator=gen(2)).to(cuda_dev); cond = torch.randn(B, 4, generator=gen(3)).to(cuda_dev)
+    opts = {"step_t": torch.tensor([1e-3])}
+    runs = {}
+    for rep in range(12):
+        for e, ctl in ((4, "device"), (3, "device"), (4, "host")):
+            with engine(e), solver.controller(ctl):
+                x, _ = sm.sample_ode_from_base(base, cond, atol=1e-5, rtol=1e-5, options=opts)
+            runs.setdefault("dopri5_" + ctl, x.clone())         # (the two controllers differ in the last place of sqrt / sin / cos)
+            assert torch.equal(runs["dopri5_" + ctl], x), (rep, e, ctl)
+        x4, _ = sm.sample_ode_from_base(base, cond, method="rk4", options={"step_size": 0.25})
+        runs.setdefault("rk4", x4.clone())
+        assert torch.equal(runs["rk4"], x4), rep
+        xe = sm.sample_sde((B, 16), cond, steps=8, x0=base, seed=7)
+        runs.setdefault("em", xe.clone())
+        assert torch.equal(runs["em"], xe), rep
+    torch.manual_seed(1234)
+    fl = F.ODEFlow(16, [128] * 4).eval().to(cuda_dev)
+    xs = torch.randn(148 * 7 + 5, 16, generator=gen(4)).to(cuda_dev)
+    sh = D.ScoreModel(D.MLP(16, 0, 8, [128] * 2), D.VPSDE(), no_sigma=True, hutchinson=True).eval().to(cuda_dev)
+    probes = torch.sign(torch.randn(xs.shape[0], 16, generator=gen(5))).to(cuda_dev)
+    for rep in range(12):
+        lp = fl.log_prob(xs)
+        runs.setdefault("lp", lp.clone())
+        assert torch.equal(runs["lp"], lp), rep
+        lh = sh.log_prob(xs, probes=probes)
+        runs.setdefault("lh", lh.clone())
+        assert torch.equal(runs["lh"], lh), rep
