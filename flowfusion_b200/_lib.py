@@ -137,7 +137,8 @@ class RkCombineArgs(C.Structure):
 
 
 class RkFinishArgs(C.Structure):
-    _fields_ = [("batch", C.c_int64), ("dim", C.c_int32), ("final", C.c_int32), ("y0", C.c_void_p),
+    _fields_ = [("batch", C.c_int64), ("dim", C.c_int32), ("final", C.c_int32), ("n_k", C.c_int32), ("_pad", C.c_int32),
+                ("y0", C.c_void_p),
                 ("y1", C.c_void_p), ("k", C.c_void_p * 7), ("lp0", C.c_void_p), ("dlp", C.c_void_p * 7),
                 ("lp1", C.c_void_p), ("cl", C.c_float * 6), ("ce", C.c_float * 7), ("cm", C.c_float * 7),
                 ("dt", C.c_float), ("atol", C.c_float), ("rtol", C.c_float), ("x_interp", C.c_float),

@@ -483,23 +483,27 @@ __global__ void k_rk_finish(const __grid_constant__ ffb_rk_finish_args a) {
   const int64_t nx = a.batch * a.dim;
   const int64_t step = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double ex = 0.0, el = 0.0, nonfinite = 0.0;
+  const int nk = (a.n_k >= 2 && a.n_k <= 7) ? a.n_k : 7;       // stage derivatives of the method; f1 = the last one
   for (int64_t i = i0; i < nx; i += step) {
     const float y0 = a.y0[i], y1 = a.y1[i];
     float kv[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) kv[j] = a.k[j][i];
+    for (int j = 0; j < 7; ++j) kv[j] = (j < nk) ? a.k[j][i] : 0.0f;
+    float f1 = kv[0];
+#pragma unroll
+    for (int j = 1; j < 7; ++j) f1 = (j == nk - 1) ? kv[j] : f1;
     if (!is_finite_f(y0)) nonfinite += 1.0;
     float err = __fmul_rn(kv[0], a.ce[0]);
 #pragma unroll
-    for (int j = 1; j < 7; ++j) err = fmaf(kv[j], a.ce[j], err);
+    for (int j = 1; j < 7; ++j) err = (j < nk) ? fmaf(kv[j], a.ce[j], err) : err;
     const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0), fabsf(y1))));
     const float q = __fdiv_rn(err, tol);
     ex += (double)q * q;
     if (a.final) {
       float mid = __fmul_rn(kv[0], a.cm[0]);
 #pragma unroll
-      for (int j = 1; j < 7; ++j) mid = fmaf(kv[j], a.cm[j], mid);
-      a.y_out[i] = dense_output(y0, y1, __fadd_rn(y0, mid), kv[0], kv[6], a.dt, a.x_interp);
+      for (int j = 1; j < 7; ++j) mid = (j < nk) ? fmaf(kv[j], a.cm[j], mid) : mid;
+      a.y_out[i] = dense_output(y0, y1, __fadd_rn(y0, mid), kv[0], f1, a.dt, a.x_interp);
     }
   }
   if (a.lp0) {
@@ -507,15 +511,18 @@ __global__ void k_rk_finish(const __grid_constant__ ffb_rk_finish_args a) {
       const float l0 = a.lp0[s];
       float kl[7];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) kl[j] = a.dlp[j][s];
+      for (int j = 0; j < 7; ++j) kl[j] = (j < nk) ? a.dlp[j][s] : 0.0f;
+      float fl1 = kl[0];
+#pragma unroll
+      for (int j = 1; j < 7; ++j) fl1 = (j == nk - 1) ? kl[j] : fl1;
       if (!is_finite_f(l0)) nonfinite += 1.0;
       float acc = __fmul_rn(kl[0], a.cl[0]);
 #pragma unroll
-      for (int j = 1; j < 6; ++j) acc = fmaf(kl[j], a.cl[j], acc);
+      for (int j = 1; j < 6; ++j) acc = (j < nk) ? fmaf(kl[j], a.cl[j], acc) : acc;
       const float l1 = __fadd_rn(l0, acc);
       float err = __fmul_rn(kl[0], a.ce[0]);
 #pragma unroll
-      for (int j = 1; j < 7; ++j) err = fmaf(kl[j], a.ce[j], err);
+      for (int j = 1; j < 7; ++j) err = (j < nk) ? fmaf(kl[j], a.ce[j], err) : err;
       const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(l0), fabsf(l1))));
       const float q = __fdiv_rn(err, tol);
       el += (double)q * q;
@@ -523,8 +530,8 @@ __global__ void k_rk_finish(const __grid_constant__ ffb_rk_finish_args a) {
       if (a.final) {
         float mid = __fmul_rn(kl[0], a.cm[0]);
 #pragma unroll
-        for (int j = 1; j < 7; ++j) mid = fmaf(kl[j], a.cm[j], mid);
-        a.lp_out[s] = dense_output(l0, l1, __fadd_rn(l0, mid), kl[0], kl[6], a.dt, a.x_interp);
+        for (int j = 1; j < 7; ++j) mid = (j < nk) ? fmaf(kl[j], a.cm[j], mid) : mid;
+        a.lp_out[s] = dense_output(l0, l1, __fadd_rn(l0, mid), kl[0], fl1, a.dt, a.x_interp);
       }
     }
   }
@@ -632,7 +639,8 @@ extern "C" int ffb_rk_combine(const ffb_rk_combine_args* a, void* stream) {
 
 extern "C" int ffb_rk_finish(const ffb_rk_finish_args* a, void* stream) {
   if (!a || !a->y0 || !a->y1 || !a->partials) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: y0, y1 and partials are required");
-  for (int j = 0; j < 7; ++j)
+  if (a->n_k != 0 && (a->n_k < 2 || a->n_k > 7)) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: n_k must be 0 (= 7) or 2..7");
+  for (int j = 0; j < (a->n_k ? a->n_k : 7); ++j)
     if (!a->k[j] || (a->lp0 && !a->dlp[j])) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: missing stage derivative");
   if (a->lp0 && !a->lp1) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: lp1 is required with lp0");
   if (a->final && (!a->y_out || (a->lp0 && !a->lp_out))) return ffb_fail(FFB_ERR_ARG, "ffb_rk_finish: final needs y_out (and lp_out)");

@@ -266,6 +266,7 @@ def _device_program(sde, W_cpu, pi_cpu, use_sigma, sde_mode):
 # ScoreModel (`diffusion.py:124-815`)
 # ----------------------------------------------------------------------------------------------
 _METHODS = {"euler": L.M_EULER, "midpoint": L.M_MIDPOINT, "rk4": L.M_RK4}
+_IMPLEMENTED = "dopri5, bosh3, adaptive_heun, fehlberg2, rk4, euler, midpoint"
 
 
 class ScoreModel(torch.nn.Module):
@@ -503,7 +504,7 @@ class ScoreModel(torch.nn.Module):
             dt, ev = _fixed_tables(self._program(), method, t0, t1, options)
             return E.staged_fixed(be, method, dt, ev)
         if method != "dopri5":
-            raise NotImplementedError(f"method {method!r} is not implemented (dopri5, rk4, euler, midpoint)")
+            raise NotImplementedError(f"method {method!r} is not implemented with Hutch++ / XTrace (dopri5, rk4, euler, midpoint)")
         be = E.StagedBackend(self._field(L.DIV_EXACT), y0, est, cond=cond)
         self.last_stats = S.dopri5(be, self._program(), t0, t1, rtol, atol, options, group=self._group())
         return be.output()
@@ -523,13 +524,13 @@ class ScoreModel(torch.nn.Module):
         prog = self._program()
         with_lp = div_mode != L.DIV_NONE
         method = "dopri5" if method is None else method
-        if method == "dopri5":
+        if method in S.ADAPTIVE_METHODS:          # dopri5 (fused attempt kernel), bosh3, adaptive_heun, fehlberg2 (stage by stage)
             be = E.CudaBackend(field, y0, cond=cond, probes=probes, with_lp=with_lp)
-            self.last_stats = S.dopri5(be, prog, t0, t1, rtol, atol, options, group=self._group())
+            self.last_stats = S.adaptive(method, be, prog, t0, t1, rtol, atol, options, group=self._group())
             return be.output()
         if method in _METHODS:
             return _solve_fixed(field, prog, method, y0, cond, probes, t0, t1, options, with_lp)
-        raise NotImplementedError(f"method {method!r} is not implemented (dopri5, rk4, euler, midpoint)")
+        raise NotImplementedError(f"method {method!r} is not implemented ({_IMPLEMENTED})")
 
 
 def _fixed_tables(prog, method, t0, t1, options):

@@ -354,6 +354,74 @@ class CudaBackend:
                 L.check(self.lib.ffb_dopri5_attempt(C.byref(self.field.c), C.byref(a), self._stream), "ffb_dopri5_attempt")
         return self._reduce()
 
+    # -- other adaptive Runge-Kutta tableaus (bosh3, adaptive_heun, fehlberg2): evaluation-at-a-time attempts -------------
+    def _rk_buffers(self, n_k):
+        if getattr(self, "_rk_n", 0) < n_k:
+            dev, B, D = self.dev, self.B, self.D
+            self._rk_k = [torch.empty(B, D, device=dev) for _ in range(max(n_k - 2, 0))]          # k2 .. k_{n-1}
+            self._rk_d = [torch.empty(B, device=dev) for _ in range(max(n_k - 2, 0))] if self.with_lp else []
+            self._rk_ystage = torch.empty(B, D, device=dev)
+            self._rk_partials = torch.zeros(L.STAGED_BLOCKS, L.NPART, dtype=torch.float64, device=dev)
+            self._rk_sums = torch.zeros(L.NPART, dtype=torch.float64, device=dev)
+            self._rk_cargs, self._rk_fargs = L.RkCombineArgs(), L.RkFinishArgs()
+            self._rk_n = n_k
+
+    def _feval_into(self, y, ev_row, f_out, dlp_out):
+        """f(y) -> f_out (and the divergence -> dlp_out) with one ``ffb_field_eval`` launch."""
+        a = self.eargs
+        a.batch, a.y, a.fbase, a.dlpbase, a.h = self.B, _ptr(y), None, None, 0.0
+        a.cond, a.probes, a.cond_state = _ptr(self.cond), _ptr(self.probes), _ptr(self.cond_state)
+        a.f, a.dlp, a.jac = _ptr(f_out), _ptr(dlp_out), None
+        ev_rows_to_struct(a.ev, ev_row[None, :])
+        a.atol, a.rtol, a.norms, a.cond_in_state = 1.0, 0.0, 0, int(self.cond_in_state)
+        a.partials, a.status, a.scratch = _ptr(self.partials), _ptr(self.status), _ptr(self.scratch)
+        with _timed("field_eval", self.B):
+            L.check(self.lib.ffb_field_eval(C.byref(self.field.c), C.byref(a), self._stream), "ffb_field_eval")
+
+    def _combine_into(self, y0, ks, coefs, out):
+        ca = self._rk_cargs
+        ca.n, ca.n_terms, ca.y0, ca.out = y0.numel(), len(ks), _ptr(y0), _ptr(out)
+        for j in range(7):
+            ca.k[j] = ks[j].data_ptr() if j < len(ks) else None
+            ca.coef[j] = float(coefs[j]) if j < len(ks) else 0.0
+        L.check(self.lib.ffb_rk_combine(C.byref(ca), self._stream), "ffb_rk_combine")
+
+    def attempt_rk(self, tab, ev, dt32, atol, rtol, final, x_interp):
+        """One attempted step of the adaptive Runge-Kutta method ``tab`` (solver.Tableau): per stage ``ffb_rk_combine``
+        (stage input, torchdiffeq's ``y0 + k[..., :i+1] @ (beta_i dt)``) + ``ffb_field_eval``, then ``ffb_rk_finish``
+        (error sums, log-det column, dense output).  Same partial sums as ``attempt``."""
+        n_k = len(tab.alpha) + 1
+        self._rk_buffers(n_k)
+        c, n = self.cur, 1 - self.cur
+        ks = [self.f[c]] + self._rk_k[: n_k - 2] + [self.f[n]]               # k1 .. k_n ; f1 = the last one
+        dks = ([self.dlp[c]] + self._rk_d[: n_k - 2] + [self.dlp[n]]) if self.with_lp else [None] * n_k
+        dt = np.float32(dt32)
+        if self.B:
+            for i in range(n_k - 1):
+                last = (i == n_k - 2)
+                out = self.y[n] if (last and tab.fsal) else self._rk_ystage
+                self._combine_into(self.y[c], ks[: i + 1], [np.float32(b) * dt for b in tab.beta[i]], out)
+                self._feval_into(out, ev[i], ks[i + 1], dks[i + 1])
+            if not tab.fsal:                                                  # y1 = y0 + k @ (dt c_sol)
+                self._combine_into(self.y[c], ks, [np.float32(cs) * dt for cs in tab.c_sol], self.y[n])
+            fa = self._rk_fargs
+            fa.batch, fa.dim, fa.final, fa.n_k = self.B, self.D, int(final), n_k
+            fa.y0, fa.y1 = _ptr(self.y[c]), _ptr(self.y[n])
+            fa.lp0, fa.lp1 = (_ptr(self.lp[c]), _ptr(self.lp[n])) if self.with_lp else (None, None)
+            for j in range(7):
+                fa.k[j] = ks[j].data_ptr() if j < n_k else None
+                fa.dlp[j] = dks[j].data_ptr() if (j < n_k and self.with_lp) else None
+                fa.ce[j] = float(np.float32(tab.c_err[j]) * dt) if j < n_k else 0.0
+                fa.cm[j] = float(np.float32(tab.c_mid[j]) * dt) if j < n_k else 0.0
+            for j in range(6):
+                fa.cl[j] = float(np.float32(tab.c_sol[j]) * dt) if j < n_k else 0.0
+            fa.dt, fa.atol, fa.rtol, fa.x_interp = float(dt), float(atol), float(rtol), float(x_interp)
+            fa.y_out, fa.lp_out, fa.partials = _ptr(self.y_out), _ptr(self.lp_out), _ptr(self._rk_partials)
+            L.check(self.lib.ffb_rk_finish(C.byref(fa), self._stream), "ffb_rk_finish")
+        L.check(self.lib.ffb_reduce_partials(_ptr(self._rk_partials), L.STAGED_BLOCKS, _ptr(self._rk_sums), self._stream),
+                "ffb_reduce_partials")
+        return self._rk_sums
+
     def accept(self):
         self.cur = 1 - self.cur
 

@@ -26,7 +26,7 @@ from . import _lib as L
 from . import dist as _dist
 from . import engine as E
 from . import solver as S
-from .diffusion import _METHODS, _eval_once, _solve_fixed
+from .diffusion import _IMPLEMENTED, _METHODS, _eval_once, _solve_fixed
 
 
 def _raw_time_program(times32: np.ndarray) -> np.ndarray:
@@ -92,14 +92,14 @@ class _FlowBase(nn.Module):
         field = self._field(div_mode)
         with_lp = div_mode != L.DIV_NONE
         method = "dopri5" if method is None else method
-        if method == "dopri5":
+        if method in S.ADAPTIVE_METHODS:
             be = E.CudaBackend(field, y0, cond=cond_net, with_lp=with_lp, cond_in_state=cond_state is not None,
                                cond_state=cond_state)
-            self.last_stats = S.dopri5(be, _raw_time_program, t0, t1, rtol, atol, options, group=self._group())
+            self.last_stats = S.adaptive(method, be, _raw_time_program, t0, t1, rtol, atol, options, group=self._group())
             return be.output()
         if method in _METHODS:
             return _solve_fixed(field, _raw_time_program, method, y0, cond_net, None, t0, t1, options, with_lp)
-        raise NotImplementedError(f"method {method!r} is not implemented (dopri5, rk4, euler, midpoint)")
+        raise NotImplementedError(f"method {method!r} is not implemented ({_IMPLEMENTED})")
 
     def _base_logprob(self, xT, log_jacobian):
         lp = E.gaussian_logprob(xT, log_jacobian, 1.0)

@@ -56,6 +56,42 @@ C_MID32 = _C_MID.astype(f32)
 
 
 @dataclasses.dataclass
+class Tableau:
+    """An adaptive explicit Runge-Kutta method as torchdiffeq 0.2.x defines it (rk_common._ButcherTableau + the mid-point
+    weights of its interpolant), coefficients rounded to float32 like the solver state.  ``fsal``: c_sol equals the last
+    beta row, i.e. the last stage's input is y1."""
+    name: str
+    order: int
+    alpha: np.ndarray
+    beta: list
+    c_sol: np.ndarray
+    c_err: np.ndarray
+    c_mid: np.ndarray
+
+    @property
+    def fsal(self) -> bool:
+        return bool(self.c_sol[-1] == 0 and len(self.beta[-1]) == len(self.c_sol) - 1
+                    and np.array_equal(self.c_sol[:-1], self.beta[-1]))
+
+
+def _tab(name, order, alpha, beta, c_sol, c_err, c_mid) -> Tableau:
+    r = lambda v: np.array(v, f64).astype(f32)        # noqa: E731
+    return Tableau(name, order, r(alpha), [r(b) for b in beta], r(c_sol), r(c_err), r(c_mid))
+
+
+# torchdiffeq/_impl/{dopri5,bosh3,adaptive_heun,fehlberg2}.py
+TABLEAUS = {
+    "dopri5": _tab("dopri5", 5, _ALPHA, _BETA, list(_BETA[-1]) + [0.0], _C_ERR, _C_MID),
+    "bosh3": _tab("bosh3", 3, [1 / 2, 3 / 4, 1.0], [[1 / 2], [0.0, 3 / 4], [2 / 9, 1 / 3, 4 / 9]], [2 / 9, 1 / 3, 4 / 9, 0.0],
+                  [2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8], [0.0, 0.5, 0.0, 0.0]),
+    "adaptive_heun": _tab("adaptive_heun", 2, [1.0], [[1.0]], [0.5, 0.5], [0.5, -0.5], [0.5, 0.0]),
+    "fehlberg2": _tab("fehlberg2", 2, [1 / 2, 1.0], [[1 / 2], [1 / 256, 255 / 256]], [1 / 512, 255 / 256, 1 / 512],
+                      [-1 / 512, 0.0, 1 / 512], [0.0, 0.5, 0.0]),
+}
+ADAPTIVE_METHODS = tuple(TABLEAUS)
+
+
+@dataclasses.dataclass
 class SolveStats:
     method: str = ""
     nfe: int = 0
@@ -126,8 +162,15 @@ def _mixed(values: Sequence[np.float32]) -> np.float32:
 # ----------------------------------------------------------------------------------------------
 # adaptive Dormand-Prince 5(4)
 # ----------------------------------------------------------------------------------------------
+def adaptive(method: str, backend, program, t0, t1, rtol, atol, options=None, group=None) -> SolveStats:
+    """``torchdiffeq.odeint(..., method=method)`` for the adaptive Runge-Kutta methods of ``TABLEAUS``: dopri5 runs on the fused
+    attempt kernel (with the device-side controller when it applies), bosh3 / adaptive_heun / fehlberg2 evaluation at a
+    time (``backend.attempt_rk``) under the same host controller with the method's own order."""
+    return dopri5(backend, program, t0, t1, rtol, atol, options, group, method=method)
+
+
 def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: float, rtol: float,
-           atol: float, options: Optional[dict] = None, group=None) -> SolveStats:
+           atol: float, options: Optional[dict] = None, group=None, method: str = "dopri5") -> SolveStats:
     """Integrate the backend's state from ``t0`` to ``t1`` (float32-representable floats).
 
     ``program(times32)`` maps float32 *user* times, shape (n,), to the (n, EV_FLOATS) rows of
@@ -136,12 +179,16 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
     (the C ABI launches on the current device with raw pointers)."""
     dev = getattr(backend, "dev", None)
     if dev is None or torch.device(dev).type != "cuda":          # the CPU model of the kernels (tests/kernel_model.py)
-        return _dopri5(backend, program, t0, t1, rtol, atol, options, group)
+        return _dopri5(backend, program, t0, t1, rtol, atol, options, group, TABLEAUS[method])
     with torch.cuda.device(dev):
-        return _dopri5(backend, program, t0, t1, rtol, atol, options, group)
+        return _dopri5(backend, program, t0, t1, rtol, atol, options, group, TABLEAUS[method])
 
 
-def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None) -> SolveStats:
+def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None, tab: Tableau = None) -> SolveStats:
+    tab = TABLEAUS["dopri5"] if tab is None else tab
+    fused = tab.name == "dopri5"                   # the fused 6-evaluation attempt kernel; other tableaus go stage by stage
+    if not fused and not hasattr(backend, "attempt_rk"):
+        raise NotImplementedError(f"method {tab.name!r} is not available with this divergence estimator (dopri5 is)")
     opts = dict(options or {})
     for k in ("norm", "dtype"):
         opts.pop(k, None)
@@ -157,7 +204,7 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None) -> S
     if opts:
         raise TypeError(f"unsupported dopri5 options: {sorted(opts)}")
 
-    st = SolveStats(method="dopri5")
+    st = SolveStats(method=tab.name)
     reverse = t0 > t1
     sgn = -1.0 if reverse else 1.0
     ts, te = (f64(-t0), f64(-t1)) if reverse else (f64(t0), f64(t1))
@@ -202,7 +249,7 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None) -> S
             if d1 <= 1e-15 and d2 <= 1e-15:
                 h1 = max(f32(1e-6), h0 * f32(1e-3))
             else:
-                h1 = (f32(0.01) / max(d1, d2)) ** f32(1.0 / 5.0)
+                h1 = (f32(0.01) / max(d1, d2)) ** f32(1.0 / float(tab.order))     # _select_initial_step(order - 1): 1 / (order - 1 + 1)
             h1 = abs(h1)
             dt = f64(min(f32(100) * h0, h1))
     else:
@@ -218,7 +265,7 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None) -> S
     grid_idx = min(bisect.bisect(grid, float(ts)), len(grid) - 1) if grid else 0
 
     spec = getattr(program, "spec", None)
-    if (_CONTROLLER != "host" and spec is not None and len(grid) <= L.CTL_MAX_GRID and counts["x"] > 0
+    if (fused and _CONTROLLER != "host" and spec is not None and len(grid) <= L.CTL_MAX_GRID and counts["x"] > 0
             and getattr(backend, "ctl_supported", lambda: False)()
             and (_CONTROLLER == "device" or backend.ctl_attempt_ms_estimate(_rows_per_rank(counts, backend, group))
                  < _CTL_AUTO_MAX_ATTEMPT_MS)):
@@ -259,20 +306,24 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None) -> S
                     t1s = nxt
                     dts = t1s - t
             t0_32, dt_32, t1_32 = f32(t), f32(dts), f32(t1s)
-            times = np.empty(6, f32)
-            for i in range(6):
-                if ALPHA32[i] == 1.0:
+            nst = len(tab.alpha)
+            times = np.empty(nst, f32)
+            for i in range(nst):
+                if tab.alpha[i] == 1.0:
                     times[i] = np.nextafter(t1_32, t1_32 - f32(1))
                 else:
-                    times[i] = t0_32 + ALPHA32[i] * dt_32
+                    times[i] = t0_32 + tab.alpha[i] * dt_32
             ev = rows(times)
+            final = not (te > t1s)
+            x_interp = f32((te - t) / (t1s - t)) if final else f32(0)
+        if fused:
             cb = BETA32 * dt_32
             ce = dt_32 * C_ERR32
             cm = dt_32 * C_MID32
-            final = not (te > t1s)
-            x_interp = f32((te - t) / (t1s - t)) if final else f32(0)
-        s = _allreduce(backend.attempt(ev, cb, ce, cm, dt_32, atol32, rtol32, final, x_interp), group).cpu().numpy()
-        st.nfe += 6
+            s = _allreduce(backend.attempt(ev, cb, ce, cm, dt_32, atol32, rtol32, final, x_interp), group).cpu().numpy()
+        else:
+            s = _allreduce(backend.attempt_rk(tab, ev, dt_32, atol32, rtol32, final, x_interp), group).cpu().numpy()
+        st.nfe += nst
         st.launches += 2
         n_steps += 1
         if s[L.P_NONFINITE] > 0:
@@ -300,7 +351,7 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None) -> S
             else:
                 dfac = f64(1.0) if ratio < 1 else dfactor
                 r = f64(ratio)
-                nxt_dt = dts * np.minimum(ifactor, np.maximum(safety / r ** f64(0.2), dfac))
+                nxt_dt = dts * np.minimum(ifactor, np.maximum(safety / r ** (f64(1.0) / f64(tab.order)), dfac))
             dt = f64(np.clip(nxt_dt, min_step, max_step)) if not np.isnan(nxt_dt) else f64(np.nan)
     assert done, "internal: integration loop ended without a final step"
     return st

@@ -357,17 +357,21 @@ typedef struct {
 } ffb_rk_combine_args;
 int ffb_rk_combine(const ffb_rk_combine_args* args, void* stream);
 
-/* end of one staged dopri5 attempt: log-det column of y1, error partial sums (P_X_ERR, P_LP_ERR,
- * P_NONFINITE), and the dense output at t_end when `final` (same statements as the fused attempt kernel) */
+/* end of one staged attempt of an adaptive Runge-Kutta method (dopri5: 7 stage derivatives; bosh3: 4; adaptive_heun: 2;
+ * fehlberg2: 3): log-det column of y1, error partial sums (P_X_ERR, P_LP_ERR, P_NONFINITE), and the dense output at
+ * t_end when `final` (same statements as the fused attempt kernel).  f1 is the LAST stage derivative, k[n_k - 1]
+ * (torchdiffeq rk_common._runge_kutta_step, also for tableaus that are not FSAL). */
 typedef struct {
   int64_t batch;
   int32_t dim;
   int32_t final;
-  const float* y0; const float* y1;       /* (B, D): y1 is the 7th stage's input            */
-  const float* k[7];                      /* k1..k7, (B, D) each                            */
+  int32_t n_k;                            /* stage derivatives in k / dlp: 2..7 (0 = 7)     */
+  int32_t _pad;
+  const float* y0; const float* y1;       /* (B, D): y1 = y0 + k @ (dt c_sol)               */
+  const float* k[7];                      /* k1..k_{n_k}, (B, D) each; the rest is ignored  */
   const float* lp0; const float* dlp[7];  /* log-det column and its 7 stage derivatives, or NULL */
   float* lp1;
-  float cl[6];                            /* fl32(beta_6j * dt)                             */
+  float cl[6];                            /* fl32(c_sol_j * dt), j < min(n_k, 6)            */
   float ce[7], cm[7];
   float dt, atol, rtol, x_interp;
   float* y_out; float* lp_out;

@@ -139,10 +139,24 @@ _DP_C_MID = [
 ]
 
 
-class _Dopri5:
-    order = 5
+# The other adaptive Runge-Kutta solvers of torchdiffeq 0.2.x (bosh3.py, adaptive_heun.py, fehlberg2.py): same driver
+# (rk_common.RKAdaptiveStepsizeODESolver), other tableau and order.  c_sol of adaptive_heun / fehlberg2 is NOT the last beta
+# row: y1 = y0 + k @ (dt c_sol) is then formed separately, while f1 is still taken from the last stage (rk_common.py).
+_TABLEAUS = {
+    "dopri5": dict(order=5, alpha=_DP_ALPHA, beta=_DP_BETA, c_sol=_DP_C_SOL, c_err=_DP_C_ERR, c_mid=_DP_C_MID),
+    "bosh3": dict(order=3, alpha=[1 / 2, 3 / 4, 1.0], beta=[[1 / 2], [0.0, 3 / 4], [2 / 9, 1 / 3, 4 / 9]],
+                  c_sol=[2 / 9, 1 / 3, 4 / 9, 0.0], c_err=[2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8],
+                  c_mid=[0.0, 0.5, 0.0, 0.0]),
+    "adaptive_heun": dict(order=2, alpha=[1.0], beta=[[1.0]], c_sol=[0.5, 0.5], c_err=[0.5, -0.5], c_mid=[0.5, 0.0]),
+    "fehlberg2": dict(order=2, alpha=[1 / 2, 1.0], beta=[[1 / 2], [1 / 256, 255 / 256]], c_sol=[1 / 512, 255 / 256, 1 / 512],
+                      c_err=[-1 / 512, 0.0, 1 / 512], c_mid=[0.0, 0.5, 0.0]),
+}
 
-    def __init__(self, func, y0, rtol, atol, norm, stats, min_step=0, max_step=float("inf"),
+
+class _Dopri5:
+    """The adaptive explicit Runge-Kutta driver; `tableau` picks the method (default: Dormand-Prince 5(4))."""
+
+    def __init__(self, func, y0, rtol, atol, norm, stats, tableau="dopri5", min_step=0, max_step=float("inf"),
                  first_step=None, step_t=None, jump_t=None, safety=0.9, ifactor=10.0,
                  dfactor=0.2, max_num_steps=2 ** 31 - 1, dtype=torch.float64, _replay=None, **unused):
         for k in unused:
@@ -166,11 +180,15 @@ class _Dopri5:
         self.step_t = None if step_t is None else as64(step_t)
         sd = dict(dtype=y0.dtype, device=dev)
         t64 = lambda v: torch.tensor(v, dtype=torch.float64)  # noqa: E731
-        self.alpha = t64(_DP_ALPHA).to(**sd)
-        self.beta = [t64(b).to(**sd) for b in _DP_BETA]
-        self.c_sol = t64(_DP_C_SOL).to(**sd)
-        self.c_err = t64(_DP_C_ERR).to(**sd)
-        self.c_mid = t64(_DP_C_MID).to(**sd)
+        tb = _TABLEAUS[tableau]
+        self.order = tb["order"]
+        self.alpha = t64(tb["alpha"]).to(**sd)
+        self.beta = [t64(b).to(**sd) for b in tb["beta"]]
+        self.c_sol = t64(tb["c_sol"]).to(**sd)
+        self.c_err = t64(tb["c_err"]).to(**sd)
+        self.c_mid = t64(tb["c_mid"]).to(**sd)
+        self.fsal = bool(self.c_sol[-1] == 0 and len(self.c_sol) - 1 == len(self.beta[-1])
+                         and (self.c_sol[:-1] == self.beta[-1]).all())
 
     # ---- T6 ----
     def _initial_step(self, t0, y0, f0):
@@ -212,7 +230,7 @@ class _Dopri5:
     def _rk_step(self, y0, f0, t0, dt, t1):
         sd = y0.dtype
         t0, dt, t1 = t0.to(sd), dt.to(sd), t1.to(sd)
-        k = torch.empty(*f0.shape, len(_DP_ALPHA) + 1, dtype=sd, device=y0.device)
+        k = torch.empty(*f0.shape, len(self.alpha) + 1, dtype=sd, device=y0.device)
         k[..., 0] = f0
         yi = y0
         for i, (a_i, b_i) in enumerate(zip(self.alpha, self.beta)):
@@ -222,7 +240,10 @@ class _Dopri5:
                 ti, perturb = t0 + a_i * dt, _NONE
             yi = y0 + k[..., : i + 1].matmul(b_i * dt).view_as(f0)
             k[..., i + 1] = self.func(ti, yi, perturb)
-        # FSAL: c_sol equals the last beta row, so the 7th stage input is y1
+        # FSAL tableaus: c_sol equals the last beta row, so the last stage input is y1; otherwise y1 is formed from c_sol
+        # -- and f1 is the last stage's derivative either way (rk_common._runge_kutta_step)
+        if not self.fsal:
+            yi = y0 + k.matmul(dt * self.c_sol).view_as(f0)
         y1, f1 = yi, k[..., -1]
         err = k.matmul(dt * self.c_err)
         return y1, f1, err, k
@@ -423,12 +444,12 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
         t = t.to(y0.device)
     f = _Wrapped(func, shapes, reverse, stats)
-    if method == "dopri5":
-        solver = _Dopri5(f, y0, rtol, atol, stats=stats, **options)
+    if method in _TABLEAUS:
+        solver = _Dopri5(f, y0, rtol, atol, stats=stats, tableau=method, **options)
     elif method in _FIXED:
         solver = _FixedGrid(method, f, y0, stats, rtol=rtol, atol=atol, **options)
     else:
-        raise ValueError('Invalid method "{}" (restated: dopri5, euler, midpoint, rk4)'.format(method))
+        raise ValueError('Invalid method "{}" (restated: dopri5, bosh3, adaptive_heun, fehlberg2, euler, midpoint, rk4)'.format(method))
     sol = solver.integrate(t)
     if shapes is not None:
         sol = _split(sol, (len(t),), shapes)

@@ -168,6 +168,42 @@ class FakeBackend:
                 self.lp_out = _dense(self.lp, l1, lmid, kl[0], kl[6], dt, x_interp)
         return s
 
+    def attempt_rk(self, tab, ev, dt32, atol, rtol, final, x_interp):
+        """Model of CudaBackend.attempt_rk: any adaptive tableau, stage by stage (torchdiffeq rk_common._runge_kutta_step)."""
+        atol, rtol = torch.tensor(float(atol)), torch.tensor(float(rtol))
+        dt = torch.tensor(float(dt32))
+        n_k = len(tab.alpha) + 1
+        T = lambda v: torch.from_numpy(np.asarray(v, np.float32))        # noqa: E731
+        k, kl = [self.f], [self.dlp]
+        yi = self.y
+        for i in range(n_k - 1):
+            b = T(tab.beta[i]) * dt
+            yi = self.y + sum(k[j] * b[j] for j in range(i + 1))
+            f, d = self._fe(ev[i], yi)
+            k.append(f); kl.append(d)
+        cs, ce, cm = T(tab.c_sol) * dt, T(tab.c_err) * dt, T(tab.c_mid) * dt
+        y1 = yi if tab.fsal else self.y + sum(k[j] * cs[j] for j in range(n_k))
+        f1 = k[-1]
+        err = sum(k[j] * ce[j] for j in range(n_k))
+        tol = atol + rtol * torch.max(self.y.abs(), y1.abs())
+        s = torch.zeros(L.NPART, dtype=torch.float64)
+        s[L.P_X_ERR] = self._ss(err / tol)
+        s[L.P_NONFINITE] = float((~torch.isfinite(self.y)).sum())
+        self._next = (y1, f1)
+        if final:
+            ymid = self.y + sum(k[j] * cm[j] for j in range(n_k))
+            self.y_out = _dense(self.y, y1, ymid, k[0], f1, dt, x_interp)
+        if self.with_lp:
+            l1 = self.lp + sum(kl[j] * cs[j] for j in range(min(n_k, 6)))
+            errl = sum(kl[j] * ce[j] for j in range(n_k))
+            toll = atol + rtol * torch.max(self.lp.abs(), l1.abs())
+            s[L.P_LP_ERR] = self._ss(errl / toll)
+            self._next_lp = (l1, kl[-1])
+            if final:
+                lmid = self.lp + sum(kl[j] * cm[j] for j in range(n_k))
+                self.lp_out = _dense(self.lp, l1, lmid, kl[0], kl[-1], dt, x_interp)
+        return s
+
     def accept(self):
         self.y, self.f = self._next
         if self.with_lp:

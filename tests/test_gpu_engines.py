@@ -570,3 +570,36 @@ def test_repeatability_stress(cuda_dev):
         lh = sh.log_prob(xs, probes=probes)
         runs.setdefault("lh", lh.clone())
         assert torch.equal(runs["lh"], lh), rep
+
+
+# ---------------------------------------------------------------------------------------------
+# the other adaptive methods of torchdiffeq (method= is a pass-through argument of the reference's entry points)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["bosh3", "adaptive_heun", "fehlberg2"])
+def test_other_adaptive_methods(cuda_dev, method):
+    D, F, Sy = _mods()
+    from oracle import port
+    tol = dict(bosh3=1e-4, adaptive_heun=1e-3, fehlberg2=1e-4)[method]
+    torch.manual_seed(21)
+    sm = D.ScoreModel(D.MLP(16, 4, 8, [128, 128]), D.VPSDE(), no_sigma=True).eval()
+    base = torch.randn(300, 16, generator=gen(1)); cond = torch.randn(300, 4, generator=gen(2))
+    opts = {"step_t": torch.tensor([1e-3])}
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    ref = port.sample_ode_from_base(M, base, cond, tol, tol, method=method, options=opts)[0]
+    rs = port.last_stats()
+    sm.to(cuda_dev)
+    x, _ = sm.sample_ode_from_base(base.to(cuda_dev), cond.to(cuda_dev), atol=tol, rtol=tol, method=method, options=opts)
+    assert rel_row_err(ref, x) < SAMPLE_TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected, sm.last_stats.nfe) == (rs.accepted, rs.rejected, rs.nfe)
+    # exact-trace log-prob (tangent-row engine, the log-det column is part of the error norm) and a conditional flow
+    torch.manual_seed(22)
+    fl = F.ConditionalODEFlow(6, 3, [64, 96]).eval()
+    xs = torch.randn(150, 6, generator=gen(3)); c = torch.randn(150, 3, generator=gen(4))
+    ref_lp = port.flow_log_prob(port.flow_from_state_dict(fl.state_dict()), xs, c, atol=tol, rtol=tol, method=method)
+    rs = port.last_stats()
+    fl.to(cuda_dev)
+    lp = fl.log_prob(xs.to(cuda_dev), c.to(cuda_dev), atol=tol, rtol=tol, method=method)
+    assert float((lp.cpu() - ref_lp).abs().max()) < LP_TOL
+    assert (fl.last_stats.accepted, fl.last_stats.rejected) == (rs.accepted, rs.rejected)
+    with pytest.raises(NotImplementedError):
+        sm.sample_ode_from_base(base.to(cuda_dev), cond.to(cuda_dev), method="dopri8")

@@ -193,3 +193,33 @@ def test_non_silu_activations_reach_the_kernels(act_cls, act_fn):
     with pytest.raises(NotImplementedError):
         with patched_engine():
             D.ScoreModel(D.MLP(4, 0, 4, [8], activation=torch.nn.Softplus(beta=2.0)), D.VESDE()).eval().sample_ode_from_base(x)
+
+
+@pytest.mark.parametrize("method", ["bosh3", "adaptive_heun", "fehlberg2"])
+def test_other_adaptive_methods_vs_oracle(method):
+    """`method=` is a pass-through argument of the reference's entry points (`diffusion.py:572-573`, `flow.py:313-314`): the
+    host controller with the method's tableau / order against the restated torchdiffeq, identical accept / reject
+    sequences: PF-ODE sampling (VE with the sigma division), exact-trace log-prob of a flow, conditional flow (the
+    conditional rides in the error norm)."""
+    from oracle import port
+    tol = dict(bosh3=1e-4, adaptive_heun=1e-3, fehlberg2=1e-4)[method]
+    torch.manual_seed(21)
+    sm = D.ScoreModel(D.MLP(5, 2, 8, [32, 32]), D.VESDE(), no_sigma=False).eval()
+    base = torch.randn(60, 5, generator=torch.Generator().manual_seed(1)); cond = torch.randn(60, 2, generator=torch.Generator().manual_seed(2))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("ve"), False)
+    ref = port.sample_ode_from_base(M, base, cond, tol, tol, method=method)[0]
+    rs = port.last_stats()
+    with patched_engine():
+        x, _ = sm.sample_ode_from_base(base, cond, atol=tol, rtol=tol, method=method)
+    assert rel_row_err(ref, x) < TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected, sm.last_stats.nfe) == (rs.accepted, rs.rejected, rs.nfe)
+    assert sm.last_stats.accept_history == rs.accept_history and sm.last_stats.method == method
+    torch.manual_seed(22)
+    fl = F.ConditionalODEFlow(4, 2, [32, 32]).eval()
+    xs = torch.randn(50, 4, generator=torch.Generator().manual_seed(3)); c = torch.randn(50, 2, generator=torch.Generator().manual_seed(4))
+    ref_lp = port.flow_log_prob(port.flow_from_state_dict(fl.state_dict()), xs, c, atol=tol, rtol=tol, method=method)
+    rs = port.last_stats()
+    with patched_engine():
+        lp = fl.log_prob(xs, c, atol=tol, rtol=tol, method=method)
+    assert float((lp - ref_lp).abs().max()) < 1e-4
+    assert (fl.last_stats.accepted, fl.last_stats.rejected) == (rs.accepted, rs.rejected)

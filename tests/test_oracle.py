@@ -218,6 +218,34 @@ def test_solver_agrees_with_scipy_rk45_on_solutions():
     assert np.allclose(got.numpy(), ref, rtol=1e-7, atol=1e-9)
 
 
+def test_other_adaptive_tableaus_order_and_scipy_rk23():
+    """bosh3 / adaptive_heun / fehlberg2 (restated from torchdiffeq 0.2.x, parity unpinned like the driver): the step
+    solution has the tableau's order (one forced step of size h: error ~ h^(order+1)), the embedded error estimate has the
+    order of the lower-order solution, bosh3's accepted-step count tracks scipy's RK23 (the same Bogacki-Shampine pair)."""
+    import math
+    from scipy.integrate import solve_ivp
+    from oracle.torchdiffeq import _solver as so
+    f = lambda t, y: torch.stack([y[1], -y[0]])                     # noqa: E731
+    y0 = torch.tensor([1.0, 0.0], dtype=torch.float64)
+    exact = lambda h: torch.tensor([math.cos(h), -math.sin(h)], dtype=torch.float64)      # noqa: E731
+    for method, order in (("bosh3", 3), ("adaptive_heun", 2), ("fehlberg2", 2), ("dopri5", 5)):
+        errs, ests = [], []
+        for h in (0.2, 0.1):
+            st = so.SolveStats()
+            sol = so._Dopri5(so._Wrapped(f, None, False, st), y0, 1e-9, 1e-9, so._rms, st, tableau=method)
+            t0, dt = torch.tensor(0.0, dtype=torch.float64), torch.tensor(h, dtype=torch.float64)
+            y1, f1, err, k = sol._rk_step(y0, f(t0, y0), t0, dt, t0 + dt)
+            errs.append(float((y1 - exact(h)).abs().max())); ests.append(float(err.abs().max()))
+        assert order + 0.6 < math.log2(errs[0] / errs[1]) < order + 1.6, (method, errs)      # local error ~ h^(order+1)
+        assert math.log2(ests[0] / ests[1]) > order - 0.5, (method, ests)                   # estimate ~ h^order or higher
+    g = lambda t, y: torch.stack([y[1], -y[0] - 0.1 * y[1] + torch.sin(2 * t)])            # noqa: E731
+    for tol in (1e-4, 1e-6):
+        tde.odeint(g, y0, torch.tensor([0.0, 5.0], dtype=torch.float64), rtol=tol, atol=tol, method="bosh3")
+        n_ours = tde.last_stats().accepted
+        r = solve_ivp(lambda t, y: [y[1], -y[0] - 0.1 * y[1] + math.sin(2 * t)], (0, 5), [1.0, 0.0], rtol=tol, atol=tol, method="RK23")
+        assert abs(n_ours - (r.t.size - 1)) <= 0.1 * n_ours + 2, (tol, n_ours, r.t.size - 1)
+
+
 @needs_ref
 def test_reference_population_wrappers_and_accelerate():
     """Row a10: the population-level wrappers (affine glue, quirks Q6-Q8) -- live reference vs port, and
