@@ -501,7 +501,7 @@ class ScoreModel(torch.nn.Module):
         method = "dopri5" if method is None else method
         if method in _METHODS:
             be = E.StagedBackend(self._field(L.DIV_EXACT), y0, est, cond=cond)
-            dt, ev = _fixed_tables(self._program(), method, t0, t1, options)
+            dt, ev = _fixed_tables(self._program(), method, t0, t1, options, y0)
             return E.staged_fixed(be, method, dt, ev)
         if method != "dopri5":
             raise NotImplementedError(f"method {method!r} is not implemented with Hutch++ / XTrace (dopri5, rk4, euler, midpoint)")
@@ -533,19 +533,18 @@ class ScoreModel(torch.nn.Module):
         raise NotImplementedError(f"method {method!r} is not implemented ({_IMPLEMENTED})")
 
 
-def _fixed_tables(prog, method, t0, t1, options):
-    """Step sizes (n,) and evaluation scalars (n, evaluations per step, EV_FLOATS) of a torchdiffeq fixed grid."""
+def _fixed_tables(prog, method, t0, t1, options, y0=None):
+    """Step sizes (n,) and evaluation scalars (n, evaluations per step, EV_FLOATS) of a torchdiffeq fixed grid
+    (FixedGridODESolver: options step_size | grid_constructor, perturb; the solve returns the state AT t1, a grid point,
+    so the interpolation mode never comes into play)."""
     opts = dict(options or {})
-    for k in ("norm", "min_step", "max_step"):
+    for k in ("norm", "min_step", "max_step", "interp"):
         opts.pop(k, None)
     h = opts.pop("step_size", None)
-    if opts.pop("perturb", False):
-        raise NotImplementedError("options['perturb'] is not supported")
-    if opts.pop("interp", "linear") != "linear" or opts.pop("grid_constructor", None) is not None:
-        raise NotImplementedError("only step_size grids with linear interpolation are supported")
+    perturb = bool(opts.pop("perturb", False))
     reverse = t0 > t1
-    grid = S.fixed_grid(t0, t1, h)
-    dt, times = S.fixed_eval_times(method, grid)
+    grid = S.fixed_grid(t0, t1, h, opts.pop("grid_constructor", None), y0)
+    dt, times = S.fixed_eval_times(method, grid, perturb)
     n, nev = times.shape
     user = (-times if reverse else times).reshape(-1).numpy().astype(np.float32)
     ev = prog(user).reshape(n, nev, L.EV_FLOATS)
@@ -554,7 +553,7 @@ def _fixed_tables(prog, method, t0, t1, options):
 
 
 def _solve_fixed(field, prog, method, y0, cond, probes, t0, t1, options, with_lp):
-    dt, ev = _fixed_tables(prog, method, t0, t1, options)
+    dt, ev = _fixed_tables(prog, method, t0, t1, options, y0)
     step_table = np.zeros((dt.shape[0], L.STEP_STRIDE), np.float32)
     step_table[:, 0] = dt
     step_table[:, 3] = np.float32(0.5) * dt

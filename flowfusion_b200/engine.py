@@ -422,6 +422,12 @@ class CudaBackend:
                 "ffb_reduce_partials")
         return self._rk_sums
 
+    def refresh_f(self, ev_row):
+        """f (and the divergence) of the CURRENT state again, at the evaluation described by ``ev_row``: torchdiffeq's
+        re-evaluation just after a ``jump_t`` discontinuity."""
+        if self.B:
+            self._feval_into(self.y[self.cur], ev_row, self.f[self.cur], self.dlp[self.cur])
+
     def accept(self):
         self.cur = 1 - self.cur
 
@@ -638,6 +644,12 @@ class StagedBackend(CudaBackend):
     def single_eval(self, ev_row):
         self._field_and_trace(self.y[self.cur], ev_row, self.f[self.cur], self.dlp[self.cur])
         return self.f[self.cur], self.dlp[self.cur]
+
+    def refresh_f(self, ev_row):
+        if self.B:
+            self._field_and_trace(self.y[self.cur], ev_row, self.f[self.cur], self.dlp[self.cur])
+
+    attempt_rk = None          # other tableaus are not offered with Hutch++ / XTrace (solver._dopri5 checks hasattr / None)
 
     # -- primitives of the fixed-grid driver (staged_fixed) ------------------------------------------------
     def state(self):

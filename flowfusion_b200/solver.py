@@ -187,18 +187,16 @@ def dopri5(backend, program: Callable[[np.ndarray], np.ndarray], t0: float, t1: 
 def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None, tab: Tableau = None) -> SolveStats:
     tab = TABLEAUS["dopri5"] if tab is None else tab
     fused = tab.name == "dopri5"                   # the fused 6-evaluation attempt kernel; other tableaus go stage by stage
-    if not fused and not hasattr(backend, "attempt_rk"):
+    if not fused and getattr(backend, "attempt_rk", None) is None:
         raise NotImplementedError(f"method {tab.name!r} is not available with this divergence estimator (dopri5 is)")
     opts = dict(options or {})
     for k in ("norm", "dtype"):
         opts.pop(k, None)
-    if opts.get("jump_t") is not None:
-        raise NotImplementedError("options['jump_t'] is not supported")
     min_step = f64(opts.pop("min_step", 0))
     max_step = f64(opts.pop("max_step", np.inf))
     first_step = opts.pop("first_step", None)
     step_t = opts.pop("step_t", None)
-    opts.pop("jump_t", None)
+    jump_t = opts.pop("jump_t", None)
     safety, ifactor, dfactor = f64(opts.pop("safety", 0.9)), f64(opts.pop("ifactor", 10.0)), f64(opts.pop("dfactor", 0.2))
     max_num_steps = int(opts.pop("max_num_steps", 2 ** 31 - 1))
     if opts:
@@ -263,9 +261,18 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None, tab:
             g = -g
         grid = sorted(float(v) for v in g if v >= ts)
     grid_idx = min(bisect.bisect(grid, float(ts)), len(grid) - 1) if grid else 0
+    # options['jump_t']: discontinuities of f.  A step lands on the next one exactly (like step_t) and, once accepted, f is
+    # evaluated again one ulp AFTER it (rk_common.py: `f1 = func(t_next, y_next, perturb=Perturb.NEXT)`): host loop only.
+    jumps: List[float] = []
+    if jump_t is not None:
+        g = np.atleast_1d(np.asarray(torch.as_tensor(jump_t, dtype=torch.float64).cpu().numpy(), f64))
+        if reverse:
+            g = -g
+        jumps = sorted(float(v) for v in g if v >= ts)
+    jump_idx = min(bisect.bisect(jumps, float(ts)), len(jumps) - 1) if jumps else 0
 
     spec = getattr(program, "spec", None)
-    if (fused and _CONTROLLER != "host" and spec is not None and len(grid) <= L.CTL_MAX_GRID and counts["x"] > 0
+    if (fused and not jumps and _CONTROLLER != "host" and spec is not None and len(grid) <= L.CTL_MAX_GRID and counts["x"] > 0
             and getattr(backend, "ctl_supported", lambda: False)()
             and (_CONTROLLER == "device" or backend.ctl_attempt_ms_estimate(_rows_per_rank(counts, backend, group))
                  < _CTL_AUTO_MAX_ATTEMPT_MS)):
@@ -305,6 +312,14 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None, tab:
                 if on_grid:
                     t1s = nxt
                     dts = t1s - t
+            on_jump = False
+            if jumps:
+                nxt = f64(jumps[jump_idx])
+                on_jump = bool(t < nxt < t + dt)
+                if on_jump:
+                    on_grid = False
+                    t1s = nxt
+                    dts = t1s - t
             t0_32, dt_32, t1_32 = f32(t), f32(dts), f32(t1s)
             nst = len(tab.alpha)
             times = np.empty(nst, f32)
@@ -341,6 +356,12 @@ def _dopri5(backend, program, t0, t1, rtol, atol, options=None, group=None, tab:
                 backend.accept()
                 if on_grid and grid_idx != len(grid) - 1:
                     grid_idx += 1
+                if on_jump:
+                    if jump_idx != len(jumps) - 1:
+                        jump_idx += 1
+                    backend.refresh_f(rows(np.array([np.nextafter(t1_32, t1_32 + f32(1))], f32))[0])
+                    st.nfe += 1
+                    st.launches += 1
                 t = t1s
                 done = final
             else:
@@ -407,11 +428,21 @@ def _dopri5_device(backend, params, st: SolveStats, ts: float, dt: float, grid_i
 # ----------------------------------------------------------------------------------------------
 # fixed grids (torchdiffeq FixedGridODESolver): time stays in float32
 # ----------------------------------------------------------------------------------------------
-def fixed_grid(t0: float, t1: float, step_size: Optional[float]) -> torch.Tensor:
-    """Solver-time grid (ascending) as torchdiffeq builds it from ``options['step_size']``."""
+def fixed_grid(t0: float, t1: float, step_size: Optional[float], grid_constructor=None, y0=None) -> torch.Tensor:
+    """Solver-time grid (ascending) as torchdiffeq's FixedGridODESolver builds it: from ``options['step_size']``, from
+    ``options['grid_constructor'](func, y0, t)`` (called with the solver's ascending ``t``; ``func`` is None here -- the
+    field lives in the kernels), or just ``t`` (one step)."""
     t = torch.tensor([t0, t1], dtype=torch.float32)
     if t[0] > t[1]:
         t = -t
+    if step_size is not None and grid_constructor is not None:
+        raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
+    if grid_constructor is not None:
+        g = torch.as_tensor(grid_constructor(None, y0, t), dtype=torch.float32).detach().cpu().reshape(-1)
+        assert g[0] == t[0] and g[-1] == t[-1]          # torchdiffeq's own assertion
+        if not bool((g[1:] > g[:-1]).all()):
+            raise ValueError("grid_constructor must return a strictly increasing grid")
+        return g
     if step_size is None:
         return t
     n = torch.ceil((t[-1] - t[0]) / step_size + 1).item()
@@ -420,16 +451,19 @@ def fixed_grid(t0: float, t1: float, step_size: Optional[float]) -> torch.Tensor
     return g
 
 
-def fixed_eval_times(method: str, grid: torch.Tensor):
-    """(dt, eval_times[nsteps, nev]) in float32, op order of torchdiffeq's step functions."""
+def fixed_eval_times(method: str, grid: torch.Tensor, perturb: bool = False):
+    """(dt, eval_times[nsteps, nev]) in float32, op order of torchdiffeq's step functions.  ``perturb`` (options['perturb']):
+    the first evaluation of a step is made one ulp AFTER t0 and rk4's last one one ulp BEFORE t1 (Perturb.NEXT / PREV)."""
     a, b = grid[:-1], grid[1:]
     dt = b - a
+    first = torch.nextafter(a, a + 1) if perturb else a
     if method == "euler":
-        times = a[:, None]
+        times = first[:, None]
     elif method == "midpoint":
-        times = torch.stack([a, a + 0.5 * dt], dim=1)
+        times = torch.stack([first, a + 0.5 * dt], dim=1)
     elif method == "rk4":
-        times = torch.stack([a, a + dt * (1 / 3), a + dt * (2 / 3), b], dim=1)
+        last = torch.nextafter(b, b - 1) if perturb else b
+        times = torch.stack([first, a + dt * (1 / 3), a + dt * (2 / 3), last], dim=1)
     else:
         raise ValueError(method)
     return dt, times

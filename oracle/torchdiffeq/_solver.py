@@ -165,8 +165,6 @@ class _Dopri5:
         # sequence instead of running the controller.  bench.py uses it to check a slice of one rank's shard of a
         # multi-GPU solve against this oracle: the step sizes of that solve came from the GLOBAL error norm.
         self.replay = _replay
-        if jump_t is not None:
-            raise NotImplementedError("jump_t is outside the restated path (SURVEY 8f-4)")
         tdt = torch.promote_types(dtype, y0.dtype)
         dev = y0.device
         as64 = lambda v: torch.as_tensor(v, dtype=tdt, device=dev)  # noqa: E731
@@ -178,6 +176,7 @@ class _Dopri5:
         self.max_num_steps = int(max_num_steps)
         self.tdtype = tdt
         self.step_t = None if step_t is None else as64(step_t)
+        self.jump_t = None if jump_t is None else as64(jump_t)          # discontinuities of f: land on them, then re-evaluate f
         sd = dict(dtype=y0.dtype, device=dev)
         t64 = lambda v: torch.tensor(v, dtype=torch.float64)  # noqa: E731
         tb = _TABLEAUS[tableau]
@@ -225,6 +224,12 @@ class _Dopri5:
             g = self.step_t[self.step_t >= t[0]]
             self.grid = torch.sort(g).values.to(self.tdtype)
         self.grid_idx = min(bisect.bisect(self.grid.tolist(), t[0]), len(self.grid) - 1)
+        if self.jump_t is None:
+            self.jumps = torch.tensor([], dtype=self.tdtype, device=self.y0.device)
+        else:
+            j = self.jump_t[self.jump_t >= t[0]]
+            self.jumps = torch.sort(j).values.to(self.tdtype)
+        self.jump_idx = min(bisect.bisect(self.jumps.tolist(), t[0]), len(self.jumps) - 1)
 
     # ---- T8 ----
     def _rk_step(self, y0, f0, t0, dt, t1):
@@ -261,6 +266,14 @@ class _Dopri5:
             if on_grid:
                 t1 = nxt
                 dt = t1 - t0
+        on_jump = False
+        if len(self.jumps):
+            nxt = self.jumps[self.jump_idx]
+            on_jump = bool(t0 < nxt < t0 + dt)
+            if on_jump:
+                on_grid = False
+                t1 = nxt
+                dt = t1 - t0
         if self.replay is not None:              # recorded (already clipped) step size of this attempt
             i = len(self.stats.dt_history)
             dt = torch.as_tensor(self.replay[0][i], dtype=self.tdtype, device=y0.device)
@@ -283,6 +296,11 @@ class _Dopri5:
             self.interp = self._fit(y0, y1, k, dt)
             if on_grid and self.grid_idx != len(self.grid) - 1:
                 self.grid_idx += 1
+            if on_jump:
+                if self.jump_idx != len(self.jumps) - 1:
+                    self.jump_idx += 1
+                # just past a discontinuity of f: take f from the side we are now on (rk_common.py)
+                f1 = self.func(t1, y1, _NEXT)
             self.y, self.f, self.t_prev, self.t = y1, f1, t0, t1
         else:
             st.rejected += 1

@@ -204,6 +204,9 @@ class FakeBackend:
                 self.lp_out = _dense(self.lp, l1, lmid, kl[0], kl[-1], dt, x_interp)
         return s
 
+    def refresh_f(self, ev_row):
+        self.f, self.dlp = self._fe(ev_row, self.y)
+
     def accept(self):
         self.y, self.f = self._next
         if self.with_lp:

@@ -603,3 +603,30 @@ def test_other_adaptive_methods(cuda_dev, method):
     assert (fl.last_stats.accepted, fl.last_stats.rejected) == (rs.accepted, rs.rejected)
     with pytest.raises(NotImplementedError):
         sm.sample_ode_from_base(base.to(cuda_dev), cond.to(cuda_dev), method="dopri8")
+
+
+def test_solver_options_perturb_grid_constructor_jump_t(cuda_dev):
+    """Pass-through `options=` of the reference's entry points beyond step_size / step_t: fixed grids with perturb and a
+    grid_constructor, dopri5 with jump_t (host controller: f is re-evaluated after each discontinuity)."""
+    D, F, Sy = _mods()
+    from oracle import port
+    torch.manual_seed(31)
+    sm = D.ScoreModel(D.MLP(8, 2, 8, [64, 64]), D.VPSDE(), no_sigma=True).eval()
+    base = torch.randn(200, 8, generator=gen(1)); cond = torch.randn(200, 2, generator=gen(2))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    gc = lambda func, y0, t: torch.tensor([float(t[0]), -0.8, -0.55, -0.3, -0.07, float(t[-1])])      # noqa: E731
+    refs = {}
+    for method in ("euler", "midpoint", "rk4"):
+        for i, opts in enumerate(({"step_size": 0.125, "perturb": True}, {"grid_constructor": gc, "perturb": True})):
+            refs[(method, i)] = (opts, port.sample_ode_from_base(M, base, cond, method=method, options=opts)[0])
+    jopts = {"step_t": torch.tensor([1e-3]), "jump_t": torch.tensor([0.6, 0.25])}
+    jref = port.sample_ode_from_base(M, base, cond, 1e-5, 1e-5, options=jopts)[0]
+    js = port.last_stats()
+    sm.to(cuda_dev)
+    b, c = base.to(cuda_dev), cond.to(cuda_dev)
+    for (method, i), (opts, ref) in refs.items():
+        x, _ = sm.sample_ode_from_base(b, c, method=method, options=opts)
+        assert rel_row_err(ref, x) < SAMPLE_TOL, (method, i)
+    x, _ = sm.sample_ode_from_base(b, c, atol=1e-5, rtol=1e-5, options=jopts)
+    assert rel_row_err(jref, x) < SAMPLE_TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected, sm.last_stats.nfe) == (js.accepted, js.rejected, js.nfe)

@@ -223,3 +223,44 @@ def test_other_adaptive_methods_vs_oracle(method):
         lp = fl.log_prob(xs, c, atol=tol, rtol=tol, method=method)
     assert float((lp - ref_lp).abs().max()) < 1e-4
     assert (fl.last_stats.accepted, fl.last_stats.rejected) == (rs.accepted, rs.rejected)
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+def test_fixed_grid_options_perturb_and_grid_constructor(method):
+    """options={'perturb': True} and options={'grid_constructor': ...} of torchdiffeq's fixed-grid solvers (pass-through
+    `options=` of the reference's entry points) against the restated torchdiffeq."""
+    from oracle import port
+    torch.manual_seed(31)
+    sm = D.ScoreModel(D.MLP(4, 0, 8, [32]), D.VPSDE(), no_sigma=True).eval()
+    base = torch.randn(30, 4, generator=torch.Generator().manual_seed(1))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    gc = lambda func, y0, t: torch.tensor([float(t[0]), -0.8, -0.55, -0.3, -0.07, float(t[-1])])      # noqa: E731  (reverse time: t is negated)
+    for opts in ({"step_size": 0.125, "perturb": True}, {"grid_constructor": gc}, {"grid_constructor": gc, "perturb": True}):
+        ref = port.sample_ode_from_base(M, base, None, method=method, options=opts)[0]
+        with patched_engine():
+            x, _ = sm.sample_ode_from_base(base, method=method, options=opts)
+        assert rel_row_err(ref, x) < TOL, opts
+    plain = port.sample_ode_from_base(M, base, None, method=method, options={"step_size": 0.125})[0]
+    pert = port.sample_ode_from_base(M, base, None, method=method, options={"step_size": 0.125, "perturb": True})[0]
+    assert not torch.equal(plain, pert)                      # the option does change the evaluation times
+
+
+def test_dopri5_jump_t():
+    """options={'jump_t': ...}: steps land on the discontinuity and f is evaluated again just after it (one extra NFE per
+    jump), against the restated torchdiffeq: identical step sequence and NFE."""
+    from oracle import port
+    torch.manual_seed(33)
+    sm = D.ScoreModel(D.MLP(4, 1, 8, [32, 32]), D.VPSDE(), no_sigma=True).eval()
+    base = torch.randn(40, 4, generator=torch.Generator().manual_seed(1)); cond = torch.randn(40, 1, generator=torch.Generator().manual_seed(2))
+    M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), True)
+    opts = {"step_t": torch.tensor([1e-3]), "jump_t": torch.tensor([0.6, 0.25])}
+    ref = port.sample_ode_from_base(M, base, cond, 1e-5, 1e-5, options=opts)[0]
+    rs = port.last_stats()
+    plain = port.sample_ode_from_base(M, base, cond, 1e-5, 1e-5, options={"step_t": torch.tensor([1e-3])})[0]
+    ps = port.last_stats()
+    assert rs.nfe != ps.nfe and not torch.equal(ref, plain)
+    with patched_engine():
+        x, _ = sm.sample_ode_from_base(base, cond, atol=1e-5, rtol=1e-5, options=opts)
+    assert rel_row_err(ref, x) < TOL
+    assert (sm.last_stats.accepted, sm.last_stats.rejected, sm.last_stats.nfe) == (rs.accepted, rs.rejected, rs.nfe)
+    assert sm.last_stats.controller == "host"
