@@ -12,15 +12,16 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
-SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu", "ffb_rd.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu", "ffb_rd.cu", "ffb_wide.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_common.cuh", "ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
                                                      "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh", "ffb_engine_rd.cuh",
-                                                     "ffb_kernels_rd.cuh", "ffb_rd.h")] + \
+                                                     "ffb_kernels_rd.cuh", "ffb_rd.h", "ffb_kernels_generic.cuh", "ffb_engine_wide.cuh", "ffb_wide.h")] + \
           [os.path.join(ROOT, "include", "ffb200.h")]
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
-ABI_VERSION = 4
-MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 8, 32, 16, 8, 128
+ABI_VERSION = 5
+MAX_LAYERS, MAX_TFEAT, NPART, STEP_STRIDE, TILE_ROWS = 16, 32, 16, 8, 128
+MAX_WIDTH = 512
 FIELD_NET, FIELD_SCORE = 0, 1
 DIV_NONE, DIV_EXACT, DIV_HUTCH = 0, 1, 2
 M_EULER, M_MIDPOINT, M_RK4, M_EM, M_LEAPFROG = 0, 1, 2, 3, 4

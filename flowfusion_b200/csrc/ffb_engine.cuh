@@ -26,7 +26,8 @@ namespace ffb {
 
 constexpr int TM = FFB_TILE_ROWS;        // rows per tile
 constexpr int LDA = TM + 4;              // smem row stride (floats) of every k-major buffer
-constexpr int KMAX = FFB_MAX_WIDTH;      // widest layer
+constexpr int KMAX = 128;                // widest layer of the tensor-core / FFMA tile engines (wider: ffb_engine_wide.cuh)
+constexpr int NET_MAXL = 8;              // Linear layers per network on those engines (deeper: ffb_engine_wide.cuh)
 constexpr int NCOMP = 256;               // compute threads
 constexpr int NTHR = NCOMP + 32;         // + producer warp
 constexpr int KC = 32;                   // weight rows per ring stage
@@ -38,18 +39,33 @@ constexpr int SLOT_Y0 = 7;
 struct NetDev {
   int n_layers;
   int t_dim, x_dim, c_dim;
-  int K[FFB_MAX_LAYERS];       // rows of the packed image (layer 0: x_dim + c_dim rounded up to 4)
-  int N[FFB_MAX_LAYERS];       // real output width
-  int Np[FFB_MAX_LAYERS];      // padded output width: 16, 32, 64 or 128
-  const float* W[FFB_MAX_LAYERS];   // packed [K][Np]
-  const float* b[FFB_MAX_LAYERS];   // packed [Np]
+  int K[NET_MAXL];       // rows of the packed image (layer 0: x_dim + c_dim rounded up to 4)
+  int N[NET_MAXL];       // real output width
+  int Np[NET_MAXL];      // padded output width: 16, 32, 64 or 128
+  const float* W[NET_MAXL];   // packed [K][Np]
+  const float* b[NET_MAXL];   // packed [Np]
   const float* Wt;                  // packed time rows [t_dim][Np[0]]
   int act;                          // FFB_ACT_* of the hidden layers
 };
 
+// One network as the wide engine (ffb_engine_wide.cuh) reads it: any number of layers up to FFB_MAX_LAYERS, widths up to
+// FFB_MAX_WIDTH.  Lives in device memory (FieldDev carries a pointer), copied to shared memory by the engine.
+constexpr int WD_MAXL = FFB_MAX_LAYERS;
+struct WideNet {
+  int n_layers, t_dim, x_dim, c_dim, act, max_k;   // max_k: widest operand (rows of a packed image) of this network
+  int K[WD_MAXL];            // rows of the packed image (layer 0: x_dim + c_dim rounded up to 4; else Np of the layer before)
+  int N[WD_MAXL];            // real output width
+  int Np[WD_MAXL];           // padded output width: 32, 64, 128 or a multiple of 128
+  const float* W[WD_MAXL];   // [Np / CW][K][CW] with CW = min(Np, 128), columns of a chunk interleaved (p = tx * C + j <-> n = j * 32 + tx)
+  const float* b[WD_MAXL];   // [Np], real column order, zero padded
+  const float* Wt;           // [t_dim][Np[0]] time rows of layer 0, real column order
+};
+
 struct FieldDev {
   int n_calls;
-  NetDev net[2];
+  NetDev net[2];             // networks that only fit the wide engine: a one-layer summary (dims, activation), no images
+  const WideNet* wide[2];    // device pointers
+  int wide_maxk;             // widest operand over the field's networks (sizes the wide engine's activation buffers)
   int in_off[2], out_off[2];
   float out_sign[2];
   int state_dim, cond_dim, kind, use_sigma, has_drift, div_mode;

@@ -140,7 +140,7 @@ __host__ __device__ inline size_t smem_layout_rr(int SD, int CD, int nslot_smem,
   v[0] = take(sizeof(float) * TC_NSTAGE * TC_STAGE_FLOATS);                 // weight ring
   v[1] = take(sizeof(float) * SD * LDA);                                    // ycur
   v[2] = take(sizeof(float) * (CD > 0 ? CD : 1) * LDA);                     // cond
-  v[3] = take(sizeof(float) * ncalls * FFB_MAX_LAYERS * KMAX);              // biases
+  v[3] = take(sizeof(float) * ncalls * NET_MAXL * KMAX);              // biases
   v[4] = take(sizeof(float) * nbeff * ncalls * KMAX);                       // layer-0 bias + time features, per evaluation
   v[5] = take(sizeof(float) * ncalls * (tdim > 0 ? tdim : 1) * KMAX);       // layer-0 time-feature rows
   v[6] = take(sizeof(double) * (RR_NCOMP / 32) * FFB_NPART);                // block-reduction scratch
@@ -191,7 +191,7 @@ struct EngineRR_ {
     for (int c = 0; c < f.n_calls; ++c) {
       for (int l = 0; l < f.net[c].n_layers; ++l)
         for (int n = threadIdx.x; n < KMAX; n += RR_NTHR)
-          cx.sbias()[(c * FFB_MAX_LAYERS + l) * KMAX + n] = (n < f.net[c].Np[l]) ? f.net[c].b[l][n] : 0.0f;
+          cx.sbias()[(c * NET_MAXL + l) * KMAX + n] = (n < f.net[c].Np[l]) ? f.net[c].b[l][n] : 0.0f;
       for (int i = threadIdx.x; i < f.net[c].t_dim * KMAX; i += RR_NTHR) {
         const int j = i / KMAX, n = i - j * KMAX;
         cx.swt()[(c * cx.tdim + j) * KMAX + n] = (n < f.net[c].Np[0]) ? f.net[c].Wt[(size_t)j * f.net[c].Np[0] + n] : 0.0f;
@@ -221,7 +221,7 @@ struct EngineRR_ {
   static __device__ __forceinline__ void prep_beff(CtxR& cx, const FieldDev& f, const float* tfeat, float* buf) {
     for (int i = cx.tid; i < f.n_calls * KMAX; i += RR_NCOMP) {
       const int c = i / KMAX, n = i - c * KMAX;
-      float b = cx.sbias()[(c * FFB_MAX_LAYERS) * KMAX + n];
+      float b = cx.sbias()[(c * NET_MAXL) * KMAX + n];
       const float* wt = cx.swt() + (c * cx.tdim) * KMAX + n;
       for (int j = 0; j < f.net[c].t_dim; ++j) b = fmaf(wt[j * KMAX], tfeat[j], b);
       buf[i] = b;
@@ -367,7 +367,7 @@ struct EngineRR_ {
   static __device__ __forceinline__ void hidden_act(CtxR& cx, const NetDev& net, int c, const float* beff) {
     for (int l = 0; l + 1 < net.n_layers; ++l) {
       const int nc = net.Np[l] / KC;
-      const float* bias = (l == 0) ? beff : cx.sbias() + (c * FFB_MAX_LAYERS + l) * KMAX;
+      const float* bias = (l == 0) ? beff : cx.sbias() + (c * NET_MAXL + l) * KMAX;
       const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
       cx.dbuf ^= 1u;
       wait_d_ready(cx, net.K[l]);
@@ -422,7 +422,7 @@ struct EngineRR_ {
   template <class F>
   static __device__ __forceinline__ void last(CtxR& cx, const NetDev& net, int c, const float* beff, F&& fn) {
     const int nl = net.n_layers, Nreal = net.N[nl - 1];
-    const float* bias = (nl == 1) ? beff : cx.sbias() + (c * FFB_MAX_LAYERS + nl - 1) * KMAX;
+    const float* bias = (nl == 1) ? beff : cx.sbias() + (c * NET_MAXL + nl - 1) * KMAX;
     const uint32_t dcol = cx.lane_addr + cx.dbuf * 128u + 8u * cx.cg;
     cx.dbuf ^= 1u;
     wait_d_ready(cx, net.K[nl - 1]);

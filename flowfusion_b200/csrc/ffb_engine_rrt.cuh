@@ -81,7 +81,7 @@ __host__ __device__ inline size_t smem_layout_rrt(int SD, int CD, int ld, int hu
   v[0] = take(sizeof(float) * TC_NSTAGE * TC_STAGE_FLOATS);
   v[1] = take(sizeof(float) * SD * ld);                            // ycur [d][sample]
   v[2] = take(sizeof(float) * (CD > 0 ? CD : 1) * ld);             // cond
-  v[3] = take(sizeof(float) * FFB_MAX_LAYERS * KMAX);              // biases
+  v[3] = take(sizeof(float) * NET_MAXL * KMAX);              // biases
   v[4] = take(sizeof(float) * nbeff * KMAX);                       // layer-0 bias + time features per evaluation
   v[5] = take(sizeof(float) * (tdim > 0 ? tdim : 1) * KMAX);       // time-feature rows
   v[6] = take(sizeof(double) * (RR_NCOMP / 32) * FFB_NPART);

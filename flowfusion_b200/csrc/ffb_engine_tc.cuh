@@ -181,7 +181,7 @@ __host__ __device__ inline size_t smem_layout_tc(int SD, int CD, int T, int hutc
   v[5] = take(T > 0 ? sizeof(float) * S * ZS : 0);                // gate = silu'(z)
   v[6] = take(sizeof(float) * SD * LDA);                          // raw output of the last layer [n][row]
   v[7] = take(sizeof(float) * KMAX);                              // beff
-  v[8] = take(sizeof(float) * ncalls * FFB_MAX_LAYERS * KMAX);    // biases, every layer of every network
+  v[8] = take(sizeof(float) * ncalls * NET_MAXL * KMAX);    // biases, every layer of every network
   v[9] = take(T > 0 ? sizeof(float) * (NSLOT + 2) * TM : 0);      // klp
   v[10] = take(sizeof(double) * 8 * FFB_NPART);                   // red
   v[11] = take(sizeof(uint64_t) * (2 * TC_NSTAGE + 4));           // barriers + tmem slot
@@ -235,7 +235,7 @@ struct EngineTC {
     for (int c = 0; c < f.n_calls; ++c) {
       for (int l = 0; l < f.net[c].n_layers; ++l)
         for (int n = threadIdx.x; n < KMAX; n += TC_NTHR)
-          cx.sbias()[(c * FFB_MAX_LAYERS + l) * KMAX + n] = (n < f.net[c].Np[l]) ? f.net[c].b[l][n] : 0.0f;
+          cx.sbias()[(c * NET_MAXL + l) * KMAX + n] = (n < f.net[c].Np[l]) ? f.net[c].b[l][n] : 0.0f;
       for (int i = threadIdx.x; i < f.net[c].t_dim * KMAX; i += TC_NTHR) {
         const int j = i / KMAX, n = i - j * KMAX;
         cx.swt()[(c * cx.tdim + j) * KMAX + n] = (n < f.net[c].Np[0]) ? f.net[c].Wt[(size_t)j * f.net[c].Np[0] + n] : 0.0f;
@@ -350,7 +350,7 @@ struct EngineTC {
       if (cx.tid == 0) trace(7, 0);
       // layer-0 bias with the (row-uniform) time features folded in
       for (int n = cx.tid; n < Np0; n += NCOMP) {
-        float b = cx.sbias()[(c * FFB_MAX_LAYERS) * KMAX + n];
+        float b = cx.sbias()[(c * NET_MAXL) * KMAX + n];
         const float* wt = cx.swt() + (c * cx.tdim) * KMAX + n;
         for (int j = 0; j < net.t_dim; ++j) b = fmaf(wt[j * KMAX], ev.tfeat[j], b);
         cx.beff()[n] = b;
@@ -386,7 +386,7 @@ struct EngineTC {
       for (int l = 0; l < nl; ++l) {
         const bool last = (l == nl - 1);
         const int Np = net.Np[l], Nreal = net.N[l];
-        const float* bias = (l == 0) ? cx.beff() : cx.sbias() + (c * FFB_MAX_LAYERS + l) * KMAX;
+        const float* bias = (l == 0) ? cx.beff() : cx.sbias() + (c * NET_MAXL + l) * KMAX;
         const int cbeg = h * (Np >> 1), cend = cbeg + (Np >> 1);     // Np is a multiple of 32
         wait_d_ready(cx);
         if (cx.tid == 0) trace(3, l);

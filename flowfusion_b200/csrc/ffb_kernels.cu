@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -26,376 +27,11 @@
 #include "ffb_engine_tc.cuh"
 #include "ffb_control.cuh"
 #include "ffb_rd.h"
+#include "ffb_wide.h"
 
 using namespace ffb;
 
-// =============================================================================================
-// small device helpers
-// =============================================================================================
-
-// k-major tile buffer <- row-major global rows [row0, row0+nv); rows nv..S-1 are zero filled
-__device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ src, int64_t row0, int nv, int S,
-                                          int D, int tid) {
-  const float* __restrict__ base = src + row0 * D;
-#pragma unroll 4
-  for (int idx = tid; idx < S * D; idx += NCOMP) {
-    const int r = fast_div(idx, D), d = idx - r * D;
-    dst[d * LDA + r] = (r < nv) ? base[idx] : 0.0f;
-  }
-}
-__device__ __forceinline__ void store_rows(float* __restrict__ dst, const float* src, int64_t row0, int nv, int D,
-                                           int tid) {
-  float* __restrict__ base = dst + row0 * D;
-#pragma unroll 4
-  for (int idx = tid; idx < nv * D; idx += NCOMP) {
-    const int r = fast_div(idx, D), d = idx - r * D;
-    base[idx] = src[d * LDA + r];
-  }
-}
-
-// deterministic block reduction of NV doubles per thread -> out[q] (thread 0 writes)
-template <int NV, class CTX>
-__device__ __forceinline__ void block_reduce_store(CTX& cx, double (&v)[NV], double* out, const int (&slot)[NV]) {
-#pragma unroll
-  for (int q = 0; q < NV; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
-  }
-  if (cx.lane == 0) {
-#pragma unroll
-    for (int q = 0; q < NV; ++q) cx.red()[cx.warp * FFB_NPART + q] = v[q];
-  }
-  bar_compute();
-  if (cx.tid == 0) {
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      double s = 0.0;
-      for (int w = 0; w < NCOMP / 32; ++w) s += cx.red()[w * FFB_NPART + q];
-      out[slot[q]] = s;
-    }
-  }
-  bar_compute();
-}
-
-// =============================================================================================
-// k_field_eval
-// =============================================================================================
-template <class ENG, bool SS>
-__global__ void __launch_bounds__(ENG::NTHR, 1) k_field_eval(const __grid_constant__ FieldDev f,
-        const __grid_constant__ ffb_eval_args a, const int64_t ntiles) {
-  typename ENG::Ctx cx;
-  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch));
-  const int S = cx.S, SD = cx.SD, CD = cx.CD;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * S;
-    const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* Y0 = slot_ptr_t<SS>(cx, SLOT_Y0);
-    float* FB = slot_ptr_t<SS>(cx, 1);
-    if (!cx.producer) {
-      load_rows(Y0, a.y, row0, nv, S, SD, cx.tid);
-      if (a.fbase) load_rows(FB, a.fbase, row0, nv, S, SD, cx.tid);
-      if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
-      if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
-      bar_compute();
-      for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
-        const int e = d * LDA + r;
-        cx.ycur()[e] = a.fbase ? __fadd_rn(Y0[e], __fmul_rn(a.h, FB[e])) : Y0[e];
-      }
-      bar_compute();
-    }
-    ENG::template eval<SS>(cx, f, a.ev, 0);
-    if (!cx.producer) {
-      const float* F = slot_ptr_t<SS>(cx, 0);
-      if (a.f) store_rows(a.f, F, row0, nv, SD, cx.tid);
-      if (a.dlp && cx.T > 0)
-        for (int s = cx.tid; s < nv; s += NCOMP) a.dlp[row0 + s] = cx.klp()[s];
-      if (a.norms) {
-        double v[6] = {0, 0, 0, 0, 0, 0};   // x_y, x_f, x_df, lp_f, lp_df, c_y
-        for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
-          if (r >= nv) continue;
-          const int e = d * LDA + r;
-          const float y0 = Y0[e];
-          const float sc = __fadd_rn(a.atol, __fmul_rn(fabsf(y0), a.rtol));
-          if (a.norms == 1) {
-            const float q0 = __fdiv_rn(y0, sc), q1 = __fdiv_rn(F[e], sc);
-            v[0] += (double)q0 * q0;
-            v[1] += (double)q1 * q1;
-          } else {
-            const float q2 = __fdiv_rn(__fsub_rn(F[e], FB[e]), sc);
-            v[2] += (double)q2 * q2;
-          }
-        }
-        if (cx.T > 0) {
-          for (int s = cx.tid; s < nv; s += NCOMP) {
-            if (a.norms == 1) {
-              const float q = __fdiv_rn(cx.klp()[s], a.atol);
-              v[3] += (double)q * q;
-            } else {
-              const float q = __fdiv_rn(__fsub_rn(cx.klp()[s], a.dlpbase[row0 + s]), a.atol);
-              v[4] += (double)q * q;
-            }
-          }
-        }
-        if (a.cond_in_state && a.norms == 1) {
-          const float* cs = a.cond_state ? a.cond_state : a.cond;
-          for (int idx = cx.tid; idx < CD * nv; idx += NCOMP) {
-            const float c = cs[row0 * CD + idx];
-            const float q = __fdiv_rn(c, __fadd_rn(a.atol, __fmul_rn(fabsf(c), a.rtol)));
-            v[5] += (double)q * q;
-          }
-        }
-        const int slot[6] = {P_X_Y, P_X_F, P_X_DF, P_LP_F, P_LP_DF, P_C_Y};
-        block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
-      }
-      bar_compute();
-    }
-  }
-  ENG::fini(cx);
-}
-
-// =============================================================================================
-// k_dopri5: one attempted step
-// =============================================================================================
-template <class ENG, bool SS>
-__global__ void __launch_bounds__(ENG::NTHR, 1) k_dopri5(const __grid_constant__ FieldDev f,
-        const __grid_constant__ ffb_dopri5_args a, const int64_t ntiles) {
-  typename ENG::Ctx cx;
-  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch));
-  const int S = cx.S, SD = cx.SD, CD = cx.CD;
-  const bool prob = cx.T > 0;
-  float* LP0 = cx.klp() + NSLOT * TM;
-  float* LPC = cx.klp() + (NSLOT + 1) * TM;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * S;
-    const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* Y0 = slot_ptr_t<SS>(cx, SLOT_Y0);
-    double nonfinite = 0.0;
-    if (!cx.producer) {
-      load_rows(Y0, a.y0, row0, nv, S, SD, cx.tid);
-      load_rows(slot_ptr_t<SS>(cx, 0), a.f0, row0, nv, S, SD, cx.tid);
-      if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
-      if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
-      if (prob)
-        for (int s = cx.tid; s < S; s += NCOMP) {
-          LP0[s] = (s < nv) ? a.lp0[row0 + s] : 0.0f;
-          cx.klp()[s] = (s < nv) ? a.dlp0[row0 + s] : 0.0f;
-          if (!is_finite_f(LP0[s])) nonfinite += 1.0;
-        }
-      bar_compute();
-    }
-    for (int i = 1; i <= 6; ++i) {
-      if (!cx.producer) {
-        for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
-          const int e = d * LDA + r;
-          float kv[6];
-#pragma unroll
-          for (int j = 0; j < 6; ++j) kv[j] = (j < i) ? slot_ptr_t<SS>(cx, j)[e] : 0.0f;
-          const float y0 = Y0[e];
-          float acc = __fmul_rn(kv[0], a.cb[i - 1][0]);
-#pragma unroll
-          for (int j = 1; j < 6; ++j) if (j < i) acc = fmaf(kv[j], a.cb[i - 1][j], acc);
-          if (i == 1 && !is_finite_f(y0)) nonfinite += 1.0;
-          cx.ycur()[e] = __fadd_rn(y0, acc);
-        }
-        bar_compute();
-      }
-      ENG::template eval<SS>(cx, f, a.ev[i - 1], i);
-    }
-    if (!cx.producer) {
-      // cx.ycur() now holds y1 (FSAL: the 7th stage input), slot 6 holds f1
-      double v[3] = {0.0, 0.0, nonfinite};
-      float* stage_out = cx.stage_buf();   // free between evaluations: staging for the interpolant
-      for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
-        if (r >= nv) continue;
-        const int e = d * LDA + r;
-        const float y0 = Y0[e], y1 = cx.ycur()[e];
-        float kv[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) kv[j] = slot_ptr_t<SS>(cx, j)[e];
-        float err = __fmul_rn(kv[0], a.ce[0]);
-#pragma unroll
-        for (int j = 1; j < 7; ++j) err = fmaf(kv[j], a.ce[j], err);
-        const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0), fabsf(y1))));
-        const float q = __fdiv_rn(err, tol);
-        v[0] += (double)q * q;
-        if (a.final) {
-          float mid = __fmul_rn(kv[0], a.cm[0]);
-#pragma unroll
-          for (int j = 1; j < 7; ++j) mid = fmaf(kv[j], a.cm[j], mid);
-          stage_out[e] = dense_output(y0, y1, __fadd_rn(y0, mid), kv[0], kv[6], a.dt, a.x_interp);
-        }
-      }
-      if (prob) {
-        for (int s = cx.tid; s < nv; s += NCOMP) {
-          const float l0 = LP0[s];
-          float acc = __fmul_rn(cx.klp()[s], a.cb[5][0]);
-          for (int j = 1; j < 6; ++j) acc = fmaf(cx.klp()[j * TM + s], a.cb[5][j], acc);
-          const float l1 = __fadd_rn(l0, acc);
-          float err = __fmul_rn(cx.klp()[s], a.ce[0]);
-          for (int j = 1; j < 7; ++j) err = fmaf(cx.klp()[j * TM + s], a.ce[j], err);
-          const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(l0), fabsf(l1))));
-          const float q = __fdiv_rn(err, tol);
-          v[1] += (double)q * q;
-          a.lp1[row0 + s] = l1;
-          a.dlp1[row0 + s] = cx.klp()[6 * TM + s];
-          if (a.final) {
-            float mid = __fmul_rn(cx.klp()[s], a.cm[0]);
-            for (int j = 1; j < 7; ++j) mid = fmaf(cx.klp()[j * TM + s], a.cm[j], mid);
-            a.lp_out[row0 + s] = dense_output(l0, l1, __fadd_rn(l0, mid), cx.klp()[s], cx.klp()[6 * TM + s], a.dt,
-                                              a.x_interp);
-          }
-        }
-      }
-      (void)LPC;
-      bar_compute();
-      store_rows(a.y1, cx.ycur(), row0, nv, SD, cx.tid);
-      store_rows(a.f1, slot_ptr_t<SS>(cx, 6), row0, nv, SD, cx.tid);
-      if (a.final) store_rows(a.y_out, stage_out, row0, nv, SD, cx.tid);
-      const int slot[3] = {P_X_ERR, P_LP_ERR, P_NONFINITE};
-      block_reduce_store(cx, v, a.partials + tile * FFB_NPART, slot);
-    }
-  }
-  ENG::fini(cx);
-}
-
-// =============================================================================================
-// k_fixed: fixed-grid integrators, the whole trajectory of a tile on-chip
-// =============================================================================================
-
-template <class ENG, bool SS>
-__global__ void __launch_bounds__(ENG::NTHR, 1) k_fixed(const __grid_constant__ FieldDev f,
-        const __grid_constant__ ffb_fixed_args a, const int64_t ntiles) {
-  typename ENG::Ctx cx;
-  ENG::init(cx, f, reinterpret_cast<float*>(a.scratch));
-  const int S = cx.S, SD = cx.SD, CD = cx.CD;
-  const bool prob = cx.T > 0;
-  const int nev = evals_per_step(a.method);
-  const float third = (float)(1.0 / 3.0);
-  float* LPC = cx.klp() + (NSLOT + 1) * TM;  // running lp
-  // column ranges produced by the two networks of a symplectic field (leapfrog only)
-  const int q_lo = f.out_off[0], q_hi = f.out_off[0] + f.net[0].N[f.net[0].n_layers - 1];
-  const int p_lo = f.out_off[1], p_hi = f.out_off[1] + f.net[1].N[f.net[1].n_layers > 0 ? f.net[1].n_layers - 1 : 0];
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * S;
-    const int nv = (int)min((int64_t)S, a.batch - row0);
-    float* Y0 = slot_ptr_t<SS>(cx, SLOT_Y0);
-    const float* K1 = slot_ptr_t<SS>(cx, 0);
-    const float* K2 = slot_ptr_t<SS>(cx, 1);
-    const float* K3 = slot_ptr_t<SS>(cx, 2);
-    const float* K4 = slot_ptr_t<SS>(cx, 3);
-    int nan_step = 0x7fffffff;            // first Euler-Maruyama step of this thread's rows that produced a NaN
-    if (!cx.producer) {
-      load_rows(cx.ycur(), a.x0, row0, nv, S, SD, cx.tid);
-      if (CD) load_rows(cx.condb(), a.cond, row0, nv, S, CD, cx.tid);
-      if (f.div_mode == FFB_DIV_HUTCH) load_rows(cx.prb(), a.probes, row0, nv, S, SD, cx.tid);
-      if (prob)
-        for (int s = cx.tid; s < S; s += NCOMP) LPC[s] = (s < nv && a.lp0) ? a.lp0[row0 + s] : 0.0f;
-      bar_compute();
-    }
-    for (int step = 0; step < a.nsteps; ++step) {
-      const float* st = a.step_table + (size_t)step * FFB_STEP_STRIDE;
-      const ffb_eval_scalars* ev = a.ev_table + (size_t)step * nev;
-      const float dt = st[0], half = st[3];
-      for (int e = 0; e < nev; ++e) {
-        // ---- which networks this evaluation runs, and where the derivative goes -----------------
-        unsigned mask = 3u;
-        int dst = e;
-        if (a.method == FFB_M_LEAPFROG) {         // e0: dp/dt(q, t0) [first step only], e1: dq/dt, e2: dp/dt
-          if (e == 0 && step > 0) mask = 0u;      // reuse the previous step's closing kick
-          else mask = (e == 1) ? 1u : 2u;
-          dst = (e == 1) ? 0 : 1;
-        }
-        if (mask) ENG::template eval<SS>(cx, f, ev[e], dst, mask);
-        if (cx.producer) continue;
-        // ---- stage algebra after evaluation e (op order of torchdiffeq's step functions) ---------
-        for (int d = cx.tid >> 7, r = cx.tid & (TM - 1); d < SD && r < S; d += NCOMP / TM) {
-          const int i = d * LDA + r;
-          float* y = cx.ycur();
-          switch (a.method) {
-            case FFB_M_EULER:
-              y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i]));
-              break;
-            case FFB_M_MIDPOINT:
-              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(K1[i], half)); }
-              else y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, K2[i]));
-              break;
-            case FFB_M_RK4:
-              if (e == 0) { const float y0 = y[i]; Y0[i] = y0; y[i] = __fadd_rn(y0, __fmul_rn(__fmul_rn(dt, K1[i]), third)); }
-              else if (e == 1) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fsub_rn(K2[i], __fmul_rn(K1[i], third))));
-              else if (e == 2) y[i] = __fadd_rn(Y0[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(K1[i], K2[i]), K3[i])));
-              else {
-                const float sum = __fadd_rn(__fadd_rn(K1[i], __fmul_rn(3.0f, __fadd_rn(K2[i], K3[i]))), K4[i]);
-                y[i] = __fadd_rn(Y0[i], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
-              }
-              break;
-            case FFB_M_LEAPFROG:
-              if (e == 1) { if (d >= q_lo && d < q_hi) y[i] = __fadd_rn(y[i], __fmul_rn(dt, K1[i])); }
-              else if (d >= p_lo && d < p_hi) y[i] = __fadd_rn(y[i], __fmul_rn(half, K2[i]));
-              break;
-            default: break;   // EM handled below (its noise is indexed row-major)
-          }
-        }
-        if (prob) {
-          for (int s = cx.tid; s < S; s += NCOMP) {
-            const float* kl = cx.klp();
-            if (a.method == FFB_M_EULER) LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, kl[s]));
-            else if (a.method == FFB_M_MIDPOINT && e == 1) LPC[s] = __fadd_rn(LPC[s], __fmul_rn(dt, kl[TM + s]));
-            else if (a.method == FFB_M_RK4 && e == 3) {
-              const float sum = __fadd_rn(__fadd_rn(kl[s], __fmul_rn(3.0f, __fadd_rn(kl[TM + s], kl[2 * TM + s]))), kl[3 * TM + s]);
-              LPC[s] = __fadd_rn(LPC[s], __fmul_rn(__fmul_rn(sum, dt), 0.125f));
-            }
-          }
-        }
-        if (a.method == FFB_M_EM) {
-          // diffusion.py:552-559: f = drift - g^2 score (ev.c = g^2); x_mean = x + f dt; x = x_mean + g dw
-          const float g = st[1], sq = st[2];
-          float* y = cx.ycur();
-          if (a.noise) {
-            for (int idx = cx.tid; idx < SD * S; idx += NCOMP) {
-              const int r = fast_div(idx, SD), d = idx - r * SD;
-              if (r >= nv) continue;
-              const int i = d * LDA + r;
-              const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
-              const float dw = __fmul_rn(a.noise[((size_t)step * a.batch + row0 + r) * SD + d], sq);
-              const float xn = __fadd_rn(xm, __fmul_rn(g, dw));
-              Y0[i] = xm;
-              y[i] = xn;
-              if (xn != xn) nan_step = min(nan_step, step);
-            }
-          } else {
-            const int ng = (SD + 3) >> 2;
-            for (int idx = cx.tid; idx < ng * S; idx += NCOMP) {
-              const int grp = fast_div(idx, S), r = idx - grp * S;
-              if (r >= nv) continue;
-              const float4 z = philox_normal4(a.philox_seed, a.philox_offset, a.row_offset + row0 + r, step, grp);
-              const float zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int d = grp * 4 + q;
-                if (d >= SD) break;
-                const int i = d * LDA + r;
-                const float xm = __fadd_rn(y[i], __fmul_rn(K1[i], dt));
-                const float xn = __fadd_rn(xm, __fmul_rn(g, __fmul_rn(zz[q], sq)));
-                Y0[i] = xm;
-                y[i] = xn;
-                if (xn != xn) nan_step = min(nan_step, step);
-              }
-            }
-          }
-        }
-        bar_compute();
-      }
-    }
-    if (!cx.producer) {
-      store_rows(a.x_out, (a.method == FFB_M_EM) ? Y0 : cx.ycur(), row0, nv, SD, cx.tid);
-      if (prob && a.lp_out)
-        for (int s = cx.tid; s < nv; s += NCOMP) a.lp_out[row0 + s] = LPC[s];
-      if (nan_step != 0x7fffffff) { atomicOr(a.status, FFB_ST_NAN_SAMPLE); atomicMin(a.status + 1, nan_step); }
-      bar_compute();
-    }
-  }
-  ENG::fini(cx);
-}
+#include "ffb_kernels_generic.cuh"
 
 #include "ffb_kernels_rr.cuh"
 #include "ffb_engine_rrt.cuh"
@@ -554,6 +190,26 @@ __global__ void k_pack_bias_tc(const float* __restrict__ b, int out_features, fl
   dst[n] = (n < out_features) ? b[n] : 0.0f;
 }
 
+// ---- wide-engine image (ffb_engine_wide.cuh): [Np / CW][K][CW], CW = min(Np, 128); inside a chunk lane tx of a warp owns
+// the packed columns tx*C .. tx*C + C-1 (C = CW / 32), which are the real columns j*32 + tx
+__global__ void k_pack_weight_wide(const float* __restrict__ W, int in_features, int out_features, float* __restrict__ dst,
+                                   int K, int Np, int CW, int x_col, int x_dim, int c_col, int c_dim, int layer0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * Np) return;
+  const int nc = idx / (K * CW), rem = idx - nc * (K * CW);
+  const int k = rem / CW, p = rem - k * CW;
+  const int C = CW / 32, tx = p / C, j = p - tx * C;
+  const int n = nc * CW + j * 32 + tx;
+  int col = -1;
+  if (layer0) {
+    if (k < x_dim) col = x_col + k;
+    else if (k < x_dim + c_dim) col = c_col + (k - x_dim);
+  } else if (k < in_features) {
+    col = k;
+  }
+  dst[idx] = (n < out_features && col >= 0) ? W[(size_t)n * in_features + col] : 0.0f;
+}
+
 // =============================================================================================
 // device-side dopri5 controller (ffb_control.cuh): one thread, between two attempt kernels
 // =============================================================================================
@@ -587,6 +243,9 @@ __global__ void k_time_program(const __grid_constant__ ffb_time_program prog, co
 struct ffb_net {
   NetDev dev;   // FP32 FFMA2 engine image
   NetDev tc;    // tensor-core (3xTF32) engine image
+  WideNet wide;             // wide-engine image (host copy of the descriptor; every network has one)
+  WideNet* wide_dev;        // the same in device memory (what FieldDev::wide points to)
+  bool narrow;              // true: dev / tc hold images (<= 8 layers, widths <= 128); false: one-layer summaries only
   std::vector<void*> allocs;
   int64_t flops;
 };
@@ -594,7 +253,8 @@ struct ffb_net {
 // engine selection: 1 = tensor cores (default: dual-tile engine for fields without tangent rows, tangent-row engine
 // for the log-likelihood paths), 3 = the same with the single-tile chunk-pipelined engine instead of the dual-tile one
 // (FFB_ENGINE=rr), 4 = the same with the dual-tile engine for every dopri5 attempt it can hold, whatever the batch
-// (FFB_ENGINE=rd; tests), 2 = the older whole-layer hand-off tile engine (FFB_ENGINE=tc_tile), 0 = FP32 FFMA2 (FFB_ENGINE=ffma)
+// (FFB_ENGINE=rd; tests), 2 = the older whole-layer hand-off tile engine (FFB_ENGINE=tc_tile), 0 = FP32 FFMA2 (FFB_ENGINE=ffma),
+// 5 = the wide engine for every field (FFB_ENGINE=wide; tests -- by default it only takes networks wider than 128 or deeper than 8)
 static int g_engine = -1;
 static int engine() {
   if (g_engine < 0) {
@@ -603,6 +263,7 @@ static int engine() {
     else if (e && (!strcmp(e, "tc_tile") || !strcmp(e, "2"))) g_engine = 2;
     else if (e && (!strcmp(e, "rr") || !strcmp(e, "3"))) g_engine = 3;
     else if (e && (!strcmp(e, "rd") || !strcmp(e, "4"))) g_engine = 4;
+    else if (e && (!strcmp(e, "wide") || !strcmp(e, "5"))) g_engine = 5;
     else g_engine = 1;
   }
   return g_engine;
@@ -615,7 +276,7 @@ extern "C" int ffb_debug_trace(long long* buf) {
   cudaMemcpyToSymbol(ffb::g_trace_pos, &zero, sizeof(zero));
   return 0;
 }
-extern "C" int ffb_set_engine(int e) { g_engine = (e == 2 || e == 3 || e == 4) ? e : (e ? 1 : 0); return g_engine; }
+extern "C" int ffb_set_engine(int e) { g_engine = (e >= 2 && e <= 5) ? e : (e ? 1 : 0); return g_engine; }
 extern "C" int ffb_get_engine(void) { return engine(); }
 
 static thread_local std::string g_err;
@@ -663,87 +324,132 @@ static int pad_width(int n) { return n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 6
 extern "C" int ffb_net_create(const ffb_net_desc* d, void* stream_, ffb_net** out) {
   if (!d || !out) return fail(FFB_ERR_ARG, "ffb_net_create: null argument");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (d->n_layers < 1 || d->n_layers > FFB_MAX_LAYERS) return fail(FFB_ERR_ARG, "ffb_net_create: 1..8 Linear layers supported");
+  if (d->n_layers < 1 || d->n_layers > FFB_MAX_LAYERS) return fail(FFB_ERR_ARG, "ffb_net_create: 1..16 Linear layers supported");
   if (d->t_dim < 0 || d->t_dim > FFB_MAX_TFEAT) return fail(FFB_ERR_ARG, "ffb_net_create: at most 32 time-feature columns");
   if (d->x_dim < 1 || d->x_dim + d->c_dim + d->t_dim != d->in_features)
     return fail(FFB_ERR_ARG, "ffb_net_create: x_dim + c_dim + t_dim must equal in_features");
-  if (d->x_dim + d->c_dim > FFB_MAX_WIDTH) return fail(FFB_ERR_ARG, "ffb_net_create: state + conditional columns exceed 128");
+  if (d->x_dim + d->c_dim > FFB_MAX_STATE) return fail(FFB_ERR_ARG, "ffb_net_create: state + conditional columns exceed 128");
   for (int l = 0; l < d->n_layers; ++l)
     if (d->widths[l] < 1 || d->widths[l] > FFB_MAX_WIDTH)
-      return fail(FFB_ERR_ARG, "ffb_net_create: layer widths must be in 1..128");
+      return fail(FFB_ERR_ARG, "ffb_net_create: layer widths must be in 1..512");
+  if (d->widths[d->n_layers - 1] > FFB_MAX_STATE) return fail(FFB_ERR_ARG, "ffb_net_create: the output layer is at most 128 wide");
   if (d->activation < FFB_ACT_SILU || d->activation > FFB_ACT_GELU) return fail(FFB_ERR_ARG, "ffb_net_create: unknown activation");
   ffb_net* net = new ffb_net();
   NetDev& nd = net->dev;
+  NetDev& nt = net->tc;
   memset(&nd, 0, sizeof(nd));
-  nd.n_layers = d->n_layers;
-  nd.t_dim = d->t_dim; nd.x_dim = d->x_dim; nd.c_dim = d->c_dim;
-  nd.act = d->activation;
+  memset(&nt, 0, sizeof(nt));
+  memset(&net->wide, 0, sizeof(net->wide));
+  net->wide_dev = nullptr;
+  net->narrow = d->n_layers <= NET_MAXL;
+  for (int l = 0; l < d->n_layers; ++l) if (d->widths[l] > KMAX) net->narrow = false;
   net->flops = 0;
   int in_f = d->in_features;
+  for (int l = 0; l < d->n_layers; ++l) { net->flops += 2LL * in_f * d->widths[l]; in_f = d->widths[l]; }
   auto cleanup = [&]() { for (void* p : net->allocs) cudaFree(p); delete net; };
-  for (int l = 0; l < d->n_layers; ++l) {
-    const int N = d->widths[l], Np = pad_width(N);
-    const int K = (l == 0) ? ((d->x_dim + d->c_dim + 3) & ~3) : nd.Np[l - 1];
-    nd.K[l] = K; nd.N[l] = N; nd.Np[l] = Np;
-    net->flops += 2LL * in_f * N;
-    float *w = nullptr, *b = nullptr;
-    if (cudaMalloc(&w, sizeof(float) * K * Np) != cudaSuccess || cudaMalloc(&b, sizeof(float) * Np) != cudaSuccess) {
-      cleanup();
-      return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed");
-    }
-    net->allocs.push_back(w); net->allocs.push_back(b);
-    k_pack_weight<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, w, K, Np, d->x_col, d->x_dim,
-                                                           d->c_col, d->c_dim, l == 0);
-    k_pack_bias<<<1, 128, 0, stream>>>(d->bias[l], N, b, Np);
-    g_launches += 2;
-    nd.W[l] = w; nd.b[l] = b;
-    if (l == 0) {
-      float* wt = nullptr;
-      const int td = d->t_dim > 0 ? d->t_dim : 1;
-      if (cudaMalloc(&wt, sizeof(float) * td * Np) != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
-      net->allocs.push_back(wt);
-      if (d->t_dim > 0) {
-        k_pack_time<<<(d->t_dim * Np + 255) / 256, 256, 0, stream>>>(d->weight[0], in_f, N, wt, d->t_dim, Np, d->t_col);
-        g_launches += 1;
+  auto dalloc = [&](size_t nfloat) -> float* {
+    float* p = nullptr;
+    if (cudaMalloc(&p, sizeof(float) * (nfloat ? nfloat : 1)) != cudaSuccess) return nullptr;
+    net->allocs.push_back(p);
+    return p;
+  };
+  const int td = d->t_dim > 0 ? d->t_dim : 1;
+  // ---- FP32 FFMA2 image and tensor-core image (networks the 128-wide engines hold) -------------------------------
+  nd.t_dim = nt.t_dim = d->t_dim; nd.x_dim = nt.x_dim = d->x_dim; nd.c_dim = nt.c_dim = d->c_dim;
+  nd.act = nt.act = d->activation;
+  if (net->narrow) {
+    nd.n_layers = nt.n_layers = d->n_layers;
+    in_f = d->in_features;
+    for (int l = 0; l < d->n_layers; ++l) {
+      const int N = d->widths[l], Np = pad_width(N);
+      const int K = (l == 0) ? ((d->x_dim + d->c_dim + 3) & ~3) : nd.Np[l - 1];
+      nd.K[l] = K; nd.N[l] = N; nd.Np[l] = Np;
+      float *w = dalloc((size_t)K * Np), *b = dalloc(Np);
+      if (!w || !b) { cleanup(); return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed"); }
+      k_pack_weight<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, w, K, Np, d->x_col, d->x_dim,
+                                                             d->c_col, d->c_dim, l == 0);
+      k_pack_bias<<<1, 128, 0, stream>>>(d->bias[l], N, b, Np);
+      g_launches += 2;
+      nd.W[l] = w; nd.b[l] = b;
+      if (l == 0) {
+        float* wt = dalloc((size_t)td * Np);
+        if (!wt) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
+        if (d->t_dim > 0) {
+          k_pack_time<<<(d->t_dim * Np + 255) / 256, 256, 0, stream>>>(d->weight[0], in_f, N, wt, d->t_dim, Np, d->t_col);
+          g_launches += 1;
+        }
+        nd.Wt = wt;
       }
-      nd.Wt = wt;
+      in_f = N;
     }
-    in_f = N;
+    in_f = d->in_features;
+    for (int l = 0; l < d->n_layers; ++l) {
+      const int N = d->widths[l], Np = (N + 31) & ~31;
+      const int K = (l == 0) ? ((d->x_dim + d->c_dim + 7) & ~7) : nt.Np[l - 1];
+      nt.K[l] = K; nt.N[l] = N; nt.Np[l] = Np;
+      float *w = dalloc((size_t)2 * K * Np), *b = dalloc(Np);
+      if (!w || !b) { cleanup(); return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed"); }
+      k_pack_weight_tc<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, w, K, Np, d->x_col, d->x_dim,
+                                                                d->c_col, d->c_dim, l == 0);
+      k_pack_bias_tc<<<1, 128, 0, stream>>>(d->bias[l], N, b, Np);
+      g_launches += 2;
+      nt.W[l] = w; nt.b[l] = b;
+      if (l == 0) {
+        float* wt = dalloc((size_t)td * Np);
+        if (!wt) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
+        if (d->t_dim > 0) {
+          k_pack_time_tc<<<(d->t_dim * Np + 255) / 256, 256, 0, stream>>>(d->weight[0], in_f, N, wt, d->t_dim, Np, d->t_col);
+          g_launches += 1;
+        }
+        nt.Wt = wt;
+      }
+      in_f = N;
+    }
+  } else {
+    // one-layer summary: what the host-side checks and the generic kernels read (dims, output width, activation)
+    nd.n_layers = nt.n_layers = 1;
+    nd.N[0] = nt.N[0] = d->widths[d->n_layers - 1];
+    nd.Np[0] = nt.Np[0] = pad_width(nd.N[0]);
+    nd.K[0] = nt.K[0] = (d->x_dim + d->c_dim + 7) & ~7;
   }
-  // ---- tensor-core image ---------------------------------------------------------------------
-  NetDev& nt = net->tc;
-  memset(&nt, 0, sizeof(nt));
-  nt.n_layers = d->n_layers;
-  nt.t_dim = d->t_dim; nt.x_dim = d->x_dim; nt.c_dim = d->c_dim;
-  nt.act = d->activation;
+  // ---- wide-engine image (every network: FFB_ENGINE=wide runs any field on it) -------------------------------------
+  WideNet& nw = net->wide;
+  nw.n_layers = d->n_layers;
+  nw.t_dim = d->t_dim; nw.x_dim = d->x_dim; nw.c_dim = d->c_dim; nw.act = d->activation;
   in_f = d->in_features;
   for (int l = 0; l < d->n_layers; ++l) {
-    const int N = d->widths[l], Np = (N + 31) & ~31;
-    const int K = (l == 0) ? ((d->x_dim + d->c_dim + 7) & ~7) : nt.Np[l - 1];
-    nt.K[l] = K; nt.N[l] = N; nt.Np[l] = Np;
-    float *w = nullptr, *b = nullptr;
-    if (cudaMalloc(&w, sizeof(float) * 2 * K * Np) != cudaSuccess || cudaMalloc(&b, sizeof(float) * Np) != cudaSuccess) {
-      cleanup();
-      return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed");
-    }
-    net->allocs.push_back(w); net->allocs.push_back(b);
-    k_pack_weight_tc<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, w, K, Np, d->x_col, d->x_dim,
-                                                              d->c_col, d->c_dim, l == 0);
-    k_pack_bias_tc<<<1, 128, 0, stream>>>(d->bias[l], N, b, Np);
+    const int N = d->widths[l];
+    const int Np = N <= 32 ? 32 : (N <= 64 ? 64 : ((N + 127) & ~127));
+    const int CW = std::min(Np, 128);
+    const int K = (l == 0) ? ((d->x_dim + d->c_dim + 3) & ~3) : nw.Np[l - 1];
+    nw.K[l] = K; nw.N[l] = N; nw.Np[l] = Np;
+    nw.max_k = std::max(nw.max_k, K);
+    float *w = dalloc((size_t)K * Np), *b = dalloc(Np);
+    if (!w || !b) { cleanup(); return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed"); }
+    k_pack_weight_wide<<<(K * Np + 255) / 256, 256, 0, stream>>>(d->weight[l], in_f, N, w, K, Np, CW, d->x_col, d->x_dim,
+                                                                d->c_col, d->c_dim, l == 0);
+    k_pack_bias_tc<<<(Np + 127) / 128, 128, 0, stream>>>(d->bias[l], N, b, Np);
     g_launches += 2;
-    nt.W[l] = w; nt.b[l] = b;
+    nw.W[l] = w; nw.b[l] = b;
     if (l == 0) {
-      float* wt = nullptr;
-      const int td = d->t_dim > 0 ? d->t_dim : 1;
-      if (cudaMalloc(&wt, sizeof(float) * td * Np) != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
-      net->allocs.push_back(wt);
+      float* wt = dalloc((size_t)td * Np);
+      if (!wt) { cleanup(); return fail(FFB_ERR_CUDA, "cudaMalloc"); }
       if (d->t_dim > 0) {
         k_pack_time_tc<<<(d->t_dim * Np + 255) / 256, 256, 0, stream>>>(d->weight[0], in_f, N, wt, d->t_dim, Np, d->t_col);
         g_launches += 1;
       }
-      nt.Wt = wt;
+      nw.Wt = wt;
     }
     in_f = N;
+  }
+  void* wdev = nullptr;
+  if (cudaMalloc(&wdev, sizeof(WideNet)) != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, "ffb_net_create: cudaMalloc failed"); }
+  net->allocs.push_back(wdev);
+  net->wide_dev = reinterpret_cast<WideNet*>(wdev);
+  // net->wide lives as long as the handle, so the asynchronous copy may read it after this call returns
+  if (cudaMemcpyAsync(wdev, &net->wide, sizeof(WideNet), cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+    cleanup();
+    return fail(FFB_ERR_CUDA, "ffb_net_create: descriptor upload failed");
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { cleanup(); return fail(FFB_ERR_CUDA, std::string("ffb_net_create: ") + cudaGetErrorString(e)); }
@@ -784,6 +490,8 @@ static int make_field(const ffb_field* f, FieldDev* out) {
     if (f->in_off[c] < 0 || f->in_off[c] + nd.x_dim > f->state_dim) return fail(FFB_ERR_ARG, "field: input block outside the state");
     if (f->out_off[c] < 0 || f->out_off[c] + dout > f->state_dim) return fail(FFB_ERR_ARG, "field: output block outside the state");
     out->net[c] = engine() ? f->net[c]->tc : nd;
+    out->wide[c] = f->net[c]->wide_dev;
+    out->wide_maxk = std::max(out->wide_maxk, f->net[c]->wide.max_k);
     out->in_off[c] = f->in_off[c];
     out->out_off[c] = f->out_off[c];
     out->out_sign[c] = f->out_sign[c];
@@ -804,6 +512,14 @@ static int make_field(const ffb_field* f, FieldDev* out) {
   const size_t with_slots = field_smem(*out, tangents_of(f), 1);
   out->slots_smem = (optin > 0 && with_slots <= (size_t)optin) ? 1 : 0;
   return FFB_OK;
+}
+
+// true when the field runs on the wide engine (ffb_engine_wide.cuh): a network wider than 128 or deeper than 8 layers,
+// or every field under FFB_ENGINE=wide
+static bool use_wide(const ffb_field* f) {
+  if (engine() == 5) return true;
+  for (int c = 0; c < f->n_calls; ++c) if (f->net[c] && !f->net[c]->narrow) return true;
+  return false;
 }
 
 static int smem_optin();
@@ -829,7 +545,7 @@ extern "C" int64_t ffb_num_tiles(const ffb_field* f, int64_t batch) {
   if (!f || !f->net[0]) return -1;
   const int S = TM / (1 + tangents_of(f));
   int64_t n = (batch + S - 1) / S;
-  if (f->div_mode != FFB_DIV_NONE) {
+  if (f->div_mode != FFB_DIV_NONE && !use_wide(f)) {
     const int td = field_tdim_host(f);
     const int configs[2][2] = {{NSLOT, 6}, {3, 1}};          // dopri5 attempt, single evaluation
     for (auto& c : configs) {
@@ -957,6 +673,10 @@ extern "C" int ffb_field_eval(const ffb_field* f, const ffb_eval_args* a, void* 
     return fail(FFB_ERR_ARG, "ffb_field_eval: norms=2 needs fbase (and dlpbase with a divergence)");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
   if (a->jac && fd.div_mode != FFB_DIV_EXACT) return fail(FFB_ERR_ARG, "ffb_field_eval: jac needs div_mode FFB_DIV_EXACT");
+  if (use_wide(f)) {
+    if (a->jac) return fail(FFB_ERR_ARG, "ffb_field_eval: jac is written by the tangent-row tensor-core engine only (widths <= 128)");
+    return wide_launch_field_eval(fd, *a, st_);
+  }
   if (const size_t smt = rrt_smem(f, &fd, 3, 1))
     return gen_act(fd) ? launch_rrt(k_field_eval_rrt<true>, smt, "ffb_field_eval", fd, *a, a->batch, st_)
                        : launch_rrt(k_field_eval_rrt<false>, smt, "ffb_field_eval", fd, *a, a->batch, st_);
@@ -992,6 +712,10 @@ extern "C" int ffb_dopri5_attempt(const ffb_field* f, const ffb_dopri5_args* a, 
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
   const bool dyn = a->ctl != nullptr;
+  if (use_wide(f)) {
+    if (dyn) return fail(FFB_ERR_ARG, "ffb_dopri5_attempt: args->ctl is not available on the wide engine (ffb_dopri5_ctl_supported)");
+    return wide_launch_dopri5(fd, *a, st_);
+  }
   if (const size_t smt = rrt_smem(f, &fd, NSLOT, 6)) {
     if (dyn) return gen_act(fd) ? launch_rrt(k_dopri5_rrt<true, true>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_)
                                 : launch_rrt(k_dopri5_rrt<false, true>, smt, "ffb_dopri5_attempt", fd, *a, a->batch, st_);
@@ -1030,6 +754,7 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
   if (fd.cond_dim && !a->cond) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: cond is required");
   if (fd.div_mode == FFB_DIV_HUTCH && !a->probes) return fail(FFB_ERR_ARG, "ffb_integrate_fixed: probes are required");
   cudaStream_t st_ = reinterpret_cast<cudaStream_t>(stream);
+  if (use_wide(f)) return wide_launch_fixed(fd, *a, st_);
   if (const size_t smt = rrt_smem(f, &fd, rr_fixed_slots(a->method), 1))
     return gen_act(fd) ? launch_rrt(k_fixed_rrt<true>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_)
                        : launch_rrt(k_fixed_rrt<false>, smt, "ffb_integrate_fixed", fd, *a, a->batch, st_);
@@ -1053,6 +778,7 @@ extern "C" int ffb_integrate_fixed(const ffb_field* f, const ffb_fixed_args* a, 
 extern "C" int ffb_dopri5_ctl_supported(const ffb_field* f) {
   FieldDev fd;
   if (make_field(f, &fd)) return 0;
+  if (use_wide(f)) return 0;
   if (rrt_smem(f, &fd, NSLOT, 6)) return 1;
   return use_rr(fd) ? 1 : 0;
 }

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_fixed_rr(const __grid_const
   auto prep_q = [&](const ffb_eval_scalars* evp, float* buf) {
     for (int i = cx.cg * 32 + cx.lane; i < bstride; i += 128) {
       const int c = i / KMAX, n = i - c * KMAX;
-      float b = cx.sbias()[(c * FFB_MAX_LAYERS) * KMAX + n];
+      float b = cx.sbias()[(c * NET_MAXL) * KMAX + n];
       const float* wt = cx.swt() + (c * cx.tdim) * KMAX + n;
       for (int j = 0; j < f.net[c].t_dim; ++j) b = fmaf(wt[j * KMAX], evp->tfeat[j], b);
       buf[i] = b;

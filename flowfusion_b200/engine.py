@@ -125,13 +125,16 @@ class PackedNet:
         lib = L.load()
         if len(linears) > L.MAX_LAYERS:
             raise NotImplementedError(f"at most {L.MAX_LAYERS} Linear layers are supported")
+        if linears[-1].out_features > 128:
+            raise NotImplementedError("the output layer is at most 128 wide (the ODE state has at most 128 columns)")
         d = L.NetDesc()
         d.n_layers = len(linears)
         d.in_features = linears[0].in_features
         self._keep = []
         for i, lin in enumerate(linears):
-            if lin.out_features > 128 or lin.in_features > 128 + L.MAX_TFEAT:
-                raise NotImplementedError("layer widths above 128 are not supported by the tile engine yet")
+            if lin.out_features > L.MAX_WIDTH:
+                raise NotImplementedError(f"layer widths above {L.MAX_WIDTH} are not supported (widths above 128 and networks "
+                                          "deeper than 8 Linear layers run on the wide FP32 engine, csrc/ffb_engine_wide.cuh)")
             w, b = _dev_f32(lin.weight, device), _dev_f32(lin.bias, device)
             self._keep += [w, b]
             d.widths[i] = lin.out_features

@@ -26,9 +26,9 @@
 extern "C" {
 #endif
 
-#define FFB_ABI_VERSION 4
-#define FFB_MAX_LAYERS 8    /* Linear layers per network                         */
-#define FFB_MAX_WIDTH 128   /* widest layer (input or output) the tile engine holds */
+#define FFB_ABI_VERSION 5
+#define FFB_MAX_LAYERS 16   /* Linear layers per network (more than 8: wide engine, FP32 pipe)     */
+#define FFB_MAX_WIDTH 512   /* widest hidden layer; above 128 the wide engine (FP32 pipe) runs the field */
 #define FFB_MAX_TFEAT 32    /* time-feature columns (embedding_dimensions or 1)  */
 #define FFB_MAX_STATE 128   /* ODE state columns                                 */
 #define FFB_TILE_ROWS 128   /* rows (trajectories x (1 + tangents)) per CTA tile */
@@ -56,8 +56,8 @@ typedef enum {
 
 /* hidden-layer activations (ffb_net_desc.activation).  SiLU is the reference's default (diffusion.py:38,
  * flow.py:41, symplectic.py:25); the others are what a user may pass as `activation=`.  Non-SiLU activations run
- * on the chunk-pipelined tensor-core engines only; the debug engines (ffb_set_engine(0) / (2)) and samples wider
- * than a tile return FFB_ERR_ARG for them. */
+ * on the chunk-pipelined tensor-core engines and on the wide engine; the debug engines (ffb_set_engine(0) / (2)) and
+ * samples wider than a tile return FFB_ERR_ARG for them. */
 #define FFB_ACT_SILU 0
 #define FFB_ACT_TANH 1
 #define FFB_ACT_RELU 2

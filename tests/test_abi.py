@@ -44,7 +44,7 @@ def test_exports_are_plain_c(lib):
 
 
 def test_abi_version_and_error_paths(lib):
-    assert lib.ffb_abi_version() == L.ABI_VERSION == 4
+    assert lib.ffb_abi_version() == L.ABI_VERSION == 5
     # null arguments are reported through the status code + ffb_last_error, no CUDA call is made
     assert lib.ffb_net_create(None, None, None) == -1
     assert b"null" in lib.ffb_last_error()
@@ -77,3 +77,18 @@ def test_library_holds_sm100a_tensor_core_code(lib):
     assert "sm_100a" in sass or "SM100" in sass.upper()
     for needle in ("UTCHMMA", "UBLKCP", "SYNCS", "FFMA2"):       # tcgen05.mma, bulk copy, mbarrier, packed FP32 FMA
         assert needle in sass, needle
+
+
+def test_net_create_refuses_shapes_beyond_the_header_limits(lib):
+    """include/ffb200.h: FFB_MAX_LAYERS = 16 Linear layers, FFB_MAX_WIDTH = 512 columns.  The checks run before any CUDA call."""
+    d = L.NetDesc()
+    d.n_layers, d.in_features, d.x_dim, d.c_dim, d.t_dim = 2, 5, 4, 0, 1
+    d.widths[0], d.widths[1] = L.MAX_WIDTH + 1, 4
+    h = C.c_void_p()
+    assert lib.ffb_net_create(C.byref(d), None, C.byref(h)) == -1 and b"1..512" in lib.ffb_last_error()
+    d.widths[0] = 64
+    d.n_layers = L.MAX_LAYERS + 1
+    assert lib.ffb_net_create(C.byref(d), None, C.byref(h)) == -1 and b"1..16" in lib.ffb_last_error()
+    d.n_layers = 2
+    d.widths[1] = 200                              # the output layer feeds the ODE state: at most 128 columns
+    assert lib.ffb_net_create(C.byref(d), None, C.byref(h)) == -1 and b"output layer" in lib.ffb_last_error()

@@ -296,7 +296,8 @@ def test_population_wrappers_row_a10(cuda_dev):
 
 
 def test_maximum_sizes(cuda_dev):
-    """The limits in include/ffb200.h: 128 state columns, 8 Linear layers of width 128, and their error paths."""
+    """The limits of the tensor-core engines: 128 state columns, 8 Linear layers of width 128 (wider / deeper networks run on
+    the wide engine, tests/test_gpu_wide.py), and the error paths of include/ffb200.h's limits."""
     D, F, Sy = _mods()
     from oracle import port
     from flowfusion_b200 import _lib
@@ -315,9 +316,9 @@ def test_maximum_sizes(cuda_dev):
     assert (sm.last_stats.accepted, sm.last_stats.rejected) == (rs.accepted, rs.rejected)
     # one layer too many / one column too wide: refused with NotImplementedError, nothing is launched
     with pytest.raises(NotImplementedError):
-        D.ScoreModel(D.MLP(4, 0, 8, [32] * 8), D.VESDE()).eval().to(cuda_dev).sample_ode_from_base(torch.zeros(4, 4, device=cuda_dev))
+        D.ScoreModel(D.MLP(4, 0, 8, [32] * 16), D.VESDE()).eval().to(cuda_dev).sample_ode_from_base(torch.zeros(4, 4, device=cuda_dev))
     with pytest.raises(NotImplementedError):
-        D.ScoreModel(D.MLP(4, 0, 8, [129]), D.VESDE()).eval().to(cuda_dev).sample_ode_from_base(torch.zeros(4, 4, device=cuda_dev))
+        D.ScoreModel(D.MLP(4, 0, 8, [513]), D.VESDE()).eval().to(cuda_dev).sample_ode_from_base(torch.zeros(4, 4, device=cuda_dev))
     # a CPU tensor is refused: there is no CPU path
     with pytest.raises(_lib.FFBError):
         sm.sample_ode_from_base(base)
