@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
-SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu", "ffb_rd.cu", "ffb_wide.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu", "ffb_rd.cu", "ffb_wide.cu", "ffb_train.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_common.cuh", "ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
                                                      "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh", "ffb_engine_rd.cuh",
                                                      "ffb_kernels_rd.cuh", "ffb_rd.h", "ffb_kernels_generic.cuh", "ffb_engine_wide.cuh", "ffb_wide.h")] + \
@@ -146,6 +146,13 @@ class RkFinishArgs(C.Structure):
                 ("y_out", C.c_void_p), ("lp_out", C.c_void_p), ("partials", C.c_void_p)]
 
 
+# ---- fused training step (include/ffb200.h, csrc/ffb_train.cu) ------------------------------------------
+class TrainArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("x_in", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p),
+                ("scale", C.c_float), ("_pad", C.c_int32), ("grad_w", C.c_void_p * MAX_LAYERS),
+                ("grad_b", C.c_void_p * MAX_LAYERS), ("grad_x", C.c_void_p), ("loss", C.c_void_p), ("work", C.c_void_p)]
+
+
 # every symbol include/ffb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ffb_abi_version": (C.c_int, []),
@@ -167,6 +174,8 @@ SYMBOLS = {
     "ffb_trace_estimate_host": (C.c_int, [C.POINTER(TraceArgs)]),
     "ffb_rk_combine": (C.c_int, [C.POINTER(RkCombineArgs), C.c_void_p]),
     "ffb_rk_finish": (C.c_int, [C.POINTER(RkFinishArgs), C.c_void_p]),
+    "ffb_train_work_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64, C.c_int32]),
+    "ffb_train_step": (C.c_int, [C.POINTER(NetDesc), C.POINTER(TrainArgs), C.c_void_p]),
     "ffb_reduce_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ffb_gaussian_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "ffb_philox_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]),

@@ -336,7 +336,8 @@ class ScoreModel(torch.nn.Module):
         return out / _bcast(self.sde.sigma(tt).reshape(-1), x)
 
     def loss_fn(self, x, conditional=None):
-        raise NotImplementedError("denoising score matching is training-side (out of scope)")
+        """`diffusion.py:240-256`: the denoising score matching loss, fused forward + backward (training.py)."""
+        return denoising_score_matching(self, x, conditional=conditional)
 
     def ode_drift(self, t, x, conditional=None):
         """`diffusion.py:258-279`, one kernel evaluation."""
@@ -635,9 +636,13 @@ class PopulationModelDiffusionConditional(torch.nn.Module):
         return E.gaussian_logprob(xT, lp.reshape(-1), sig).view(-1, 1)
 
 
-def denoising_score_matching(score_model, x, conditional=None):
-    raise NotImplementedError("training losses are out of scope of the B200 sampling / density path")
+def denoising_score_matching(score_model, x, conditional=None, **draws):
+    """`diffusion.py:1369-1414` on the fused training kernels (csrc/ffb_train.cu); ``z=`` / ``t=`` replay the draws."""
+    from . import training
+    return training.denoising_score_matching(score_model, x, conditional, **draws)
 
 
-def log_prob_score_matching(score_model, x, conditional=None):
-    raise NotImplementedError("training losses are out of scope of the B200 sampling / density path")
+def log_prob_score_matching(score_model, x, conditional=None, **draws):
+    """`diffusion.py:1417-1463` (likelihood weighting) on the fused training kernels."""
+    from . import training
+    return training.log_prob_score_matching(score_model, x, conditional, **draws)

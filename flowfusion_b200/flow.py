@@ -106,11 +106,18 @@ class _FlowBase(nn.Module):
         return lp - torch.sum(torch.log(self.target_scale))
 
     # training side ---------------------------------------------------------------------------
-    def compute_linear_velocity_field(self, *a, **k):
-        raise NotImplementedError("flow-matching training targets are out of scope of the B200 path")
+    def compute_linear_velocity_field(self, x0, xT, t):
+        """`flow.py:191-224` / `:679-714`."""
+        from . import training
+        return training.compute_linear_velocity_field(self, x0, xT, t)
 
-    def flow_matching_loss(self, *a, **k):
-        raise NotImplementedError("flow-matching training loss is out of scope of the B200 path")
+    def flow_matching_loss(self, x, conditional=None, **draws):
+        """`flow.py:226-256` (x) / `:716-747` (x, conditional): fused forward + backward (csrc/ffb_train.cu); ``xT=`` /
+        ``t=`` replay the draws."""
+        from . import training
+        if (conditional is None) != (self._cdim() == 0):
+            raise TypeError("flow_matching_loss: a conditional flow takes (x, conditional), an unconditional one (x)")
+        return training.flow_matching_loss(self, x, conditional, **draws)
 
 
 class ODEFlow(_FlowBase):

@@ -379,6 +379,31 @@ typedef struct {
 } ffb_rk_finish_args;
 int ffb_rk_finish(const ffb_rk_finish_args* args, void* stream);
 
+/* ---- fused training step (diffusion.py:1369-1463, flow.py:191-256, :679-747) ----------------
+ * Every loss of the reference is  loss = scale * sum_{b,d} ( alpha_b * net(X)_{b,d} + beta_{b,d} )^2  for per-row scalars
+ * alpha and per-element offsets beta that do not depend on the weights (denoising score matching: alpha = 1 or sigma_b,
+ * beta = z; likelihood weighting: alpha = g_b / sigma_b or g_b, beta = (g_b / sigma_b) z; flow matching: alpha = 1,
+ * beta = x0 - xT).  ffb_train_step evaluates the network on X (B, in_features: the layer-0 input rows in the
+ * network's own column order, time features included), the loss and its gradient with respect to every weight and
+ * bias (torch.nn.Linear layout, written -- not accumulated) and optionally X, in four launches; deterministic.
+ * `net` is read as raw torch weights (weight / bias / widths / in_features / activation; the column map is unused):
+ * the weights change every optimiser step, so nothing is cached between calls. */
+typedef struct {
+  int64_t batch;
+  const float* x_in;                  /* (B, in_features)                                   */
+  const float* alpha;                 /* (B,) or NULL (= 1)                                 */
+  const float* beta;                  /* (B, out_features)                                  */
+  float scale;
+  int32_t _pad;
+  float* grad_w[FFB_MAX_LAYERS];      /* out: (out, in) row-major                           */
+  float* grad_b[FFB_MAX_LAYERS];      /* out: (out,)                                        */
+  float* grad_x;                      /* out: (B, in_features) or NULL                      */
+  double* loss;                       /* out: one double (device)                           */
+  float* work;                        /* ffb_train_work_bytes(net, batch, grad_x != NULL)   */
+} ffb_train_args;
+size_t ffb_train_work_bytes(const ffb_net_desc* net, int64_t batch, int32_t want_grad_x);
+int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* args, void* stream);
+
 /* sums[FFB_NPART] = sum over tiles of partials, in tile order (deterministic) */
 int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream);
 /* out[b] = sum_d ( -0.5*x^2 - 0.5*log(2*pi*var) ) + (add ? add[b] : 0)   (flow.py:434, diffusion.py:814) */

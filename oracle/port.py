@@ -407,6 +407,54 @@ def symplectic_log_prob(Sy, x, p0, cond=None, atol=1e-5, rtol=1e-5):
 
 
 # ------------------------------------------------------------------------------------
+# training losses with the draws passed in; `*_and_grads` add d loss / d (weights, biases)
+# ------------------------------------------------------------------------------------
+def sde_marginal_scalars(s, t):
+    """`diffusion.py:907-924` (VE), `:1133-1156` (VP), `:1318-1342` (subVP): (nu, eta) of p[x(t) | x(0)]."""
+    if s["kind"] == "ve":
+        return torch.ones_like(t), sde_sigma(s, t)
+    lc = 0.5 * (s["beta_max"] - s["beta_min"]) * t ** 2 / s["T"] + s["beta_min"] * t
+    return torch.exp(-0.5 * lc), sde_sigma(s, t)
+
+
+def dsm_loss(M, x, z, t, cond=None):
+    """`diffusion.py:1369-1414` with the draws z (`:1392`) and t (`:1395-1398`) given."""
+    nu, eta = sde_marginal_scalars(M["sde"], t)
+    mean, sigma = nu.view(-1, 1) * x, eta.view(-1, 1)
+    return torch.sum((z + sigma * score(M, t, mean + sigma * z, cond)) ** 2) / x.shape[0]
+
+
+def lpsm_loss(M, x, z, t, cond=None):
+    """`diffusion.py:1417-1463` (likelihood weighting)."""
+    g = sde_diffusion(M["sde"], t, x)
+    nu, eta = sde_marginal_scalars(M["sde"], t)
+    mean, sigma = nu.view(-1, 1) * x, eta.view(-1, 1)
+    return torch.sum(((g / sigma) * z + g * score(M, t, mean + sigma * z, cond)) ** 2) / x.shape[0]
+
+
+def fm_loss(Fl, x, xT, t, cond=None):
+    """`flow.py:226-256` / `:716-747` with the draws xT and t (B, 1) given."""
+    x0 = (x - Fl["shift"]) / Fl["scale"]                  # `flow.py:220`
+    xt, v_hat = (1 - t) * x0 + t * xT, xT - x0
+    return torch.mean((flow_velocity(Fl, t, xt, cond) - v_hat) ** 2)
+
+
+def loss_and_grads(loss_fn, net, *args, **kw):
+    """(loss, [dW_0, db_0, dW_1, db_1, ...]) by autograd over the weight dict ``net`` = {"w": [...], "b": [...]}."""
+    saved = (net["w"], net["b"])
+    net["w"] = [w.clone().requires_grad_(True) for w in saved[0]]
+    net["b"] = [b.clone().requires_grad_(True) for b in saved[1]]
+    try:
+        with torch.set_grad_enabled(True):
+            loss = loss_fn(*args, **kw)
+            params = [p for wb in zip(net["w"], net["b"]) for p in wb]
+            grads = torch.autograd.grad(loss, params)
+    finally:
+        net["w"], net["b"] = saved
+    return loss.detach(), [g.detach() for g in grads]
+
+
+# ------------------------------------------------------------------------------------
 # builders from state_dicts that use the reference's key layout (SURVEY section 5)
 # ------------------------------------------------------------------------------------
 def score_model_from_state_dict(sd, sde, no_sigma, prefix="model.", act=None):

@@ -1,0 +1,124 @@
+"""GPU tests of the fused training step (csrc/ffb_train.cu; run with `pytest -m gpu`): loss and every parameter gradient against
+the golden vectors of the UNMODIFIED reference (oracle/make_golden_train.py) and the CPU oracle, through the reference's own
+entry points (denoising_score_matching, log_prob_score_matching, ScoreModel.loss_fn, flow_matching_loss) and autograd."""
+import pytest
+import torch
+
+from conftest import load_golden
+from test_training import ACT, ACT_MOD, SCORE_CASES, FLOW_CASES, _close, cpu_train_step
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-5        # relative
+GRAD_TOL = 5e-5        # of max(1, |grad|_inf): FP32 sums over the batch in a different order
+
+
+@pytest.mark.parametrize("name", SCORE_CASES)
+def test_score_losses_match_reference_golden(cuda_dev, name):
+    import flowfusion_b200.diffusion as D
+    meta, sd, ins, outs = load_golden(name)
+    kw = {} if meta["activation"] is None else {"activation": ACT_MOD[meta["activation"]]()}
+    sde = {"vp": D.VPSDE, "ve": D.VESDE, "subvp": D.SUBVPSDE}[meta["sde"]]()
+    sm = D.ScoreModel(D.MLP(**meta["ctor"], **kw), sde, no_sigma=meta["no_sigma"]).train()
+    sm.load_state_dict(sd)
+    sm.to(cuda_dev)
+    g = {k: v.to(cuda_dev) for k, v in ins.items()}
+    fn = D.denoising_score_matching if meta["loss"] == "dsm" else D.log_prob_score_matching
+    loss = fn(sm, g["x"], conditional=g.get("cond"), z=g["z"], t=g["t"])
+    assert loss.dim() == 0 and loss.is_cuda and loss.requires_grad
+    assert _close(outs["loss"], loss.detach().cpu(), LOSS_TOL)
+    loss.backward()
+    for k, p in sm.named_parameters():
+        if p.requires_grad:
+            assert _close(outs["grad/" + k], p.grad.cpu(), GRAD_TOL), k
+    # same call, same bits (no atomics anywhere)
+    sm.zero_grad()
+    loss2 = fn(sm, g["x"], conditional=g.get("cond"), z=g["z"], t=g["t"])
+    loss2.backward()
+    assert torch.equal(loss, loss2)
+    # the reference's internal draws: finite, right scale
+    lf = sm.loss_fn(g["x"], conditional=g.get("cond")) if meta["loss"] == "dsm" else fn(sm, g["x"], conditional=g.get("cond"))
+    assert torch.isfinite(lf) and float(lf) > 0
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+def test_flow_matching_loss_matches_reference_golden(cuda_dev, name):
+    import flowfusion_b200.flow as F
+    meta, sd, ins, outs = load_golden(name)
+    kw = {} if meta.get("activation") is None else {"activation": ACT_MOD[meta["activation"]]}
+    cls = F.ConditionalODEFlow if meta["case"] == "cflow_loss" else F.ODEFlow
+    m = cls(**meta["ctor"], **kw).train()
+    m.load_state_dict(sd)
+    m.to(cuda_dev)
+    g = {k: v.to(cuda_dev) for k, v in ins.items()}
+    args = (g["x"],) + ((g["cond"],) if "cond" in g else ())
+    loss = m.flow_matching_loss(*args, xT=g["xT"], t=g["t"])
+    assert _close(outs["loss"], loss.detach().cpu(), LOSS_TOL)
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert _close(outs["grad/" + k], p.grad.cpu(), GRAD_TOL), k
+
+
+@pytest.mark.parametrize("units,B,act", [([256] * 3, 1000, 0), ([128] * 9, 77, 0), ([48], 1, 1), ([200, 72], 4097, 3), ([], 300, 0)])
+def test_train_step_shapes_vs_cpu_model(cuda_dev, units, B, act):
+    """The raw fused call on wide / deep / single-layer networks and ragged batches, d loss / d X included, against autograd."""
+    from flowfusion_b200 import training
+    torch.manual_seed(len(units) + B)
+    dims = [21] + units + [9]
+    lin = [torch.nn.Linear(dims[i], dims[i + 1]) for i in range(len(dims) - 1)]
+    x = torch.randn(B, 21); alpha = torch.rand(B) + 0.5; beta = torch.randn(B, 9)
+    rl, rg, rx = cpu_train_step(lin, act, x, alpha, beta, 0.37, want_grad_x=True)
+    gl = [l.to(cuda_dev) for l in lin]
+    loss, grads, gx = training.train_step(gl, act, x.to(cuda_dev), alpha.to(cuda_dev), beta.to(cuda_dev), 0.37, want_grad_x=True)
+    assert abs(float(loss) - float(rl)) <= LOSS_TOL * max(1.0, abs(float(rl)))
+    for a, b in zip(rg, grads):
+        assert _close(a, b.cpu(), GRAD_TOL)
+    assert _close(rx, gx.cpu(), GRAD_TOL)
+    # alpha = None means 1
+    rl1, rg1, _ = cpu_train_step(lin, act, x, None, beta, 1.0)
+    loss1, grads1, gx1 = training.train_step(gl, act, x.to(cuda_dev), None, beta.to(cuda_dev), 1.0)
+    assert gx1 is None and abs(float(loss1) - float(rl1)) <= LOSS_TOL * max(1.0, abs(float(rl1)))
+    assert _close(rg1[0], grads1[0].cpu(), GRAD_TOL)
+
+
+def test_training_loop_follows_the_oracle(cuda_dev):
+    """Five SGD steps on the GPU (fused loss + autograd + torch.optim.SGD) against the same steps on the CPU oracle."""
+    import flowfusion_b200.flow as F
+    from oracle import port
+    torch.manual_seed(9)
+    m = F.ODEFlow(6, [64, 64], target_shift=torch.zeros(6) + 0.1, target_scale=torch.ones(6) * 1.3).train()
+    Fl = port.flow_from_state_dict(m.state_dict())
+    m.to(cuda_dev)
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    gen = torch.Generator().manual_seed(5)
+    losses_gpu, losses_cpu = [], []
+    for step in range(5):
+        x = torch.randn(512, 6, generator=gen); xT = torch.randn(512, 6, generator=gen); t = torch.rand(512, 1, generator=gen)
+        opt.zero_grad()
+        loss = m.flow_matching_loss(x.to(cuda_dev), xT=xT.to(cuda_dev), t=t.to(cuda_dev))
+        loss.backward()
+        opt.step()
+        losses_gpu.append(float(loss))
+        pl, pg = port.loss_and_grads(port.fm_loss, Fl["net"], Fl, x, xT, t)
+        Fl["net"]["w"] = [w - 0.05 * pg[2 * i] for i, w in enumerate(Fl["net"]["w"])]
+        Fl["net"]["b"] = [b - 0.05 * pg[2 * i + 1] for i, b in enumerate(Fl["net"]["b"])]
+        losses_cpu.append(float(pl))
+    assert max(abs(a - b) / max(1.0, abs(b)) for a, b in zip(losses_gpu, losses_cpu)) < 1e-4
+    assert losses_gpu[-1] < losses_gpu[0]
+    lin = [l for l in m.layers if isinstance(l, torch.nn.Linear)]
+    for i, l in enumerate(lin):
+        assert _close(Fl["net"]["w"][i], l.weight.detach().cpu(), 1e-4)
+    # the trained weights are what the sampling kernels see next (re-packed on change)
+    m.eval()
+    xs = m.sample(torch.randn(64, 6, generator=gen).to(cuda_dev))
+    assert torch.isfinite(xs).all()
+
+
+def test_training_limits(cuda_dev):
+    from flowfusion_b200 import training, _lib
+    lin = [torch.nn.Linear(8, 512), torch.nn.Linear(512, 512), torch.nn.Linear(512, 4)]
+    lin = [l.to(cuda_dev) for l in lin]
+    with pytest.raises(_lib.FFBError, match="shared memory"):
+        training.train_step(lin, 0, torch.zeros(10, 8, device=cuda_dev), None, torch.zeros(10, 4, device=cuda_dev), 1.0)
+    with pytest.raises(_lib.FFBError):                 # no CPU path
+        training.train_step([l.cpu() for l in lin], 0, torch.zeros(10, 8), None, torch.zeros(10, 4), 1.0)
