@@ -150,7 +150,8 @@ class RkFinishArgs(C.Structure):
 class TrainArgs(C.Structure):
     _fields_ = [("batch", C.c_int64), ("x_in", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p),
                 ("scale", C.c_float), ("_pad", C.c_int32), ("grad_w", C.c_void_p * MAX_LAYERS),
-                ("grad_b", C.c_void_p * MAX_LAYERS), ("grad_x", C.c_void_p), ("loss", C.c_void_p), ("work", C.c_void_p)]
+                ("grad_b", C.c_void_p * MAX_LAYERS), ("grad_x", C.c_void_p), ("loss", C.c_void_p), ("work", C.c_void_p),
+                ("cot", C.c_void_p), ("out", C.c_void_p)]
 
 
 # every symbol include/ffb200.h declares: name -> (restype, argtypes)

@@ -59,6 +59,8 @@ struct TrainPlan {
   const float* x_in;          // (B, in_features)
   const float* alpha;         // (B,) or NULL
   const float* beta;          // (B, N[L-1])
+  const float* cot;           // (B, N[L-1]) or NULL: VJP mode, delta_L = scale * cot and loss = scale * sum(cot * net)
+  float* out;                 // (B, N[L-1]) or NULL: the network output
   float scale;
   float* grad_x;              // (B, in_features) or NULL
   double* pass_loss;          // [npass]
@@ -206,10 +208,18 @@ __device__ __forceinline__ void train_passes(CtxW& cx, const TrainPlan& p, float
           for (int i = 0; i < 4; ++i) {
             d[i] = 0.0f;
             if (n < Nout && row0 + i < p.batch) {
-              const float al = p.alpha ? p.alpha[row0 + i] : 1.0f;
-              const float r = fmaf(al, v[i] + bj, p.beta[(row0 + i) * Nout + n]);
-              loss += (double)r * (double)r;
-              d[i] = 2.0f * p.scale * al * r;
+              const float o = v[i] + bj;
+              if (p.out) p.out[(row0 + i) * Nout + n] = o;
+              if (p.cot) {
+                const float ct = p.cot[(row0 + i) * Nout + n];
+                loss += (double)ct * (double)o;
+                d[i] = p.scale * ct;
+              } else {
+                const float al = p.alpha ? p.alpha[row0 + i] : 1.0f;
+                const float r = fmaf(al, o, p.beta[(row0 + i) * Nout + n]);
+                loss += (double)r * (double)r;
+                d[i] = 2.0f * p.scale * al * r;
+              }
             }
           }
           *reinterpret_cast<float4*>(Bf + (size_t)n * WD_RS + r0w) = make_float4(d[0], d[1], d[2], d[3]);
@@ -461,7 +471,8 @@ extern "C" size_t ffb_train_work_bytes(const ffb_net_desc* net, int64_t batch, i
 
 extern "C" int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* a, void* stream_) {
   if (!net || !a) return ffb_fail(FFB_ERR_ARG, "ffb_train_step: null argument");
-  if (!a->x_in || !a->beta || !a->loss || !a->work) return ffb_fail(FFB_ERR_ARG, "ffb_train_step: x_in, beta, loss and work are required");
+  if (!a->x_in || (!a->beta && !a->cot) || !a->loss || !a->work)
+    return ffb_fail(FFB_ERR_ARG, "ffb_train_step: x_in, beta (or cot), loss and work are required");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   TrainPlan p; TrainLayout lay;
   int rc = train_plan(net, a->batch, a->grad_x != nullptr, &p, &lay, a->work);
@@ -475,6 +486,7 @@ extern "C" int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* a, 
     o.gw[l] = a->grad_w[l]; o.gb[l] = a->grad_b[l];
   }
   p.x_in = a->x_in; p.alpha = a->alpha; p.beta = a->beta; p.scale = a->scale; p.grad_x = a->grad_x;
+  p.cot = a->cot; p.out = a->out;
   o.loss = a->loss; o.nblocks_loss = lay.grid;
   const size_t smem = train_smem(lay.zfloats, lay.maxk, nullptr);
   if ((int)smem > tr_smem_optin())

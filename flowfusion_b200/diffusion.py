@@ -323,8 +323,9 @@ class ScoreModel(torch.nn.Module):
 
     def _check_supported(self):
         if self.training:
-            raise NotImplementedError("training=True selects odeint_adjoint (gradients through the solver): "
-                                      "training side, out of scope -- call .eval() first")
+            raise NotImplementedError("training=True selects odeint_adjoint: gradients through the solver are implemented for "
+                                      "sample_ode_from_base only (the log-likelihood paths would need second derivatives "
+                                      "of the network) -- call .eval() first")
 
     # -- reference API ------------------------------------------------------------------------
     def score(self, t, x, conditional=None):
@@ -469,12 +470,26 @@ class ScoreModel(torch.nn.Module):
 
     def sample_ode_from_base(self, base_samples, conditional=None, atol=1e-4, rtol=1e-4, method="dopri5",
                              options=None):
-        """Probability-flow ODE from t=1.0 to epsilon (`diffusion.py:566-640`).  Returns ``(x, [])``."""
-        self._check_supported()
+        """Probability-flow ODE from t=1.0 to epsilon (`diffusion.py:566-640`).  Returns ``(x, [])``.  In training mode the
+        reference solves with ``odeint_adjoint`` (`:620-629`): the samples are then attached to ``base_samples`` and to the
+        network's weights, and their backward pass is the adjoint solve of ``flowfusion_b200/adjoint.py``."""
         E.require_cuda(base_samples, "base_samples")
         z = base_samples * self.sde.sigma_max if hasattr(self.sde, "sigma_max") else base_samples
         self.prob = False
         self.conditional = conditional
+        if self.training:
+            from . import adjoint
+            if (method or "dopri5") not in S.ADAPTIVE_METHODS:
+                raise NotImplementedError(f"training=True (odeint_adjoint) is implemented for {', '.join(S.ADAPTIVE_METHODS)}")
+            if self._group() is not None:
+                raise NotImplementedError("training=True (odeint_adjoint) is not implemented for a sharded batch")
+            eps = float(self.sde.epsilon)
+
+            def solve(y):
+                return self._solve(y, conditional, 1.0, eps, atol, rtol, method, options, L.DIV_NONE, None)[0]
+            x = adjoint.solve_with_adjoint(self, adjoint._ScoreField(self, conditional), solve, z, 1.0, eps, rtol, atol,
+                                           method, options)
+            return x, []
         x, _ = self._solve(z, conditional, 1.0, float(self.sde.epsilon), atol, rtol, method, options,
                            L.DIV_NONE, None)
         return x, []

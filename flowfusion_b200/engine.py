@@ -11,6 +11,7 @@ tensor these classes raise.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import threading
 from typing import List, Optional, Sequence
@@ -73,7 +74,10 @@ def on_device(device):
     """Context manager: make ``device`` the current CUDA device.  The C ABI launches on the current device with raw
     pointers, so every entry point runs under the device of its state tensor (a model on cuda:1 works while
     cuda:0 is current, as it does in the reference)."""
-    return torch.cuda.device(torch.device(device))
+    device = torch.device(device)
+    if device.type != "cuda":          # the torch-CPU model of the kernels (tests/kernel_model.py): nothing to select
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
 
 
 def _dev_f32(t: torch.Tensor, device) -> torch.Tensor:

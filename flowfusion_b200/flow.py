@@ -142,10 +142,16 @@ class ODEFlow(_FlowBase):
         return self.dynamics(t, states)
 
     def sample(self, xT: torch.Tensor, gradients: bool = False):
-        """`flow.py:259-306`: integrate 1 -> 0 with torchdiffeq's default tolerances."""
-        if gradients:
-            raise NotImplementedError("gradients=True (odeint_adjoint) is training-side, out of scope")
+        """`flow.py:259-306`: integrate 1 -> 0 with torchdiffeq's default tolerances.  ``gradients=True`` is the reference's
+        ``odeint_adjoint`` branch (`:286-295`): the samples are attached to ``xT`` and the weights (adjoint.py)."""
         E.require_cuda(xT, "xT")
+        if gradients:
+            from . import adjoint
+
+            def solve(y):
+                return self._integrate(y, None, None, 1.0, 0.0, 1e-9, 1e-7, None, None, L.DIV_NONE)[0]
+            x = adjoint.solve_with_adjoint(self, adjoint._FlowField(self), solve, xT, 1.0, 0.0, 1e-7, 1e-9, None, None)
+            return x * self.target_scale + self.target_shift
         with torch.no_grad():
             x, _ = self._integrate(xT, None, None, 1.0, 0.0, 1e-9, 1e-7, None, None, L.DIV_NONE)
             return x * self.target_scale + self.target_shift
@@ -153,7 +159,7 @@ class ODEFlow(_FlowBase):
     def solve_ode_forward(self, x, atol=1e-5, rtol=1e-5, method="dopri5", options=None, adjoint=False):
         """`flow.py:308-384` -> (x(T), log-Jacobian (B, 1))."""
         if adjoint:
-            raise NotImplementedError("adjoint=True is training-side, out of scope")
+            raise NotImplementedError("adjoint=True of the log-likelihood solve is not implemented (it needs second derivatives of the network); sample(gradients=True) is")
         E.require_cuda(x, "x")
         with torch.no_grad():
             xT, lj = self._integrate(x, None, None, 0.0, 1.0, atol, rtol, method, options, L.DIV_EXACT)
@@ -203,7 +209,8 @@ class ConditionalODEFlow(_FlowBase):
     def sample(self, xT, conditional, gradients: bool = False):
         """`flow.py:750-799`."""
         if gradients:
-            raise NotImplementedError("gradients=True (odeint_adjoint) is training-side, out of scope")
+            raise NotImplementedError("gradients=True (odeint_adjoint) of a conditional flow is not implemented: the "
+                                      "conditional is part of its ODE state (ODEFlow.sample(gradients=True) is)")
         E.require_cuda(xT, "xT")
         with torch.no_grad():
             x, _ = self._integrate(xT, self._norm_cond(conditional), conditional, 1.0, 0.0, 1e-9, 1e-7, None, None,
@@ -213,7 +220,7 @@ class ConditionalODEFlow(_FlowBase):
     def solve_ode_forward(self, x, conditional, atol=1e-5, rtol=1e-5, method="dopri5", options=None, adjoint=False):
         """`flow.py:801-883`."""
         if adjoint:
-            raise NotImplementedError("adjoint=True is training-side, out of scope")
+            raise NotImplementedError("adjoint=True of the log-likelihood solve is not implemented (it needs second derivatives of the network); sample(gradients=True) is")
         E.require_cuda(x, "x")
         with torch.no_grad():
             xT, lj = self._integrate(x, self._norm_cond(conditional), conditional, 0.0, 1.0, atol, rtol, method,

@@ -20,9 +20,18 @@ from . import _lib as L
 from . import engine as E
 
 
+def param_sizes(linears: Sequence[torch.nn.Linear]) -> List[int]:
+    """Element counts of [W_0, b_0, W_1, b_1, ...]."""
+    return [n for lin in linears for n in (lin.weight.numel(), lin.bias.numel())]
+
+
 def train_step(linears: Sequence[torch.nn.Linear], activation: int, x_in: torch.Tensor, alpha: Optional[torch.Tensor],
-               beta: torch.Tensor, scale: float, want_grad_x: bool = False):
-    """One fused call -> (loss (0-d float64 device tensor), [dW_0, db_0, dW_1, db_1, ...], dX or None)."""
+               beta: Optional[torch.Tensor], scale: float, want_grad_x: bool = False, cot: Optional[torch.Tensor] = None,
+               want_out: bool = False, grad_flat: Optional[torch.Tensor] = None):
+    """One fused call -> (loss (0-d float64 device tensor), [dW_0, db_0, dW_1, db_1, ...], dX or None[, net(X)]).
+
+    ``cot`` switches to the vector-Jacobian mode (loss = scale * sum(cot * net(X)); alpha / beta unused).  ``grad_flat``: a
+    float32 device vector of sum(param_sizes) elements to write the gradients into (the returned list are views of it)."""
     lib = L.load()
     E.require_cuda(x_in, "x")
     dev = x_in.device
@@ -43,21 +52,30 @@ def train_step(linears: Sequence[torch.nn.Linear], activation: int, x_in: torch.
     d.x_dim, d.activation = linears[0].in_features, int(activation)
     B = x_in.shape[0]
     x_in = E._dev_f32(x_in, dev)
-    beta = E._dev_f32(beta, dev)
-    if x_in.shape != (B, linears[0].in_features) or beta.shape != (B, linears[-1].out_features):
-        raise ValueError("train_step: x_in must be (B, in_features) and beta (B, out_features)")
+    tgt = E._dev_f32(beta if cot is None else cot, dev)
+    if x_in.shape != (B, linears[0].in_features) or tgt.shape != (B, linears[-1].out_features):
+        raise ValueError("train_step: x_in must be (B, in_features) and beta / cot (B, out_features)")
     if alpha is not None:
         alpha = E._dev_f32(alpha.reshape(-1), dev)
         if alpha.shape[0] != B:
             raise ValueError("train_step: alpha must have one entry per row")
     a = L.TrainArgs()
-    a.batch, a.x_in, a.alpha, a.beta = B, x_in.data_ptr(), (alpha.data_ptr() if alpha is not None else None), beta.data_ptr()
+    a.batch, a.x_in, a.alpha = B, x_in.data_ptr(), (alpha.data_ptr() if alpha is not None else None)
+    if cot is None:
+        a.beta = tgt.data_ptr()
+    else:
+        a.cot = tgt.data_ptr()
     a.scale = float(scale)
-    grads: List[torch.Tensor] = []
-    for i, lin in enumerate(linears):
-        gw, gb = torch.empty_like(keep[2 * i]), torch.empty_like(keep[2 * i + 1])
-        grads += [gw, gb]
-        a.grad_w[i], a.grad_b[i] = gw.data_ptr(), gb.data_ptr()
+    out = torch.empty(B, linears[-1].out_features, device=dev) if want_out else None
+    a.out = out.data_ptr() if out is not None else None
+    sizes = param_sizes(linears)
+    if grad_flat is None:
+        grad_flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+    elif grad_flat.numel() != sum(sizes) or grad_flat.dtype != torch.float32 or not grad_flat.is_contiguous() or grad_flat.device != dev:
+        raise ValueError("train_step: grad_flat must be a contiguous float32 device vector of sum(param_sizes) elements")
+    grads: List[torch.Tensor] = [g.view_as(k) for g, k in zip(torch.split(grad_flat, sizes), keep)]
+    for i in range(len(linears)):
+        a.grad_w[i], a.grad_b[i] = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
     gx = torch.empty_like(x_in) if want_grad_x else None
     a.grad_x = gx.data_ptr() if gx is not None else None
     loss = torch.empty((), dtype=torch.float64, device=dev)
@@ -72,8 +90,10 @@ def train_step(linears: Sequence[torch.nn.Linear], activation: int, x_in: torch.
     # the launches read `keep`, the inputs and `work` asynchronously: record them on the stream so that the caching
     # allocator does not hand the memory to another stream before they have run
     st = torch.cuda.current_stream(dev)
-    for t in keep + [x_in, beta, work] + ([alpha] if alpha is not None else []):
+    for t in keep + [x_in, tgt, work] + ([alpha] if alpha is not None else []):
         t.record_stream(st)
+    if want_out:
+        return loss, grads, gx, out
     return loss, grads, gx
 
 

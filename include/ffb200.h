@@ -400,6 +400,11 @@ typedef struct {
   float* grad_x;                      /* out: (B, in_features) or NULL                      */
   double* loss;                       /* out: one double (device)                           */
   float* work;                        /* ffb_train_work_bytes(net, batch, grad_x != NULL)   */
+  /* vector-Jacobian mode (the adjoint ODE of SURVEY 8f rank 3, diffusion.py:620-629, flow.py:286-295): with cot != NULL
+   * the "loss" is scale * sum(cot * net(X)), i.e. grad_w / grad_b / grad_x are scale * cot^T d net / d (W, b, X);
+   * alpha and beta are ignored. */
+  const float* cot;                   /* (B, out_features) or NULL                          */
+  float* out;                         /* out: (B, out_features) network output, or NULL     */
 } ffb_train_args;
 size_t ffb_train_work_bytes(const ffb_net_desc* net, int64_t batch, int32_t want_grad_x);
 int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* args, void* stream);

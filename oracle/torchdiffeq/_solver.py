@@ -66,7 +66,7 @@ def _split(flat: torch.Tensor, lead: Sequence[int], shapes) -> tuple:
     out, pos = [], 0
     for shp in shapes:
         n = int(math.prod(shp))
-        out.append(flat[..., pos:pos + n].reshape(*lead, *shp))
+        out.append(flat[..., pos:pos + n].reshape(tuple(lead) + tuple(shp)))
         pos += n
     return tuple(out)
 
@@ -474,6 +474,99 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     return sol
 
 
-def odeint_adjoint(*args, **kwargs):
-    """Back-propagation through the solve is training-side: not restated."""
-    raise NotImplementedError("odeint_adjoint is outside the restated sampling / density path")
+# --------------------------------------------------------------------------------------
+# odeint_adjoint: torchdiffeq/_impl/adjoint.py restated.  Forward = odeint without a graph; backward =
+# ONE more solve, backwards over each output interval, of the augmented system
+#     d/dt (vjp_t, y, adj_y, adj_params) = (0, f, -adj_y^T df/dy, -adj_y^T df/dparams)
+# started from (0, y(t_end), dL/dy(t_end), 0), with torchdiffeq's default adjoint norm
+#     max(|vjp_t|, state_norm(y), state_norm(adj_y), mixed_rms(adj_params))
+# and the forward solve's rtol / atol / method / options (minus `norm`) unless adjoint_* say otherwise.  Gradients with
+# respect to t are not restated (the reference never asks for them).  PARITY UNPINNED like the driver above.
+# --------------------------------------------------------------------------------------
+class _OdeintAdjoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, shapes, func, y0, t, rtol, atol, method, options, adj_rtol, adj_atol, adj_method, adj_options, *params):
+        ctx.cfg = (shapes, func, adj_rtol, adj_atol, adj_method, adj_options)
+        with torch.no_grad():
+            sol = odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+        ctx.save_for_backward(t, sol, *params)
+        return sol
+
+    @staticmethod
+    def backward(ctx, grad_sol):
+        shapes, func, rtol, atol, method, options = ctx.cfg
+        t, sol, *params = ctx.saved_tensors
+        params = tuple(params)
+        with torch.no_grad():
+            aug = [torch.zeros((), dtype=sol.dtype), sol[-1], grad_sol[-1]] + [torch.zeros_like(p) for p in params]
+
+            def augmented_dynamics(tt, y_aug):
+                y, adj_y = y_aug[1], y_aug[2]
+                with torch.enable_grad():
+                    t_ = tt.detach()
+                    y = y.detach().requires_grad_(True)
+                    f = func(t_, y)
+                    vjp_y, *vjp_p = torch.autograd.grad(f, (y,) + params, -adj_y, allow_unused=True, retain_graph=True)
+                vjp_y = torch.zeros_like(y) if vjp_y is None else vjp_y
+                vjp_p = [torch.zeros_like(p) if v is None else v for p, v in zip(params, vjp_p)]
+                return (torch.zeros_like(t_), f.detach(), vjp_y, *vjp_p)
+
+            for i in range(len(t) - 1, 0, -1):
+                out = odeint(augmented_dynamics, tuple(aug), t[i - 1:i + 1].flip(0), rtol=rtol, atol=atol, method=method,
+                             options=options)
+                aug = [a[1] for a in out]
+                aug[1] = sol[i - 1]
+                aug[2] = aug[2] + grad_sol[i - 1]
+        return (None, None, aug[2], None, None, None, None, None, None, None, None, None, *aug[3:])
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, adjoint_rtol=None,
+                   adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
+    """Restated ``torchdiffeq.odeint_adjoint`` (no events, no gradients with respect to ``t``)."""
+    if event_fn is not None:
+        raise NotImplementedError("event handling is outside the restated path")
+    if adjoint_params is None and not isinstance(func, torch.nn.Module):
+        raise ValueError("func must be an instance of nn.Module to specify the adjoint parameters; alternatively they can be "
+                         "specified explicitly via the `adjoint_params` argument.")
+    adjoint_rtol = rtol if adjoint_rtol is None else adjoint_rtol
+    adjoint_atol = atol if adjoint_atol is None else adjoint_atol
+    adjoint_method = method if adjoint_method is None else adjoint_method
+    if adjoint_options is None:
+        adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
+    else:
+        adjoint_options = dict(adjoint_options)
+    params = tuple(func.parameters()) if adjoint_params is None else tuple(adjoint_params)
+    params = tuple(p for p in params if p.requires_grad)
+    shapes = None
+    flat_func = func
+    if not isinstance(y0, torch.Tensor):                      # T1: the adjoint works on the flattened state
+        shapes = [y_.shape for y_ in y0]
+        y0 = torch.cat([y_.reshape(-1) for y_ in y0])
+
+        def flat_func(tt, y, _f=func, _s=shapes):
+            out = _f(tt, _split(y, (), _s))
+            return torch.cat([o.reshape(-1) for o in out])
+    state_norm = (options or {}).get("norm")
+    if state_norm is None:
+        state_norm = _rms if shapes is None else (lambda flat: _mixed_rms(_split(flat, (), shapes)))
+    elif shapes is not None:
+        user_norm = state_norm
+        state_norm = lambda flat: user_norm(_split(flat, (), shapes))      # noqa: E731
+    if "norm" not in adjoint_options:
+        def default_adjoint_norm(parts):
+            tt, y, adj_y, *adj_params = parts
+            return max(tt.abs(), state_norm(y), state_norm(adj_y), _mixed_rms(adj_params))
+        adjoint_options["norm"] = default_adjoint_norm
+    fwd_options = None
+    if options is not None:
+        fwd_options = dict(options)
+        if shapes is not None and "norm" in fwd_options:
+            fwd_options["norm"] = state_norm
+    if shapes is not None and (fwd_options is None or "norm" not in fwd_options):
+        fwd_options = dict(fwd_options or {})
+        fwd_options["norm"] = state_norm
+    sol = _OdeintAdjoint.apply(shapes, flat_func, y0, t, rtol, atol, method, fwd_options, adjoint_rtol, adjoint_atol,
+                               adjoint_method, adjoint_options, *params)
+    if shapes is not None:
+        sol = _split(sol, (len(t),), shapes)
+    return sol

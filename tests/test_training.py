@@ -37,8 +37,8 @@ def test_oracle_losses_match_reference_golden(name):
         assert _close(outs[k], g, 2e-5), k
 
 
-def cpu_train_step(linears, activation, x_in, alpha, beta, scale, want_grad_x=False):
-    """torch-CPU model of ffb_train_step: same arguments, same returns."""
+def cpu_train_step(linears, activation, x_in, alpha, beta, scale, want_grad_x=False, cot=None, want_out=False, grad_flat=None):
+    """torch-CPU model of ffb_train_step (csrc/ffb_train.cu): same arguments, same returns as training.train_step."""
     act = [torch.nn.functional.silu, torch.tanh, torch.relu, torch.nn.functional.softplus, torch.nn.functional.gelu][activation]
     params = []
     for lin in linears:
@@ -50,10 +50,21 @@ def cpu_train_step(linears, activation, x_in, alpha, beta, scale, want_grad_x=Fa
             h = torch.nn.functional.linear(h, params[2 * i], params[2 * i + 1])
             if i < len(linears) - 1:
                 h = act(h)
-        a = 1.0 if alpha is None else alpha.reshape(-1, 1)
-        loss = scale * torch.sum((a * h + beta) ** 2)
+        if cot is not None:
+            loss = scale * torch.sum(cot.detach() * h)
+        else:
+            a = 1.0 if alpha is None else alpha.reshape(-1, 1)
+            loss = scale * torch.sum((a * h + beta) ** 2)
         grads = torch.autograd.grad(loss, params + ([x0] if want_grad_x else []))
-    return loss.detach().double(), list(grads[: len(params)]), (grads[-1] if want_grad_x else None)
+    pg = list(grads[: len(params)])
+    if grad_flat is not None:
+        pos = 0
+        for i, g in enumerate(pg):
+            grad_flat[pos: pos + g.numel()].copy_(g.reshape(-1))
+            pg[i] = grad_flat[pos: pos + g.numel()].view_as(g)
+            pos += g.numel()
+    res = (loss.detach().double(), pg, (grads[-1] if want_grad_x else None))
+    return res + (h.detach(),) if want_out else res
 
 
 @pytest.fixture
