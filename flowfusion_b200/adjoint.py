@@ -1,6 +1,6 @@
 """Gradients through the sampler: ``torchdiffeq.odeint_adjoint`` for the reference's sampling
 entry points -- ``ScoreModel.sample_ode_from_base`` in training mode (`diffusion.py:620-629`) and
-``ODEFlow.sample(gradients=True)`` (`flow.py:286-295`).
+``ODEFlow.sample(gradients=True)`` (`flow.py:286-295`) / ``ConditionalODEFlow.sample(..., gradients=True)`` (`:775-785`).
 
 Forward: the ordinary fused solve (no graph), as ``odeint_adjoint`` does.  Backward: ONE more adaptive solve, from the end
 time back to the start time, of the augmented system of torchdiffeq's ``OdeintAdjointMethod.backward``
@@ -16,8 +16,9 @@ the Runge-Kutta stage algebra and the error norms of the flat augmented state (2
 torchdiffeq's flattened tuple) are device-tensor operations driven by ``FlatAdaptiveRK`` below -- the same controller
 statements as ``solver._dopri5`` (float64 time bookkeeping, float32 stage times, one-ulp perturbation of the stages with
 alpha = 1, ``step_t`` landing, dense output at the end time).  Gradients with respect to ``t``, adjoints of the
-log-likelihood paths (the divergence needs second derivatives of the network) and conditional flows (the conditional is
-part of their ODE state) are not implemented and raise ``NotImplementedError``."""
+log-likelihood paths (the divergence needs second derivatives of the network) are not implemented and raise
+``NotImplementedError``.  ``ConditionalODEFlow.sample(gradients=True)`` (`flow.py:775-785`) carries the conditional in the
+ODE state as the reference does: it takes part in the norms and receives its own gradient."""
 from __future__ import annotations
 
 import bisect
@@ -210,63 +211,102 @@ class _FlowField:
         return torch.cat([y, tcol], dim=1), 0.0, -1.0, 0
 
 
+class _CondFlowField:
+    """Velocity of a conditional flow (`flow.py:553-596`): f = net(cat[x, t, (c - cshift) / cscale]); the conditional is part of
+    the ODE state with zero derivative, so it takes part in the norms and collects its own adjoint."""
+
+    def __init__(self, flow):
+        self.linears = [l for l in flow.layers if isinstance(l, torch.nn.Linear)]
+        self.act = E.activation_of(flow.layers)
+        self.D, self.C = flow.target_dimension, flow.conditional_dimension
+        self.cshift, self.cscale = flow.conditional_shift, flow.conditional_scale
+        self.params = [p for lin in self.linears for p in (lin.weight, lin.bias)]
+
+    def rows(self, t32, y, c):
+        tcol = torch.full((y.shape[0], 1), float(t32), dtype=torch.float32, device=y.device)
+        return torch.cat([y, tcol, (c - self.cshift) / self.cscale], dim=1), 0.0, -1.0, 0
+
+    def static_vjp(self, gx):
+        """adj_x^T df/dc from the kernel's d/dX: the conditional's columns, through the normalisation."""
+        return gx[:, self.D + 1: self.D + 1 + self.C] / self.cscale
+
+
 def adjoint_backward(field, y_end: torch.Tensor, grad_end: torch.Tensor, t_start: float, t_end: float, rtol, atol,
-                     method="dopri5", options=None):
-    """-> (dL/dy(t_start), [dL/dparam ...], SolveStats): the backward pass of ``odeint_adjoint`` for a solve that ran from
-    ``t_start`` to ``t_end`` and produced ``y_end``; ``grad_end`` = dL/dy(t_end)."""
+                     method="dopri5", options=None, static: Optional[torch.Tensor] = None):
+    """-> (dL/dy(t_start), dL/dstatic or None, [dL/dparam ...], SolveStats): the backward pass of ``odeint_adjoint`` for a solve
+    that ran from ``t_start`` to ``t_end`` and produced ``y_end``; ``grad_end`` = dL/dy(t_end).  ``static``: (B, C) state columns
+    with zero derivative that the field reads (the conditional of a conditional flow)."""
     E.require_cuda(y_end, "state")
     B, D = y_end.shape
-    n = B * D
+    Cs = 0 if static is None else static.shape[1]
+    nx, nc = B * D, B * Cs
+    n = nx + nc                                   # flattened forward state: [x | static], as torchdiffeq flattens the tuple
     sizes = T.param_sizes(field.linears)
     P = sum(sizes)
-    segs, pos = [(0, n), (n, 2 * n)], 2 * n
+    segs = [(0, nx), (nx, n), (n, n + nx), (n + nx, 2 * n)]
+    pos = 2 * n
     for s in sizes:
         segs.append((pos, pos + s))
         pos += s
 
     def aug(t32, v):
-        y, adj = v[:n].view(B, D), v[n: 2 * n].view(B, D)
-        x_in, lin, kk, x_col = field.rows(t32, y)
+        y, adj = v[:nx].view(B, D), v[n: n + nx].view(B, D)
+        if Cs:
+            x_in, lin, kk, x_col = field.rows(t32, y, v[nx:n].view(B, Cs))
+        else:
+            x_in, lin, kk, x_col = field.rows(t32, y)
         out = torch.empty_like(v)
         # one fused call: net(X), (-kk adj)^T d net / d (W, b) straight into the flat derivative, (-kk adj)^T d net / d X
         _, _, gx, o = T.train_step(field.linears, field.act, x_in, None, None, -kk, want_grad_x=True, cot=adj, want_out=True,
                                    grad_flat=out[2 * n:])
         out[2 * n:].neg_()                                              # d adj_params / dt = -adj^T df/dparams
         vjp_y = gx[:, x_col: x_col + D]
-        out[:n].view(B, D).copy_(lin * y - kk * o if lin != 0.0 else -kk * o)     # f
-        out[n: 2 * n].view(B, D).copy_(-(lin * adj + vjp_y) if lin != 0.0 else -vjp_y)   # d adj_y / dt = -adj^T df/dy
+        out[:nx].view(B, D).copy_(lin * y - kk * o if lin != 0.0 else -kk * o)          # f
+        out[n: n + nx].view(B, D).copy_(-(lin * adj + vjp_y) if lin != 0.0 else -vjp_y)  # d adj_y / dt = -adj^T df/dy
+        if Cs:
+            out[nx:n].zero_()                                           # the conditional does not move (`flow.py:591-596`)
+            out[n + nx: 2 * n].view(B, Cs).copy_(-field.static_vjp(gx))
         return out
 
     drv = FlatAdaptiveRK(aug, segs, rtol, atol, method or "dopri5", options)
-    v0 = torch.cat([y_end.reshape(-1).float(), grad_end.reshape(-1).float(), torch.zeros(P, dtype=torch.float32, device=y_end.device)])
-    with torch.no_grad(), E.on_device(y_end.device):
+    dev = y_end.device
+    parts = [y_end.reshape(-1).float()] + ([static.reshape(-1).float()] if Cs else []) + [grad_end.reshape(-1).float()]
+    parts += [torch.zeros(nc + P, dtype=torch.float32, device=dev)]     # dL/dstatic(t_end) = 0, adj_params = 0
+    v0 = torch.cat(parts)
+    with torch.no_grad(), E.on_device(dev):
         v1 = drv.integrate(v0, float(t_end), float(t_start))
     grads = [g.view_as(p) for g, p in zip(torch.split(v1[2 * n:], sizes), field.params)]
-    return v1[n: 2 * n].view(B, D), grads, drv.stats
+    gstatic = v1[n + nx: 2 * n].view(B, Cs) if Cs else None
+    return v1[n: n + nx].view(B, D), gstatic, grads, drv.stats
 
 
 class _AdjointSolve(torch.autograd.Function):
     """forward: the model's own fused solve; backward: ``adjoint_backward``."""
 
     @staticmethod
-    def forward(ctx, y0, owner, field, solve, t_start, t_end, rtol, atol, method, options, *params):
+    def forward(ctx, y0, static, owner, field, solve, t_start, t_end, rtol, atol, method, options, *params):
         with torch.no_grad():
             y1 = solve(y0.detach())
         ctx.cfg = (owner, field, t_start, t_end, rtol, atol, method, options)
-        ctx.save_for_backward(y1)
+        ctx.has_static = static is not None
+        ctx.save_for_backward(y1, *([static.detach()] if static is not None else []))
         return y1.clone()
 
     @staticmethod
     def backward(ctx, grad_y1):
         owner, field, t_start, t_end, rtol, atol, method, options = ctx.cfg
-        (y1,) = ctx.saved_tensors
+        y1 = ctx.saved_tensors[0]
+        static = ctx.saved_tensors[1] if ctx.has_static else None
         adj_opts = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
-        gy0, gparams, stats = adjoint_backward(field, y1, grad_y1.contiguous(), t_start, t_end, rtol, atol, method, adj_opts)
+        gy0, gstatic, gparams, stats = adjoint_backward(field, y1, grad_y1.contiguous(), t_start, t_end, rtol, atol, method,
+                                                        adj_opts, static=static)
         owner.last_adjoint_stats = stats
-        return (gy0, None, None, None, None, None, None, None, None, None) + tuple(gparams)
+        return (gy0, gstatic, None, None, None, None, None, None, None, None, None) + tuple(gparams)
 
 
-def solve_with_adjoint(owner, field, solve, y0, t_start, t_end, rtol, atol, method, options):
+def solve_with_adjoint(owner, field, solve, y0, t_start, t_end, rtol, atol, method, options, static=None):
     """``odeint_adjoint`` for one of the reference's sampling solves: ``solve(y0) -> y(t_end)`` is the model's forward solve
-    (no graph); the result is attached to ``y0`` and to the network's weights and biases."""
-    return _AdjointSolve.apply(y0, owner, field, solve, float(t_start), float(t_end), rtol, atol, method, options, *field.params)
+    (no graph); the result is attached to ``y0``, to ``static`` (a conditional carried in the ODE state) and to the network's
+    weights and biases."""
+    return _AdjointSolve.apply(y0, static, owner, field, solve, float(t_start), float(t_end), rtol, atol, method, options,
+                               *field.params)

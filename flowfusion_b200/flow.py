@@ -208,10 +208,16 @@ class ConditionalODEFlow(_FlowBase):
 
     def sample(self, xT, conditional, gradients: bool = False):
         """`flow.py:750-799`."""
-        if gradients:
-            raise NotImplementedError("gradients=True (odeint_adjoint) of a conditional flow is not implemented: the "
-                                      "conditional is part of its ODE state (ODEFlow.sample(gradients=True) is)")
         E.require_cuda(xT, "xT")
+        if gradients:                              # `flow.py:775-785`: odeint_adjoint over the state (xT, conditional)
+            from . import adjoint
+
+            def solve(y):
+                return self._integrate(y, self._norm_cond(conditional.detach()), conditional.detach(), 1.0, 0.0, 1e-9, 1e-7,
+                                       None, None, L.DIV_NONE)[0]
+            x = adjoint.solve_with_adjoint(self, adjoint._CondFlowField(self), solve, xT, 1.0, 0.0, 1e-7, 1e-9, None, None,
+                                           static=conditional)
+            return x * self.target_scale + self.target_shift
         with torch.no_grad():
             x, _ = self._integrate(xT, self._norm_cond(conditional), conditional, 1.0, 0.0, 1e-9, 1e-7, None, None,
                                    L.DIV_NONE)

@@ -6,7 +6,7 @@ back-propagation through a fixed-step integrator).
     python oracle/make_golden_adjoint.py    # writes tests/golden/adjoint_*.npz
 
 Cases: ``ScoreModel.sample_ode_from_base`` in training mode (`diffusion.py:620-629`) for a conditional VP model (no_sigma) and a
-VE model with sigma division, and ``ODEFlow.sample(gradients=True)`` (`flow.py:286-295`).  Stored: inputs, samples, the
+VE model with sigma division, and ``ODEFlow.sample(gradients=True)`` (`flow.py:286-295`) and ``ConditionalODEFlow.sample(gradients=True)`` (`:775-785`).  Stored: inputs, samples, the
 cotangent dL/dx used (L = sum(w * x) for a fixed random w), dL/d(base samples) and dL/d(every weight and bias), and the
 step counts of the backward solve.
 """
@@ -66,6 +66,24 @@ def main():
     outs.update({"grad/" + k: p.grad for k, p in m.named_parameters()})
     save("adjoint_flow_sample", dict(case="flow_adjoint", ctor=dict(target_dimension=3, hidden_units=[32, 32]),
                                      stats_forward=fwd, stats_backward=bwd), m.state_dict(), {"xT": xT.detach(), "w": w}, outs)
+
+    print("adjoint_cflow_sample")
+    torch.manual_seed(WSEED)
+    m = F.ConditionalODEFlow(3, 2, [32, 24], conditional_shift=torch.tensor([0.5, -0.5]),
+                             conditional_scale=torch.tensor([2.0, 0.5])).train()
+    xT = torch.randn(50, 3, generator=gen(46)).requires_grad_(True)
+    c = torch.randn(50, 2, generator=gen(47)).requires_grad_(True)
+    w = torch.randn(50, 3, generator=gen(48))
+    x = m.sample(xT, c, gradients=True)
+    fwd = stats_dict()
+    (x * w).sum().backward()
+    bwd = stats_dict()
+    print(f"  forward {fwd['accepted']}/{fwd['rejected']}  backward {bwd['accepted']}/{bwd['rejected']}")
+    outs = {"x": x.detach(), "grad/xT": xT.grad, "grad/cond": c.grad}
+    outs.update({"grad/" + k: p.grad for k, p in m.named_parameters()})
+    save("adjoint_cflow_sample", dict(case="cflow_adjoint", ctor=dict(target_dimension=3, conditional_dimension=2, hidden_units=[32, 24]),
+                                      stats_forward=fwd, stats_backward=bwd), m.state_dict(),
+         {"xT": xT.detach(), "cond": c.detach(), "w": w}, outs)
     print("done")
 
 

@@ -100,6 +100,22 @@ def test_flow_sampler_adjoint_host_logic(cpu_kernels):
         assert _close(outs["grad/" + k], p.grad, GRAD_TOL), k
     with pytest.raises(NotImplementedError):
         m.solve_ode_forward(ins["xT"], adjoint=True)
-    c = F.ConditionalODEFlow(3, 2, [8]).train()
+
+
+def test_conditional_flow_sampler_adjoint_host_logic(cpu_kernels):
+    """`flow.py:775-785`: the conditional rides in the ODE state, takes part in the norms and gets its own gradient."""
+    import flowfusion_b200.flow as F
+    meta, sd, ins, outs = load_golden("adjoint_cflow_sample")
+    m = F.ConditionalODEFlow(**meta["ctor"]).train()
+    m.load_state_dict(sd)
+    xT = ins["xT"].clone().requires_grad_(True)
+    c = ins["cond"].clone().requires_grad_(True)
+    x = m.sample(xT, c, gradients=True)
+    assert _close(outs["x"], x.detach(), 1e-4)
+    (x * ins["w"]).sum().backward()
+    assert _close(outs["grad/xT"], xT.grad, GRAD_TOL)
+    assert _close(outs["grad/cond"], c.grad, GRAD_TOL)
+    for k, p in m.named_parameters():
+        assert _close(outs["grad/" + k], p.grad, GRAD_TOL), k
     with pytest.raises(NotImplementedError):
-        c.sample(ins["xT"], torch.zeros(60, 2), gradients=True)
+        m.log_prob(ins["xT"], ins["cond"], adjoint=True)

@@ -51,6 +51,23 @@ def test_flow_sampler_adjoint_matches_reference_golden(cuda_dev):
         assert _close(outs["grad/" + k], p.grad.cpu(), GRAD_TOL), k
 
 
+def test_conditional_flow_sampler_adjoint_matches_reference_golden(cuda_dev):
+    import flowfusion_b200.flow as F
+    meta, sd, ins, outs = load_golden("adjoint_cflow_sample")
+    m = F.ConditionalODEFlow(**meta["ctor"]).train()
+    m.load_state_dict(sd)
+    m.to(cuda_dev)
+    xT = ins["xT"].to(cuda_dev).requires_grad_(True)
+    c = ins["cond"].to(cuda_dev).requires_grad_(True)
+    x = m.sample(xT, c, gradients=True)
+    assert _close(outs["x"], x.detach().cpu(), 1e-4)
+    (x * ins["w"].to(cuda_dev)).sum().backward()
+    assert _close(outs["grad/xT"], xT.grad.cpu(), GRAD_TOL)
+    assert _close(outs["grad/cond"], c.grad.cpu(), GRAD_TOL)
+    for k, p in m.named_parameters():
+        assert _close(outs["grad/" + k], p.grad.cpu(), GRAD_TOL), k
+
+
 def test_vjp_mode_of_the_training_kernel(cuda_dev):
     """cot != NULL: grad_w / grad_b / grad_x are scale * cot^T d net / d (W, b, X), `out` is the network output."""
     import copy
