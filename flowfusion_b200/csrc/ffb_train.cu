@@ -14,7 +14,7 @@
 //                    packed FFMA2): forward keeping the pre-activations z_l in shared memory, the loss residual, then the
 //                    backward sweep delta_{l-1} = (W_l^T delta_l) * act'(z_{l-1}); h_l and delta_l go to global memory
 //                    (L2-resident at training batch sizes) for the weight gradients, FP64 loss partial per pass;
-//   k_train_dw       dW_l = delta_l^T h_{l-1}, db_l = sum_b delta_l: 32 x 32 patches, the batch split over grid.y;
+//   k_train_dw       dW_l = delta_l^T h_{l-1}, db_l = sum_b delta_l: 64 x 64 patches (4 x 4 per thread, FFMA2), the batch split over grid.y;
 //   k_train_reduce   sums the split partials in a fixed order into the caller's gradient tensors (torch layout) and the
 //                    pass partials into the loss: deterministic, no atomics.
 #include <cuda_runtime.h>
@@ -295,21 +295,30 @@ __global__ void __launch_bounds__(NTHR, 1) k_train_fwdbwd(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// weight gradients: 32 x 32 patches of dW_l (+ db_l from the patches with k0 = 0), batch split over grid.y
+// weight gradients: 64 x 64 patches of dW_l (+ db_l from the patches with k0 = 0), batch split over grid.y.
+// A thread owns 4 x 4 outputs: per batch row one LDS.128 of delta (broadcast to the 16 threads that share the rows of
+// the patch), one LDS.128 of h, 8 packed FFMA2.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int DW_P = 64;             // patch edge
+constexpr int DW_LD = DW_P + 4;      // shared-memory row stride (floats): float4-aligned, conflict-free for the two access patterns
+__host__ __device__ inline int dw_patches(const TrainPlan& p) {
+  int n = 0;
+  for (int l = 0; l < p.n_layers; ++l) n += ((p.N[l] + DW_P - 1) / DW_P) * ((p.Kin[l] + DW_P - 1) / DW_P);
+  return n;
+}
 __global__ void __launch_bounds__(256) k_train_dw(const __grid_constant__ TrainPlan p) {
-  __shared__ float sd[32][33];
-  __shared__ float sh[32][33];
+  __shared__ __align__(16) float sd[32][DW_LD];
+  __shared__ __align__(16) float sh[32][DW_LD];
   // which layer / patch is this block?
   int l = 0, pid = blockIdx.x;
   for (; l < p.n_layers; ++l) {
-    const int np = ((p.N[l] + 31) / 32) * ((p.Kin[l] + 31) / 32);
+    const int np = ((p.N[l] + DW_P - 1) / DW_P) * ((p.Kin[l] + DW_P - 1) / DW_P);
     if (pid < np) break;
     pid -= np;
   }
   if (l >= p.n_layers) return;
-  const int kb = (p.Kin[l] + 31) / 32;
-  const int n0 = (pid / kb) * 32, k0 = (pid % kb) * 32;
+  const int kb = (p.Kin[l] + DW_P - 1) / DW_P;
+  const int n0 = (pid / kb) * DW_P, k0 = (pid % kb) * DW_P;
   const int N = p.N[l], Kin = p.Kin[l];
   const float* __restrict__ dl = p.dl[l];
   const int ldd = p.Np[l];
@@ -317,13 +326,15 @@ __global__ void __launch_bounds__(256) k_train_dw(const __grid_constant__ TrainP
   const int ldh = (l == 0) ? p.in_features : p.Np[l - 1];
   const int64_t per = (p.batch + p.splits - 1) / p.splits;
   const int64_t b0 = (int64_t)blockIdx.y * per, b1 = min(p.batch, b0 + per);
-  const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;     // 2 x 2 outputs: n0 + 2 tn + {0,1}, k0 + 2 tk + {0,1}
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  float accb[2] = {0.f, 0.f};
-  const int lr = threadIdx.x >> 5, lc = threadIdx.x & 31;
+  const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;     // outputs n0 + 4 tn + {0..3}, k0 + 4 tk + {0..3}
+  float2 acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+  const int lr = threadIdx.x >> 6, lc = threadIdx.x & 63;
   for (int64_t bb = b0; bb < b1; bb += 32) {
 #pragma unroll
-    for (int r = lr; r < 32; r += 8) {
+    for (int r = lr; r < 32; r += 4) {
       const int64_t b = bb + r;
       sd[r][lc] = (b < b1 && n0 + lc < ldd) ? dl[b * ldd + n0 + lc] : 0.0f;
       sh[r][lc] = (b < b1 && k0 + lc < Kin) ? hin[b * ldh + k0 + lc] : 0.0f;
@@ -331,23 +342,30 @@ __global__ void __launch_bounds__(256) k_train_dw(const __grid_constant__ TrainP
     __syncthreads();
 #pragma unroll 8
     for (int r = 0; r < 32; ++r) {
-      const float d0 = sd[r][2 * tn], d1 = sd[r][2 * tn + 1];
-      const float h0 = sh[r][2 * tk], h1 = sh[r][2 * tk + 1];
-      acc[0][0] = fmaf(d0, h0, acc[0][0]); acc[0][1] = fmaf(d0, h1, acc[0][1]);
-      acc[1][0] = fmaf(d1, h0, acc[1][0]); acc[1][1] = fmaf(d1, h1, acc[1][1]);
-      accb[0] += d0; accb[1] += d1;
+      const float4 d4 = *reinterpret_cast<const float4*>(&sd[r][4 * tn]);
+      const float4 h4 = *reinterpret_cast<const float4*>(&sh[r][4 * tk]);
+      const float2 h01 = make_float2(h4.x, h4.y), h23 = make_float2(h4.z, h4.w);
+      const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 di = make_float2(dd[i], dd[i]);
+        acc[i][0] = __ffma2_rn(di, h01, acc[i][0]);
+        acc[i][1] = __ffma2_rn(di, h23, acc[i][1]);
+        accb[i] += dd[i];
+      }
     }
     __syncthreads();
   }
   float* out = p.dw_part + (size_t)blockIdx.y * p.n_param;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int n = n0 + 2 * tn + i;
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + 4 * tn + i;
     if (n >= N) continue;
+    const float v[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int k = k0 + 2 * tk + j;
-      if (k < Kin) out[p.off_w[l] + (size_t)n * Kin + k] = acc[i][j];
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + 4 * tk + j;
+      if (k < Kin) out[p.off_w[l] + (size_t)n * Kin + k] = v[j];
     }
     if (k0 == 0 && tk == 0) out[p.off_b[l] + n] = accb[i];
   }
@@ -429,8 +447,7 @@ static int train_plan(const ffb_net_desc* d, int64_t batch, int want_dx, TrainPl
   lay->grid = (int)std::max<int64_t>(1, std::min<int64_t>(npass, sms));
   lay->zfloats = zf; lay->maxk = maxk;
   // enough (patch, split) blocks of k_train_dw to cover the SMs, at least 256 rows per split
-  int patches = 0;
-  for (int l = 0; l < d->n_layers; ++l) patches += ((p->N[l] + 31) / 32) * ((p->Kin[l] + 31) / 32);
+  const int patches = dw_patches(*p);
   int splits = (2 * sms + patches - 1) / patches;
   splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, (batch + 255) / 256));
   splits = std::min(splits, 64);
@@ -496,9 +513,7 @@ extern "C" int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* a, 
   k_train_pack<<<2 * ffb_num_sms(), 256, 0, st>>>(p);
   TR_CUDA_TRY(cudaFuncSetAttribute(k_train_fwdbwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_train_fwdbwd<<<lay.grid, NTHR, smem, st>>>(p, npass, lay.zfloats);
-  int patches = 0;
-  for (int l = 0; l < p.n_layers; ++l) patches += ((p.N[l] + 31) / 32) * ((p.Kin[l] + 31) / 32);
-  k_train_dw<<<dim3(patches, p.splits), 256, 0, st>>>(p);
+  k_train_dw<<<dim3(dw_patches(p), p.splits), 256, 0, st>>>(p);
   k_train_reduce<<<ffb_num_sms(), 256, 0, st>>>(p, o);
   ffb_count_launches(4);
   TR_CUDA_TRY(cudaGetLastError());

@@ -103,6 +103,7 @@ class SolveStats:
     ratio_history: List[float] = dataclasses.field(default_factory=list)
     launches: int = 0
     controller: str = "host"
+    history_truncated: bool = False     # device controller: only the first CTL_HIST attempts are in the *_history lists
 
 
 # Where torchdiffeq's accept / step-size loop runs: "device" = csrc/ffb_control.cuh between two attempt kernels
@@ -411,6 +412,7 @@ def _dopri5_device(backend, params, st: SolveStats, ts: float, dt: float, grid_i
     n = int(c.n_attempts)
     st.nfe += 6 * n
     st.accepted, st.rejected = int(c.n_accepted), int(c.n_rejected)
+    st.history_truncated = n > L.CTL_HIST
     for i in range(min(n, L.CTL_HIST)):
         st.dt_history.append(float(c.hist_dt[i]))
         st.accept_history.append(bool(c.hist_accept[i]))
