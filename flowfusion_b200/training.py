@@ -87,11 +87,8 @@ def train_step(linears: Sequence[torch.nn.Linear], activation: int, x_in: torch.
     a.work = work.data_ptr()
     with E.on_device(dev):
         L.check(lib.ffb_train_step(C.byref(d), C.byref(a), E._stream(dev)), "ffb_train_step")
-    # the launches read `keep`, the inputs and `work` asynchronously: record them on the stream so that the caching
-    # allocator does not hand the memory to another stream before they have run
-    st = torch.cuda.current_stream(dev)
-    for t in keep + [x_in, tgt, work] + ([alpha] if alpha is not None else []):
-        t.record_stream(st)
+    # `keep`, the inputs and `work` are allocated and consumed on the current stream: the caching allocator reuses their
+    # memory in stream order, so nothing has to be recorded
     if want_out:
         return loss, grads, gx, out
     return loss, grads, gx
@@ -103,18 +100,22 @@ class _FusedAffineMSE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_in, alpha, beta, scale, activation, linears, *params):
         want_gx = bool(x_in.requires_grad)
-        loss, grads, gx = train_step(linears, activation, x_in, alpha, beta, scale, want_grad_x=want_gx)
-        ctx.save_for_backward(*grads, *([gx] if gx is not None else []))
+        sizes = param_sizes(linears)
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=x_in.device)
+        loss, grads, gx = train_step(linears, activation, x_in, alpha, beta, scale, want_grad_x=want_gx, grad_flat=flat)
+        ctx.save_for_backward(flat, *([gx] if gx is not None else []))
         ctx.has_gx = gx is not None
-        ctx.n_params = len(params)
+        ctx.shapes = [g.shape for g in grads]
+        ctx.sizes = sizes
         return loss.to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):
         saved = ctx.saved_tensors
-        grads = saved[: ctx.n_params]
-        gx = saved[ctx.n_params] * g if ctx.has_gx else None
-        return (gx, None, None, None, None, None) + tuple(g * gr for gr in grads)
+        scaled = saved[0] * g                      # ONE launch for every parameter: the gradients live in one flat vector
+        grads = tuple(v.view(shp) for v, shp in zip(torch.split(scaled, ctx.sizes), ctx.shapes))
+        gx = saved[1] * g if ctx.has_gx else None
+        return (gx, None, None, None, None, None) + grads
 
 
 def fused_affine_mse(linears: Sequence[torch.nn.Linear], activation: int, x_in, alpha, beta, scale: float) -> torch.Tensor:
