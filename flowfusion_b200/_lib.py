@@ -154,6 +154,11 @@ class TrainArgs(C.Structure):
                 ("cot", C.c_void_p), ("out", C.c_void_p)]
 
 
+class HamiltonianArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("dim", C.c_int32), ("cond_dim", C.c_int32), ("z0", C.c_void_p), ("cond", C.c_void_p),
+                ("z_out", C.c_void_p), ("h_out", C.c_void_p), ("n_steps", C.c_int32), ("dt", C.c_float), ("work", C.c_void_p)]
+
+
 # every symbol include/ffb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "ffb_abi_version": (C.c_int, []),
@@ -177,6 +182,7 @@ SYMBOLS = {
     "ffb_rk_finish": (C.c_int, [C.POINTER(RkFinishArgs), C.c_void_p]),
     "ffb_train_work_bytes": (C.c_size_t, [C.POINTER(NetDesc), C.c_int64, C.c_int32]),
     "ffb_train_step": (C.c_int, [C.POINTER(NetDesc), C.POINTER(TrainArgs), C.c_void_p]),
+    "ffb_hamiltonian_leapfrog": (C.c_int, [C.POINTER(NetDesc), C.POINTER(HamiltonianArgs), C.c_void_p]),
     "ffb_reduce_partials": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ffb_gaussian_logprob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
     "ffb_philox_normal": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p]),

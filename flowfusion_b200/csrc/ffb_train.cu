@@ -401,6 +401,173 @@ __global__ void k_train_reduce(const __grid_constant__ TrainPlan p, const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Hamiltonian leapfrog: the gradient dH/d(q, p) of a scalar-output MLP is the forward pass + the backward sweep to the
+// inputs of the kernel above with delta_L = 1, kept entirely on-chip; one launch carries a pass of 32 trajectories
+// through every kick-drift-kick step (BASELINE.json north_star / configs[4]).  Extension: the reference's own symplectic
+// networks output dq/dt and dp/dt directly and run on the two-network field of ffb_integrate_fixed.
+// ---------------------------------------------------------------------------------------------------------------
+struct HamArgs {
+  int64_t batch;
+  int D, C, n_steps;
+  float dt;
+  const float* z0;
+  const float* cond;
+  float* z_out;
+  float* h_out;
+};
+// shared memory: the training layout + the state rows [q | p | cond] and the gradient rows, both k-major
+__host__ __device__ inline size_t ham_smem(int zfloats, int maxk, int kp0, int kb0, size_t* off /*[7]*/) {
+  size_t v[7];
+  size_t o = train_smem(zfloats, maxk, v);
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~size_t(127); return r; };
+  v[5] = take(sizeof(float) * kp0 * WD_RS);
+  v[6] = take(sizeof(float) * kb0 * WD_RS);
+  if (off) for (int i = 0; i < 7; ++i) off[i] = v[i];
+  return o;
+}
+
+// H and dH/d(inputs) at the state rows S of this warp: forward keeping z_l, delta_L = 1, backward sweep to the inputs -> G
+template <int ACT>
+__device__ __forceinline__ void ham_grad(CtxW& cx, const TrainPlan& p, float* zreg, float* op, const float* S, float* G, float (&hval)[4]) {
+  const int L = p.n_layers, r0w = cx.warp * 4;
+  float* A = op;
+  float* Bf = op + (size_t)p.maxk * WD_RS;
+  for (int k = cx.lane; k < p.Kp[0]; k += 32)
+    *reinterpret_cast<float4*>(A + (size_t)k * WD_RS + r0w) = *reinterpret_cast<const float4*>(S + (size_t)k * WD_RS + r0w);
+  __syncwarp();
+  for (int l = 0; l < L; ++l) {
+    const float* bias = p.bp[l];
+    if (l < L - 1) {
+      float* z = zreg + p.zoff[l];
+      train_layer(cx, A, p.Kp[l], p.Np[l], [&](int n, float (&v)[4]) {
+        const float bj = bias[n];
+        float h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] += bj; h[i] = act_fwd<ACT>(v[i]); }
+        *reinterpret_cast<float4*>(z + (size_t)n * WD_RS + r0w) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(Bf + (size_t)n * WD_RS + r0w) = make_float4(h[0], h[1], h[2], h[3]);
+      });
+    } else {
+      train_layer(cx, A, p.Kp[l], p.Np[l], [&](int n, float (&v)[4]) {
+        const float one = (n == 0) ? 1.0f : 0.0f;          // delta_L: d H / d (output column 0)
+        if (n == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hval[i] = v[i] + bias[0];
+        }
+        *reinterpret_cast<float4*>(Bf + (size_t)n * WD_RS + r0w) = make_float4(one, one, one, one);
+      });
+    }
+    float* t = A; A = Bf; Bf = t;
+  }
+  for (int l = L - 1; l >= 1; --l) {
+    const float* z = zreg + p.zoff[l - 1];
+    train_layer(cx, A, p.Np[l], p.Kp[l], [&](int k, float (&v)[4]) {
+      const float4 z4 = *reinterpret_cast<const float4*>(z + (size_t)k * WD_RS + r0w);
+      const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+      float d[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { float a, g; act_fwd_grad<ACT>(zz[i], a, g); d[i] = v[i] * g; }
+      *reinterpret_cast<float4*>(Bf + (size_t)k * WD_RS + r0w) = make_float4(d[0], d[1], d[2], d[3]);
+    });
+    float* t = A; A = Bf; Bf = t;
+  }
+  train_layer(cx, A, p.Np[0], p.KB0, [&](int k, float (&v)[4]) {
+    *reinterpret_cast<float4*>(G + (size_t)k * WD_RS + r0w) = make_float4(v[0], v[1], v[2], v[3]);
+  });
+}
+
+template <int ACT>
+__device__ __forceinline__ void ham_passes(CtxW& cx, const TrainPlan& p, const HamArgs& a, float* zreg, float* op, float* S, float* G,
+                                           int64_t npass) {
+  const int D = a.D, C = a.C, r0w = cx.warp * 4;
+  const float dt = a.dt, half = 0.5f * a.dt;
+  for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
+    const int64_t row0 = pass * WD_R + r0w;
+    for (int k = cx.lane; k < p.Kp[0]; k += 32) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x = 0.0f;
+        if (row0 + i < a.batch) {
+          if (k < 2 * D) x = a.z0[(row0 + i) * 2 * D + k];
+          else if (k < 2 * D + C) x = a.cond[(row0 + i) * C + (k - 2 * D)];
+        }
+        v[i] = x;
+      }
+      *reinterpret_cast<float4*>(S + (size_t)k * WD_RS + r0w) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncwarp();
+    float h0[4], h1[4];
+    // target[k] += coef * G[src[k]] on this warp's rows
+    auto axpy = [&](int dst0, int src0, float coef) {
+      __syncwarp();
+      for (int k = cx.lane; k < D; k += 32) {
+        float4 s4 = *reinterpret_cast<float4*>(S + (size_t)(dst0 + k) * WD_RS + r0w);
+        const float4 g4 = *reinterpret_cast<const float4*>(G + (size_t)(src0 + k) * WD_RS + r0w);
+        s4.x = fmaf(coef, g4.x, s4.x); s4.y = fmaf(coef, g4.y, s4.y); s4.z = fmaf(coef, g4.z, s4.z); s4.w = fmaf(coef, g4.w, s4.w);
+        *reinterpret_cast<float4*>(S + (size_t)(dst0 + k) * WD_RS + r0w) = s4;
+      }
+      __syncwarp();
+    };
+    for (int step = 0; step < a.n_steps; ++step) {
+      ham_grad<ACT>(cx, p, zreg, op, S, G, step == 0 ? h0 : h1);
+      axpy(D, 0, -half);                        // kick:  p -= dt/2 dH/dq (q, p)
+      ham_grad<ACT>(cx, p, zreg, op, S, G, h1);
+      axpy(0, D, dt);                           // drift: q += dt dH/dp (q, p_half)
+      ham_grad<ACT>(cx, p, zreg, op, S, G, h1);
+      axpy(D, 0, -half);                        // kick:  p -= dt/2 dH/dq (q_new, p_half)
+    }
+    ham_grad<ACT>(cx, p, zreg, op, S, G, h1);    // H at the end (and at the start when there are no steps)
+    if (a.n_steps == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h0[i] = h1[i];
+    }
+    __syncwarp();
+    for (int k = cx.lane; k < 2 * D; k += 32) {
+      const float4 s4 = *reinterpret_cast<const float4*>(S + (size_t)k * WD_RS + r0w);
+      const float v[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (row0 + i < a.batch) a.z_out[(row0 + i) * 2 * D + k] = v[i];
+    }
+    if (a.h_out && cx.lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (row0 + i < a.batch) { a.h_out[(row0 + i) * 2] = h0[i]; a.h_out[(row0 + i) * 2 + 1] = h1[i]; }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(NTHR, 1) k_ham_leapfrog(const __grid_constant__ TrainPlan p, const __grid_constant__ HamArgs a,
+                                                          const int64_t npass, const int zfloats) {
+  CtxW cx;
+  size_t off[7];
+  ham_smem(zfloats, p.maxk, p.Kp[0], p.KB0, off);
+  float* zreg = reinterpret_cast<float*>(smem_base() + off[0]);
+  float* op = reinterpret_cast<float*>(smem_base() + off[1]);
+  cx.o_ring = (uint32_t)off[2]; cx.o_bar = (uint32_t)off[3];
+  float* S = reinterpret_cast<float*>(smem_base() + off[5]);
+  float* G = reinterpret_cast<float*>(smem_base() + off[6]);
+  cx.tid = threadIdx.x; cx.lane = threadIdx.x & 31; cx.warp = threadIdx.x >> 5;
+  cx.producer = (cx.warp == NCOMP / 32);
+  cx.stage = 0; cx.phase = cx.producer ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WD_NSTAGE; ++s) { mbar_init(&cx.full()[s], 1); mbar_init(&cx.empty()[s], NCOMP / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (cx.producer) {
+    for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x)
+      for (int e = 0; e < 3 * a.n_steps + 1; ++e) {
+        for (int l = 0; l < p.n_layers; ++l) train_produce(cx, p.Wf[l], p.Kp[l], p.Np[l]);
+        for (int l = p.n_layers - 1; l >= 1; --l) train_produce(cx, p.Wb[l], p.Np[l], p.Kp[l]);
+        train_produce(cx, p.Wb[0], p.Np[0], p.KB0);
+      }
+    return;
+  }
+  FFB_ACT_DISPATCH(p.act, (ham_passes<ACT>(cx, p, a, zreg, op, S, G, npass)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------
 static int tr_smem_optin() {
@@ -516,6 +683,41 @@ extern "C" int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* a, 
   k_train_dw<<<dim3(dw_patches(p), p.splits), 256, 0, st>>>(p);
   k_train_reduce<<<ffb_num_sms(), 256, 0, st>>>(p, o);
   ffb_count_launches(4);
+  TR_CUDA_TRY(cudaGetLastError());
+  return FFB_OK;
+}
+
+extern "C" int ffb_hamiltonian_leapfrog(const ffb_net_desc* net, const ffb_hamiltonian_args* a, void* stream_) {
+  if (!net || !a) return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: null argument");
+  if (!a->z0 || !a->z_out || !a->work) return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: z0, z_out and work are required");
+  if (a->dim < 1 || a->cond_dim < 0 || 2 * a->dim + a->cond_dim != net->in_features)
+    return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: the network's in_features must be 2 * dim + cond_dim ([q | p | cond])");
+  if (net->n_layers < 1 || net->widths[net->n_layers - 1] != 1)
+    return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: H is a scalar: the last layer must have one output");
+  if (a->cond_dim > 0 && !a->cond) return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: cond is required");
+  if (a->n_steps < 0) return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: negative n_steps");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  TrainPlan p; TrainLayout lay;
+  int rc = train_plan(net, 0, 1, &p, &lay, a->work);       // batch 0: only the weight images live in `work`
+  if (rc) return rc;
+  for (int l = 0; l < net->n_layers; ++l) {
+    if (!net->weight[l] || !net->bias[l]) return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: weight and bias are required for every layer");
+    p.W[l] = net->weight[l]; p.B[l] = net->bias[l];
+  }
+  HamArgs h;
+  h.batch = a->batch; h.D = a->dim; h.C = a->cond_dim; h.n_steps = a->n_steps; h.dt = a->dt;
+  h.z0 = a->z0; h.cond = a->cond; h.z_out = a->z_out; h.h_out = a->h_out;
+  const size_t smem = ham_smem(lay.zfloats, lay.maxk, p.Kp[0], p.KB0, nullptr);
+  if ((int)smem > tr_smem_optin())
+    return ffb_fail(FFB_ERR_ARG, "ffb_hamiltonian_leapfrog: the network needs " + std::to_string(smem) + " B of shared memory, the device allows " +
+                    std::to_string(tr_smem_optin()));
+  const int64_t npass = (a->batch + WD_R - 1) / WD_R;
+  if (npass == 0) return FFB_OK;
+  k_train_pack<<<2 * ffb_num_sms(), 256, 0, st>>>(p);
+  TR_CUDA_TRY(cudaFuncSetAttribute(k_ham_leapfrog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(npass, ffb_num_sms());
+  k_ham_leapfrog<<<grid, NTHR, smem, st>>>(p, h, npass, lay.zfloats);
+  ffb_count_launches(2);
   TR_CUDA_TRY(cudaGetLastError());
   return FFB_OK;
 }

@@ -10,6 +10,10 @@ acting on the (q | p) column blocks of a 2D-wide state.
   (``method="leapfrog"``; the reference has no leapfrog, SURVEY H5 -- validated by reversibility,
   volume preservation and 2nd-order convergence instead of an oracle).
 * ``SymplecticFlowModel.log_prob``  `symplectic.py:203-254`  dopri5 on the plain (B, 2D) state.
+* ``HamiltonianMLP`` (extension, BASELINE.json north_star "the leapfrog integrator's dH/dq, dH/dp is a fused
+  forward+backward MLP kernel"): a scalar Hamiltonian network whose leapfrog runs in ONE launch, the gradient being the
+  fused forward + backward sweep of csrc/ffb_train.cu.  The reference has no such model (its networks output the
+  derivatives); the oracle is autograd on the CPU (oracle/port.py: hamiltonian_leapfrog).
 """
 from __future__ import annotations
 
@@ -151,3 +155,56 @@ class SymplecticFlowModel(nn.Module):
         log_p_z1 = E.gaussian_logprob(z1, None, 1.0)
         log_p_p0 = E.gaussian_logprob(p0, None, 1.0)
         return log_p_z1 - log_p_p0 - torch.sum(torch.log(self.scale))
+
+
+class HamiltonianMLP(nn.Module):
+    """Scalar Hamiltonian ``H(q, p[, c]) = MLP(cat[q, p, c])`` and its kick-drift-kick leapfrog flow on the fused
+    forward+backward kernel (``ffb_hamiltonian_leapfrog``).  Extension beyond the reference (see the module docstring)."""
+
+    def __init__(self, n_data_dims, n_conditionals=0, units=(128, 128), activation=nn.SiLU()):
+        super().__init__()
+        self.n_data_dims, self.n_conditionals = n_data_dims, n_conditionals
+        layers, cur = [], 2 * n_data_dims + n_conditionals
+        for u in units:
+            layers += [nn.Linear(cur, u), activation]
+            cur = u
+        layers.append(nn.Linear(cur, 1))
+        self.net = nn.Sequential(*layers)
+
+    @torch.no_grad()
+    def leapfrog(self, z0, conditional=None, num_steps=100, dt=0.01, return_energy=False):
+        """z0 (B, 2D) = [q | p] -> z after ``num_steps`` steps of p -= dt/2 dH/dq; q += dt dH/dp; p -= dt/2 dH/dq.
+        ``return_energy``: also (B, 2) = H at the start and at the end."""
+        import ctypes as C
+        E.require_cuda(z0, "z0")
+        lib, dev, D, Cn = L.load(), z0.device, self.n_data_dims, self.n_conditionals
+        lin = [m for m in self.net if isinstance(m, nn.Linear)]
+        if z0.shape[1] != 2 * D or (Cn > 0) != (conditional is not None):
+            raise ValueError("leapfrog: z0 must be (B, 2 * n_data_dims) and the conditional given iff n_conditionals > 0")
+        d = L.NetDesc()
+        d.n_layers, d.in_features = len(lin), lin[0].in_features
+        keep = []
+        for i, m in enumerate(lin):
+            w, b = E._dev_f32(m.weight, dev), E._dev_f32(m.bias, dev)
+            keep += [w, b]
+            d.widths[i], d.weight[i], d.bias[i] = m.out_features, w.data_ptr(), b.data_ptr()
+        d.x_dim, d.activation = lin[0].in_features, E.activation_of(list(self.net))
+        a = L.HamiltonianArgs()
+        z0 = E._dev_f32(z0, dev)
+        cond = E._dev_f32(conditional, dev) if conditional is not None else None
+        out = torch.empty_like(z0)
+        h = torch.empty(z0.shape[0], 2, device=dev) if return_energy else None
+        nbytes = int(lib.ffb_train_work_bytes(C.byref(d), 0, 1))
+        if nbytes == 0:
+            raise L.FFBError("ffb_train_work_bytes: " + lib.ffb_last_error().decode())
+        work = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+        a.batch, a.dim, a.cond_dim = z0.shape[0], D, Cn
+        a.z0, a.cond, a.z_out = z0.data_ptr(), (cond.data_ptr() if cond is not None else None), out.data_ptr()
+        a.h_out, a.n_steps, a.dt, a.work = (h.data_ptr() if h is not None else None), int(num_steps), float(dt), work.data_ptr()
+        with E.on_device(dev):
+            L.check(lib.ffb_hamiltonian_leapfrog(C.byref(d), C.byref(a), E._stream(dev)), "ffb_hamiltonian_leapfrog")
+        return (out, h) if return_energy else out
+
+    def energy(self, z, conditional=None):
+        """H(q, p[, c]) for every row, (B,)."""
+        return self.leapfrog(z, conditional, num_steps=0, return_energy=True)[1][:, 0]

@@ -409,6 +409,27 @@ typedef struct {
 size_t ffb_train_work_bytes(const ffb_net_desc* net, int64_t batch, int32_t want_grad_x);
 int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* args, void* stream);
 
+/* ---- Hamiltonian leapfrog (BASELINE.json north_star: "the leapfrog integrator's dH/dq, dH/dp is a fused forward+backward
+ * MLP kernel"; configs[4]).  H(q, p [, cond]) is a scalar-output MLP on the input rows [q | p | cond] (raw torch weights as
+ * in ffb_train_step); one launch carries every trajectory through n_steps kick-drift-kick steps
+ *     p -= dt/2 dH/dq(q, p);  q += dt dH/dp(q, p);  p -= dt/2 dH/dq(q, p)
+ * the gradient being a forward pass that keeps the pre-activations in shared memory and the backward sweep to the inputs,
+ * entirely on-chip.  Extension: the reference's own symplectic networks output dq/dt and dp/dt directly
+ * (symplectic.py:80-123) and run on the two-network field of ffb_integrate_fixed (FFB_M_EULER / FFB_M_LEAPFROG). */
+typedef struct {
+  int64_t batch;
+  int32_t dim;                        /* D: q and p have D columns each                       */
+  int32_t cond_dim;
+  const float* z0;                    /* (B, 2D) [q | p]                                      */
+  const float* cond;                  /* (B, cond_dim) or NULL                                */
+  float* z_out;                       /* out: (B, 2D)                                         */
+  float* h_out;                       /* out: (B, 2) H at the start and at the end, or NULL   */
+  int32_t n_steps;
+  float dt;
+  float* work;                        /* ffb_train_work_bytes(net, 0, 1)                      */
+} ffb_hamiltonian_args;
+int ffb_hamiltonian_leapfrog(const ffb_net_desc* net, const ffb_hamiltonian_args* args, void* stream);
+
 /* sums[FFB_NPART] = sum over tiles of partials, in tile order (deterministic) */
 int ffb_reduce_partials(const double* partials, int64_t n_tiles, double* sums, void* stream);
 /* out[b] = sum_d ( -0.5*x^2 - 0.5*log(2*pi*var) ) + (add ? add[b] : 0)   (flow.py:434, diffusion.py:814) */

@@ -406,6 +406,28 @@ def symplectic_log_prob(Sy, x, p0, cond=None, atol=1e-5, rtol=1e-5):
     return n01.log_prob(z1).sum(dim=-1) - n01.log_prob(p0).sum(dim=-1) - torch.sum(torch.log(Sy["scale"]))
 
 
+def hamiltonian_leapfrog(net, z0, cond=None, n_steps=1, dt=0.01):
+    """Oracle of the scalar-Hamiltonian leapfrog EXTENSION (flowfusion_b200.symplectic.HamiltonianMLP; the reference has no
+    such model): H = MLP(cat[q, p, c]); p -= dt/2 dH/dq; q += dt dH/dp; p -= dt/2 dH/dq with autograd gradients.
+    -> (z, H at the start, H at the end)."""
+    D = z0.shape[1] // 2
+
+    def H_and_grad(q, p):
+        with torch.set_grad_enabled(True):
+            z = torch.cat([q, p], dim=1).detach().requires_grad_(True)
+            h = _mlp(net, torch.cat([z, cond], dim=1) if cond is not None else z)[:, 0]
+            g = torch.autograd.grad(h.sum(), z)[0]
+        return h.detach(), g[:, :D], g[:, D:]
+
+    q, p = z0[:, :D].clone(), z0[:, D:].clone()
+    h0 = H_and_grad(q, p)[0]
+    for _ in range(n_steps):
+        p = p - 0.5 * dt * H_and_grad(q, p)[1]
+        q = q + dt * H_and_grad(q, p)[2]
+        p = p - 0.5 * dt * H_and_grad(q, p)[1]
+    return torch.cat([q, p], dim=1), h0, H_and_grad(q, p)[0]
+
+
 # ------------------------------------------------------------------------------------
 # training losses (SURVEY 8f rank 2) with the draws passed in; `*_and_grads` add d loss / d (weights, biases)
 # ------------------------------------------------------------------------------------

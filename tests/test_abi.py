@@ -59,16 +59,16 @@ def test_abi_version_and_error_paths(lib):
 def test_struct_sizes_match_the_header(lib, tmp_path):
     """Compile a 10-line C program against include/ffb200.h and compare sizeof() with the ctypes mirrors."""
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "ffb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "ffb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(ffb_net_desc),sizeof(ffb_field),sizeof(ffb_eval_scalars),sizeof(ffb_eval_args),"
                    "sizeof(ffb_dopri5_args),sizeof(ffb_fixed_args),sizeof(ffb_time_program),"
                    "sizeof(ffb_dopri5_ctl_params),sizeof(ffb_dopri5_ctl),sizeof(ffb_trace_args),sizeof(ffb_rk_combine_args),"
-                   "sizeof(ffb_rk_finish_args),sizeof(ffb_train_args));return 0;}\n")
+                   "sizeof(ffb_rk_finish_args),sizeof(ffb_train_args),sizeof(ffb_hamiltonian_args));return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(t) for t in (L.NetDesc, L.Field, L.EvalScalars, L.EvalArgs, L.Dopri5Args, L.FixedArgs,
-                                  L.TimeProgram, L.CtlParams, L.Ctl, L.TraceArgs, L.RkCombineArgs, L.RkFinishArgs, L.TrainArgs)]
+                                  L.TimeProgram, L.CtlParams, L.Ctl, L.TraceArgs, L.RkCombineArgs, L.RkFinishArgs, L.TrainArgs, L.HamiltonianArgs)]
     assert got == want
 
 

@@ -123,3 +123,35 @@ def test_training_limits(cuda_dev):
     lin = [l.to(cuda_dev) for l in lin]
     with pytest.raises(_lib.FFBError, match="shared memory"):
         training.train_step(lin, 0, torch.zeros(10, 8, device=cuda_dev), None, torch.zeros(10, 4, device=cuda_dev), 1.0)
+
+
+@pytest.mark.parametrize("D_,C_,units,act_cls,act_fn", [(32, 0, [128] * 4, torch.nn.SiLU, None), (3, 2, [48, 40], torch.nn.Tanh, torch.tanh),
+                                                       (1, 0, [16], torch.nn.Softplus, torch.nn.functional.softplus)])
+def test_hamiltonian_leapfrog_fused_gradient(cuda_dev, D_, C_, units, act_cls, act_fn):
+    """BASELINE.json configs[4] / north_star: leapfrog whose dH/dq, dH/dp is a fused forward+backward MLP kernel (extension; the
+    oracle is autograd on the CPU): trajectories, energies, time reversibility and O(dt^2) energy drift."""
+    import flowfusion_b200.symplectic as Sy
+    from oracle import port
+    torch.manual_seed(70 + D_)
+    m = Sy.HamiltonianMLP(D_, C_, units, activation=act_cls())
+    net = port.net_from_state_dict(m.state_dict(), "net.", 2, act=act_fn)
+    B = 203                                           # ragged: 6 passes of 32 rows + 11
+    z0 = torch.randn(B, 2 * D_, generator=torch.Generator().manual_seed(1))
+    c = torch.randn(B, C_, generator=torch.Generator().manual_seed(2)) if C_ else None
+    zr, h0r, h1r = port.hamiltonian_leapfrog(net, z0, c, n_steps=20, dt=0.02)
+    m.to(cuda_dev)
+    cg = c.to(cuda_dev) if c is not None else None
+    z, h = m.leapfrog(z0.to(cuda_dev), cg, num_steps=20, dt=0.02, return_energy=True)
+    assert _close(zr, z.cpu(), 1e-4)
+    assert _close(h0r, h[:, 0].cpu(), 1e-5) and _close(h1r, h[:, 1].cpu(), 1e-4)
+    assert _close(h0r, m.energy(z0.to(cuda_dev), cg).cpu(), 1e-5)
+    # time reversibility
+    zb = m.leapfrog(z, cg, num_steps=20, dt=-0.02)             # kick-drift-kick is symmetric: a negative step retraces it
+    assert _close(z0, zb.cpu(), 2e-4)
+    # symplectic integrator: the energy error of a step halves ~4x when dt halves (2nd order), and stays bounded
+    _, ha = m.leapfrog(z0.to(cuda_dev), cg, num_steps=10, dt=0.04, return_energy=True)
+    _, hb = m.leapfrog(z0.to(cuda_dev), cg, num_steps=20, dt=0.02, return_energy=True)
+    ea, eb = (ha[:, 1] - ha[:, 0]).abs().mean(), (hb[:, 1] - hb[:, 0]).abs().mean()
+    assert float(eb) < 0.5 * float(ea) + 1e-5
+    # zero steps: the state comes back untouched
+    assert torch.equal(m.leapfrog(z0.to(cuda_dev), cg, num_steps=0).cpu(), z0)
