@@ -6,8 +6,9 @@ rep, lib, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
-cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
+dis = []                                   # one cubin per translation unit: look in all of them
+for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
 line_of, cur, infunc = {}, None, False
 for l in dis:
     if l.startswith(".text."):

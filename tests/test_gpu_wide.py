@@ -173,3 +173,34 @@ def test_wide_limits(cuda_dev):
     xb = torch.cat([sm.sample_ode_from_base(base[:129], method="rk4", options={"step_size": 0.125})[0],
                     sm.sample_ode_from_base(base[129:], method="rk4", options={"step_size": 0.125})[0]])
     assert torch.equal(xa, xb)
+
+
+def test_new_kernels_repeat_bit_for_bit(cuda_dev):
+    """Stand-in for racecheck (compute-sanitizer is closed on the GPU pool, profiles/r02_sanitizer_unavailable.txt): the wide
+    engine's dopri5 attempts, the fused training step (loss, gradients, d/dX) and the Hamiltonian leapfrog, 8 runs each on the
+    same inputs, must agree bit for bit -- a race on the weight ring's mbarriers or on a warp's activation rows would not."""
+    import copy
+    D, F, Sy = _mods()
+    from flowfusion_b200 import training
+    torch.manual_seed(3)
+    sm = D.ScoreModel(D.MLP(16, 4, 8, [256, 256]), D.VPSDE(), no_sigma=True).eval().to(cuda_dev)
+    base = torch.randn(1500, 16, generator=gen(1)).to(cuda_dev); cond = torch.randn(1500, 4, generator=gen(2)).to(cuda_dev)
+    fl = F.ODEFlow(8, [192, 256]).eval().to(cuda_dev)
+    xs = torch.randn(200, 8, generator=gen(3)).to(cuda_dev)
+    lin = [torch.nn.Linear(21, 128), torch.nn.Linear(128, 128), torch.nn.Linear(128, 9)]
+    lin = [copy.deepcopy(l).to(cuda_dev) for l in lin]
+    x = torch.randn(1000, 21, generator=gen(4)).to(cuda_dev); beta = torch.randn(1000, 9, generator=gen(5)).to(cuda_dev)
+    ham = Sy.HamiltonianMLP(8, 0, [128, 128]).to(cuda_dev)
+    z0 = torch.randn(777, 16, generator=gen(6)).to(cuda_dev)
+    ref = None
+    for _ in range(8):
+        a, _ = sm.sample_ode_from_base(base, cond, atol=1e-5, rtol=1e-5, options={"step_t": torch.tensor([1e-3])})
+        b = fl.log_prob(xs)
+        loss, grads, gx = training.train_step(lin, 0, x, None, beta, 0.01, want_grad_x=True)
+        z = ham.leapfrog(z0, num_steps=7, dt=0.03)
+        cur = [a, b, loss, gx, z] + grads
+        if ref is None:
+            ref = [t.clone() for t in cur]
+        else:
+            for r, c in zip(ref, cur):
+                assert torch.equal(r, c)
