@@ -121,7 +121,7 @@ class FixedArgs(C.Structure):
 
 # ---- staged solves (Hutch++ / XTrace): include/ffb200.h, csrc/ffb_staged.cu ----------------------------
 TRACE_HUTCHPP, TRACE_XTRACE = 1, 2
-TRACE_MAX_DIM, TRACE_MAX_RANK, STAGED_BLOCKS = 32, 8, 1024
+TRACE_MAX_DIM, TRACE_MAX_RANK, STAGED_BLOCKS = 124, 8, 1024
 
 
 class TraceArgs(C.Structure):

@@ -573,12 +573,20 @@ static int trace_kernel_choice() {
 template <int DMAX, int KMAX>
 static int launch_trace(const ffb_trace_args* a, cudaStream_t stream) {
   const int choice = trace_kernel_choice();
-  if (choice == 0) {
+  if constexpr (DMAX <= 32) {
+   if (choice == 0) {
     constexpr int GPB = 128 / DMAX;
     const int64_t blocks = (a->batch + GPB - 1) / GPB;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, FFB_STAGED_BLOCKS));
     k_trace_coop<DMAX, KMAX><<<grid, 128, 0, stream>>>(*a, a->batch);
-  } else {
+    ffb_count_launches(1);
+    CUDA_TRY(cudaGetLastError());
+    return FFB_OK;
+   }
+  }
+  {
+    // thread per sample: the A/B twin of the cooperative kernel for D <= 32, and THE kernel for 32 < D <= 124 (a row of
+    // the Jacobian no longer fits the lanes of a warp; the work arrays of the per-sample algebra live in local memory)
     const int threads = 128;
     const int64_t ntiles = (a->batch + threads - 1) / threads;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, FFB_STAGED_BLOCKS));
@@ -593,15 +601,16 @@ static void host_trace(const ffb_trace_args* a) {
   const int DD = a->dim * a->dim;
   for (int64_t b = 0; b < a->batch; ++b) a->dlp[b] = ffb::trace_estimate_one<DMAX, KMAX>(*a, a->jac + b * DD, b);
 }
-// work-array sizes: DMAX in {16, 32}, KMAX in {1, 2, 4, 8}
+// work-array sizes: DMAX in {16, 32, 64, 128}, KMAX in {1, 2, 4, 8}
+#define TRACE_DISPATCH_K(CALL, DM)                                                    \
+  do { if (kk == 1) CALL(DM, 1); else if (kk == 2) CALL(DM, 2); else if (kk == 4) CALL(DM, 4); else CALL(DM, 8); } while (0)
 #define TRACE_DISPATCH(CALL)                                                          \
   do {                                                                                \
     const int kk = a->rank <= 1 ? 1 : (a->rank <= 2 ? 2 : (a->rank <= 4 ? 4 : 8));    \
-    if (a->dim <= 16) {                                                               \
-      if (kk == 1) CALL(16, 1); else if (kk == 2) CALL(16, 2); else if (kk == 4) CALL(16, 4); else CALL(16, 8); \
-    } else {                                                                          \
-      if (kk == 1) CALL(32, 1); else if (kk == 2) CALL(32, 2); else if (kk == 4) CALL(32, 4); else CALL(32, 8); \
-    }                                                                                 \
+    if (a->dim <= 16) TRACE_DISPATCH_K(CALL, 16);                                     \
+    else if (a->dim <= 32) TRACE_DISPATCH_K(CALL, 32);                                \
+    else if (a->dim <= 64) TRACE_DISPATCH_K(CALL, 64);                                \
+    else TRACE_DISPATCH_K(CALL, 128);                                                 \
   } while (0)
 
 extern "C" int ffb_trace_estimate(const ffb_trace_args* a, void* stream) {

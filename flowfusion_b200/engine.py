@@ -543,7 +543,7 @@ class TraceEstimator:
         self.nvec = int(G.shape[0]) if G is not None else 0
         D = int(S.shape[2])
         if D > L.TRACE_MAX_DIM or self.rank > L.TRACE_MAX_RANK:
-            raise NotImplementedError(f"Hutch++ / XTrace kernels hold D <= {L.TRACE_MAX_DIM} and rank <= "
+            raise NotImplementedError(f"Hutch++ / XTrace hold D <= {L.TRACE_MAX_DIM} (a sample and its tangents share one tile) and rank <= "
                                       f"{L.TRACE_MAX_RANK} (got D = {D}, rank = {self.rank})")
         if self.rank > D:
             raise ValueError("rank must not exceed the state dimension")

@@ -318,7 +318,7 @@ int ffb_time_program_rows(const ffb_time_program* prog, const float* times, int3
  * the same FFB_NPART partial sums the fused attempt kernel does (the host controller does not change).      */
 #define FFB_TRACE_HUTCHPP 1   /* diffusion.py:336-400 */
 #define FFB_TRACE_XTRACE 2    /* diffusion.py:402-481 */
-#define FFB_TRACE_MAX_DIM 32  /* state columns D                                   */
+#define FFB_TRACE_MAX_DIM 124 /* state columns D (above 32: thread-per-sample kernel)  */
 #define FFB_TRACE_MAX_RANK 8  /* Hutch++ r = min(hpp_rank, D); XTrace m = xt_vecs  */
 #define FFB_STAGED_BLOCKS 1024 /* rows of the `partials` buffer the staged kernels write (caller zero-fills once) */
 typedef struct {

@@ -104,7 +104,7 @@ def _port_case(kind, no_sigma, Dn, Cn, seed):
 
 
 @pytest.mark.parametrize("kind,no_sigma,Dn,Cn", [("vp", True, 8, 2), ("ve", False, 12, 0), ("subvp", False, 16, 0),
-                                                 ("vp", False, 32, 1), ("ve", True, 5, 0)])
+                                                 ("vp", False, 32, 1), ("ve", True, 5, 0), ("vp", True, 48, 0), ("ve", False, 100, 2)])
 def test_c_twin_of_the_kernel_matches_the_oracle(kind, no_sigma, Dn, Cn):
     M, t, x, cond, jac, scal = _port_case(kind, no_sigma, Dn, Cn, 11)
     B = x.shape[0]
@@ -207,9 +207,9 @@ def test_flag_priority_probe_shapes_and_refusals():
         sm.train()
         with pytest.raises(NotImplementedError):
             sm.solve_odes_forward(x0)
-    wide = D.ScoreModel(D.MLP(40, 0, 4, [32]), D.VPSDE(), hutchpp=True).eval()
+    wide = D.ScoreModel(D.MLP(126, 0, 4, [32]), D.VPSDE(), hutchpp=True).eval()     # a sample + its tangents must share one tile
     with patched_engine(), pytest.raises(NotImplementedError):
-        wide.solve_odes_forward(torch.zeros(4, 40))
+        wide.solve_odes_forward(torch.zeros(4, 126))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -237,7 +237,8 @@ def test_gpu_logprob_matches_reference_golden(name, cuda_dev):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,no_sigma,Dn,Cn,B", [("vp", True, 16, 4, 1000), ("subvp", False, 8, 0, 129), ("ve", False, 32, 2, 77),
-                                                   ("vp", True, 5, 0, 64)])
+                                                   ("vp", True, 5, 0, 64), ("vp", True, 48, 0, 40), ("ve", False, 100, 2, 20),
+                                                   ("vp", True, 124, 0, 9)])
 def test_gpu_jacobian_and_estimators_vs_oracle(kind, no_sigma, Dn, Cn, B, cuda_dev):
     """One evaluation: the Jacobian the tangent engine writes vs autograd, both estimators vs the oracle."""
     from flowfusion_b200 import engine as E
