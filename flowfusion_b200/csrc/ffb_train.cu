@@ -43,6 +43,7 @@ constexpr int TR_MAXL = FFB_MAX_LAYERS;
 // Everything the kernels need to know about one training step (passed by value).
 struct TrainPlan {
   int n_layers, in_features, act, want_dx;
+  int fwd_only;         // forward pass only (out = net(X)): no pre-activations kept, no backward sweep, no weight gradients
   int64_t batch;
   int N[TR_MAXL];       // real output width of layer l
   int Kin[TR_MAXL];     // real input width of layer l
@@ -193,10 +194,12 @@ __device__ __forceinline__ void train_passes(CtxW& cx, const TrainPlan& p, float
           float h[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) { v[i] += bj; h[i] = act_fwd<ACT>(v[i]); }
-          *reinterpret_cast<float4*>(z + (size_t)n * WD_RS + r0w) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(Bf + (size_t)n * WD_RS + r0w) = make_float4(h[0], h[1], h[2], h[3]);
+          if (!p.fwd_only) {
+            *reinterpret_cast<float4*>(z + (size_t)n * WD_RS + r0w) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) if (row0 + i < p.batch) hg[(row0 + i) * Np + n] = h[i];
+            for (int i = 0; i < 4; ++i) if (row0 + i < p.batch) hg[(row0 + i) * Np + n] = h[i];
+          }
         });
       } else {
         const int Nout = p.N[l];
@@ -210,6 +213,7 @@ __device__ __forceinline__ void train_passes(CtxW& cx, const TrainPlan& p, float
             if (n < Nout && row0 + i < p.batch) {
               const float o = v[i] + bj;
               if (p.out) p.out[(row0 + i) * Nout + n] = o;
+              if (p.fwd_only) continue;
               if (p.cot) {
                 const float ct = p.cot[(row0 + i) * Nout + n];
                 loss += (double)ct * (double)o;
@@ -222,6 +226,7 @@ __device__ __forceinline__ void train_passes(CtxW& cx, const TrainPlan& p, float
               }
             }
           }
+          if (p.fwd_only) return;
           *reinterpret_cast<float4*>(Bf + (size_t)n * WD_RS + r0w) = make_float4(d[0], d[1], d[2], d[3]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) if (row0 + i < p.batch) dg[(row0 + i) * Np + n] = d[i];
@@ -229,6 +234,7 @@ __device__ __forceinline__ void train_passes(CtxW& cx, const TrainPlan& p, float
       }
       float* t = A; A = Bf; Bf = t;
     }
+    if (p.fwd_only) continue;
     // ---- backward sweep: A holds delta_{L-1} (k-major over the output columns) --------------------------------------
     for (int l = L - 1; l >= 1; --l) {
       const float* z = zreg + p.zoff[l - 1];
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_train_fwdbwd(const __grid_constant_
   if (cx.producer) {
     for (int64_t pass = blockIdx.x; pass < npass; pass += gridDim.x) {
       for (int l = 0; l < p.n_layers; ++l) train_produce(cx, p.Wf[l], p.Kp[l], p.Np[l]);
+      if (p.fwd_only) continue;
       for (int l = p.n_layers - 1; l >= 1; --l) train_produce(cx, p.Wb[l], p.Np[l], p.Kp[l]);
       if (p.want_dx) train_produce(cx, p.Wb[0], p.Np[0], p.KB0);
     }
@@ -593,7 +600,10 @@ static int train_plan(const ffb_net_desc* d, int64_t batch, int want_dx, TrainPl
   if (d->activation < FFB_ACT_SILU || d->activation > FFB_ACT_GELU) return ffb_fail(FFB_ERR_ARG, "ffb_train: unknown activation");
   if (batch < 0) return ffb_fail(FFB_ERR_ARG, "ffb_train: negative batch");
   memset(p, 0, sizeof(*p));
+  const bool fwd = (want_dx == 2);          // forward-only sizing: weight images and biases, nothing per row
+  want_dx = (want_dx == 1) ? 1 : 0;
   p->n_layers = d->n_layers; p->in_features = d->in_features; p->act = d->activation; p->want_dx = want_dx; p->batch = batch;
+  p->fwd_only = fwd ? 1 : 0;
   int in_f = d->in_features, zf = 0, maxk = 0;
   int64_t np = 0;
   for (int l = 0; l < d->n_layers; ++l) {
@@ -627,14 +637,14 @@ static int train_plan(const ffb_net_desc* d, int64_t batch, int want_dx, TrainPl
     const size_t KB = (l == 0) ? (size_t)p->KB0 : (size_t)p->Kp[l];
     const size_t b = (l >= 1 || want_dx) ? take((size_t)p->Np[l] * KB) : 0;
     const size_t c = take(p->Np[l]);
-    const size_t h = (l >= 1) ? take((size_t)batch * p->Np[l - 1]) : 0;
-    const size_t dd = take((size_t)batch * p->Np[l]);
+    const size_t h = (l >= 1 && !fwd) ? take((size_t)batch * p->Np[l - 1]) : 0;
+    const size_t dd = fwd ? 0 : take((size_t)batch * p->Np[l]);
     if (work) {
       p->Wf[l] = work + a; p->Wb[l] = (l >= 1 || want_dx) ? work + b : nullptr; p->bp[l] = work + c;
-      p->hin[l] = (l >= 1) ? work + h : nullptr; p->dl[l] = work + dd;
+      p->hin[l] = (l >= 1 && !fwd) ? work + h : nullptr; p->dl[l] = fwd ? nullptr : work + dd;
     }
   }
-  const size_t dwp = take((size_t)splits * np);
+  const size_t dwp = fwd ? 0 : take((size_t)splits * np);
   if (work) p->dw_part = work + dwp;
   lay->total_floats = o;
   lay->loss_off_bytes = (o * sizeof(float) + 255) & ~size_t(255);
@@ -655,16 +665,20 @@ extern "C" size_t ffb_train_work_bytes(const ffb_net_desc* net, int64_t batch, i
 
 extern "C" int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* a, void* stream_) {
   if (!net || !a) return ffb_fail(FFB_ERR_ARG, "ffb_train_step: null argument");
-  if (!a->x_in || (!a->beta && !a->cot) || !a->loss || !a->work)
-    return ffb_fail(FFB_ERR_ARG, "ffb_train_step: x_in, beta (or cot), loss and work are required");
+  // forward only: no loss / gradient outputs at all, just out = net(X) (a network evaluation at per-row inputs, e.g. the
+  // reference's score(t, x) with one time per sample, diffusion.py:82-121)
+  const bool fwd_only = a->out && !a->loss && !a->grad_x && !a->grad_w[0] && !a->grad_b[0];
+  if (!a->x_in || !a->work || (!fwd_only && ((!a->beta && !a->cot) || !a->loss)))
+    return ffb_fail(FFB_ERR_ARG, "ffb_train_step: x_in, beta (or cot), loss and work are required (or only `out` for a forward pass)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   TrainPlan p; TrainLayout lay;
-  int rc = train_plan(net, a->batch, a->grad_x != nullptr, &p, &lay, a->work);
+  int rc = train_plan(net, a->batch, fwd_only ? 2 : (a->grad_x != nullptr ? 1 : 0), &p, &lay, a->work);
   if (rc) return rc;
+  if (fwd_only) lay.zfloats = 0;
   TrainOut o;
   memset(&o, 0, sizeof(o));
   for (int l = 0; l < net->n_layers; ++l) {
-    if (!net->weight[l] || !net->bias[l] || !a->grad_w[l] || !a->grad_b[l])
+    if (!net->weight[l] || !net->bias[l] || (!fwd_only && (!a->grad_w[l] || !a->grad_b[l])))
       return ffb_fail(FFB_ERR_ARG, "ffb_train_step: weight, bias, grad_w and grad_b are required for every layer");
     p.W[l] = net->weight[l]; p.B[l] = net->bias[l];
     o.gw[l] = a->grad_w[l]; o.gb[l] = a->grad_b[l];
@@ -680,9 +694,11 @@ extern "C" int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* a, 
   k_train_pack<<<2 * ffb_num_sms(), 256, 0, st>>>(p);
   TR_CUDA_TRY(cudaFuncSetAttribute(k_train_fwdbwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_train_fwdbwd<<<lay.grid, NTHR, smem, st>>>(p, npass, lay.zfloats);
-  k_train_dw<<<dim3(dw_patches(p), p.splits), 256, 0, st>>>(p);
-  k_train_reduce<<<ffb_num_sms(), 256, 0, st>>>(p, o);
-  ffb_count_launches(4);
+  if (!fwd_only) {
+    k_train_dw<<<dim3(dw_patches(p), p.splits), 256, 0, st>>>(p);
+    k_train_reduce<<<ffb_num_sms(), 256, 0, st>>>(p, o);
+  }
+  ffb_count_launches(fwd_only ? 2 : 4);
   TR_CUDA_TRY(cudaGetLastError());
   return FFB_OK;
 }

@@ -96,7 +96,13 @@ class MLP(torch.nn.Module):
         tt = torch.as_tensor(t, dtype=torch.float32).detach()
         if tt.dim() > 0:
             if not bool((tt == tt.reshape(-1)[0]).all()):
-                raise NotImplementedError("per-sample times are a training-side call (out of scope)")
+                # one time per sample (`diffusion.py:104-113`): the network's input rows are built as the reference builds
+                # them and evaluated by the forward-only mode of the fused training kernel
+                from . import training
+                tt = tt.to(x.device).reshape(-1)
+                proj = tt[:, None] * self.W[None, :] * 2 * self.pi
+                cols = [torch.sin(proj), torch.cos(proj), x] + ([conditional] if conditional is not None else [])
+                return training.mlp_forward(list(self.NN), E.activation_code(self.activation), torch.cat(cols, dim=1))
             tt = tt.reshape(-1)[0]
         field = E.FieldSpec([self._net()], self.n_dimensions, self.n_conditionals)
         rows = np.zeros((1, L.EV_FLOATS), np.float32)

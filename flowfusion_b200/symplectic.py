@@ -90,7 +90,20 @@ class SymplecticMLP(nn.Module):
         tt = torch.as_tensor(t, dtype=torch.float32).detach()
         if tt.dim() > 0:
             if not bool((tt == tt.reshape(-1)[0]).all()):
-                raise NotImplementedError("per-sample times are a training-side call (out of scope)")
+                # one time per sample (`symplectic.py:101-114`): the two networks on explicit input rows
+                from . import training
+                D = self._dims[0]
+                tt = tt.to(state.device).reshape(-1)
+                q, p = state[:, :D], state[:, D:]
+                proj = tt[:, None] * self.W[None, :] * 2 * math.pi
+                temb = torch.cat([torch.sin(proj), torch.cos(proj)], dim=1)
+                mid = [conditional] if conditional is not None else []
+                lq = [m for m in self.mlp_q_dynamics if isinstance(m, nn.Linear)]
+                lp = [m for m in self.mlp_p_dynamics if isinstance(m, nn.Linear)]
+                act = E.activation_of(list(self.mlp_q_dynamics) + list(self.mlp_p_dynamics))
+                v_q = training.mlp_forward(lq, act, torch.cat([p] + mid + [temb], dim=1))
+                v_p = -training.mlp_forward(lp, act, torch.cat([q] + mid + [temb], dim=1))
+                return torch.cat([v_q, v_p], dim=-1)
             tt = tt.reshape(-1)[0]
         row = self._program()(tt.cpu().reshape(1).numpy())[0]
         return E.CudaBackend(self._field(), state, cond=conditional).single_eval(row)[0]

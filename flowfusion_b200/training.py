@@ -94,6 +94,39 @@ def train_step(linears: Sequence[torch.nn.Linear], activation: int, x_in: torch.
     return loss, grads, gx
 
 
+def mlp_forward(linears: Sequence[torch.nn.Linear], activation: int, x_in: torch.Tensor) -> torch.Tensor:
+    """net(x_in) for per-row inputs (B, in_features) on the forward-only mode of ``ffb_train_step`` (two launches): what the
+    reference's ``MLP.forward`` / ``score`` do when every sample has its own time (`diffusion.py:82-121`)."""
+    lib = L.load()
+    E.require_cuda(x_in, "x")
+    dev = x_in.device
+    if len(linears) > L.MAX_LAYERS:
+        raise NotImplementedError(f"at most {L.MAX_LAYERS} Linear layers are supported")
+    d = L.NetDesc()
+    d.n_layers, d.in_features = len(linears), linears[0].in_features
+    keep = []
+    for i, lin in enumerate(linears):
+        if lin.out_features > L.MAX_WIDTH or lin.in_features > L.MAX_WIDTH:
+            raise NotImplementedError(f"layer widths above {L.MAX_WIDTH} are not supported")
+        w, b = E._dev_f32(lin.weight, dev), E._dev_f32(lin.bias, dev)
+        keep += [w, b]
+        d.widths[i], d.weight[i], d.bias[i] = lin.out_features, w.data_ptr(), b.data_ptr()
+    d.x_dim, d.activation = linears[0].in_features, int(activation)
+    x_in = E._dev_f32(x_in, dev)
+    if x_in.dim() != 2 or x_in.shape[1] != linears[0].in_features:
+        raise ValueError("mlp_forward: x_in must be (B, in_features)")
+    a = L.TrainArgs()
+    out = torch.empty(x_in.shape[0], linears[-1].out_features, device=dev)
+    nbytes = int(lib.ffb_train_work_bytes(C.byref(d), x_in.shape[0], 2))
+    if nbytes == 0:
+        raise L.FFBError("ffb_train_work_bytes: " + lib.ffb_last_error().decode())
+    work = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+    a.batch, a.x_in, a.out, a.work, a.scale = x_in.shape[0], x_in.data_ptr(), out.data_ptr(), work.data_ptr(), 1.0
+    with E.on_device(dev):
+        L.check(lib.ffb_train_step(C.byref(d), C.byref(a), E._stream(dev)), "ffb_train_step")
+    return out
+
+
 class _FusedAffineMSE(torch.autograd.Function):
     """loss = scale * sum((alpha * net(x_in) + beta)**2) with the parameter gradients computed by the same call."""
 

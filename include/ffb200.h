@@ -406,6 +406,9 @@ typedef struct {
   const float* cot;                   /* (B, out_features) or NULL                          */
   float* out;                         /* out: (B, out_features) network output, or NULL     */
 } ffb_train_args;
+/* Forward only: with `out` set and loss, grad_x, grad_w[0], grad_b[0] all NULL the call just evaluates out = net(X) at
+ * per-row inputs (two launches; e.g. the reference's score(t, x) with one time per sample, diffusion.py:82-121); any width
+ * up to FFB_MAX_WIDTH fits.  Size `work` with want_grad_x = 2 for that mode. */
 size_t ffb_train_work_bytes(const ffb_net_desc* net, int64_t batch, int32_t want_grad_x);
 int ffb_train_step(const ffb_net_desc* net, const ffb_train_args* args, void* stream);
 

@@ -155,3 +155,34 @@ def test_hamiltonian_leapfrog_fused_gradient(cuda_dev, D_, C_, units, act_cls, a
     assert float(eb) < 0.5 * float(ea) + 1e-5
     # zero steps: the state comes back untouched
     assert torch.equal(m.leapfrog(z0.to(cuda_dev), cg, num_steps=0).cpu(), z0)
+
+
+def test_per_sample_times_forward_only(cuda_dev):
+    """`MLP.forward` / `ScoreModel.score` / `SymplecticMLP.forward` with ONE TIME PER SAMPLE (`diffusion.py:104-113`,
+    `symplectic.py:101-114`): the forward-only mode of the fused kernel, against the oracle; a 512-wide network fits there."""
+    import flowfusion_b200.diffusion as D
+    import flowfusion_b200.symplectic as Sy
+    from oracle import port
+    torch.manual_seed(12)
+    for units in ([128, 128], [512, 512, 512]):
+        sm = D.ScoreModel(D.MLP(6, 2, 8, units), D.VPSDE(), no_sigma=False).eval()
+        g = torch.Generator().manual_seed(1)
+        x, c, t = torch.randn(301, 6, generator=g), torch.randn(301, 2, generator=g), torch.rand(301, generator=g) * 0.9 + 0.05
+        M = port.score_model_from_state_dict(sm.state_dict(), port.make_sde("vp"), False)
+        ref_net, ref_score = port.score_net(M["P"], t, x, c), port.score(M, t, x, c)
+        sm.to(cuda_dev)
+        out = sm.model(t.to(cuda_dev), x.to(cuda_dev), conditional=c.to(cuda_dev))
+        assert _close(ref_net, out.cpu(), 2e-5)
+        sc = sm.score(t.to(cuda_dev), x.to(cuda_dev), conditional=c.to(cuda_dev))
+        assert _close(ref_score, sc.cpu(), 2e-5)
+    net = Sy.SymplecticMLP(4, 1, 8, [64, 64])
+    z = torch.randn(77, 8); c = torch.randn(77, 1); t = torch.rand(77)
+    Syp = port.symplectic_from_state_dict({"model." + k: v for k, v in net.state_dict().items()} |
+                                          {"shift": torch.zeros(4), "scale": torch.ones(4), "conditional_shift": torch.zeros(1),
+                                           "conditional_scale": torch.ones(1)})
+    q, p = z[:, :4], z[:, 4:]
+    temb = port.fourier_features(t, Syp["W"], torch.tensor(3.141592653589793))
+    ref = torch.cat([port._mlp(Syp["net_q"], torch.cat([p, c, temb], 1)), -port._mlp(Syp["net_p"], torch.cat([q, c, temb], 1))], 1)
+    net.to(cuda_dev)
+    v = net(t.to(cuda_dev), z.to(cuda_dev), c.to(cuda_dev))
+    assert _close(ref, v.cpu(), 2e-5)
