@@ -446,8 +446,10 @@ int ffb_ffma_peak(int32_t iters, float* tflops, void* stream);
 /* contraction engine: 1 = tcgen05 tensor cores, 3xTF32 (default: the dual-tile engine takes the dopri5 attempts of
  * fields without a divergence when the batch holds at least two tiles per SM, the single-tile engine everything else);
  * 3 = single-tile engine only; 4 = dual-tile engine for every dopri5 attempt it can hold (tests); 2 = the older
- * whole-layer hand-off tile engine; 0 = FP32 FFMA2 (debug / A-B checks).  Engines 1, 3 and 4 give the same bits.
- * The environment variable FFB_ENGINE = ffma | tc_tile | rr | rd selects 0 | 2 | 3 | 4 at load time. */
+ * whole-layer hand-off tile engine; 0 = FP32 FFMA2 (debug / A-B checks); 5 = the wide engine (FP32 pipe, 32-row passes)
+ * for every field -- by default it only takes networks with a hidden width above 128 or more than 8 Linear layers, whatever
+ * this setting.  Engines 1, 3 and 4 give the same bits.
+ * The environment variable FFB_ENGINE = ffma | tc_tile | rr | rd | wide selects 0 | 2 | 3 | 4 | 5 at load time. */
 int ffb_set_engine(int engine);
 int ffb_get_engine(void);
 /* debug: hand-off timelines of CTA 0 (libraries built with -DFFB_TRACE only; scripts/trace_rr.py, scripts/trace_rd.py).
