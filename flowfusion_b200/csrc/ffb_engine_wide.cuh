@@ -64,11 +64,15 @@ __device__ __forceinline__ float* slot_ptr_t(const CtxW& cx, int slot) {
   return cx.scr + (size_t)slot * cx.SD * LDA;
 }
 
-__host__ __device__ inline size_t smem_layout_wide(int SD, int CD, int T, int hutch, int slots_smem, int maxk, size_t* off /*[12]*/) {
+// H = 32-row halves of a pass (1 or 2): with two halves a thread owns 8 rows x C columns, which halves the weight-operand
+// LDS traffic and the operand-duplication MOVs per FFMA2 and doubles the independent work per warp; the activation buffers
+// double with it, so the launchers take H = 2 only when the field still fits shared memory (widths up to 256).
+__host__ __device__ inline size_t smem_layout_wide(int SD, int CD, int T, int hutch, int slots_smem, int maxk, size_t* off /*[12]*/,
+                                                   int H = 1) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 127) & ~size_t(127); return r; };
   size_t v[12];
-  const size_t act_floats = (size_t)2 * maxk * WD_RS, stage_floats = (size_t)SD * LDA;
+  const size_t act_floats = (size_t)2 * maxk * (32 * H + 4), stage_floats = (size_t)SD * LDA;
   v[0] = take(sizeof(float) * (act_floats > stage_floats ? act_floats : stage_floats));   // activations (ping-pong) / staging
   v[1] = take(sizeof(float) * WD_NSTAGE * WD_STAGE_FLOATS);       // weight ring
   v[2] = take(sizeof(float) * SD * LDA);                          // ycur
@@ -85,14 +89,18 @@ __host__ __device__ inline size_t smem_layout_wide(int SD, int CD, int T, int hu
   return o;
 }
 
-struct EngineWide {
+// GEN = true: every activation of ffb200.h through a compile-time dispatch per pass; false: SiLU only (the two-half variant is
+// instantiated for SiLU alone to keep the build time of this translation unit in check)
+template <int H, bool GEN = true>
+struct EngineWideT {
   using Ctx = CtxW;
   static constexpr int NTHR = ffb::NTHR;      // 8 compute warps + the producer warp
+  static constexpr int RS = 32 * H + 4;       // row stride (floats) of the k-major activation buffers
 
   static __device__ __forceinline__ void init(CtxW& cx, const FieldDev& f, float* scratch) {
     const int T = (f.div_mode == FFB_DIV_EXACT) ? f.net[0].x_dim : (f.div_mode == FFB_DIV_HUTCH ? 1 : 0);
     size_t off[12];
-    smem_layout_wide(f.state_dim, f.cond_dim, T, f.div_mode == FFB_DIV_HUTCH, f.slots_smem, f.wide_maxk, off);
+    smem_layout_wide(f.state_dim, f.cond_dim, T, f.div_mode == FFB_DIV_HUTCH, f.slots_smem, f.wide_maxk, off, H);
     cx.o_act = (uint32_t)off[0]; cx.o_ring = (uint32_t)off[1]; cx.o_ycur = (uint32_t)off[2]; cx.o_cond = (uint32_t)off[3];
     cx.o_prb = (uint32_t)off[4]; cx.o_tan = (uint32_t)off[5]; cx.o_beff = (uint32_t)off[6]; cx.o_klp = (uint32_t)off[7];
     cx.o_red = (uint32_t)off[8]; cx.o_bar = (uint32_t)off[9]; cx.o_net = (uint32_t)off[10]; cx.o_slots = (uint32_t)off[11];
@@ -142,30 +150,33 @@ struct EngineWide {
       }
   }
 
-  // ---- this thread's 4 rows x C columns of one chunk: acc[i][j] = (rows 2i, 2i+1) x column j -----------------
+  // ---- this thread's 4 H rows x C columns of one chunk: acc[2 h + i][j] = (rows 2i, 2i+1 of half h) x column j -----------
   template <int C>
-  static __device__ __forceinline__ void gemm_chunk(CtxW& cx, const float* actin, int K, float2 (&acc)[2][C]) {
+  static __device__ __forceinline__ void gemm_chunk(CtxW& cx, const float* actin, int K, float2 (&acc)[2 * H][C]) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2 * H; ++i)
 #pragma unroll
       for (int j = 0; j < C; ++j) acc[i][j] = make_float2(0.f, 0.f);
     constexpr int CW = 32 * C;
     for (int k0 = 0; k0 < K; k0 += WD_KC) {
       const int rows = min(WD_KC, K - k0);
       mbar_wait(&cx.full()[cx.stage], cx.phase);
-      const float* ap = actin + (size_t)k0 * WD_RS + cx.warp * 4;
+      const float* ap = actin + (size_t)k0 * RS + cx.warp * 4;
       const float* bp = cx.ring() + cx.stage * WD_STAGE_FLOATS + cx.lane * C;
 #pragma unroll 4
       for (int kk = 0; kk < rows; ++kk) {
-        const float4 a = *reinterpret_cast<const float4*>(ap + kk * WD_RS);
         float b[C];
         load_b<C>(b, bp + kk * CW);
-        const float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
 #pragma unroll
-        for (int j = 0; j < C; ++j) {
-          const float2 bb = make_float2(b[j], b[j]);
-          acc[0][j] = __ffma2_rn(a01, bb, acc[0][j]);
-          acc[1][j] = __ffma2_rn(a23, bb, acc[1][j]);
+        for (int h = 0; h < H; ++h) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + kk * RS + 32 * h);
+          const float2 a01 = make_float2(a.x, a.y), a23 = make_float2(a.z, a.w);
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            const float2 bb = make_float2(b[j], b[j]);
+            acc[2 * h][j] = __ffma2_rn(a01, bb, acc[2 * h][j]);
+            acc[2 * h + 1][j] = __ffma2_rn(a23, bb, acc[2 * h + 1][j]);
+          }
         }
       }
       __syncwarp();
@@ -196,64 +207,69 @@ struct EngineWide {
   template <int C, int ACT, bool SS>
   static __device__ __forceinline__ void chunk(CtxW& cx, const FieldDev& f, const WideNet& net, const ffb_eval_scalars& ev,
                                                int c, int dst, const float* actin, float* actout, int l, int nc,
-                                               const int (&s)[4], const int (&jt)[4]) {
-    float2 acc[2][C];
+                                               const int (&s)[H][4], const int (&jt)[H][4]) {
+    float2 acc[2 * H][C];
     gemm_chunk<C>(cx, actin, net.K[l], acc);
-    float v[4][C];
-#pragma unroll
-    for (int j = 0; j < C; ++j) { v[0][j] = acc[0][j].x; v[1][j] = acc[0][j].y; v[2][j] = acc[1][j].x; v[3][j] = acc[1][j].y; }
     const bool last = (l == net.n_layers - 1);
     const float* bias = (l == 0) ? cx.beff() : net.b[l];
     const int T = cx.T;
-    if (!last) {
-#pragma unroll
-      for (int j = 0; j < C; ++j) {
-        const int n = nc * (32 * C) + j * 32 + cx.lane;
-        const float bj = bias[n];
-        if (T == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i][j] = act_fwd<ACT>(v[i][j] + bj);
-        } else if (T == 1) {
-          float a, g;
-          act_fwd_grad<ACT>(v[0][j] + bj, a, g); v[0][j] = a; v[1][j] *= g;
-          act_fwd_grad<ACT>(v[2][j] + bj, a, g); v[2][j] = a; v[3][j] *= g;
-        } else {
-          float a, g;
-          act_fwd_grad<ACT>(v[0][j] + bj, a, g);
-          v[0][j] = a; v[1][j] *= g; v[2][j] *= g; v[3][j] *= g;
-        }
-        *reinterpret_cast<float4*>(actout + (size_t)n * WD_RS + cx.warp * 4) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
-      }
-      return;
-    }
-    // last layer (one chunk: its width is at most the state's 128 columns)
     const int Dout = net.N[l];
     float* kd = slot_ptr_t<SS>(cx, dst) + f.out_off[c] * LDA;
     const float* yc = cx.ycur() + f.out_off[c] * LDA;
     const float sgn = ev.sign * f.out_sign[c];
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      const int n = j * 32 + cx.lane;
-      if (n >= Dout) continue;
-      const float bj = bias[n];
+    for (int h = 0; h < H; ++h) {
+      float v[4][C];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (s[i] < 0) continue;
-        if (jt[i] < 0) {
-          const float o = v[i][j] + bj;
-          float xd_;
-          if (f.kind == FFB_FIELD_SCORE) {
-            const float sc = f.use_sigma ? __fdiv_rn(o, ev.sigma) : o;
-            const float lin = f.has_drift ? __fmul_rn(ev.a, yc[n * LDA + s[i]]) : 0.0f;
-            xd_ = __fsub_rn(lin, __fmul_rn(ev.c, sc));
+      for (int j = 0; j < C; ++j) {
+        v[0][j] = acc[2 * h][j].x; v[1][j] = acc[2 * h][j].y; v[2][j] = acc[2 * h + 1][j].x; v[3][j] = acc[2 * h + 1][j].y;
+      }
+      if (!last) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          const int n = nc * (32 * C) + j * 32 + cx.lane;
+          const float bj = bias[n];
+          if (T == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i][j] = act_fwd<ACT>(v[i][j] + bj);
+          } else if (T == 1) {
+            float a, g;
+            act_fwd_grad<ACT>(v[0][j] + bj, a, g); v[0][j] = a; v[1][j] *= g;
+            act_fwd_grad<ACT>(v[2][j] + bj, a, g); v[2][j] = a; v[3][j] *= g;
           } else {
-            xd_ = o;
+            float a, g;
+            act_fwd_grad<ACT>(v[0][j] + bj, a, g);
+            v[0][j] = a; v[1][j] *= g; v[2][j] *= g; v[3][j] *= g;
           }
-          kd[n * LDA + s[i]] = xd_ * sgn;
-        } else if (f.div_mode == FFB_DIV_HUTCH) {
-          cx.tan()[n * LDA + s[i]] = v[i][j];
-        } else if (n == jt[i]) {
-          cx.tan()[n * LDA + s[i]] = v[i][j];
+          *reinterpret_cast<float4*>(actout + (size_t)n * RS + 32 * h + cx.warp * 4) = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+        }
+        continue;
+      }
+      // last layer (one chunk: its width is at most the state's 128 columns)
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const int n = j * 32 + cx.lane;
+        if (n >= Dout) continue;
+        const float bj = bias[n];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (s[h][i] < 0) continue;
+          if (jt[h][i] < 0) {
+            const float o = v[i][j] + bj;
+            float xd_;
+            if (f.kind == FFB_FIELD_SCORE) {
+              const float sc = f.use_sigma ? __fdiv_rn(o, ev.sigma) : o;
+              const float lin = f.has_drift ? __fmul_rn(ev.a, yc[n * LDA + s[h][i]]) : 0.0f;
+              xd_ = __fsub_rn(lin, __fmul_rn(ev.c, sc));
+            } else {
+              xd_ = o;
+            }
+            kd[n * LDA + s[h][i]] = xd_ * sgn;
+          } else if (f.div_mode == FFB_DIV_HUTCH) {
+            cx.tan()[n * LDA + s[h][i]] = v[i][j];
+          } else if (n == jt[h][i]) {
+            cx.tan()[n * LDA + s[h][i]] = v[i][j];
+          }
         }
       }
     }
@@ -266,27 +282,31 @@ struct EngineWide {
     const int K0 = net.K[0], xd = net.x_dim, cd = net.c_dim;
     const float* ycin = cx.ycur() + f.in_off[c] * LDA;
     for (int p = 0; p < npass; ++p) {
-      int s[4], jt[4];
-      rowmap(T, S, ngt, p * (NCOMP / 32) + cx.warp, s, jt);
+      int s[H][4], jt[H][4];
+#pragma unroll
+      for (int h = 0; h < H; ++h) rowmap(T, S, ngt, (p * H + h) * (NCOMP / 32) + cx.warp, s[h], jt[h]);
       float* A = cx.act();
-      float* B = cx.act() + (size_t)cx.maxk * WD_RS;
+      float* B = cx.act() + (size_t)cx.maxk * RS;
       // layer-0 operand of this warp's rows: [x | cond | zero pad]; tangent rows: one-hot (exact) or the probe (Hutchinson)
       for (int k = cx.lane; k < K0; k += 32) {
-        float val[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float x = 0.0f;
-          if (s[i] >= 0) {
-            if (jt[i] < 0) {
-              if (k < xd) x = ycin[k * LDA + s[i]];
-              else if (k < xd + cd) x = cx.condb()[(k - xd) * LDA + s[i]];
-            } else if (k < xd) {
-              x = (f.div_mode == FFB_DIV_EXACT) ? (k == jt[i] ? 1.0f : 0.0f) : cx.prb()[k * LDA + s[i]];
+        for (int h = 0; h < H; ++h) {
+          float val[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float x = 0.0f;
+            if (s[h][i] >= 0) {
+              if (jt[h][i] < 0) {
+                if (k < xd) x = ycin[k * LDA + s[h][i]];
+                else if (k < xd + cd) x = cx.condb()[(k - xd) * LDA + s[h][i]];
+              } else if (k < xd) {
+                x = (f.div_mode == FFB_DIV_EXACT) ? (k == jt[h][i] ? 1.0f : 0.0f) : cx.prb()[k * LDA + s[h][i]];
+              }
             }
+            val[i] = x;
           }
-          val[i] = x;
+          *reinterpret_cast<float4*>(A + (size_t)k * RS + 32 * h + cx.warp * 4) = make_float4(val[0], val[1], val[2], val[3]);
         }
-        *reinterpret_cast<float4*>(A + (size_t)k * WD_RS + cx.warp * 4) = make_float4(val[0], val[1], val[2], val[3]);
       }
       __syncwarp();
       for (int l = 0; l < net.n_layers; ++l) {
@@ -312,7 +332,7 @@ struct EngineWide {
       const int T = cx.T, S = cx.S;
       const int ngt = (T + 2) / 3;
       const int ngroups = (T == 0) ? (S + 3) / 4 : (T == 1 ? (S + 1) / 2 : S * ngt);
-      const int npass = (ngroups + NCOMP / 32 - 1) / (NCOMP / 32);
+      const int npass = (ngroups + H * (NCOMP / 32) - 1) / (H * (NCOMP / 32));
       if (cx.producer) { produce(cx, net, npass); continue; }
       const int Np0 = net.Np[0];
       for (int n = cx.tid; n < Np0; n += NCOMP) {
@@ -321,7 +341,11 @@ struct EngineWide {
         cx.beff()[n] = b;
       }
       bar_compute();
-      FFB_ACT_DISPATCH(net.act, (passes<ACT, SS>(cx, f, net, ev, c, dst, npass, ngt)));
+      if constexpr (GEN) {
+        FFB_ACT_DISPATCH(net.act, (passes<ACT, SS>(cx, f, net, ev, c, dst, npass, ngt)));
+      } else {
+        passes<FFB_ACT_SILU, SS>(cx, f, net, ev, c, dst, npass, ngt);
+      }
       bar_compute();                        // derivative slot and tangent outputs complete
       if (T > 0) {
         const int xd = net.x_dim;
@@ -347,5 +371,7 @@ struct EngineWide {
     }
   }
 };
+
+using EngineWide = EngineWideT<1, true>;      // the training / Hamiltonian kernels (csrc/ffb_train.cu) use its contraction and ring
 
 }  // namespace ffb

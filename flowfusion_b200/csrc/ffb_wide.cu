@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <string>
 
@@ -30,12 +31,21 @@ static int wd_smem_optin() {
 static int wd_tangents(const FieldDev& fd) {
   return fd.div_mode == FFB_DIV_EXACT ? fd.net[0].x_dim : (fd.div_mode == FFB_DIV_HUTCH ? 1 : 0);
 }
-// shared-memory block of the field; picks fd.slots_smem
-static size_t wd_pick_smem(FieldDev* fd) {
+// shared-memory block of the field for H halves per pass; picks fd.slots_smem
+static size_t wd_pick_smem(FieldDev* fd, int H) {
   const int T = wd_tangents(*fd), hutch = fd->div_mode == FFB_DIV_HUTCH;
-  const size_t with_slots = smem_layout_wide(fd->state_dim, fd->cond_dim, T, hutch, 1, fd->wide_maxk, nullptr);
+  const size_t with_slots = smem_layout_wide(fd->state_dim, fd->cond_dim, T, hutch, 1, fd->wide_maxk, nullptr, H);
   fd->slots_smem = (with_slots <= (size_t)wd_smem_optin()) ? 1 : 0;
-  return fd->slots_smem ? with_slots : smem_layout_wide(fd->state_dim, fd->cond_dim, T, hutch, 0, fd->wide_maxk, nullptr);
+  return fd->slots_smem ? with_slots : smem_layout_wide(fd->state_dim, fd->cond_dim, T, hutch, 0, fd->wide_maxk, nullptr, H);
+}
+// two 32-row halves per pass (8 rows per thread) when the doubled activation buffers still fit, else one
+// (FFB_WIDE_HALVES=1 forces one: A/B runs)
+static int wd_halves(const FieldDev& fd) {
+  static const int forced = [] { const char* e = getenv("FFB_WIDE_HALVES"); return e ? atoi(e) : 0; }();
+  if (forced == 1) return 1;
+  for (int c = 0; c < fd.n_calls; ++c) if (fd.net[c].act != FFB_ACT_SILU) return 1;      // the two-half kernels are SiLU-only
+  FieldDev tmp = fd;
+  return wd_pick_smem(&tmp, 2) <= (size_t)wd_smem_optin() ? 2 : 1;
 }
 
 template <typename Kern, typename Args>
@@ -55,20 +65,18 @@ static int wd_launch(Kern kern, size_t smem, const char* name, const FieldDev& f
   return FFB_OK;
 }
 
-int wide_launch_field_eval(FieldDev fd, const ffb_eval_args& a, cudaStream_t st) {
-  const size_t smem = wd_pick_smem(&fd);
-  if (fd.slots_smem) return wd_launch(k_field_eval<EngineWide, true>, smem, "ffb_field_eval", fd, a, a.batch, st);
-  return wd_launch(k_field_eval<EngineWide, false>, smem, "ffb_field_eval", fd, a, a.batch, st);
-}
-int wide_launch_dopri5(FieldDev fd, const ffb_dopri5_args& a, cudaStream_t st) {
-  const size_t smem = wd_pick_smem(&fd);
-  if (fd.slots_smem) return wd_launch(k_dopri5<EngineWide, true>, smem, "ffb_dopri5_attempt", fd, a, a.batch, st);
-  return wd_launch(k_dopri5<EngineWide, false>, smem, "ffb_dopri5_attempt", fd, a, a.batch, st);
-}
-int wide_launch_fixed(FieldDev fd, const ffb_fixed_args& a, cudaStream_t st) {
-  const size_t smem = wd_pick_smem(&fd);
-  if (fd.slots_smem) return wd_launch(k_fixed<EngineWide, true>, smem, "ffb_integrate_fixed", fd, a, a.batch, st);
-  return wd_launch(k_fixed<EngineWide, false>, smem, "ffb_integrate_fixed", fd, a, a.batch, st);
-}
+#define WD_DISPATCH(KERNEL, NAME, BATCH)                                                                        \
+  const int H = wd_halves(fd);                                                                                  \
+  const size_t smem = wd_pick_smem(&fd, H);                                                                     \
+  if (H == 2) {                                                                                                 \
+    if (fd.slots_smem) return wd_launch(KERNEL<EngineWideT<2, false>, true>, smem, NAME, fd, a, BATCH, st);            \
+    return wd_launch(KERNEL<EngineWideT<2, false>, false>, smem, NAME, fd, a, BATCH, st);                              \
+  }                                                                                                             \
+  if (fd.slots_smem) return wd_launch(KERNEL<EngineWideT<1, true>, true>, smem, NAME, fd, a, BATCH, st);              \
+  return wd_launch(KERNEL<EngineWideT<1, true>, false>, smem, NAME, fd, a, BATCH, st)
+
+int wide_launch_field_eval(FieldDev fd, const ffb_eval_args& a, cudaStream_t st) { WD_DISPATCH(k_field_eval, "ffb_field_eval", a.batch); }
+int wide_launch_dopri5(FieldDev fd, const ffb_dopri5_args& a, cudaStream_t st) { WD_DISPATCH(k_dopri5, "ffb_dopri5_attempt", a.batch); }
+int wide_launch_fixed(FieldDev fd, const ffb_fixed_args& a, cudaStream_t st) { WD_DISPATCH(k_fixed, "ffb_integrate_fixed", a.batch); }
 
 }  // namespace ffb
