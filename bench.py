@@ -56,6 +56,10 @@ WORKLOADS = {
                  B=1_250_000, cpu_B=20_000, metric="samples/s", unit="samples/s"),
     "cfg5": dict(desc="SymplecticMLP(32,0,8,[128]*4): forward-Euler sampling, 100 steps, 64-D phase space",
                  B=4_000_000, cpu_B=200_000, metric="samples/s", unit="samples/s"),
+    # not a BASELINE config: the cfg2 workload with a 256-wide network, which runs on the wide engine (FP32 pipe,
+    # csrc/ffb_engine_wide.cuh) -- read `roofline.frac_of_ffma2_peak`, not `frac` (that one is against the tensor peak)
+    "wide256": dict(desc="MLP(16,4,8,[256]*4)+VPSDE no_sigma: PF-ODE sampling, dopri5 atol=rtol=1e-5, step_t=[eps]; wide engine (FP32 pipe)",
+                    B=250_000, cpu_B=100_000, metric="samples/s", unit="samples/s"),
 }
 
 
@@ -66,6 +70,8 @@ def make_model(name, ns):
         return ns.F.ODEFlow(2, [64, 64, 64]).eval()
     if name == "cfg2":
         return ns.D.ScoreModel(ns.D.MLP(16, 4, 8, [128] * 4), ns.D.VPSDE(), no_sigma=True).eval()
+    if name == "wide256":
+        return ns.D.ScoreModel(ns.D.MLP(16, 4, 8, [256] * 4), ns.D.VPSDE(), no_sigma=True).eval()
     if name == "cfg3":
         return ns.F.ODEFlow(16, [128] * 4).eval()
     if name == "cfg4":
@@ -80,7 +86,7 @@ def make_inputs(name, B, rank=0):
     s = 1000 * rank
     if name == "cfg1":
         return {"xT": torch.randn(B, 2, generator=_gen(1 + s))}
-    if name == "cfg2":
+    if name in ("cfg2", "wide256"):
         return {"base": torch.randn(B, 16, generator=_gen(2 + s)), "cond": torch.randn(B, 4, generator=_gen(3 + s))}
     if name == "cfg3":
         return {"x": torch.randn(B, 16, generator=_gen(4 + s))}
@@ -95,7 +101,7 @@ def run_gpu(name, model, inp):
     """One step through the package's public API; returns the result tensor (on device)."""
     if name == "cfg1":
         return model.sample(inp["xT"])
-    if name == "cfg2":
+    if name in ("cfg2", "wide256"):
         return model.sample_ode_from_base(inp["base"], inp["cond"], atol=1e-5, rtol=1e-5,
                                           options={"step_t": torch.tensor([1e-3])})[0]
     if name == "cfg3":
@@ -113,7 +119,7 @@ def run_cpu_port(name, model, inp):
     sd = model.state_dict()
     if name == "cfg1":
         return port.flow_sample(port.flow_from_state_dict(sd), inp["xT"])
-    if name == "cfg2":
+    if name in ("cfg2", "wide256"):
         M = port.score_model_from_state_dict(sd, port.make_sde("vp"), True)
         return port.sample_ode_from_base(M, inp["base"], inp["cond"], 1e-5, 1e-5, options={"step_t": torch.tensor([1e-3])})[0]
     if name == "cfg3":
@@ -296,7 +302,7 @@ def shard_check(name, model, inp, out, rows=4096):
     sub = {k: v[:n].cpu() for k, v in inp.items()}
     sd = {k: v.cpu() for k, v in model.state_dict().items()}
     replay = None if st is None else (list(st.dt_history), list(st.accept_history))
-    if name == "cfg2":
+    if name in ("cfg2", "wide256"):
         M = port.score_model_from_state_dict(sd, port.make_sde("vp"), True)
         ref = port.sample_ode_from_base(M, sub["base"], sub["cond"], 1e-5, 1e-5,
                                         options={"step_t": torch.tensor([1e-3]), "_replay": replay})[0]
@@ -460,7 +466,8 @@ def main():
     roof = None
     if kname:
         n_l, k_ms, k_rows = prof[kname]
-        field_flops = {"cfg1": 17024, "cfg2": 109568, "cfg3": 1683712, "cfg4": 116736, "cfg5": 233472}[name]
+        field_flops = {"cfg1": 17024, "cfg2": 109568, "cfg3": 1683712, "cfg4": 116736, "cfg5": 233472,
+                       "wide256": 2 * (28 * 256 + 3 * 256 * 256 + 256 * 16)}[name]
         evals_per_launch = {"dopri5_attempt": 6, "field_eval": 1, "integrate_fixed": nfe or 1}[kname]
         flop_per_launch = field_flops * evals_per_launch * (k_rows / n_l)
         achieved = flop_per_launch / (k_ms / n_l * 1e-3) / 1e12
@@ -479,10 +486,13 @@ def main():
             t = json.load(open(tpath)).get(name)
             if t and t["kernel"].startswith({"dopri5_attempt": "k_dopri5", "integrate_fixed": "k_fixed", "field_eval": "k_field_eval"}[kname]):
                 traffic = t["dram_bytes_per_launch"] / t["rows"] * (k_rows / n_l)
-        roof = {"bound": "tensor", "achieved": achieved, "peak": tensor_fp32_equiv, "unit": "TFLOP/s",
+        if name == "wide256":      # the wide engine runs on the FP32 pipe: its roofline is the measured FFMA2 peak
+            tensor_fp32_equiv, peak_src = ffma_peak, "measured in this run by ffb_ffma_peak (FP32 FFMA2 pipe: the wide engine's bound)"
+        roof = {"bound": "fp32" if name == "wide256" else "tensor", "achieved": achieved, "peak": tensor_fp32_equiv, "unit": "TFLOP/s",
                 "frac": achieved / tensor_fp32_equiv, "traffic": traffic,
                 "kernel": kname, "launches": n_l, "avg_launch_ms": k_ms / n_l, "share_of_step": k_ms / ms,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_src}) / 6 = 3xTF32 FP32-equivalent tensor peak",
+                "peak_source": (peak_src if name == "wide256" else
+                                f"MEASURED_PEAKS.json bf16_tflops ({peak_src}) / 6 = 3xTF32 FP32-equivalent tensor peak"),
                 "fp32_ffma2_peak_measured": ffma_peak, "frac_of_ffma2_peak": achieved / ffma_peak,
                 "tf32_gemm_tflops_measured": tf32_gemm, "frac_of_tf32_gemm_over_3": achieved / (tf32_gemm / 3.0),
                 "tcgen05_3xtf32_instruction_rate_tflops": instr_rate, "frac_of_instruction_rate": achieved / instr_rate,
