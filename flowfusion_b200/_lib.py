@@ -203,7 +203,9 @@ class FFBError(RuntimeError):
 
 _NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(_HERE, "csrc"), "-Xcompiler", "-fPIC"]
-# (-split-compile 0 would cut the build time further but the kernels it produces are 7 % slower)
+# -split-compile 0 (one ptxas job per kernel, in parallel) cuts the build time but the tensor-core kernels it produces are
+# 7 % slower: only the translation units without tcgen05 kernels take it
+_SPLIT_COMPILE = ("ffb_wide.cu", "ffb_staged.cu", "ffb_train.cu")
 
 
 def _obj(src):
@@ -212,7 +214,8 @@ def _obj(src):
 
 def nvcc_commands(out=LIB_PATH):
     """One compile command per translation unit (run in parallel) and the link command."""
-    compiles = [["nvcc"] + _NVCC_FLAGS + ["-c", src, "-o", _obj(src)] for src in SOURCES]
+    compiles = [["nvcc"] + _NVCC_FLAGS + (["-split-compile", "0"] if os.path.basename(src) in _SPLIT_COMPILE else []) +
+                ["-c", src, "-o", _obj(src)] for src in SOURCES]
     link = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [_obj(src) for src in SOURCES]
     return compiles, link
 

@@ -601,7 +601,7 @@ static void host_trace(const ffb_trace_args* a) {
   const int DD = a->dim * a->dim;
   for (int64_t b = 0; b < a->batch; ++b) a->dlp[b] = ffb::trace_estimate_one<DMAX, KMAX>(*a, a->jac + b * DD, b);
 }
-// work-array sizes: DMAX in {16, 32, 64, 128}, KMAX in {1, 2, 4, 8}
+// work-array sizes: DMAX in {16, 32}, KMAX in {1, 2, 4, 8}; DMAX in {64, 128}, KMAX in {2, 8} (fewer instantiations: build time)
 #define TRACE_DISPATCH_K(CALL, DM)                                                    \
   do { if (kk == 1) CALL(DM, 1); else if (kk == 2) CALL(DM, 2); else if (kk == 4) CALL(DM, 4); else CALL(DM, 8); } while (0)
 #define TRACE_DISPATCH(CALL)                                                          \
@@ -609,8 +609,8 @@ static void host_trace(const ffb_trace_args* a) {
     const int kk = a->rank <= 1 ? 1 : (a->rank <= 2 ? 2 : (a->rank <= 4 ? 4 : 8));    \
     if (a->dim <= 16) TRACE_DISPATCH_K(CALL, 16);                                     \
     else if (a->dim <= 32) TRACE_DISPATCH_K(CALL, 32);                                \
-    else if (a->dim <= 64) TRACE_DISPATCH_K(CALL, 64);                                \
-    else TRACE_DISPATCH_K(CALL, 128);                                                 \
+    else if (a->dim <= 64) { if (kk <= 2) CALL(64, 2); else CALL(64, 8); }            \
+    else { if (kk <= 2) CALL(128, 2); else CALL(128, 8); }                            \
   } while (0)
 
 extern "C" int ffb_trace_estimate(const ffb_trace_args* a, void* stream) {

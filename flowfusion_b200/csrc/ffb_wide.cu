@@ -65,6 +65,11 @@ static int wd_launch(Kern kern, size_t smem, const char* name, const FieldDev& f
   return FFB_OK;
 }
 
+// (the single evaluation keeps one half per pass: it is a small share of a solve, and every instantiation costs build time)
+#define WD_DISPATCH_ONE(KERNEL, NAME, BATCH)                                                                    \
+  const size_t smem = wd_pick_smem(&fd, 1);                                                                     \
+  if (fd.slots_smem) return wd_launch(KERNEL<EngineWideT<1, true>, true>, smem, NAME, fd, a, BATCH, st);        \
+  return wd_launch(KERNEL<EngineWideT<1, true>, false>, smem, NAME, fd, a, BATCH, st)
 #define WD_DISPATCH(KERNEL, NAME, BATCH)                                                                        \
   const int H = wd_halves(fd);                                                                                  \
   const size_t smem = wd_pick_smem(&fd, H);                                                                     \
@@ -75,7 +80,7 @@ static int wd_launch(Kern kern, size_t smem, const char* name, const FieldDev& f
   if (fd.slots_smem) return wd_launch(KERNEL<EngineWideT<1, true>, true>, smem, NAME, fd, a, BATCH, st);              \
   return wd_launch(KERNEL<EngineWideT<1, true>, false>, smem, NAME, fd, a, BATCH, st)
 
-int wide_launch_field_eval(FieldDev fd, const ffb_eval_args& a, cudaStream_t st) { WD_DISPATCH(k_field_eval, "ffb_field_eval", a.batch); }
+int wide_launch_field_eval(FieldDev fd, const ffb_eval_args& a, cudaStream_t st) { WD_DISPATCH_ONE(k_field_eval, "ffb_field_eval", a.batch); }
 int wide_launch_dopri5(FieldDev fd, const ffb_dopri5_args& a, cudaStream_t st) { WD_DISPATCH(k_dopri5, "ffb_dopri5_attempt", a.batch); }
 int wide_launch_fixed(FieldDev fd, const ffb_fixed_args& a, cudaStream_t st) { WD_DISPATCH(k_fixed, "ffb_integrate_fixed", a.batch); }
 
