@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("FFB_LIB") or os.path.join(_HERE, "libffb200.so")
-SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu", "ffb_rd.cu", "ffb_wide.cu", "ffb_train.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", n) for n in ("ffb_kernels.cu", "ffb_staged.cu", "ffb_rd.cu", "ffb_wide.cu", "ffb_wide2.cu", "ffb_train.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", h) for h in ("ffb_common.cuh", "ffb_engine.cuh", "ffb_engine_tc.cuh", "ffb_engine_rr.cuh",
                                                      "ffb_kernels_rr.cuh", "ffb_engine_rrt.cuh", "ffb_control.cuh", "ffb_engine_rd.cuh",
                                                      "ffb_kernels_rd.cuh", "ffb_rd.h", "ffb_kernels_generic.cuh", "ffb_engine_wide.cuh", "ffb_wide.h")] + \
@@ -205,7 +205,7 @@ _NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
                "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(_HERE, "csrc"), "-Xcompiler", "-fPIC"]
 # -split-compile 0 (one ptxas job per kernel, in parallel) cuts the build time but the tensor-core kernels it produces are
 # 7 % slower: only the translation units without tcgen05 kernels take it
-_SPLIT_COMPILE = ("ffb_wide.cu", "ffb_staged.cu", "ffb_train.cu")
+_SPLIT_COMPILE = ("ffb_staged.cu", "ffb_train.cu")      # (the two-half wide kernels lose 15 % with it)
 
 
 def _obj(src):

@@ -65,23 +65,21 @@ static int wd_launch(Kern kern, size_t smem, const char* name, const FieldDev& f
   return FFB_OK;
 }
 
-// (the single evaluation keeps one half per pass: it is a small share of a solve, and every instantiation costs build time)
+// The two-half kernels live in their own translation unit (ffb_wide2.cu) so that the two compile in parallel.
 #define WD_DISPATCH_ONE(KERNEL, NAME, BATCH)                                                                    \
   const size_t smem = wd_pick_smem(&fd, 1);                                                                     \
   if (fd.slots_smem) return wd_launch(KERNEL<EngineWideT<1, true>, true>, smem, NAME, fd, a, BATCH, st);        \
   return wd_launch(KERNEL<EngineWideT<1, true>, false>, smem, NAME, fd, a, BATCH, st)
-#define WD_DISPATCH(KERNEL, NAME, BATCH)                                                                        \
-  const int H = wd_halves(fd);                                                                                  \
-  const size_t smem = wd_pick_smem(&fd, H);                                                                     \
-  if (H == 2) {                                                                                                 \
-    if (fd.slots_smem) return wd_launch(KERNEL<EngineWideT<2, false>, true>, smem, NAME, fd, a, BATCH, st);            \
-    return wd_launch(KERNEL<EngineWideT<2, false>, false>, smem, NAME, fd, a, BATCH, st);                              \
-  }                                                                                                             \
-  if (fd.slots_smem) return wd_launch(KERNEL<EngineWideT<1, true>, true>, smem, NAME, fd, a, BATCH, st);              \
-  return wd_launch(KERNEL<EngineWideT<1, true>, false>, smem, NAME, fd, a, BATCH, st)
 
+// (the single evaluation keeps one half per pass: it is a small share of a solve, and every instantiation costs build time)
 int wide_launch_field_eval(FieldDev fd, const ffb_eval_args& a, cudaStream_t st) { WD_DISPATCH_ONE(k_field_eval, "ffb_field_eval", a.batch); }
-int wide_launch_dopri5(FieldDev fd, const ffb_dopri5_args& a, cudaStream_t st) { WD_DISPATCH(k_dopri5, "ffb_dopri5_attempt", a.batch); }
-int wide_launch_fixed(FieldDev fd, const ffb_fixed_args& a, cudaStream_t st) { WD_DISPATCH(k_fixed, "ffb_integrate_fixed", a.batch); }
+int wide_launch_dopri5(FieldDev fd, const ffb_dopri5_args& a, cudaStream_t st) {
+  if (wd_halves(fd) == 2) { const size_t smem = wd_pick_smem(&fd, 2); return wide2_launch_dopri5(fd, a, smem, st); }
+  WD_DISPATCH_ONE(k_dopri5, "ffb_dopri5_attempt", a.batch);
+}
+int wide_launch_fixed(FieldDev fd, const ffb_fixed_args& a, cudaStream_t st) {
+  if (wd_halves(fd) == 2) { const size_t smem = wd_pick_smem(&fd, 2); return wide2_launch_fixed(fd, a, smem, st); }
+  WD_DISPATCH_ONE(k_fixed, "ffb_integrate_fixed", a.batch);
+}
 
 }  // namespace ffb

@@ -12,4 +12,8 @@ namespace ffb {
 FFB_HIDDEN int wide_launch_field_eval(FieldDev fd, const ffb_eval_args& a, cudaStream_t st);
 FFB_HIDDEN int wide_launch_dopri5(FieldDev fd, const ffb_dopri5_args& a, cudaStream_t st);
 FFB_HIDDEN int wide_launch_fixed(FieldDev fd, const ffb_fixed_args& a, cudaStream_t st);
+// two 32-row halves per pass (EngineWideT<2, false>, SiLU): translation unit ffb_wide2.cu; `smem` and fd.slots_smem are
+// chosen by the caller (ffb_wide.cu: wd_pick_smem)
+FFB_HIDDEN int wide2_launch_dopri5(const FieldDev& fd, const ffb_dopri5_args& a, size_t smem, cudaStream_t st);
+FFB_HIDDEN int wide2_launch_fixed(const FieldDev& fd, const ffb_fixed_args& a, size_t smem, cudaStream_t st);
 }  // namespace ffb
