@@ -205,7 +205,7 @@ _NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
                "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(_HERE, "csrc"), "-Xcompiler", "-fPIC"]
 # -split-compile 0 (one ptxas job per kernel, in parallel) cuts the build time but the tensor-core kernels it produces are
 # 7 % slower: only the translation units without tcgen05 kernels take it
-_SPLIT_COMPILE = ("ffb_staged.cu", "ffb_train.cu")      # (the two-half wide kernels lose 15 % with it)
+_SPLIT_COMPILE = ("ffb_staged.cu", "ffb_train.cu", "ffb_wide.cu")      # (not ffb_wide2.cu: the two-half wide kernels lose 15 % with it; the one-half ones gain 8 %)
 
 
 def _obj(src):
