@@ -326,7 +326,17 @@ struct EngineRRT_ {
     RR_TRACE(cx, 13);
     if (tc.kind == RT_OWNER && cx.cg == 0) {
       float tr = 0.0f;
-      if (tc.exact) { for (int j = 0; j < tc.T; ++j) tr += tc.diag()[s * tc.T + j]; }
+      if (tc.exact) {
+        // same order of additions; the loads of a group of 8 are issued together instead of one dependent load per term
+        const float* dg = tc.diag() + s * tc.T;
+        for (int j0 = 0; j0 < tc.T; j0 += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = dg[min(j0 + u, tc.T - 1)];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) if (j0 + u < tc.T) tr += v[u];
+        }
+      }
       else { for (int g = 0; 8 * g < xd; ++g) tr += tc.diag()[s * 16 + g]; }
       float dv;
       if (score) {
@@ -338,6 +348,7 @@ struct EngineRRT_ {
       }
       tc.klp()[dst * ld + s] = dv * ev.sign();
     }
+    RR_TRACE(cx, 28);
   }
 };
 using EngineRRT = EngineRRT_<false>;
@@ -491,8 +502,14 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
   const int SD = cx.SD, CD = cx.CD, S = tc.S, ld = tc.ld;
   const bool owner = (tc.kind == RT_OWNER);
   float* LP0 = tc.klp() + NSLOT * ld;
+  // idx / S by multiplication: the 64-bit division behind the constant costs several hundred cycles, so it is done ONCE
+  // per kernel, not once per stage (S >= 2 here would not even need the special case, S = 1 does: umulhi(idx, 2^32) overflows)
+  const unsigned div_s = (S == 1) ? 0u : (unsigned)((0x100000000ull + (unsigned)S - 1u) / (unsigned)S);
+  auto elem = [&](int idx) { const int d = (S == 1) ? idx : (int)__umulhi((unsigned)idx, div_s); return d * ld + (idx - d * S); };
+  __shared__ float cbs[36];      // the stage coefficients cb[i][j]: read once (launch arguments or the controller block)
   if (!cx.producer) {
     for (int s = 0; s < 6; ++s) EngineRR::prep_beff(cx, f, DYN ? a.ctl->ev[s].tfeat : a.ev[s].tfeat, cx.beff() + s * KMAX);
+    if (cx.tid < 36) cbs[cx.tid] = FFB_STEP(cb[cx.tid / 6][cx.tid % 6]);
     rr_bar();
   }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -514,45 +531,38 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
         if (!is_finite_f(LP0[s])) nonfinite += 1.0;
       }
       rr_bar();
-      if (owner) {
+      {
+        // Stage algebra, one (state column, sample) element per thread: a tile holds few samples (7 for 16 tangents), so
+        // leaving it to the samples' owner rows (28 threads, 8 strided elements each) cost ~1.9 k cycles per evaluation
+        // during which the tensor pipe idles; spread over the compute threads it is a few hundred.  Same statements, same bits.
         const float c00 = FFB_STEP(cb[0][0]);
         const float* K1 = ENGT::slot(cx, tc, 0);
-        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
-          float y0v[8], kv[8], y[8];
-          rt_load8(cx, tc, Y0, d0, y0v);
-          rt_load8(cx, tc, K1, d0, kv);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (d0 + u < SD && !is_finite_f(y0v[u])) nonfinite += 1.0;
-            y[u] = __fadd_rn(y0v[u], __fmul_rn(kv[u], c00));
-          }
-          rt_store8(cx, tc, cx.ycur(), d0, y);
+        float* yc = cx.ycur();
+        for (int idx = cx.tid; idx < S * SD; idx += RR_NCOMP) {
+          const int e = elem(idx);
+          const float y0v = Y0[e];
+          if (!is_finite_f(y0v)) nonfinite += 1.0;
+          yc[e] = __fadd_rn(y0v, __fmul_rn(K1[e], c00));
         }
       }
     }
     for (int i = 1; i <= 6; ++i) {
       if constexpr (DYN) ENGT::eval_ev(cx, tc, f, EvCtl{a.ctl, i - 1}, cx.beff() + (i - 1) * KMAX, i);
       else ENGT::eval(cx, tc, f, a.ev[i - 1].a, a.ev[i - 1].c, a.ev[i - 1].sigma, a.ev[i - 1].sign, cx.beff() + (i - 1) * KMAX, i);
-      if (!cx.producer && owner && i < 6) {
+      if (!cx.producer && i < 6) {
+        RR_TRACE(cx, 26);
         float cbi[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) cbi[j] = FFB_STEP(cb[i][j]);
-        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
-          float y0v[8], kv[8], acc[8];
-          rt_load8(cx, tc, Y0, d0, y0v);
-          rt_load8(cx, tc, ENGT::slot(cx, tc, 0), d0, kv);
+        for (int j = 0; j < 6; ++j) cbi[j] = cbs[i * 6 + j];
+        float* yc = cx.ycur();
+        for (int idx = cx.tid; idx < S * SD; idx += RR_NCOMP) {
+          const int e = elem(idx);
+          float acc = __fmul_rn(ENGT::slot(cx, tc, 0)[e], cbi[0]);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) acc[u] = __fmul_rn(kv[u], cbi[0]);
-#pragma unroll
-          for (int j = 1; j < 6; ++j) {
-            rt_load8_if(cx, tc, j <= i, ENGT::slot(cx, tc, j), d0, kv);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc[u] = fmaf(kv[u], cbi[j], acc[u]);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc[u] = __fadd_rn(y0v[u], acc[u]);
-          rt_store8(cx, tc, cx.ycur(), d0, acc);
+          for (int j = 1; j < 6; ++j) acc = fmaf((j <= i) ? ENGT::slot(cx, tc, j)[e] : 0.0f, cbi[j], acc);
+          yc[e] = __fadd_rn(Y0[e], acc);
         }
+        RR_TRACE(cx, 27);
       }
     }
     if (!cx.producer) {
@@ -561,34 +571,27 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
       const int final_ = FFB_STEP(final);
       const bool sw = FFB_SWAPPED();
       float* OUT = ENGT::slot(cx, tc, 1);              // K2 of an element is dead once its sums are formed
-      if (owner && tc.smp < nv) {
-        float ce[7], cm[7];
+      float ce[7], cm[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) { ce[j] = FFB_STEP(ce[j]); cm[j] = FFB_STEP(cm[j]); }
-        const float dt_ = FFB_STEP(dt), xi_ = FFB_STEP(x_interp);
-        for (int d0 = 8 * cx.cg; d0 < SD; d0 += 32) {
-          float y0v[8], y1v[8], k0[8], kv[8], err[8], mid[8];
-          rt_load8(cx, tc, Y0, d0, y0v);
-          rt_load8(cx, tc, cx.ycur(), d0, y1v);
-          rt_load8(cx, tc, ENGT::slot(cx, tc, 0), d0, k0);
+      for (int j = 0; j < 7; ++j) { ce[j] = FFB_STEP(ce[j]); cm[j] = FFB_STEP(cm[j]); }
+      const float dt_ = FFB_STEP(dt), xi_ = FFB_STEP(x_interp);
+      // error / mid-point sums and the dense output, one (state column, sample) element per thread
+      for (int idx = cx.tid; idx < S * SD; idx += RR_NCOMP) {
+        const int e = elem(idx), sm = e % ld;
+        if (sm >= nv) continue;
+        const float y0v = Y0[e], y1v = cx.ycur()[e], k0 = ENGT::slot(cx, tc, 0)[e];
+        float err = __fmul_rn(k0, ce[0]), mid = __fmul_rn(k0, cm[0]), kv = k0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) { err[u] = __fmul_rn(k0[u], ce[0]); mid[u] = __fmul_rn(k0[u], cm[0]); }
-#pragma unroll
-          for (int j = 1; j < 7; ++j) {
-            rt_load8(cx, tc, ENGT::slot(cx, tc, j), d0, kv);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { err[u] = fmaf(kv[u], ce[j], err[u]); mid[u] = fmaf(kv[u], cm[j], mid[u]); }
-          }
-          float out[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0v[u]), fabsf(y1v[u]))));
-            const float q = __fdiv_rn(err[u], tol);
-            if (d0 + u < SD) v[0] += (double)q * q;
-            out[u] = final_ ? dense_output(y0v[u], y1v[u], __fadd_rn(y0v[u], mid[u]), k0[u], kv[u], dt_, xi_) : 0.0f;
-          }
-          if (final_) rt_store8(cx, tc, OUT, d0, out);
+        for (int j = 1; j < 7; ++j) {
+          kv = ENGT::slot(cx, tc, j)[e];
+          err = fmaf(kv, ce[j], err); mid = fmaf(kv, cm[j], mid);
         }
+        const float tol = __fadd_rn(a.atol, __fmul_rn(a.rtol, fmaxf(fabsf(y0v), fabsf(y1v))));
+        const float q = __fdiv_rn(err, tol);
+        v[0] += (double)q * q;
+        if (final_) OUT[e] = dense_output(y0v, y1v, __fadd_rn(y0v, mid), k0, kv, dt_, xi_);
+      }
+      if (owner && tc.smp < nv) {
         if (cx.cg == 0) {
           // the log-det column: same formulas on (lp0, d(logp)/dt of the 7 stages)
           const int s = tc.smp;

@@ -530,7 +530,7 @@ static int rrt_plan(const ffb_field* f, int state_dim, int cond_dim, int tdim, i
   int S = rrt_rowmap(tangents_of(f), -1, nullptr);
   for (; S >= 1; --S) {
     const size_t smem = smem_layout_rrt(state_dim, cond_dim, rrt_ld(S), f->div_mode == FFB_DIV_HUTCH, nslot, tdim, nbeff, nullptr);
-    if (smem <= (size_t)smem_optin()) { if (smem_out) *smem_out = smem; return S; }
+    if (smem + 256 <= (size_t)smem_optin()) { if (smem_out) *smem_out = smem; return S; }   // 256: the kernels' static shared memory
   }
   return 0;
 }

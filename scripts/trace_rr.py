@@ -39,7 +39,7 @@ for role in range(3):
 rows.sort()
 t0 = rows[0][0]
 def name(tag):
-    if 20 <= tag < 30: return {20:'last: ld issued',21:'last: wait_ld done',22:'last: transform stored',23:'buildA: split done',24:'buildA: st issued',25:'signal: wait_st done',26:'kernel: algebra begin',27:'kernel: algebra end'}[tag]
+    if 20 <= tag < 30: return {20:'last: ld issued',21:'last: wait_ld done',22:'last: transform stored',23:'buildA: split done',24:'buildA: st issued',25:'signal: wait_st done',26:'kernel: algebra begin',27:'kernel: algebra end',28:'eval: trace summed'}[tag]
     if tag == 10: return 'eval: ycur final (qbar passed)'
     if tag == 11: return 'eval: layer-0 operand handed over'
     if tag == 12: return 'eval: last-layer output consumed'
