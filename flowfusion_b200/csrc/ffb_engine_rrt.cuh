@@ -245,9 +245,12 @@ struct EngineRRT_ {
     eval_ev(cx, tc, f, EvVals{ev_a, ev_c, ev_sigma, ev_sign}, beff, dst);
   }
   // EV: source of the per-evaluation scalars, fetched where they are used (see EngineRR_::eval_ev)
-  template <class EV>
+  // DEFER: leave this evaluation's divergence to the caller (finish_trace); `prev` / `prev_dst` (>= 0): the deferred divergence
+  // of the previous evaluation, finished here once the layer-0 operand is handed over (the owner threads would otherwise idle
+  // until layer 0's accumulators arrive)
+  template <class EV, bool DEFER = false>
   static __device__ __forceinline__ void eval_ev(CtxR& cx, const TanCtx& tc, const FieldDev& f, const EV& ev,
-                                                 const float* beff, int dst) {
+                                                 const float* beff, int dst, const EV* prev = nullptr, int prev_dst = -1) {
     const NetDev& net = f.net[0];
     if (cx.warp == RR_WLOAD) { EngineRR::load_net(cx, net); return; }
     if (cx.warp == RR_WMMA) { EngineRR::mma_net(cx, net); return; }
@@ -257,6 +260,7 @@ struct EngineRRT_ {
     RR_TRACE(cx, 10);
     build_A(cx, tc, f);
     RR_TRACE(cx, 11);
+    if (prev_dst >= 0) finish_trace(cx, tc, f, *prev, prev_dst);
     hidden(cx, tc, net, beff);
     // ---- last layer ---------------------------------------------------------------------------------
     const int nl = net.n_layers, Nreal = net.N[nl - 1];
@@ -324,6 +328,19 @@ struct EngineRRT_ {
     RR_TRACE(cx, 12);
     rr_bar();                                  // slot dst and the trace pieces are complete
     RR_TRACE(cx, 13);
+    if (!DEFER) finish_trace(cx, tc, f, ev, dst);
+    RR_TRACE(cx, 28);
+  }
+
+  // divergence of the evaluation whose last layer left its trace pieces in tc.diag(): sum them (fixed order) and apply the
+  // field transform -> klp[dst].  Run by the samples' owner threads; with DEFER the caller runs it for the PREVIOUS evaluation
+  // while layer 0 of the next one is on the tensor pipe (nothing reads klp before the end of the attempt), or right away
+  // after the last evaluation.
+  template <class EV>
+  static __device__ __forceinline__ void finish_trace(CtxR& cx, const TanCtx& tc, const FieldDev& f, const EV& ev, int dst) {
+    if (cx.producer) return;
+    const int ld = tc.ld, s = tc.smp, xd = f.net[0].x_dim;
+    const bool score = (f.kind == FFB_FIELD_SCORE), use_sigma = f.use_sigma != 0, has_drift = f.has_drift != 0;
     if (tc.kind == RT_OWNER && cx.cg == 0) {
       float tr = 0.0f;
       if (tc.exact) {
@@ -348,7 +365,6 @@ struct EngineRRT_ {
       }
       tc.klp()[dst * ld + s] = dv * ev.sign();
     }
-    RR_TRACE(cx, 28);
   }
 };
 using EngineRRT = EngineRRT_<false>;
@@ -547,8 +563,19 @@ __global__ void __launch_bounds__(ffb::RR_NTHR, 1) k_dopri5_rrt(const __grid_con
       }
     }
     for (int i = 1; i <= 6; ++i) {
-      if constexpr (DYN) ENGT::eval_ev(cx, tc, f, EvCtl{a.ctl, i - 1}, cx.beff() + (i - 1) * KMAX, i);
-      else ENGT::eval(cx, tc, f, a.ev[i - 1].a, a.ev[i - 1].c, a.ev[i - 1].sigma, a.ev[i - 1].sign, cx.beff() + (i - 1) * KMAX, i);
+      // the divergence of evaluation i - 1 is finished inside evaluation i (after its layer-0 operand is handed over), the
+      // last one right after the loop: klp is only read at the end of the attempt
+      if constexpr (DYN) {
+        const EvCtl cur{a.ctl, i - 1}, prv{a.ctl, i - 2};
+        ENGT::template eval_ev<EvCtl, true>(cx, tc, f, cur, cx.beff() + (i - 1) * KMAX, i, &prv, i > 1 ? i - 1 : -1);
+        if (i == 6) ENGT::finish_trace(cx, tc, f, cur, 6);
+      } else {
+        const EvVals cur{a.ev[i - 1].a, a.ev[i - 1].c, a.ev[i - 1].sigma, a.ev[i - 1].sign};
+        const int ip = i > 1 ? i - 2 : 0;
+        const EvVals prv{a.ev[ip].a, a.ev[ip].c, a.ev[ip].sigma, a.ev[ip].sign};
+        ENGT::template eval_ev<EvVals, true>(cx, tc, f, cur, cx.beff() + (i - 1) * KMAX, i, &prv, i > 1 ? i - 1 : -1);
+        if (i == 6) ENGT::finish_trace(cx, tc, f, cur, 6);
+      }
       if (!cx.producer && i < 6) {
         RR_TRACE(cx, 26);
         float cbi[6];
